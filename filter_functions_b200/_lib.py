@@ -1,0 +1,138 @@
+"""ctypes binding of ``libffb200.so`` (C ABI declared in ``include/ffb200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` (plain ``nvcc`` for sm_100a).  There is
+NO CPU fallback: if the shared object is missing, or no sm_100 GPU is visible, every compute call
+raises.  Importing this module never touches the GPU, so the package can be imported on a CPU-only
+box (the ``-m "not gpu"`` tests check that the library loads and exports every declared symbol).
+"""
+import ctypes
+import os
+import threading
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
+
+import numpy as np
+
+__all__ = ['lib', 'context', 'check', 'library_path', 'FFBError', 'EXPORTED_SYMBOLS']
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+library_path = os.path.join(_HERE, 'csrc', 'libffb200.so')
+
+FFB_OK, FFB_EINVAL, FFB_ENODEVICE, FFB_ECUDA, FFB_ENOMEM, FFB_ENOTCONV = 0, -1, -2, -3, -4, -5
+
+_dp = POINTER(c_double)
+_ip = POINTER(c_int)
+
+#: every ``extern "C"`` symbol declared in include/ffb200.h with its (restype, argtypes)
+EXPORTED_SYMBOLS = {
+    'ffb_init': (c_int, [POINTER(c_void_p), c_int]),
+    'ffb_destroy': (None, [c_void_p]),
+    'ffb_last_error': (c_char_p, [c_void_p]),
+    'ffb_version': (c_char_p, []),
+    'ffb_set_stream': (c_int, [c_void_p, c_void_p]),
+    'ffb_sync': (c_int, [c_void_p]),
+    'ffb_launch_count': (c_int64, [c_void_p]),
+    'ffb_device_info': (c_int, [c_void_p, _ip, _ip, _ip, POINTER(c_size_t)]),
+    'ffb_measure_fp64_peak': (c_int, [c_void_p, _dp, _dp]),
+    'ffb_diagonalize': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p]),
+    'ffb_control_matrix_from_scratch': (c_int, [c_void_p] + [c_int]*5 + [c_void_p]*10),
+    'ffb_filter_function': (c_int, [c_void_p] + [c_int]*4 + [c_void_p, c_int, c_void_p]),
+    'ffb_control_matrix_from_atomic': (c_int, [c_void_p] + [c_int]*4 + [c_void_p]*3
+                                       + [c_int, c_int, c_void_p]),
+    'ffb_infidelity': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                               c_int, c_int, c_void_p, c_int, c_void_p]),
+    'ffb_liouville_representation': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                             c_void_p]),
+    'ffb_cexp': (c_int, [c_void_p, c_int, c_void_p, c_double, c_void_p]),
+    'ffb_pulse_filter_function': (c_int, [c_void_p] + [c_int]*6 + [c_void_p]*9 + [c_int, c_int]
+                                  + [c_void_p]*6),
+    'ffb_dev_diagonalize': (c_int, [c_void_p, c_int, c_int, c_int] + [c_void_p]*6),
+    'ffb_dev_control_matrix_from_scratch': (c_int, [c_void_p] + [c_int]*5 + [c_void_p]*9
+                                            + [c_int, c_void_p]),
+    'ffb_dev_filter_function': (c_int, [c_void_p] + [c_int]*4 + [c_void_p, c_int, c_void_p]),
+    'ffb_dev_control_matrix_from_atomic': (c_int, [c_void_p] + [c_int]*4 + [c_void_p]*3
+                                           + [c_int, c_int, c_void_p]),
+    'ffb_dev_infidelity': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                   c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    'ffb_dev_alloc': (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
+    'ffb_dev_free': (c_int, [c_void_p, c_void_p]),
+    'ffb_memcpy_h2d': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    'ffb_memcpy_d2h': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    'ffb_kernel_timing_enable': (c_int, [c_void_p, c_int]),
+    'ffb_kernel_timing_read': (c_int, [c_void_p, _dp, POINTER(c_int64), c_int]),
+}
+
+
+class FFBError(RuntimeError):
+    """CUDA / device failure inside libffb200."""
+
+
+_lib = None
+_lib_lock = threading.Lock()
+_contexts = {}
+
+
+def lib():
+    """Load (once) and return the shared library.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lib_lock:
+            if _lib is None:
+                if not os.path.exists(library_path):
+                    raise FFBError(
+                        f'{library_path} not found. Build it with '
+                        '`python -c "import __graft_entry__ as g; g.build()"` from the repository '
+                        'root (needs nvcc). filter_functions_b200 has no CPU fallback.')
+                handle = ctypes.CDLL(library_path)
+                for name, (restype, argtypes) in EXPORTED_SYMBOLS.items():
+                    fn = getattr(handle, name)
+                    fn.restype = restype
+                    fn.argtypes = argtypes
+                _lib = handle
+    return _lib
+
+
+def context(device=None):
+    """The (cached) engine context for ``device`` (default: ``FFB200_DEVICE``, else ``LOCAL_RANK``,
+    else 0)."""
+    if device is None:
+        device = int(os.environ.get('FFB200_DEVICE', os.environ.get('LOCAL_RANK', 0)))
+    ctx = _contexts.get(device)
+    if ctx is None:
+        handle = c_void_p()
+        rc = lib().ffb_init(byref(handle), device)
+        if rc != FFB_OK:
+            msg = lib().ffb_last_error(None).decode()
+            raise FFBError(f'ffb_init(device={device}) failed: {msg}')
+        ctx = _contexts[device] = handle
+    return ctx
+
+
+def check(ctx, rc):
+    """Map a negative return code to the Python exception the reference would raise."""
+    if rc == FFB_OK:
+        return
+    msg = lib().ffb_last_error(ctx).decode()
+    if rc == FFB_EINVAL:
+        raise ValueError(msg)
+    if rc == FFB_ENOMEM:
+        raise MemoryError(msg)
+    if rc == FFB_ENOTCONV:
+        from .util import CalculationError
+        raise CalculationError(msg)
+    raise FFBError(msg)
+
+
+def ptr(arr):
+    """Raw pointer of a C-contiguous ndarray (``None`` -> NULL)."""
+    if arr is None:
+        return None
+    return arr.ctypes.data_as(c_void_p)
+
+
+def as_c128(x):
+    return np.ascontiguousarray(x, dtype=np.complex128)
+
+
+def as_f64(x):
+    return np.ascontiguousarray(x, dtype=np.float64)

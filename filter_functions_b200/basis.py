@@ -1,0 +1,243 @@
+"""Operator bases consumed by the engine as dense ``(n_basis, d, d)`` complex128 arrays.
+
+Host-side set-up, executed once per pulse; the reference's ``basis.py`` (815 lines, sparse trace
+tensors, basis completion) is out of scope.  What the hot path needs
+is restated here: the ``Basis`` ndarray subclass with the predicates the path branches on, the
+Pauli and generalised Gell-Mann constructors, and basis expansion.
+"""
+from functools import cached_property
+from itertools import product
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import util
+
+__all__ = ['Basis', 'expand', 'ggm_expand', 'normalize']
+
+
+class Basis(np.ndarray):
+    """ndarray subclass of shape (n_basis, d, d) (reference ``basis.py:58-392``).
+
+    ``Basis(array_like, traceless=None, btype=None, labels=None)`` wraps the given elements as they
+    are; :meth:`pauli` and :meth:`ggm` build the two orthonormal Hermitian bases the reference
+    ships.
+    """
+
+    def __new__(cls, basis_array, traceless: Optional[bool] = None, btype: Optional[str] = None,
+                labels: Optional[Sequence[str]] = None) -> 'Basis':
+        if not util.is_sequence_like(basis_array):
+            raise TypeError('Invalid data type. Must be array_like')
+        if isinstance(basis_array, cls):
+            basis = basis_array
+        else:
+            if hasattr(basis_array, 'shape') and len(basis_array.shape) == 2:
+                basis_array = [basis_array]
+            basis = util.parse_operators(basis_array, 'basis_array')
+            if basis.shape[0] > np.prod(basis.shape[1:]):
+                raise ValueError('Given overcomplete set of basis matrices. '
+                                 'Not linearly independent.')
+        basis = basis.view(cls)
+        basis.btype = btype or 'Custom'
+        basis.d = basis.shape[-1]
+        if labels is not None:
+            if len(labels) != len(basis):
+                raise ValueError(f'Got {len(labels)} basis labels but expected {len(basis)}')
+            basis.labels = labels
+        else:
+            basis.labels = [f'$C_{{{i}}}$' for i in range(len(basis))]
+        return basis
+
+    def __array_finalize__(self, basis) -> None:
+        if basis is None:
+            return
+        self.btype = getattr(basis, 'btype', 'Custom')
+        self.labels = getattr(basis, 'labels', [f'$C_{{{i}}}$' for i in range(len(basis))])
+        self.d = getattr(basis, 'd', basis.shape[-1])
+        self._eps = np.finfo(complex).eps
+        self._atol = self._eps*self.d**3
+        self._rtol = 0
+
+    def __eq__(self, other) -> bool:
+        try:
+            if self.shape != other.shape:
+                return False
+        except AttributeError:
+            return np.equal(self, other)
+        return np.allclose(self.view(np.ndarray), np.asarray(other), atol=self._atol,
+                           rtol=self._rtol)
+
+    __hash__ = None
+
+    def __contains__(self, item) -> bool:
+        return any(np.isclose(np.asarray(item), self.view(np.ndarray), rtol=self._rtol,
+                              atol=self._atol).all(axis=(1, 2)))
+
+    def __array_wrap__(self, arr, context=None, return_scalar=False):
+        if arr.ndim == 0:
+            return arr[()]
+        return super().__array_wrap__(arr, context, return_scalar)
+
+    @cached_property
+    def isherm(self) -> bool:
+        return self.H == self
+
+    @cached_property
+    def isnorm(self) -> bool:
+        return normalize(self) == self
+
+    @cached_property
+    def isorthogonal(self) -> bool:
+        if self.ndim == 2 or len(self) == 1:
+            return True
+        flat = self.view(np.ndarray).reshape(len(self), -1)
+        gram = flat.conj() @ flat.T
+        off = gram[~np.identity(len(self), dtype=bool)]
+        return np.allclose(off, 0, atol=self._eps*(self.d**2)**3, rtol=self._rtol)
+
+    @cached_property
+    def isorthonorm(self) -> bool:
+        return self.isorthogonal and self.isnorm
+
+    @cached_property
+    def istraceless(self) -> bool:
+        """True if all elements are traceless except possibly one proportional to the identity."""
+        arr = self.view(np.ndarray)
+        trace = np.einsum('...jj', arr)
+        trace = np.where(np.abs(trace) <= self._eps*self.d**2, 0, trace)
+        nonzero = np.atleast_1d(trace).nonzero()[0]
+        if nonzero.size == 0:
+            return True
+        if nonzero.size == 1:
+            elem = arr[nonzero[0]] if arr.ndim == 3 else arr
+            offdiag = elem[~np.eye(self.d, dtype=bool)]
+            return bool((np.diag(elem) == elem[0, 0]).all() and not offdiag.any())
+        return False
+
+    @cached_property
+    def iscomplete(self) -> bool:
+        flat = self.view(np.ndarray).reshape(self.shape[0], -1)
+        return np.linalg.matrix_rank(flat) == self.d**2
+
+    @property
+    def H(self) -> 'Basis':
+        return self.T.conj()
+
+    @property
+    def T(self) -> 'Basis':
+        return self.swapaxes(-1, -2) if self.ndim >= 2 else self
+
+    @cached_property
+    def four_element_traces(self) -> np.ndarray:
+        """T_ijkl = tr(C_i C_j C_k C_l) as a dense array (reference ``basis.py:330-348`` keeps it
+        sparse; dense is n_basis^4 * 16 B, fine for d <= 4)."""
+        arr = self.view(np.ndarray)
+        pair = np.einsum('iab,jbc->ijac', arr, arr)
+        return np.einsum('ijac,klca->ijkl', pair, pair)
+
+    def normalize(self, copy: bool = False):
+        if copy:
+            return normalize(self)
+        self /= _norm(self)
+        return None
+
+    def expand(self, M, hermitian: bool = False, traceless: bool = False, tidyup: bool = False):
+        if self.btype == 'GGM' and self.iscomplete:
+            return ggm_expand(M, traceless, hermitian, tidyup)
+        return expand(M, self, self.isnorm, hermitian, tidyup)
+
+    @classmethod
+    def pauli(cls, n: int) -> 'Basis':
+        """Normalised n-qubit Pauli basis {I,X,Y,Z}^n / sqrt(2^n) (reference ``basis.py:393-426``)."""
+        elems = util.paulis
+        for _ in range(n - 1):
+            elems = np.einsum('aij,bkl->abikjl', elems, util.paulis).reshape(
+                len(elems)*4, elems.shape[1]*2, elems.shape[2]*2)
+        elems = elems/np.sqrt(2**n)
+        labels = [''.join(tup) for tup in product(['I', 'X', 'Y', 'Z'], repeat=n)]
+        return cls(elems, btype='Pauli', labels=labels)
+
+    @classmethod
+    def ggm(cls, d: int) -> 'Basis':
+        """Normalised generalised Gell-Mann basis: identity, symmetric, antisymmetric, diagonal
+        elements in this order (reference ``basis.py:428-489``)."""
+        out = np.zeros((d*d, d, d), dtype=complex)
+        out[0] = np.eye(d)/np.sqrt(d)
+        pairs = [(j, k) for j in range(d) for k in range(j + 1, d)]
+        n_sym = len(pairs)
+        for i, (j, k) in enumerate(pairs, start=1):
+            out[i, j, k] = out[i, k, j] = 1/np.sqrt(2)
+            out[i + n_sym, j, k] = -1j/np.sqrt(2)
+            out[i + n_sym, k, j] = 1j/np.sqrt(2)
+        for l in range(1, d):
+            diag = np.zeros(d)
+            diag[:l] = 1
+            diag[l] = -l
+            out[2*n_sym + l] = np.diag(diag/np.sqrt(l*(l + 1)))
+        return cls(out, btype='GGM', labels=[rf'$\Lambda_{{{i}}}$' for i in range(d*d)])
+
+
+def _norm(b) -> np.ndarray:
+    b = np.asarray(b)
+    return np.linalg.norm(b, axis=(-1, -2))[..., None, None]
+
+
+def normalize(b: Basis) -> Basis:
+    """Copy of ``b`` normalised to unit Frobenius norm (reference ``basis.py:625-647``)."""
+    arr = np.asarray(b)
+    return (arr/_norm(arr)).view(Basis)
+
+
+def _tidy(arr):
+    eps = np.finfo(arr.dtype).eps*(arr.shape[-1] if arr.ndim else 1)
+    if np.iscomplexobj(arr):
+        arr.real[np.abs(arr.real) <= eps] = 0
+        arr.imag[np.abs(arr.imag) <= eps] = 0
+    else:
+        arr[np.abs(arr) <= eps] = 0
+    return arr
+
+
+def expand(M, basis, normalized: bool = True, hermitian: bool = False, tidyup: bool = False):
+    """Coefficients c_j = tr(M C_j) / tr(C_j^dagger C_j) (reference ``basis.py:650-698``)."""
+    M = np.asarray(M)
+    arr = np.asarray(basis)
+    real = hermitian and bool(getattr(basis, 'isherm', False))
+    coeffs = np.tensordot(M, arr, axes=[(-2, -1), (-1, -2)])
+    if real:
+        coeffs = coeffs.real
+    if not normalized:
+        norms = np.einsum('bij,bji->b', arr, arr)
+        coeffs = coeffs/(norms.real if real else norms)
+    return _tidy(coeffs) if tidyup else coeffs
+
+
+def ggm_expand(M, traceless: bool = False, hermitian: bool = False, tidyup: bool = False):
+    """Expansion in the GGM basis from its construction rule (reference ``basis.py:701-787``)."""
+    M = np.asarray(M)
+    if M.shape[-1] != M.shape[-2]:
+        raise ValueError('M should be square in its last two axes')
+    square = M.ndim < 3
+    if square:
+        M = M[None]
+    d = M.shape[-1]
+    pairs = [(j, k) for j in range(d) for k in range(j + 1, d)]
+    n_sym = len(pairs)
+    coeffs = np.zeros((*M.shape[:-2], d*d), dtype=float if hermitian else complex)
+
+    def cast(x):
+        return x.real if hermitian else x
+
+    if not traceless:
+        coeffs[..., 0] = cast(np.trace(M, axis1=-2, axis2=-1))/np.sqrt(d)
+    if pairs:
+        js, ks = (np.array(ix) for ix in zip(*pairs))
+        upper, lower = M[..., js, ks], M[..., ks, js]
+        coeffs[..., 1:n_sym + 1] = cast(upper + lower)/np.sqrt(2)
+        coeffs[..., n_sym + 1:2*n_sym + 1] = cast(1j*(upper - lower))/np.sqrt(2)
+    diag = np.diagonal(M, axis1=-2, axis2=-1)
+    for l in range(1, d):
+        coeffs[..., 2*n_sym + l] = cast(diag[..., :l].sum(axis=-1) - l*diag[..., l])/np.sqrt(l*(l + 1))
+    if square:
+        coeffs = coeffs[0]
+    return _tidy(coeffs) if tidyup else coeffs

@@ -1,0 +1,560 @@
+// C ABI of libffb200 (include/ffb200.h): context, memory pool, host-pointer wrappers.
+#include <cstdarg>
+#include <cstring>
+
+#include "ffb_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing / pool / staging
+// ------------------------------------------------------------------------------------------------
+static std::string g_init_error;
+
+int ffb_fail(ffb_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  else g_init_error = buf;
+  return code;
+}
+
+int ffb_pool_alloc(ffb_ctx* ctx, size_t bytes, void** ptr) {
+  bytes = (bytes + 511) & ~(size_t)511;
+  auto it = ctx->free_blocks.lower_bound(bytes);
+  // accept a cached block if it wastes at most 2x
+  if (it != ctx->free_blocks.end() && it->first <= 2 * bytes + (1 << 20)) {
+    *ptr = it->second;
+    ctx->live_blocks[*ptr] = it->first;
+    ctx->free_blocks.erase(it);
+    return FFB_OK;
+  }
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) {
+    // give cached blocks back to the driver and retry once
+    (void)cudaGetLastError();
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->free_blocks) {
+      cudaFree(kv.second);
+      ctx->pool_bytes -= kv.first;
+    }
+    ctx->free_blocks.clear();
+    e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return ffb_fail(ctx, FFB_ENOMEM, "device allocation of %zu bytes failed: %s", bytes,
+                      cudaGetErrorString(e));
+    }
+  }
+  ctx->pool_bytes += bytes;
+  ctx->live_blocks[*ptr] = bytes;
+  return FFB_OK;
+}
+
+void ffb_pool_release(ffb_ctx* ctx, void* ptr) {
+  auto it = ctx->live_blocks.find(ptr);
+  if (it == ctx->live_blocks.end()) return;
+  ctx->free_blocks.emplace(it->second, ptr);
+  ctx->live_blocks.erase(it);
+}
+
+int ffb_h2d(ffb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return FFB_OK;
+  FFB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_d2h(ffb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return FFB_OK;
+  FFB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_time_begin(ffb_ctx* ctx, int* slot) {
+  *slot = -1;
+  if (!ctx->timing) return FFB_OK;
+  std::pair<cudaEvent_t, cudaEvent_t> ev;
+  if (!ctx->event_pool.empty()) {
+    ev = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+  } else {
+    FFB_CUDA(ctx, cudaEventCreate(&ev.first));
+    FFB_CUDA(ctx, cudaEventCreate(&ev.second));
+  }
+  FFB_CUDA(ctx, cudaEventRecord(ev.first, ctx->stream));
+  ctx->pending_events.push_back(ev);
+  *slot = (int)ctx->pending_events.size() - 1;
+  return FFB_OK;
+}
+
+int ffb_time_end(ffb_ctx* ctx, int slot) {
+  if (slot < 0) return FFB_OK;
+  FFB_CUDA(ctx, cudaEventRecord(ctx->pending_events[slot].second, ctx->stream));
+  return FFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* ffb_version(void) { return "ffb200 0.1.0 (sm_100a)"; }
+
+int ffb_init(ffb_ctx** out, int device) {
+  if (!out) return FFB_EINVAL;
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    (void)cudaGetLastError();
+    return ffb_fail(nullptr, FFB_ENODEVICE, "no CUDA device available (%s); ffb200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= n_dev)
+    return ffb_fail(nullptr, FFB_EINVAL, "device %d out of range [0, %d)", device, n_dev);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return ffb_fail(nullptr, FFB_ECUDA, "%s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return ffb_fail(nullptr, FFB_ENODEVICE,
+                    "device %d (%s) has compute capability %d.%d; libffb200 is built for sm_100a only",
+                    device, prop.name, prop.major, prop.minor);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return ffb_fail(nullptr, FFB_ECUDA, "%s", cudaGetErrorString(e));
+  ffb_ctx* ctx = new ffb_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  ctx->total_mem = prop.totalGlobalMem;
+  e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return ffb_fail(nullptr, FFB_ECUDA, "%s", cudaGetErrorString(e));
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return FFB_OK;
+}
+
+void ffb_destroy(ffb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+  for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
+  for (auto& ev : ctx->event_pool) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  for (auto& ev : ctx->pending_events) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* ffb_last_error(const ffb_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_init_error.c_str();
+}
+
+int ffb_set_stream(ffb_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return FFB_EINVAL;
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return FFB_OK;
+}
+
+int ffb_sync(ffb_ctx* ctx) {
+  if (!ctx) return FFB_EINVAL;
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+int64_t ffb_launch_count(const ffb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ffb_device_info(ffb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
+  if (!ctx) return FFB_EINVAL;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (total_mem) *total_mem = ctx->total_mem;
+  return FFB_OK;
+}
+
+int ffb_measure_fp64_peak(ffb_ctx* ctx, double* dfma_tflops, double* dmma_tflops) {
+  if (!ctx) return FFB_EINVAL;
+  FFB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return ffbi_fp64_peak(ctx, dfma_tflops, dmma_tflops);
+}
+
+int ffb_kernel_timing_enable(ffb_ctx* ctx, int enable) {
+  if (!ctx) return FFB_EINVAL;
+  ctx->timing = enable != 0;
+  return FFB_OK;
+}
+
+int ffb_kernel_timing_read(ffb_ctx* ctx, double* total_ms, int64_t* launches, int reset) {
+  if (!ctx) return FFB_EINVAL;
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& ev : ctx->pending_events) {
+    float ms = 0.f;
+    FFB_CUDA(ctx, cudaEventElapsedTime(&ms, ev.first, ev.second));
+    ctx->timed_ms += ms;
+    ctx->timed_launches++;
+    ctx->event_pool.push_back(ev);
+  }
+  ctx->pending_events.clear();
+  if (total_ms) *total_ms = ctx->timed_ms;
+  if (launches) *launches = ctx->timed_launches;
+  if (reset) {
+    ctx->timed_ms = 0.0;
+    ctx->timed_launches = 0;
+  }
+  return FFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// raw device memory
+// ------------------------------------------------------------------------------------------------
+int ffb_dev_alloc(ffb_ctx* ctx, size_t bytes, void** ptr) {
+  if (!ctx || !ptr) return FFB_EINVAL;
+  FFB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return ffb_pool_alloc(ctx, bytes ? bytes : 8, ptr);
+}
+
+int ffb_dev_free(ffb_ctx* ctx, void* ptr) {
+  if (!ctx) return FFB_EINVAL;
+  ffb_pool_release(ctx, ptr);
+  return FFB_OK;
+}
+
+int ffb_memcpy_h2d(ffb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  if (!ctx) return FFB_EINVAL;
+  FFB_TRY(ffb_h2d(ctx, dst_dev, src_host, bytes));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_memcpy_d2h(ffb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  if (!ctx) return FFB_EINVAL;
+  FFB_TRY(ffb_d2h(ctx, dst_host, src_dev, bytes));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-pointer entry points
+// ------------------------------------------------------------------------------------------------
+int ffb_dev_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_opers,
+                        const double* c_coeffs, const double* dt, double* eigvals, double* eigvecs,
+                        double* propagators) {
+  if (!ctx) return FFB_EINVAL;
+  return ffbi_diagonalize(ctx, G, d, n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs, propagators);
+}
+
+int ffb_dev_control_matrix_from_scratch(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis,
+                                        int n_omega, const double* eigvals, const double* eigvecs,
+                                        const double* propagators, const double* omega,
+                                        const double* basis, const double* n_opers,
+                                        const double* n_coeffs, const double* dt, const double* t,
+                                        int herm_flags, double* out) {
+  if (!ctx) return FFB_EINVAL;
+  return ffbi_control_matrix(ctx, G, d, n_nops, n_basis, n_omega, eigvals, eigvecs, propagators,
+                             omega, basis, n_opers, n_coeffs, dt, t, herm_flags, out);
+}
+
+int ffb_dev_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+                            const double* B, int generalized, double* F) {
+  if (!ctx) return FFB_EINVAL;
+  return ffbi_filter_function(ctx, P, n_nops, n_basis, n_omega, B, generalized, F);
+}
+
+int ffb_dev_control_matrix_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+                                       const double* phases, const double* B_atomic,
+                                       const double* Q_liouville, int q_is_complex,
+                                       int correlations, double* out) {
+  if (!ctx) return FFB_EINVAL;
+  return ffbi_from_atomic(ctx, P, n_nops, n_basis, n_omega, phases, B_atomic, Q_liouville,
+                          q_is_complex, correlations, out);
+}
+
+int ffb_dev_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* idx,
+                       int n_omega, const double* F, const double* spectrum, int spectrum_ndim,
+                       int spectrum_is_complex, const double* omega, int d, double* out) {
+  if (!ctx) return FFB_EINVAL;
+  return ffbi_infidelity(ctx, n_lead, n_nops, n_sel, idx, n_omega, F, spectrum, spectrum_ndim,
+                         spectrum_is_complex, omega, d, out);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// host-pointer entry points
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// exact Hermiticity test of a stack of d x d complex matrices (host side, O(n d^2))
+bool all_hermitian(const double* m, int n, int d) {
+  for (int i = 0; i < n; ++i) {
+    const double* a = m + (size_t)i * 2 * d * d;
+    for (int r = 0; r < d; ++r) {
+      for (int c = r; c < d; ++c) {
+        if (a[2 * (r * d + c)] != a[2 * (c * d + r)]) return false;
+        if (a[2 * (r * d + c) + 1] != -a[2 * (c * d + r) + 1]) return false;
+      }
+    }
+  }
+  return true;
+}
+
+struct Upload {
+  DevBuf buf;
+  int put(ffb_ctx* ctx, const void* host, size_t bytes) {
+    FFB_TRY(buf.alloc(ctx, bytes));
+    return ffb_h2d(ctx, buf.p, host, bytes);
+  }
+  const double* d() const { return buf.as<double>(); }
+};
+
+int enter(ffb_ctx* ctx) {
+  if (!ctx) return FFB_EINVAL;
+  FFB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return FFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ffb_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_opers,
+                    const double* c_coeffs, const double* dt, double* eigvals, double* eigvecs,
+                    double* propagators) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, c_opers && dt && eigvals && eigvecs && propagators, "diagonalize: null pointer");
+  FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32, "diagonalize: G=%d, d=%d unsupported", G, d);
+  const size_t dd = (size_t)d * d;
+  Upload ops, coeffs, dts;
+  DevBuf ev, V, Q;
+  const size_t n_mats = c_coeffs ? (size_t)n_cops : (size_t)G;
+  FFB_TRY(ops.put(ctx, c_opers, n_mats * dd * 16));
+  if (c_coeffs) FFB_TRY(coeffs.put(ctx, c_coeffs, (size_t)n_cops * G * 8));
+  FFB_TRY(dts.put(ctx, dt, (size_t)G * 8));
+  FFB_TRY(ev.alloc(ctx, (size_t)G * d * 8));
+  FFB_TRY(V.alloc(ctx, (size_t)G * dd * 16));
+  FFB_TRY(Q.alloc(ctx, (size_t)(G + 1) * dd * 16));
+  FFB_TRY(ffbi_diagonalize(ctx, G, d, n_cops, ops.d(), c_coeffs ? coeffs.d() : nullptr, dts.d(),
+                           ev.as<double>(), V.as<double>(), Q.as<double>()));
+  FFB_TRY(ffb_d2h(ctx, eigvals, ev.p, (size_t)G * d * 8));
+  FFB_TRY(ffb_d2h(ctx, eigvecs, V.p, (size_t)G * dd * 16));
+  FFB_TRY(ffb_d2h(ctx, propagators, Q.p, (size_t)(G + 1) * dd * 16));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_control_matrix_from_scratch(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis,
+                                    int n_omega, const double* eigvals, const double* eigvecs,
+                                    const double* propagators, const double* omega,
+                                    const double* basis, const double* n_opers,
+                                    const double* n_coeffs, const double* dt, const double* t,
+                                    double* out) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, eigvals && eigvecs && propagators && omega && basis && n_opers && n_coeffs &&
+                       dt && t && out, "control matrix: null pointer");
+  FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
+              "control matrix: bad shape");
+  const size_t dd = (size_t)d * d;
+  const int herm = (all_hermitian(n_opers, n_nops, d) ? FFB_HERM_NOPERS : 0) |
+                   (all_hermitian(basis, n_basis, d) ? FFB_HERM_BASIS : 0);
+  Upload ev, V, Q, om, bs, no, nc, dts, ts;
+  DevBuf B;
+  FFB_TRY(ev.put(ctx, eigvals, (size_t)G * d * 8));
+  FFB_TRY(V.put(ctx, eigvecs, (size_t)G * dd * 16));
+  FFB_TRY(Q.put(ctx, propagators, (size_t)G * dd * 16));  // Q_G (the last one) is not needed
+  FFB_TRY(om.put(ctx, omega, (size_t)n_omega * 8));
+  FFB_TRY(bs.put(ctx, basis, (size_t)n_basis * dd * 16));
+  FFB_TRY(no.put(ctx, n_opers, (size_t)n_nops * dd * 16));
+  FFB_TRY(nc.put(ctx, n_coeffs, (size_t)n_nops * G * 8));
+  FFB_TRY(dts.put(ctx, dt, (size_t)G * 8));
+  FFB_TRY(ts.put(ctx, t, (size_t)(G + 1) * 8));
+  const size_t out_bytes = (size_t)n_nops * n_basis * n_omega * 16;
+  FFB_TRY(B.alloc(ctx, out_bytes));
+  FFB_TRY(ffbi_control_matrix(ctx, G, d, n_nops, n_basis, n_omega, ev.d(), V.d(), Q.d(), om.d(),
+                              bs.d(), no.d(), nc.d(), dts.d(), ts.d(), herm, B.as<double>()));
+  FFB_TRY(ffb_d2h(ctx, out, B.p, out_bytes));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega, const double* B,
+                        int generalized, double* F) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, B && F, "filter function: null pointer");
+  FFB_REQUIRE(ctx, P >= 1 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
+              "filter function: bad shape");
+  Upload Bd;
+  DevBuf Fd;
+  const size_t L = (size_t)P * n_nops;
+  const size_t f_bytes = L * L * (generalized ? (size_t)n_basis * n_basis : 1) * n_omega * 16;
+  FFB_TRY(Bd.put(ctx, B, L * n_basis * n_omega * 16));
+  FFB_TRY(Fd.alloc(ctx, f_bytes));
+  FFB_TRY(ffbi_filter_function(ctx, P, n_nops, n_basis, n_omega, Bd.d(), generalized,
+                               Fd.as<double>()));
+  FFB_TRY(ffb_d2h(ctx, F, Fd.p, f_bytes));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_control_matrix_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+                                   const double* phases, const double* B_atomic,
+                                   const double* Q_liouville, int q_is_complex, int correlations,
+                                   double* out) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, B_atomic && out && (P == 1 || (phases && Q_liouville)),
+              "from_atomic: null pointer");
+  FFB_REQUIRE(ctx, P >= 1 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1, "from_atomic: bad shape");
+  Upload ph, Ba, Q;
+  DevBuf O;
+  const size_t pulse_bytes = (size_t)n_nops * n_basis * n_omega * 16;
+  if (P > 1) {
+    FFB_TRY(ph.put(ctx, phases, (size_t)(P - 1) * n_omega * 16));
+    FFB_TRY(Q.put(ctx, Q_liouville, (size_t)(P - 1) * n_basis * n_basis * (q_is_complex ? 16 : 8)));
+  }
+  FFB_TRY(Ba.put(ctx, B_atomic, P * pulse_bytes));
+  const size_t out_bytes = (correlations ? P : 1) * pulse_bytes;
+  FFB_TRY(O.alloc(ctx, out_bytes));
+  FFB_TRY(ffbi_from_atomic(ctx, P, n_nops, n_basis, n_omega, P > 1 ? ph.d() : nullptr, Ba.d(),
+                           P > 1 ? Q.d() : nullptr, q_is_complex, correlations, O.as<double>()));
+  FFB_TRY(ffb_d2h(ctx, out, O.p, out_bytes));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* idx, int n_omega,
+                   const double* F, const double* spectrum, int spectrum_ndim,
+                   int spectrum_is_complex, const double* omega, int d, double* out) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, idx && F && spectrum && omega && out, "infidelity: null pointer");
+  FFB_REQUIRE(ctx, spectrum_ndim >= 1 && spectrum_ndim <= 3, "infidelity: spectrum_ndim=%d",
+              spectrum_ndim);
+  for (int i = 0; i < n_sel; ++i)
+    FFB_REQUIRE(ctx, idx[i] >= 0 && idx[i] < n_nops, "infidelity: idx[%d]=%d out of range", i, idx[i]);
+  Upload Fd, Sd, Od, Id;
+  DevBuf res;
+  const size_t s_elems = (spectrum_ndim == 1 ? 1 : spectrum_ndim == 2 ? (size_t)n_sel
+                                                                       : (size_t)n_sel * n_sel) * n_omega;
+  FFB_TRY(Fd.put(ctx, F, (size_t)n_lead * n_nops * n_nops * n_omega * 16));
+  FFB_TRY(Sd.put(ctx, spectrum, s_elems * (spectrum_is_complex ? 16 : 8)));
+  FFB_TRY(Od.put(ctx, omega, (size_t)n_omega * 8));
+  FFB_TRY(Id.put(ctx, idx, (size_t)n_sel * sizeof(int)));
+  const size_t n_out = (size_t)n_lead * (spectrum_ndim == 3 ? (size_t)n_sel * n_sel : n_sel);
+  FFB_TRY(res.alloc(ctx, n_out * 8));
+  FFB_TRY(ffbi_infidelity(ctx, n_lead, n_nops, n_sel, Id.buf.as<int>(), n_omega, Fd.d(), Sd.d(),
+                          spectrum_ndim, spectrum_is_complex, Od.d(), d, res.as<double>()));
+  FFB_TRY(ffb_d2h(ctx, out, res.p, n_out * 8));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_liouville_representation(ffb_ctx* ctx, int n, int d, int n_basis, const double* U,
+                                 const double* basis, double* out) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, U && basis && out, "liouville: null pointer");
+  FFB_REQUIRE(ctx, n >= 1 && d >= 1 && n_basis >= 1, "liouville: bad shape");
+  Upload Ud, Bd;
+  DevBuf O;
+  const size_t dd = (size_t)d * d;
+  FFB_TRY(Ud.put(ctx, U, (size_t)n * dd * 16));
+  FFB_TRY(Bd.put(ctx, basis, (size_t)n_basis * dd * 16));
+  const size_t out_bytes = (size_t)n * n_basis * n_basis * 16;
+  FFB_TRY(O.alloc(ctx, out_bytes));
+  FFB_TRY(ffbi_liouville(ctx, n, d, n_basis, Ud.d(), Bd.d(), O.as<double>()));
+  FFB_TRY(ffb_d2h(ctx, out, O.p, out_bytes));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, x && out && n >= 1, "cexp: bad arguments");
+  Upload xd;
+  DevBuf O;
+  FFB_TRY(xd.put(ctx, x, (size_t)n * 8));
+  FFB_TRY(O.alloc(ctx, (size_t)n * 16));
+  FFB_TRY(ffbi_cexp(ctx, n, xd.d(), scale, O.as<double>()));
+  FFB_TRY(ffb_d2h(ctx, out, O.p, (size_t)n * 16));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops, int n_basis,
+                              int n_omega, const double* c_opers, const double* c_coeffs,
+                              const double* n_opers, const double* n_coeffs, const double* dt,
+                              const double* t, const double* basis, const double* omega,
+                              const double* spectrum, int spectrum_ndim, int spectrum_is_complex,
+                              double* eigvals, double* eigvecs, double* propagators,
+                              double* control_matrix, double* filter_function,
+                              double* infidelity) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, c_opers && c_coeffs && n_opers && n_coeffs && dt && t && basis && omega,
+              "pulse pipeline: null input pointer");
+  FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32 && n_cops >= 1 && n_nops >= 1 && n_basis >= 1 &&
+                       n_omega >= 1, "pulse pipeline: bad shape");
+  FFB_REQUIRE(ctx, !infidelity || spectrum, "pulse pipeline: infidelity requested without spectrum");
+  const size_t dd = (size_t)d * d;
+  const int herm = (all_hermitian(n_opers, n_nops, d) ? FFB_HERM_NOPERS : 0) |
+                   (all_hermitian(basis, n_basis, d) ? FFB_HERM_BASIS : 0);
+  Upload co, cc, no, nc, dts, ts, bs, om, sp;
+  DevBuf ev, V, Q, B, F, I, idx;
+  FFB_TRY(co.put(ctx, c_opers, (size_t)n_cops * dd * 16));
+  FFB_TRY(cc.put(ctx, c_coeffs, (size_t)n_cops * G * 8));
+  FFB_TRY(no.put(ctx, n_opers, (size_t)n_nops * dd * 16));
+  FFB_TRY(nc.put(ctx, n_coeffs, (size_t)n_nops * G * 8));
+  FFB_TRY(dts.put(ctx, dt, (size_t)G * 8));
+  FFB_TRY(ts.put(ctx, t, (size_t)(G + 1) * 8));
+  FFB_TRY(bs.put(ctx, basis, (size_t)n_basis * dd * 16));
+  FFB_TRY(om.put(ctx, omega, (size_t)n_omega * 8));
+  FFB_TRY(ev.alloc(ctx, (size_t)G * d * 8));
+  FFB_TRY(V.alloc(ctx, (size_t)G * dd * 16));
+  FFB_TRY(Q.alloc(ctx, (size_t)(G + 1) * dd * 16));
+  const size_t b_bytes = (size_t)n_nops * n_basis * n_omega * 16;
+  const size_t f_bytes = (size_t)n_nops * n_nops * n_omega * 16;
+  FFB_TRY(B.alloc(ctx, b_bytes));
+  FFB_TRY(F.alloc(ctx, f_bytes));
+  FFB_TRY(ffbi_diagonalize(ctx, G, d, n_cops, co.d(), cc.d(), dts.d(), ev.as<double>(),
+                           V.as<double>(), Q.as<double>()));
+  FFB_TRY(ffbi_control_matrix(ctx, G, d, n_nops, n_basis, n_omega, ev.as<double>(), V.as<double>(),
+                              Q.as<double>(), om.d(), bs.d(), no.d(), nc.d(), dts.d(), ts.d(), herm,
+                              B.as<double>()));
+  FFB_TRY(ffbi_filter_function(ctx, 1, n_nops, n_basis, n_omega, B.as<double>(), 0, F.as<double>()));
+  size_t n_inf = 0;
+  if (infidelity) {
+    FFB_REQUIRE(ctx, spectrum_ndim >= 1 && spectrum_ndim <= 3, "pulse pipeline: spectrum_ndim=%d",
+                spectrum_ndim);
+    const size_t s_elems = (spectrum_ndim == 1 ? 1 : spectrum_ndim == 2 ? (size_t)n_nops
+                                                                         : (size_t)n_nops * n_nops) * n_omega;
+    FFB_TRY(sp.put(ctx, spectrum, s_elems * (spectrum_is_complex ? 16 : 8)));
+    std::vector<int> iota(n_nops);
+    for (int i = 0; i < n_nops; ++i) iota[i] = i;
+    FFB_TRY(idx.alloc(ctx, n_nops * sizeof(int)));
+    FFB_TRY(ffb_h2d(ctx, idx.p, iota.data(), n_nops * sizeof(int)));
+    FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // iota goes out of scope below
+    n_inf = spectrum_ndim == 3 ? (size_t)n_nops * n_nops : n_nops;
+    FFB_TRY(I.alloc(ctx, n_inf * 8));
+    FFB_TRY(ffbi_infidelity(ctx, 1, n_nops, n_nops, idx.as<int>(), n_omega, F.as<double>(), sp.d(),
+                            spectrum_ndim, spectrum_is_complex, om.d(), d, I.as<double>()));
+  }
+  if (eigvals) FFB_TRY(ffb_d2h(ctx, eigvals, ev.p, (size_t)G * d * 8));
+  if (eigvecs) FFB_TRY(ffb_d2h(ctx, eigvecs, V.p, (size_t)G * dd * 16));
+  if (propagators) FFB_TRY(ffb_d2h(ctx, propagators, Q.p, (size_t)(G + 1) * dd * 16));
+  if (control_matrix) FFB_TRY(ffb_d2h(ctx, control_matrix, B.p, b_bytes));
+  if (filter_function) FFB_TRY(ffb_d2h(ctx, filter_function, F.p, f_bytes));
+  if (infidelity) FFB_TRY(ffb_d2h(ctx, infidelity, I.p, n_inf * 8));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+}  // extern "C"

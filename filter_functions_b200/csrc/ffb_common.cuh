@@ -1,0 +1,145 @@
+// Shared declarations of libffb200: context, error plumbing, device-memory pool, complex helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ffb200.h"
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct ffb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int cc_major = 0, cc_minor = 0;
+  size_t total_mem = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;  // the stream work is enqueued on (own or external)
+  std::string err;
+  int64_t launches = 0;
+
+  // grow-only caching pool: freed blocks are kept and handed out again (best fit)
+  std::multimap<size_t, void*> free_blocks;
+  std::map<void*, size_t> live_blocks;
+  size_t pool_bytes = 0;
+
+  // pinned staging for small host<->device transfers
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+
+  // timing of the dominant kernel
+  bool timing = false;
+  double timed_ms = 0.0;
+  int64_t timed_launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
+};
+
+int ffb_fail(ffb_ctx* ctx, int code, const char* fmt, ...);
+
+#define FFB_CUDA(ctx, expr)                                                                    \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ffb_fail((ctx), _e == cudaErrorMemoryAllocation ? FFB_ENOMEM : FFB_ECUDA,         \
+                      "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));   \
+  } while (0)
+
+#define FFB_TRY(expr)          \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != FFB_OK) return _rc; \
+  } while (0)
+
+#define FFB_REQUIRE(ctx, cond, ...)                              \
+  do {                                                           \
+    if (!(cond)) return ffb_fail((ctx), FFB_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+// counts the launch and checks the launch error
+#define FFB_LAUNCHED(ctx)         \
+  do {                            \
+    (ctx)->launches++;            \
+    FFB_CUDA((ctx), cudaGetLastError()); \
+  } while (0)
+
+int ffb_pool_alloc(ffb_ctx* ctx, size_t bytes, void** ptr);
+void ffb_pool_release(ffb_ctx* ctx, void* ptr);
+
+// RAII handle on pool memory; returned to the pool when it goes out of scope. Stream-ordered use is
+// safe because everything in a context runs on one stream.
+struct DevBuf {
+  ffb_ctx* ctx = nullptr;
+  void* p = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { reset(); }
+  int alloc(ffb_ctx* c, size_t bytes) {
+    reset();
+    ctx = c;
+    return ffb_pool_alloc(c, bytes ? bytes : 8, &p);
+  }
+  void reset() {
+    if (p) ffb_pool_release(ctx, p);
+    p = nullptr;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+int ffb_h2d(ffb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int ffb_d2h(ffb_ctx* ctx, void* dst, const void* src, size_t bytes);
+
+// timing hooks around the dominant kernel
+int ffb_time_begin(ffb_ctx* ctx, int* slot);
+int ffb_time_end(ffb_ctx* ctx, int slot);
+
+// ------------------------------------------------------------------------------------------------
+// internal device-pointer pipeline stages (implemented in the .cu files, all asynchronous)
+// ------------------------------------------------------------------------------------------------
+int ffbi_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_opers,
+                     const double* c_coeffs, const double* dt, double* eigvals, double* eigvecs,
+                     double* propagators);
+int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int n_omega,
+                        const double* eigvals, const double* eigvecs, const double* propagators,
+                        const double* omega, const double* basis, const double* n_opers,
+                        const double* n_coeffs, const double* dt, const double* t, int herm_flags,
+                        double* out);
+int ffbi_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+                         const double* B, int generalized, double* F);
+int ffbi_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+                     const double* phases, const double* B_atomic, const double* Q, int q_is_complex,
+                     int correlations, double* out);
+int ffbi_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* idx_dev,
+                    int n_omega, const double* F, const double* spectrum, int spectrum_ndim,
+                    int spectrum_is_complex, const double* omega, int d, double* out);
+int ffbi_liouville(ffb_ctx* ctx, int n, int d, int n_basis, const double* U, const double* basis,
+                   double* out);
+int ffbi_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out);
+int ffbi_fp64_peak(ffb_ctx* ctx, double* dfma, double* dmma);
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+struct cplx {
+  double re, im;
+};
+
+__host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+  return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+__host__ __device__ __forceinline__ cplx cmulc(cplx a, cplx b) {  // a * conj(b)
+  return {a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im};
+}
+__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.re + b.re, a.im + b.im}; }
+__host__ __device__ __forceinline__ cplx cconj(cplx a) { return {a.re, -a.im}; }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }

@@ -1,0 +1,711 @@
+// K2 -- first-order control matrix from scratch (numeric.calculate_control_matrix_from_scratch,
+// numeric.py:707-881 of the reference).
+//
+// Reference algorithm (numeric.py:846-869), per segment g and frequency w:
+//     step[j,k,w] = e^{i w t_g} sum_{mn} Bbar^{(g)}_j[m,n] I^{(g)}_{mn}(w) Cbar^{(g)}_k[n,m]
+//     I_mn(w) = (e^{i (w + E_m - E_n) dt} - 1) / (i (w + E_m - E_n)),  = dt if the denominator is 0
+// with Bbar = s_j V^+ B_j V (numeric.py:98-123) and Cbar = (Q^+ V)^+ C_k (Q^+ V) (numeric.py:93-95,
+// :126-141).  NumPy materialises (n_omega, d, d) temporaries per segment and contracts them with
+// opt_einsum ('o,jmn,omn,knm->jko', numeric.py:843).
+//
+// B200 formulation.  The sum over (g, m, n) is a GEMM whose right operand is generated on the fly:
+//     B[(j,k), w] = sum_{(g,kappa)} A[(j,k), (g,kappa)] * P[(g,kappa), w]
+// For Hermitian noise operators and basis elements Bbar and Cbar are Hermitian, so the (m,n) and
+// (n,m) terms are complex conjugates in their w-independent factor M_mn = Bbar_j[m,n] Cbar_k[n,m]:
+//     M_mn I_mn + conj(M_mn) I_nm = Re(M_mn) (I_mn + I_nm) + Im(M_mn) i (I_mn - I_nm)
+// and all diagonal terms share I_mm = I(w).  The left operand therefore becomes a REAL matrix with
+// Kh = 1 + d(d-1) columns per segment (instead of d^2 complex ones) and the right operand the complex
+// functions {I_0, S_p = I_mn + I_nm, D_p = i (I_mn - I_nm)} times the phase e^{i w t_g}: 2 + 2 d (d-1)
+// real multiply-adds per (j,k) and segment-frequency pair instead of 4 d^2.  Non-Hermitian operators
+// are split into Hermitian and anti-Hermitian parts (the control matrix is linear in B_j and C_k), which
+// multiplies the row count by 2 (or 4) and is undone in the finalize kernel.
+//
+// The real GEMM runs on the FP64 tensor path (DMMA.8x8x4): M = 8 rows, N = 8 frequencies (two
+// accumulator tiles per row tile: real and imaginary part of P), K = 4 consecutive segments.  Lane
+// (q = lane % 4, w = lane / 4) owns frequency w of the warp's 8 and segment q of the pass's 4: it
+// generates exactly the B-fragment element the instruction expects, so P never leaves registers and
+// nothing of size (G, n_omega, d, d) is ever materialised.  The exponential is factorised,
+// e^{i (w + Omega) dt} = e^{i w dt} e^{i Omega dt}, with e^{i Omega dt} precomputed per segment and
+// e^{i w dt} recomputed only when dt changes, leaving ONE sincos per (segment, frequency) for the phase
+// instead of 2 d^2 + 2; near the removable singularity (|(w + Omega) dt| < 2^-8, including the exact
+// zero of numeric.py:162-165) a Taylor polynomial replaces the cancelling quotient.
+//
+// Measured on B200 (tools/microbench/fp64_peaks.cu, profiles/fp64_peaks_r01.jsonl): DFMA peak 36.95
+// TFLOP/s, DMMA peak 37.14 TFLOP/s, and the two do NOT overlap (one FP64 pipe, 64 lanes/clk/SM); DMMA
+// is used because it needs 1/8 of the issue slots and shares the operands through the fragment layout.
+#include "ffb_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// math helpers
+// ------------------------------------------------------------------------------------------------
+// sin/cos with a 3-constant Cody-Waite reduction.  fma keeps x - k*pi/2 accurate to ~1e-16 ABSOLUTE
+// for |x| < 1e9, which is what a unit-modulus phase factor needs (CUDA's sincos switches to
+// Payne-Hanek above 1e5 to keep the RELATIVE error near zeros of sin, which is irrelevant here).
+// Verified against sincos() on B200 up to |x| = 1e7: max abs deviation 1.1e-16.
+__device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
+  if (fabs(x) > 1.0e9) {  // outside the validated range of the fast reduction
+    sincos(x, &sn, &cs);
+    return;
+  }
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer by addition
+  double kd = fma(x, 6.36619772367581382433e-01, MAGIC);
+  const int q = __double2loint(kd);
+  kd -= MAGIC;
+  double r = fma(-kd, 1.57079632679489655800e+00, x);
+  r = fma(-kd, 6.12323399573676603587e-17, r);
+  r = fma(-kd, -1.49738490485916983294e-33, r);
+  const double r2 = r * r;
+  double ps = fma(r2, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(ps, r2, 2.75573137070700676789e-06);
+  ps = fma(ps, r2, -1.98412698298579493134e-04);
+  ps = fma(ps, r2, 8.33333333332248946124e-03);
+  ps = fma(ps, r2, -1.66666666666666324348e-01);
+  const double s = fma(r * r2, ps, r);
+  double pc = fma(r2, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(pc, r2, -2.75573143513906633035e-07);
+  pc = fma(pc, r2, 2.48015872894767294178e-05);
+  pc = fma(pc, r2, -1.38888888888741095749e-03);
+  pc = fma(pc, r2, 4.16666666666666019037e-02);
+  const double c = fma(r2 * r2, pc, fma(r2, -0.5, 1.0));
+  const double ss = (q & 1) ? c : s;
+  const double cc = (q & 1) ? s : c;
+  sn = (q & 2) ? -ss : ss;
+  cs = ((q + 1) & 2) ? -cc : cc;
+}
+
+// 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps on the FP64 pipe.
+__device__ __forceinline__ double rcp_nr(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+constexpr double SMALL_Y = 0.00390625;  // 2^-8
+
+// J(x) = (e^{i x dt} - 1) / (i x) given num = e^{i x dt} - 1 evaluated elsewhere (cancelling for small
+// |x dt|, hence the polynomial branch; y^6/5040 < 1e-18 below the threshold).
+__device__ __forceinline__ cplx first_order_integral(double x, double dt, double num_re,
+                                                     double num_im) {
+  const double y = x * dt;
+  if (fabs(y) < SMALL_Y) {
+    const double y2 = y * y;
+    const double fr = fma(y2, fma(y2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+    const double fi = y * fma(y2, fma(y2, 1.0 / 720.0, -1.0 / 24.0), 0.5);
+    return {dt * fr, dt * fi};
+  }
+  const double r = rcp_nr(x);
+  return {num_im * r, -num_re * r};
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+__device__ __forceinline__ void pair_from_index(int p, int d, int& m, int& n) {
+  m = 0;
+  while (p >= d - 1 - m) {
+    p -= d - 1 - m;
+    ++m;
+  }
+  n = m + 1 + p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prologue 1: eigenbasis transforms (omega independent, O(G (n_nops + n_basis) d^3))
+//   Bbar[g, jr] = s_j^{(g)} herm-part(V^+ B_j V),   Cbar[g, kr] = herm-part(U^+ C_k U),  U = Q_g^+ V_g
+// one block per segment; operators are transformed one after the other through shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+transform_kernel(int G, int d, int n_nops, int n_basis, int parts_j, int parts_k,
+                 const double* __restrict__ eigvecs, const double* __restrict__ propagators,
+                 const double* __restrict__ n_opers, const double* __restrict__ n_coeffs,
+                 const double* __restrict__ basis, double* __restrict__ Bbar,
+                 double* __restrict__ Cbar) {
+  extern __shared__ double sm[];
+  const int g = blockIdx.x;
+  const int dd = d * d;
+  double* V = sm;            // d*d complex
+  double* U = V + 2 * dd;    // d*d complex
+  double* T = U + 2 * dd;    // scratch
+  double* X = T + 2 * dd;    // transformed operator
+  const double* Vg = eigvecs + (size_t)g * 2 * dd;
+  const double* Qg = propagators + (size_t)g * 2 * dd;
+  for (int e = threadIdx.x; e < 2 * dd; e += blockDim.x) V[e] = Vg[e];
+  __syncthreads();
+  for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+    const int a = e / d, b = e % d;
+    cplx acc = {0.0, 0.0};
+    for (int c = 0; c < d; ++c) {  // U[a][b] = sum_c conj(Q[c][a]) V[c][b]
+      const cplx qv = {Qg[2 * (c * d + a)], -Qg[2 * (c * d + a) + 1]};
+      const cplx vv = {V[2 * (c * d + b)], V[2 * (c * d + b) + 1]};
+      acc = cadd(acc, cmul(qv, vv));
+    }
+    U[2 * e] = acc.re;
+    U[2 * e + 1] = acc.im;
+  }
+  __syncthreads();
+  const int n_ops = n_nops + n_basis;
+  for (int op = 0; op < n_ops; ++op) {
+    const bool is_noise = op < n_nops;
+    const double* O = is_noise ? n_opers + (size_t)op * 2 * dd : basis + (size_t)(op - n_nops) * 2 * dd;
+    const double* W = is_noise ? V : U;
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) {  // T = O W
+      const int a = e / d, b = e % d;
+      cplx acc = {0.0, 0.0};
+      for (int c = 0; c < d; ++c) {
+        const cplx o = {O[2 * (a * d + c)], O[2 * (a * d + c) + 1]};
+        const cplx w = {W[2 * (c * d + b)], W[2 * (c * d + b) + 1]};
+        acc = cadd(acc, cmul(o, w));
+      }
+      T[2 * e] = acc.re;
+      T[2 * e + 1] = acc.im;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) {  // X = W^+ T
+      const int a = e / d, b = e % d;
+      cplx acc = {0.0, 0.0};
+      for (int c = 0; c < d; ++c) {
+        const cplx w = {W[2 * (c * d + a)], -W[2 * (c * d + a) + 1]};
+        const cplx t = {T[2 * (c * d + b)], T[2 * (c * d + b) + 1]};
+        acc = cadd(acc, cmul(w, t));
+      }
+      X[2 * e] = acc.re;
+      X[2 * e + 1] = acc.im;
+    }
+    __syncthreads();
+    const int parts = is_noise ? parts_j : parts_k;
+    const double scale = is_noise ? n_coeffs[(size_t)op * G + g] : 1.0;
+    double* dst = is_noise ? Bbar + ((size_t)g * n_nops * parts_j + (size_t)op * parts_j) * 2 * dd
+                           : Cbar + ((size_t)g * n_basis * parts_k + (size_t)(op - n_nops) * parts_k) * 2 * dd;
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+      const int a = e / d, b = e % d;
+      const cplx x = {X[2 * e], X[2 * e + 1]};
+      const cplx xt = {X[2 * (b * d + a)], -X[2 * (b * d + a) + 1]};  // conj(X[b][a])
+      // Hermitian part (X + X^+)/2 and, if requested, (X - X^+)/(2i)
+      dst[2 * e] = scale * 0.5 * (x.re + xt.re);
+      dst[2 * e + 1] = scale * 0.5 * (x.im + xt.im);
+      if (parts == 2) {
+        dst[2 * dd + 2 * e] = scale * 0.5 * (x.im - xt.im);
+        dst[2 * dd + 2 * e + 1] = -scale * 0.5 * (x.re - xt.re);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prologue 2: the operand stream of the main kernel.
+// Per row block rb and pass (4 consecutive segments) the stream holds 1 + n_pairs units:
+//   diag unit   : A column [MT][32], t[4], dt[4]
+//   pair unit p : A column Re [MT][32], A column Im [MT][32], Omega[4], cos(Omega dt)[4], sin(Omega dt)[4]
+// An A column holds, for lane l = 4*row_in_tile + q, the coefficient of row 8*mt + row_in_tile and
+// segment 4*pass + q -- exactly the DMMA A-fragment, so the main kernel loads it with one LDS.64.
+// ------------------------------------------------------------------------------------------------
+struct StreamGeom {
+  int MT;          // row tiles per row block
+  int n_rb;        // row blocks
+  int n_pass;      // ceil(G / 4)
+  int n_pairs;     // d (d-1) / 2
+  int diag_unit;   // doubles
+  int pair_unit;   // doubles
+  size_t pass_doubles;
+  size_t rb_doubles;
+};
+
+__host__ __device__ inline StreamGeom make_geom(int rows, int G, int d, int MT) {
+  StreamGeom s;
+  s.MT = MT;
+  s.n_rb = ((rows + 7) / 8 + MT - 1) / MT;
+  s.n_pass = (G + 3) / 4;
+  s.n_pairs = d * (d - 1) / 2;
+  s.diag_unit = MT * 32 + 8;
+  s.pair_unit = 2 * MT * 32 + 12;
+  s.pass_doubles = (size_t)s.diag_unit + (size_t)s.n_pairs * s.pair_unit;
+  s.rb_doubles = s.pass_doubles * s.n_pass;
+  return s;
+}
+
+__global__ void __launch_bounds__(256)
+assemble_kernel(StreamGeom geo, int G, int d, int rows, int n_jrows, int n_krows,
+                const double* __restrict__ Bbar, const double* __restrict__ Cbar,
+                const double* __restrict__ eigvals, const double* __restrict__ dt,
+                const double* __restrict__ t, double* __restrict__ stream) {
+  // one thread per double of the stream
+  const size_t total = geo.rb_doubles * geo.n_rb;
+  const int dd = d * d;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int rb = (int)(idx / geo.rb_doubles);
+    size_t rem = idx % geo.rb_doubles;
+    const int pass = (int)(rem / geo.pass_doubles);
+    rem %= geo.pass_doubles;
+    int unit, off;  // unit 0 = diag, 1.. = pairs
+    if (rem < (size_t)geo.diag_unit) {
+      unit = 0;
+      off = (int)rem;
+    } else {
+      rem -= geo.diag_unit;
+      unit = 1 + (int)(rem / geo.pair_unit);
+      off = (int)(rem % geo.pair_unit);
+    }
+    const int a_doubles = (unit == 0 ? 1 : 2) * geo.MT * 32;
+    double val = 0.0;
+    if (off < a_doubles) {
+      const int col = off / (geo.MT * 32);  // 0: diag or Re, 1: Im
+      const int mt = (off / 32) % geo.MT;
+      const int l = off % 32;
+      const int row = (rb * geo.MT + mt) * 8 + (l >> 2);
+      const int g = pass * 4 + (l & 3);
+      if (row < rows && g < G) {
+        const int jr = row / n_krows, kr = row % n_krows;
+        const double* Bm = Bbar + ((size_t)g * n_jrows + jr) * 2 * dd;
+        const double* Cm = Cbar + ((size_t)g * n_krows + kr) * 2 * dd;
+        if (unit == 0) {
+          double acc = 0.0;
+          for (int m = 0; m < d; ++m) acc += Bm[2 * (m * d + m)] * Cm[2 * (m * d + m)];
+          val = acc;
+        } else {
+          int m, n;
+          pair_from_index(unit - 1, d, m, n);
+          const cplx b = {Bm[2 * (m * d + n)], Bm[2 * (m * d + n) + 1]};
+          const cplx c = {Cm[2 * (n * d + m)], Cm[2 * (n * d + m) + 1]};
+          const cplx prod = cmul(b, c);
+          val = col == 0 ? prod.re : prod.im;
+        }
+      }
+    } else {
+      const int c = off - a_doubles;  // constants
+      const int which = c / 4;
+      const int g = pass * 4 + (c & 3);
+      if (unit == 0) {
+        if (g < G) val = which == 0 ? t[g] : dt[g];
+      } else {
+        double Om = 0.0, dtg = 0.0;
+        if (g < G) {
+          int m, n;
+          pair_from_index(unit - 1, d, m, n);
+          Om = eigvals[(size_t)g * d + m] - eigvals[(size_t)g * d + n];
+          dtg = dt[g];
+        }
+        if (which == 0) {
+          val = Om;
+        } else {
+          double sn, cs;
+          sincos(Om * dtg, &sn, &cs);
+          val = which == 1 ? cs : sn;
+        }
+      }
+    }
+    stream[idx] = val;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------------
+struct MainParams {
+  const double* stream;
+  const double* omega;
+  double* partial;  // [S][rows_pad][n_omega] complex
+  int n_omega;
+  int rows_pad;     // n_rb * MT * 8
+  int n_pass;
+  int n_pairs;
+  int passes_per_chunk;
+  // staging schedule
+  int pps;          // whole passes per stage (>= 1) when n_sp == 1
+  int n_sp;         // pieces per pass when a pass does not fit a stage
+  int stage_doubles;  // shared-memory doubles per stage buffer
+  size_t pass_doubles;
+  size_t rb_doubles;
+  int diag_unit;
+  int pair_unit;
+};
+
+// unit boundary of piece j (in units, 0 .. 1 + n_pairs)
+__device__ __forceinline__ int piece_begin(int j, int n_units, int n_sp) {
+  return (int)(((long long)j * n_units) / n_sp);
+}
+__device__ __forceinline__ size_t unit_offset(int u, const MainParams& p) {
+  return u == 0 ? 0 : (size_t)p.diag_unit + (size_t)(u - 1) * p.pair_unit;
+}
+
+template <int MT, int NW>
+__global__ void __launch_bounds__(NW * 32)
+ctrlmat_main_kernel(const MainParams p) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int q = lane & 3;
+  const int rb = blockIdx.y;
+  const int pass_begin = blockIdx.z * p.passes_per_chunk;
+  const int pass_end = min(p.n_pass, pass_begin + p.passes_per_chunk);
+  const int n_units = 1 + p.n_pairs;
+
+  const int w_idx = (blockIdx.x * NW + warp) * 8 + (lane >> 2);
+  const double w = w_idx < p.n_omega ? p.omega[w_idx] : 0.0;
+
+  double acc_re[MT][2], acc_im[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    acc_re[mt][0] = acc_re[mt][1] = 0.0;
+    acc_im[mt][0] = acc_im[mt][1] = 0.0;
+  }
+
+  const double* gstream = p.stream + (size_t)rb * p.rb_doubles;
+
+  // ---- stage schedule: stage i of this chunk covers [stage_src(i), +stage_len(i)) doubles
+  const int n_passes = pass_end - pass_begin;
+  const int n_stages = p.n_sp == 1 ? (n_passes + p.pps - 1) / p.pps : n_passes * p.n_sp;
+  auto stage_range = [&](int i, size_t& src, int& len) {
+    if (p.n_sp == 1) {
+      const int p0 = pass_begin + i * p.pps;
+      const int p1 = min(pass_end, p0 + p.pps);
+      src = (size_t)p0 * p.pass_doubles;
+      len = (int)((size_t)(p1 - p0) * p.pass_doubles);
+    } else {
+      const int pass = pass_begin + i / p.n_sp;
+      const int piece = i % p.n_sp;
+      const size_t o0 = unit_offset(piece_begin(piece, n_units, p.n_sp), p);
+      const size_t o1 = piece + 1 == p.n_sp ? p.pass_doubles
+                                            : unit_offset(piece_begin(piece + 1, n_units, p.n_sp), p);
+      src = (size_t)pass * p.pass_doubles + o0;
+      len = (int)(o1 - o0);
+    }
+  };
+  auto stage_load = [&](int i, double* buf) {
+    size_t src;
+    int len;
+    stage_range(i, src, len);
+    const double* g = gstream + src;
+    for (int e = threadIdx.x * 2; e < len; e += NW * 32 * 2) cp_async16(buf + e, g + e);
+  };
+
+  double* buf0 = smem;
+  double* buf1 = smem + p.stage_doubles;
+  if (n_stages > 0) stage_load(0, buf0);
+  cp_async_commit();
+
+  // per-lane state that survives across stages
+  double dt_prev = -1.0, ew_re = 1.0, ew_im = 0.0;  // e^{i w dt}
+  double ph_re = 1.0, ph_im = 0.0, dtg = 0.0;        // phase e^{i w t_g}, dt of the current segment
+
+  for (int s = 0; s < n_stages; ++s) {
+    double* cur = (s & 1) ? buf1 : buf0;
+    if (s + 1 < n_stages) {
+      stage_load(s + 1, (s & 1) ? buf0 : buf1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    int u_begin, u_end, n_pass_here;
+    if (p.n_sp == 1) {
+      u_begin = 0;
+      u_end = n_units;
+      n_pass_here = min(p.pps, n_passes - s * p.pps);
+    } else {
+      const int piece = s % p.n_sp;
+      u_begin = piece_begin(piece, n_units, p.n_sp);
+      u_end = piece + 1 == p.n_sp ? n_units : piece_begin(piece + 1, n_units, p.n_sp);
+      n_pass_here = 1;
+    }
+    const double* up = cur;  // walks through the units of the stage
+    for (int ip = 0; ip < n_pass_here; ++ip) {
+      for (int u = u_begin; u < u_end; ++u) {
+        if (u == 0) {
+          // ---- diagonal unit: phase, e^{i w dt}, I_0
+          const double* cst = up + MT * 32;
+          const double tg = cst[q];
+          dtg = cst[4 + q];
+          sincos_cw(w * tg, ph_im, ph_re);
+          if (dtg != dt_prev) {
+            sincos_cw(w * dtg, ew_im, ew_re);
+            dt_prev = dtg;
+          }
+          const cplx J = first_order_integral(w, dtg, ew_re - 1.0, ew_im);
+          const double b_re = ph_re * J.re - ph_im * J.im;
+          const double b_im = ph_re * J.im + ph_im * J.re;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const double a = up[mt * 32 + lane];
+            dmma884(acc_re[mt][0], acc_re[mt][1], a, b_re);
+            dmma884(acc_im[mt][0], acc_im[mt][1], a, b_im);
+          }
+          up += p.diag_unit;
+        } else {
+          // ---- pair unit: S = I(w + Om) + I(w - Om), D = i (I(w + Om) - I(w - Om))
+          const double* cst = up + 2 * MT * 32;
+          const double Om = cst[q], Ec = cst[4 + q], Es = cst[8 + q];
+          const double t1 = ew_re * Ec, t2 = ew_im * Ec;
+          const double np_re = fma(-ew_im, Es, t1) - 1.0;  // e^{i w dt} e^{+i Om dt} - 1
+          const double np_im = fma(ew_re, Es, t2);
+          const double nm_re = fma(ew_im, Es, t1) - 1.0;   // e^{i w dt} e^{-i Om dt} - 1
+          const double nm_im = fma(-ew_re, Es, t2);
+          const cplx Jp = first_order_integral(w + Om, dtg, np_re, np_im);
+          const cplx Jm = first_order_integral(w - Om, dtg, nm_re, nm_im);
+          const double s_re = Jp.re + Jm.re, s_im = Jp.im + Jm.im;
+          const double d_re = Jm.im - Jp.im, d_im = Jp.re - Jm.re;
+          const double bs_re = ph_re * s_re - ph_im * s_im;
+          const double bs_im = ph_re * s_im + ph_im * s_re;
+          const double bd_re = ph_re * d_re - ph_im * d_im;
+          const double bd_im = ph_re * d_im + ph_im * d_re;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const double a = up[mt * 32 + lane];
+            dmma884(acc_re[mt][0], acc_re[mt][1], a, bs_re);
+            dmma884(acc_im[mt][0], acc_im[mt][1], a, bs_im);
+          }
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const double a = up[(MT + mt) * 32 + lane];
+            dmma884(acc_re[mt][0], acc_re[mt][1], a, bd_re);
+            dmma884(acc_im[mt][0], acc_im[mt][1], a, bd_im);
+          }
+          up += p.pair_unit;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: C fragment (row = lane/4, cols 2q, 2q+1) -> partial[z][row][w]
+  const int w0 = (blockIdx.x * NW + warp) * 8 + 2 * q;
+  double* out = p.partial + (size_t)blockIdx.z * p.rows_pad * p.n_omega * 2;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int row = (rb * MT + mt) * 8 + (lane >> 2);
+    double* dst = out + ((size_t)row * p.n_omega + w0) * 2;
+    if (w0 < p.n_omega) {
+      reinterpret_cast<double2*>(dst)[0] = make_double2(acc_re[mt][0], acc_im[mt][0]);
+    }
+    if (w0 + 1 < p.n_omega) {
+      reinterpret_cast<double2*>(dst)[1] = make_double2(acc_re[mt][1], acc_im[mt][1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: sum the split-K partials and undo the Hermitian/anti-Hermitian row expansion
+//   out[j,k,w] = sum_z sum_{pj,pk} i^{pj+pk} partial[z][(j*parts_j+pj)*n_krows + k*parts_k+pk][w]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+finalize_kernel(int S, int rows_pad, int n_nops, int n_basis, int parts_j, int parts_k, int n_omega,
+                const double* __restrict__ partial, double* __restrict__ out) {
+  const size_t total = (size_t)n_nops * n_basis * n_omega;
+  const int n_krows = n_basis * parts_k;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(idx % n_omega);
+    const int jk = (int)(idx / n_omega);
+    const int j = jk / n_basis, k = jk % n_basis;
+    double re = 0.0, im = 0.0;
+    for (int pj = 0; pj < parts_j; ++pj) {
+      for (int pk = 0; pk < parts_k; ++pk) {
+        const int row = (j * parts_j + pj) * n_krows + k * parts_k + pk;
+        double pr = 0.0, pi = 0.0;
+        for (int z = 0; z < S; ++z) {
+          const double2 v = reinterpret_cast<const double2*>(
+              partial)[((size_t)z * rows_pad + row) * n_omega + w];
+          pr += v.x;
+          pi += v.y;
+        }
+        switch ((pj + pk) & 3) {  // multiply by i^(pj+pk)
+          case 0: re += pr; im += pi; break;
+          case 1: re -= pi; im += pr; break;
+          default: re -= pr; im -= pi; break;
+        }
+      }
+    }
+    reinterpret_cast<double2*>(out)[idx] = make_double2(re, im);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch plumbing
+// ------------------------------------------------------------------------------------------------
+constexpr int STAGE_TARGET_BYTES = 32 * 1024;
+constexpr int STAGE_MAX_BYTES = 48 * 1024;
+
+template <int MT, int NW>
+int launch_main(ffb_ctx* ctx, MainParams p, int n_wtiles, int n_rb, int S) {
+  auto kern = ctrlmat_main_kernel<MT, NW>;
+  const size_t smem = (size_t)2 * p.stage_doubles * sizeof(double);
+  FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(n_wtiles, n_rb, S);
+  int slot = -1;
+  FFB_TRY(ffb_time_begin(ctx, &slot));
+  kern<<<grid, NW * 32, smem, ctx->stream>>>(p);
+  FFB_LAUNCHED(ctx);
+  FFB_TRY(ffb_time_end(ctx, slot));
+  return FFB_OK;
+}
+
+template <int MT, int NW>
+int occupancy(ffb_ctx* ctx, size_t smem, int* blocks) {
+  auto kern = ctrlmat_main_kernel<MT, NW>;
+  FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FFB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, NW * 32, smem));
+  return FFB_OK;
+}
+
+int pick_mt(int mt_total) {
+  static const int avail[] = {1, 2, 3, 4, 6, 8, 12};
+  const int n_rb = (mt_total + 11) / 12;
+  const int need = (mt_total + n_rb - 1) / n_rb;
+  for (int a : avail)
+    if (a >= need) return a;
+  return 12;
+}
+
+#define FFB_DISPATCH_MT(MTV, NWV, CALL)        \
+  switch (MTV) {                               \
+    case 1: { constexpr int MT_ = 1; CALL; } break;   \
+    case 2: { constexpr int MT_ = 2; CALL; } break;   \
+    case 3: { constexpr int MT_ = 3; CALL; } break;   \
+    case 4: { constexpr int MT_ = 4; CALL; } break;   \
+    case 6: { constexpr int MT_ = 6; CALL; } break;   \
+    case 8: { constexpr int MT_ = 8; CALL; } break;   \
+    default: { constexpr int MT_ = 12; CALL; } break; \
+  }
+
+}  // namespace
+
+int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int n_omega,
+                        const double* eigvals, const double* eigvecs, const double* propagators,
+                        const double* omega, const double* basis, const double* n_opers,
+                        const double* n_coeffs, const double* dt, const double* t, int herm_flags,
+                        double* out) {
+  FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32, "control matrix: G=%d, d=%d unsupported", G, d);
+  FFB_REQUIRE(ctx, n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
+              "control matrix: n_nops=%d n_basis=%d n_omega=%d must all be positive", n_nops,
+              n_basis, n_omega);
+  const int dd = d * d;
+  const int parts_j = (herm_flags & FFB_HERM_NOPERS) ? 1 : 2;
+  const int parts_k = (herm_flags & FFB_HERM_BASIS) ? 1 : 2;
+  const int n_jrows = n_nops * parts_j, n_krows = n_basis * parts_k;
+  const int rows = n_jrows * n_krows;
+  const int MT = pick_mt(ceil_div(rows, 8));
+  constexpr int NW = 8;
+  const StreamGeom geo = make_geom(rows, G, d, MT);
+  const int rows_pad = geo.n_rb * MT * 8;
+
+  DevBuf Bbar, Cbar, stream, partial;
+  FFB_TRY(Bbar.alloc(ctx, (size_t)G * n_jrows * dd * 16));
+  FFB_TRY(Cbar.alloc(ctx, (size_t)G * n_krows * dd * 16));
+  FFB_TRY(stream.alloc(ctx, geo.rb_doubles * geo.n_rb * sizeof(double)));
+
+  {
+    const size_t smem = (size_t)8 * dd * sizeof(double);
+    FFB_CUDA(ctx, cudaFuncSetAttribute(transform_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    transform_kernel<<<G, 128, smem, ctx->stream>>>(G, d, n_nops, n_basis, parts_j, parts_k, eigvecs,
+                                                    propagators, n_opers, n_coeffs, basis,
+                                                    Bbar.as<double>(), Cbar.as<double>());
+    FFB_LAUNCHED(ctx);
+  }
+  {
+    const size_t total = geo.rb_doubles * geo.n_rb;
+    const unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total, 256), (size_t)ctx->sm_count * 32);
+    assemble_kernel<<<blocks, 256, 0, ctx->stream>>>(geo, G, d, rows, n_jrows, n_krows,
+                                                     Bbar.as<double>(), Cbar.as<double>(), eigvals,
+                                                     dt, t, stream.as<double>());
+    FFB_LAUNCHED(ctx);
+  }
+
+  MainParams p;
+  p.stream = stream.as<double>();
+  p.omega = omega;
+  p.n_omega = n_omega;
+  p.rows_pad = rows_pad;
+  p.n_pass = geo.n_pass;
+  p.n_pairs = geo.n_pairs;
+  p.pass_doubles = geo.pass_doubles;
+  p.rb_doubles = geo.rb_doubles;
+  p.diag_unit = geo.diag_unit;
+  p.pair_unit = geo.pair_unit;
+  const size_t pass_bytes = geo.pass_doubles * sizeof(double);
+  if (pass_bytes <= (size_t)STAGE_MAX_BYTES) {
+    p.n_sp = 1;
+    p.pps = (int)std::max<size_t>(1, STAGE_TARGET_BYTES / pass_bytes);
+    p.pps = std::min(p.pps, 32);
+    p.stage_doubles = (int)(p.pps * geo.pass_doubles);
+  } else {
+    p.pps = 1;
+    const int n_units = 1 + geo.n_pairs;
+    int n_sp = (int)ceil_div_sz(pass_bytes, STAGE_TARGET_BYTES);
+    n_sp = std::min(n_sp, n_units);
+    // largest piece under this split
+    int max_piece = 0;
+    for (;;) {
+      max_piece = 0;
+      for (int j = 0; j < n_sp; ++j) {
+        const int u0 = (int)(((long long)j * n_units) / n_sp);
+        const int u1 = (int)(((long long)(j + 1) * n_units) / n_sp);
+        int len = (u1 - u0) * geo.pair_unit;
+        if (u0 == 0) len += geo.diag_unit - geo.pair_unit;
+        max_piece = std::max(max_piece, len);
+      }
+      if ((size_t)max_piece * sizeof(double) <= (size_t)STAGE_MAX_BYTES || n_sp == n_units) break;
+      ++n_sp;
+    }
+    p.n_sp = n_sp;
+    p.stage_doubles = max_piece;
+  }
+  FFB_REQUIRE(ctx, (size_t)2 * p.stage_doubles * sizeof(double) <= 200 * 1024,
+              "control matrix: stage of %d doubles does not fit shared memory", p.stage_doubles);
+
+  // split the segment axis so that the grid fills the machine a few times over
+  const int n_wtiles = ceil_div(n_omega, NW * 8);
+  int blocks_per_sm = 1;
+  const size_t smem = (size_t)2 * p.stage_doubles * sizeof(double);
+  FFB_DISPATCH_MT(MT, NW, FFB_TRY((occupancy<MT_, NW>(ctx, smem, &blocks_per_sm))));
+  blocks_per_sm = std::max(1, blocks_per_sm);
+  const long long slots = (long long)ctx->sm_count * blocks_per_sm;
+  const long long base_ctas = (long long)n_wtiles * geo.n_rb;
+  const int min_passes = std::max(p.pps * 2, 8);  // do not cut chunks shorter than this
+  int S = 1;
+  if (base_ctas < 4 * slots) {
+    S = (int)std::min<long long>((4 * slots + base_ctas - 1) / base_ctas,
+                                 std::max(1, geo.n_pass / min_passes));
+    S = std::max(1, S);
+  }
+  int ppc = ceil_div(geo.n_pass, S);
+  ppc = ceil_div(ppc, p.pps) * p.pps;
+  S = ceil_div(geo.n_pass, ppc);
+  p.passes_per_chunk = ppc;
+
+  FFB_TRY(partial.alloc(ctx, (size_t)S * rows_pad * n_omega * 16));
+  p.partial = partial.as<double>();
+
+  FFB_DISPATCH_MT(MT, NW, FFB_TRY((launch_main<MT_, NW>(ctx, p, n_wtiles, geo.n_rb, S))));
+
+  {
+    const size_t total = (size_t)n_nops * n_basis * n_omega;
+    const unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total, 256), (size_t)ctx->sm_count * 16);
+    finalize_kernel<<<blocks, 256, 0, ctx->stream>>>(S, rows_pad, n_nops, n_basis, parts_j, parts_k,
+                                                     n_omega, partial.as<double>(), out);
+    FFB_LAUNCHED(ctx);
+  }
+  return FFB_OK;
+}

@@ -1,0 +1,350 @@
+// K1 -- batched Hermitian eigendecomposition, piecewise propagators and their running product.
+//
+// Replaces PulseSequence.diagonalize (pulse_sequence.py:577-586) and numeric.diagonalize
+// (numeric.py:1886-1935) of the reference:
+//     H_g = sum_i a_i(t_g) A_i                                    (einsum 'ijk,il->ljk')
+//     H_g = V_g D_g V_g^dagger, eigenvalues ascending             (numpy.linalg.eigh)
+//     P_g = V_g exp(-i D_g dt_g) V_g^dagger
+//     Q   = [1, P_0, P_1 P_0, ...]                                (util.adot, util.py:868-877)
+//
+// B200 mapping: one warp per segment runs a cyclic complex Jacobi iteration with the d x d matrix
+// and the accumulating eigenvector matrix in shared memory (lanes own rows / columns); the
+// running product, which the reference forms with G sequential matmuls, is a three-phase parallel
+// scan over the (associative, non-commutative) matrix product.
+#include "ffb_common.cuh"
+
+namespace {
+
+constexpr int DIAG_WARPS = 4;
+constexpr int MAX_D = 32;  // one lane per row/column
+constexpr int MAX_SWEEPS = 40;
+
+__device__ __forceinline__ cplx lds_c(const double* m, int i) { return {m[2 * i], m[2 * i + 1]}; }
+__device__ __forceinline__ void sts_c(double* m, int i, cplx v) {
+  m[2 * i] = v.re;
+  m[2 * i + 1] = v.im;
+}
+
+// One warp per segment. Shared memory per warp: H (d*d c128), V (d*d c128), ev (d), perm (d ints).
+__global__ void __launch_bounds__(DIAG_WARPS * 32)
+diag_kernel(int G, int d, int n_cops, const double* __restrict__ c_opers,
+            const double* __restrict__ c_coeffs, const double* __restrict__ dt,
+            double* __restrict__ eigvals, double* __restrict__ eigvecs,
+            double* __restrict__ piecewise, int* __restrict__ not_converged) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int g = blockIdx.x * DIAG_WARPS + warp;
+  if (g >= G) return;
+  const int dd = d * d;
+  const int per_warp = 4 * dd + 2 * d;  // doubles
+  double* H = smem + (size_t)warp * per_warp;
+  double* V = H + 2 * dd;
+  double* ev = V + 2 * dd;
+  int* perm = reinterpret_cast<int*>(ev + d);
+
+  // ---- build H_g (lower triangle is authoritative, as LAPACK's UPLO='L' in numpy.linalg.eigh)
+  for (int e = lane; e < dd; e += 32) {
+    cplx h = {0.0, 0.0};
+    if (c_coeffs != nullptr) {
+      for (int i = 0; i < n_cops; ++i) {
+        const double a = c_coeffs[(size_t)i * G + g];
+        h.re += a * c_opers[2 * ((size_t)i * dd + e)];
+        h.im += a * c_opers[2 * ((size_t)i * dd + e) + 1];
+      }
+    } else {
+      h.re = c_opers[2 * ((size_t)g * dd + e)];
+      h.im = c_opers[2 * ((size_t)g * dd + e) + 1];
+    }
+    sts_c(H, e, h);
+    const int r = e / d, c = e % d;
+    sts_c(V, e, cplx{r == c ? 1.0 : 0.0, 0.0});
+  }
+  __syncwarp();
+  for (int e = lane; e < dd; e += 32) {
+    const int r = e / d, c = e % d;
+    if (r < c) sts_c(H, e, cconj(lds_c(H, c * d + r)));
+    if (r == c) H[2 * e + 1] = 0.0;
+  }
+  __syncwarp();
+
+  double norm2 = 0.0;
+  for (int e = lane; e < dd; e += 32) {
+    const cplx h = lds_c(H, e);
+    norm2 += h.re * h.re + h.im * h.im;
+  }
+  for (int o = 16; o > 0; o >>= 1) norm2 += __shfl_xor_sync(0xffffffffu, norm2, o);
+
+  // ---- cyclic Jacobi sweeps
+  bool converged = (d == 1);
+  for (int sweep = 0; sweep < MAX_SWEEPS && !converged; ++sweep) {
+    double off = 0.0;
+    for (int e = lane; e < dd; e += 32) {
+      const int r = e / d, c = e % d;
+      if (r < c) {
+        const cplx h = lds_c(H, e);
+        off += h.re * h.re + h.im * h.im;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xffffffffu, off, o);
+    if (off <= 1e-34 * norm2 || off == 0.0) {
+      converged = true;
+      break;
+    }
+    for (int p = 0; p < d - 1; ++p) {
+      for (int q = p + 1; q < d; ++q) {
+        const cplx h = lds_c(H, p * d + q);
+        const double beta = hypot(h.re, h.im);
+        if (beta == 0.0) continue;  // warp-uniform (all lanes read the same element)
+        const cplx w = {h.re / beta, h.im / beta};
+        const double a = H[2 * (p * d + p)], b = H[2 * (q * d + q)];
+        const double tau = (b - a) / (2.0 * beta);
+        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+        const double c = 1.0 / sqrt(1.0 + t * t);
+        const double s = t * c;
+        const cplx swc = {s * w.re, -s * w.im};  // s * conj(w)
+        const cplx cwc = {c * w.re, -c * w.im};  // c * conj(w)
+        __syncwarp();
+        // columns p, q of H and V:  X[:,p] <- c X[:,p] - s conj(w) X[:,q];  X[:,q] <- s X[:,p] + c conj(w) X[:,q]
+        if (lane < d) {
+          const int k = lane;
+          cplx xp = lds_c(H, k * d + p), xq = lds_c(H, k * d + q);
+          cplx a1 = cmul(swc, xq), a2 = cmul(cwc, xq);
+          sts_c(H, k * d + p, cplx{c * xp.re - a1.re, c * xp.im - a1.im});
+          sts_c(H, k * d + q, cplx{s * xp.re + a2.re, s * xp.im + a2.im});
+          xp = lds_c(V, k * d + p);
+          xq = lds_c(V, k * d + q);
+          a1 = cmul(swc, xq);
+          a2 = cmul(cwc, xq);
+          sts_c(V, k * d + p, cplx{c * xp.re - a1.re, c * xp.im - a1.im});
+          sts_c(V, k * d + q, cplx{s * xp.re + a2.re, s * xp.im + a2.im});
+        }
+        __syncwarp();
+        // rows p, q of H:  H[p,:] <- c H[p,:] - s w H[q,:];  H[q,:] <- s H[p,:] + c w H[q,:]
+        if (lane < d) {
+          const int k = lane;
+          const cplx yp = lds_c(H, p * d + k), yq = lds_c(H, q * d + k);
+          const cplx sw = {s * w.re, s * w.im}, cw = {c * w.re, c * w.im};
+          const cplx a1 = cmul(sw, yq), a2 = cmul(cw, yq);
+          sts_c(H, p * d + k, cplx{c * yp.re - a1.re, c * yp.im - a1.im});
+          sts_c(H, q * d + k, cplx{s * yp.re + a2.re, s * yp.im + a2.im});
+        }
+        __syncwarp();
+        if (lane == 0) {
+          sts_c(H, p * d + q, cplx{0.0, 0.0});
+          sts_c(H, q * d + p, cplx{0.0, 0.0});
+          H[2 * (p * d + p) + 1] = 0.0;
+          H[2 * (q * d + q) + 1] = 0.0;
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if (!converged && lane == 0) atomicAdd(not_converged, 1);
+
+  // ---- ascending order (stable), as numpy.linalg.eigh returns them
+  if (lane < d) ev[lane] = H[2 * (lane * d + lane)];
+  __syncwarp();
+  if (lane < d) {
+    const double mine = ev[lane];
+    int rank = 0;
+    for (int j = 0; j < d; ++j) {
+      const double other = ev[j];
+      rank += (other < mine) || (other == mine && j < lane);
+    }
+    perm[rank] = lane;
+  }
+  __syncwarp();
+  if (lane < d) eigvals[(size_t)g * d + lane] = ev[perm[lane]];
+  for (int e = lane; e < dd; e += 32) {
+    const int r = e / d, c = e % d;
+    const cplx v = lds_c(V, r * d + perm[c]);
+    eigvecs[2 * ((size_t)g * dd + e)] = v.re;
+    eigvecs[2 * ((size_t)g * dd + e) + 1] = v.im;
+  }
+
+  // ---- P_g = V exp(-i D dt) V^dagger  (order of eigenpairs is irrelevant here)
+  const double dtg = dt[g];
+  for (int e = lane; e < dd; e += 32) {
+    const int r = e / d, c = e % d;
+    cplx acc = {0.0, 0.0};
+    for (int j = 0; j < d; ++j) {
+      double sn, cs;
+      sincos(-dtg * ev[j], &sn, &cs);
+      const cplx vv = cmulc(lds_c(V, r * d + j), lds_c(V, c * d + j));
+      acc.re += vv.re * cs - vv.im * sn;
+      acc.im += vv.re * sn + vv.im * cs;
+    }
+    piecewise[2 * ((size_t)g * dd + e)] = acc.re;
+    piecewise[2 * ((size_t)g * dd + e) + 1] = acc.im;
+  }
+}
+
+// ---- parallel scan of Q_{g+1} = P_g Q_g -----------------------------------------------------------
+// phase A: warp c forms the running products inside chunk c: local[g+1] = P_g ... P_{c*L}, written to
+//          propagators[g+1]; the chunk total goes to totals[c].
+__global__ void __launch_bounds__(DIAG_WARPS * 32)
+scan_local_kernel(int G, int d, int L, const double* __restrict__ piecewise,
+                  double* __restrict__ propagators, double* __restrict__ totals) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * DIAG_WARPS + warp;
+  const int g0 = c * L;
+  if (g0 >= G) return;
+  const int g1 = min(G, g0 + L);
+  const int dd = d * d;
+  double* R0 = smem + (size_t)warp * 4 * dd;
+  double* R1 = R0 + 2 * dd;
+  for (int e = lane; e < dd; e += 32) {
+    sts_c(R0, e, cplx{piecewise[2 * ((size_t)g0 * dd + e)], piecewise[2 * ((size_t)g0 * dd + e) + 1]});
+  }
+  __syncwarp();
+  for (int e = lane; e < 2 * dd; e += 32) propagators[(size_t)(g0 + 1) * 2 * dd + e] = R0[e];
+  double* cur = R0;
+  double* nxt = R1;
+  for (int g = g0 + 1; g < g1; ++g) {
+    const double* Pg = piecewise + (size_t)g * 2 * dd;
+    for (int e = lane; e < dd; e += 32) {
+      const int r = e / d, col = e % d;
+      cplx acc = {0.0, 0.0};
+      for (int j = 0; j < d; ++j) {
+        const cplx a = {Pg[2 * (r * d + j)], Pg[2 * (r * d + j) + 1]};
+        const cplx b = lds_c(cur, j * d + col);
+        acc.re += a.re * b.re - a.im * b.im;
+        acc.im += a.re * b.im + a.im * b.re;
+      }
+      sts_c(nxt, e, acc);
+      propagators[2 * ((size_t)(g + 1) * dd + e)] = acc.re;
+      propagators[2 * ((size_t)(g + 1) * dd + e) + 1] = acc.im;
+    }
+    __syncwarp();
+    double* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  for (int e = lane; e < 2 * dd; e += 32) totals[(size_t)c * 2 * dd + e] = cur[e];
+}
+
+// phase B: one warp, exclusive prefix over the chunk totals: prefix[c] = totals[c-1] ... totals[0]
+__global__ void __launch_bounds__(32)
+scan_totals_kernel(int n_chunks, int d, const double* __restrict__ totals,
+                   double* __restrict__ prefix) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x;
+  const int dd = d * d;
+  double* cur = smem;
+  double* nxt = smem + 2 * dd;
+  for (int e = lane; e < dd; e += 32) {
+    const int r = e / d, col = e % d;
+    sts_c(cur, e, cplx{r == col ? 1.0 : 0.0, 0.0});
+  }
+  __syncwarp();
+  for (int c = 0; c < n_chunks; ++c) {
+    for (int e = lane; e < 2 * dd; e += 32) prefix[(size_t)c * 2 * dd + e] = cur[e];
+    if (c + 1 == n_chunks) break;
+    const double* T = totals + (size_t)c * 2 * dd;
+    for (int e = lane; e < dd; e += 32) {
+      const int r = e / d, col = e % d;
+      cplx acc = {0.0, 0.0};
+      for (int j = 0; j < d; ++j) {
+        const cplx a = {T[2 * (r * d + j)], T[2 * (r * d + j) + 1]};
+        const cplx b = lds_c(cur, j * d + col);
+        acc.re += a.re * b.re - a.im * b.im;
+        acc.im += a.re * b.im + a.im * b.re;
+      }
+      sts_c(nxt, e, acc);
+    }
+    __syncwarp();
+    double* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+}
+
+// phase C: propagators[g+1] = local[g+1] * prefix[chunk(g)]; propagators[0] = 1. One thread per matrix
+// element; the local products live in a scratch buffer so nothing is updated in place.
+__global__ void scan_apply_from_kernel(int G, int d, int L, const double* __restrict__ local,
+                                       const double* __restrict__ prefix,
+                                       double* __restrict__ propagators) {
+  const int dd = d * d;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (size_t)(G + 1) * dd) return;
+  const int gi = (int)(tid / dd);
+  const int e = (int)(tid % dd);
+  const int r = e / d, col = e % d;
+  if (gi == 0) {
+    propagators[2 * tid] = (r == col) ? 1.0 : 0.0;
+    propagators[2 * tid + 1] = 0.0;
+    return;
+  }
+  const int c = (gi - 1) / L;
+  const double* Lm = local + (size_t)gi * 2 * dd;
+  if (c == 0) {
+    propagators[2 * tid] = Lm[2 * e];
+    propagators[2 * tid + 1] = Lm[2 * e + 1];
+    return;
+  }
+  const double* T = prefix + (size_t)c * 2 * dd;
+  cplx acc = {0.0, 0.0};
+  for (int j = 0; j < d; ++j) {
+    const cplx a = {Lm[2 * (r * d + j)], Lm[2 * (r * d + j) + 1]};
+    const cplx b = {T[2 * (j * d + col)], T[2 * (j * d + col) + 1]};
+    acc.re += a.re * b.re - a.im * b.im;
+    acc.im += a.re * b.im + a.im * b.re;
+  }
+  propagators[2 * tid] = acc.re;
+  propagators[2 * tid + 1] = acc.im;
+}
+}  // namespace
+
+int ffbi_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_opers,
+                     const double* c_coeffs, const double* dt, double* eigvals, double* eigvecs,
+                     double* propagators) {
+  FFB_REQUIRE(ctx, G >= 1, "diagonalize: need at least one segment (G=%d)", G);
+  FFB_REQUIRE(ctx, d >= 1 && d <= MAX_D, "diagonalize: dimension d=%d outside [1, %d]", d, MAX_D);
+  FFB_REQUIRE(ctx, c_coeffs == nullptr || n_cops >= 1, "diagonalize: n_cops=%d", n_cops);
+  const int dd = d * d;
+  int L = 8;
+  while ((long long)L * L < G && L < 256) L *= 2;
+  const int n_chunks = ceil_div(G, L);
+
+  DevBuf piecewise, local, totals, prefix, flag;
+  FFB_TRY(piecewise.alloc(ctx, (size_t)G * dd * 16));
+  FFB_TRY(local.alloc(ctx, (size_t)(G + 1) * dd * 16));
+  FFB_TRY(totals.alloc(ctx, (size_t)n_chunks * dd * 16));
+  FFB_TRY(prefix.alloc(ctx, (size_t)n_chunks * dd * 16));
+  FFB_TRY(flag.alloc(ctx, sizeof(int)));
+  FFB_CUDA(ctx, cudaMemsetAsync(flag.p, 0, sizeof(int), ctx->stream));
+
+  {
+    const size_t smem = (size_t)DIAG_WARPS * (4 * dd + 2 * d) * sizeof(double);
+    FFB_CUDA(ctx, cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    diag_kernel<<<ceil_div(G, DIAG_WARPS), DIAG_WARPS * 32, smem, ctx->stream>>>(
+        G, d, n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs, piecewise.as<double>(),
+        flag.as<int>());
+    FFB_LAUNCHED(ctx);
+  }
+  {
+    const size_t smem = (size_t)DIAG_WARPS * 4 * dd * sizeof(double);
+    FFB_CUDA(ctx, cudaFuncSetAttribute(scan_local_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scan_local_kernel<<<ceil_div(n_chunks, DIAG_WARPS), DIAG_WARPS * 32, smem, ctx->stream>>>(
+        G, d, L, piecewise.as<double>(), local.as<double>(), totals.as<double>());
+    FFB_LAUNCHED(ctx);
+  }
+  {
+    const size_t smem = (size_t)4 * dd * sizeof(double);
+    scan_totals_kernel<<<1, 32, smem, ctx->stream>>>(n_chunks, d, totals.as<double>(),
+                                                     prefix.as<double>());
+    FFB_LAUNCHED(ctx);
+  }
+  {
+    const size_t n = (size_t)(G + 1) * dd;
+    scan_apply_from_kernel<<<(unsigned)ceil_div_sz(n, 256), 256, 0, ctx->stream>>>(
+        G, d, L, local.as<double>(), prefix.as<double>(), propagators);
+    FFB_LAUNCHED(ctx);
+  }
+  return FFB_OK;
+}

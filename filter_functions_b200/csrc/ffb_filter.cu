@@ -1,0 +1,159 @@
+// K3 / K5 -- filter functions from control matrices and the infidelity integral.
+//
+// Replaces numeric.calculate_filter_function (numeric.py:1413-1467),
+// numeric.calculate_pulse_correlation_filter_function (numeric.py:1821-1883) and the integrand +
+// trapezoid of numeric.infidelity (numeric.py:2318-2320, :259-374, util.py:880-906).
+//
+// These stages are HBM/L2-bound streaming reductions: omega is the fastest axis of every array, so a
+// warp reads 32 consecutive complex128 values (512 B) per row and the basis axis is reduced in
+// registers.
+#include "ffb_common.cuh"
+
+namespace {
+
+// F[(l), (r), w] = sum_k conj(B[l,k,w]) B[r,k,w];  l, r run over (pulse, noise operator) rows.
+// Output index (P = n_pulses, l = (g,a), r = (h,b)): (((g*P + h)*n_nops + a)*n_nops + b)*n_omega + w
+template <int RT>
+__global__ void __launch_bounds__(256)
+ff_fidelity_kernel(int P, int n_nops, int n_basis, int n_omega, const double2* __restrict__ B,
+                   double2* __restrict__ F) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_omega) return;
+  const int L = P * n_nops;
+  const int l = blockIdx.y;
+  const int r0 = blockIdx.z * RT;
+  double2 acc[RT];
+#pragma unroll
+  for (int i = 0; i < RT; ++i) acc[i] = make_double2(0.0, 0.0);
+  const double2* Bl = B + (size_t)l * n_basis * n_omega + w;
+  for (int k = 0; k < n_basis; ++k) {
+    const double2 x = Bl[(size_t)k * n_omega];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+      const int r = r0 + i;
+      if (r < L) {
+        const double2 y = B[((size_t)r * n_basis + k) * n_omega + w];
+        // conj(x) * y
+        acc[i].x += x.x * y.x + x.y * y.y;
+        acc[i].y += x.x * y.y - x.y * y.x;
+      }
+    }
+  }
+  const int g = l / n_nops, a = l % n_nops;
+#pragma unroll
+  for (int i = 0; i < RT; ++i) {
+    const int r = r0 + i;
+    if (r < L) {
+      const int h = r / n_nops, b = r % n_nops;
+      F[((((size_t)g * P + h) * n_nops + a) * n_nops + b) * n_omega + w] = acc[i];
+    }
+  }
+}
+
+// F[(l), (r), k, m, w] = conj(B[l,k,w]) B[r,m,w]   (write-bound outer product)
+__global__ void __launch_bounds__(256)
+ff_generalized_kernel(int P, int n_nops, int n_basis, int n_omega, const double2* __restrict__ B,
+                      double2* __restrict__ F) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_omega) return;
+  const int l = blockIdx.y / n_basis, k = blockIdx.y % n_basis;
+  const int r = blockIdx.z;
+  const double2 x = B[((size_t)l * n_basis + k) * n_omega + w];
+  const int g = l / n_nops, a = l % n_nops;
+  const int h = r / n_nops, b = r % n_nops;
+  double2* dst = F + ((((((size_t)g * P + h) * n_nops + a) * n_nops + b) * n_basis + k) * n_basis) *
+                         (size_t)n_omega + w;
+  const double2* Br = B + (size_t)r * n_basis * n_omega + w;
+  for (int m = 0; m < n_basis; ++m) {
+    const double2 y = Br[(size_t)m * n_omega];
+    dst[(size_t)m * n_omega] = make_double2(x.x * y.x + x.y * y.y, x.x * y.y - x.y * y.x);
+  }
+}
+
+// One block per output element: trapezoid of Re(F S) over omega, warp-shuffle + shared reduction in a
+// fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+infidelity_kernel(int n_nops, int n_sel, const int* __restrict__ idx, int n_omega,
+                  const double2* __restrict__ F, const double* __restrict__ spectrum,
+                  int spectrum_ndim, int spectrum_is_complex, const double* __restrict__ omega,
+                  double norm, double* __restrict__ out) {
+  __shared__ double warp_sums[8];
+  const int o = blockIdx.x;  // output index
+  int lead, a, b;
+  if (spectrum_ndim == 3) {
+    lead = o / (n_sel * n_sel);
+    a = (o / n_sel) % n_sel;
+    b = o % n_sel;
+  } else {
+    lead = o / n_sel;
+    a = b = o % n_sel;
+  }
+  const double2* Frow = F + (((size_t)lead * n_nops + idx[a]) * n_nops + idx[b]) * n_omega;
+  size_t s_off = 0;
+  if (spectrum_ndim == 2) s_off = (size_t)a * n_omega;
+  if (spectrum_ndim == 3) s_off = ((size_t)a * n_sel + b) * n_omega;
+  auto integrand = [&](int i) -> double {
+    const double2 f = Frow[i];
+    if (spectrum_is_complex) {
+      const double2 s = reinterpret_cast<const double2*>(spectrum)[s_off + i];
+      return f.x * s.x - f.y * s.y;
+    }
+    return f.x * spectrum[s_off + i];
+  };
+  double sum = 0.0;
+  for (int i = threadIdx.x; i < n_omega - 1; i += blockDim.x) {
+    sum += (integrand(i + 1) + integrand(i)) * (omega[i + 1] - omega[i]);
+  }
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.0;
+    for (int i = 0; i < 8; ++i) total += warp_sums[i];
+    out[o] = total / 2.0 / norm;
+  }
+}
+
+}  // namespace
+
+int ffbi_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+                         const double* B, int generalized, double* F) {
+  FFB_REQUIRE(ctx, P >= 1 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
+              "filter function: bad shape (P=%d, n_nops=%d, n_basis=%d, n_omega=%d)", P, n_nops,
+              n_basis, n_omega);
+  const int L = P * n_nops;
+  FFB_REQUIRE(ctx, L <= 65535 && (long long)L * n_basis <= 65535 * 1LL,
+              "filter function: too many rows (%d x %d)", L, n_basis);
+  const int wt = ceil_div(n_omega, 256);
+  if (!generalized) {
+    constexpr int RT = 4;
+    dim3 grid(wt, L, ceil_div(L, RT));
+    ff_fidelity_kernel<RT><<<grid, 256, 0, ctx->stream>>>(
+        P, n_nops, n_basis, n_omega, reinterpret_cast<const double2*>(B),
+        reinterpret_cast<double2*>(F));
+  } else {
+    dim3 grid(wt, L * n_basis, L);
+    ff_generalized_kernel<<<grid, 256, 0, ctx->stream>>>(
+        P, n_nops, n_basis, n_omega, reinterpret_cast<const double2*>(B),
+        reinterpret_cast<double2*>(F));
+  }
+  FFB_LAUNCHED(ctx);
+  return FFB_OK;
+}
+
+int ffbi_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* idx_dev,
+                    int n_omega, const double* F, const double* spectrum, int spectrum_ndim,
+                    int spectrum_is_complex, const double* omega, int d, double* out) {
+  FFB_REQUIRE(ctx, spectrum_ndim >= 1 && spectrum_ndim <= 3, "infidelity: spectrum_ndim=%d",
+              spectrum_ndim);
+  FFB_REQUIRE(ctx, n_lead >= 1 && n_sel >= 1 && n_omega >= 1 && d >= 1,
+              "infidelity: bad shape (n_lead=%d, n_sel=%d, n_omega=%d, d=%d)", n_lead, n_sel,
+              n_omega, d);
+  const int n_out = n_lead * (spectrum_ndim == 3 ? n_sel * n_sel : n_sel);
+  const double norm = 2.0 * 3.141592653589793238462643383279502884 * d;
+  infidelity_kernel<<<n_out, 256, 0, ctx->stream>>>(
+      n_nops, n_sel, idx_dev, n_omega, reinterpret_cast<const double2*>(F), spectrum,
+      spectrum_ndim, spectrum_is_complex, omega, norm, out);
+  FFB_LAUNCHED(ctx);
+  return FFB_OK;
+}

@@ -1,0 +1,285 @@
+"""Numerics of the control-matrix / filter-function / infidelity path, executed on the GPU.
+
+Same public names, signatures, defaults, return shapes and error behaviour as the hot-path functions
+of the reference's ``numeric.py``; the bodies call ``libffb200`` (hand-written sm_100a kernels) through
+ctypes.  NumPy arrays in, NumPy arrays out.  There is no CPU fallback.
+
+=====================================================  ==========================================
+this module                                            reference ``numeric.py``
+=====================================================  ==========================================
+:func:`diagonalize`                                    ``:1886-1935``
+:func:`calculate_control_matrix_from_scratch`          ``:707-881``
+:func:`calculate_control_matrix_from_atomic`           ``:621-704``
+:func:`calculate_filter_function`                      ``:1413-1467``
+:func:`calculate_pulse_correlation_filter_function`    ``:1821-1883``
+:func:`infidelity`                                     ``:2062-2334``
+=====================================================  ==========================================
+"""
+from typing import Optional
+
+import numpy as np
+from numpy import ndarray
+
+from . import _lib, util
+
+__all__ = ['calculate_control_matrix_from_atomic', 'calculate_control_matrix_from_scratch',
+           'calculate_filter_function', 'calculate_pulse_correlation_filter_function',
+           'diagonalize', 'infidelity']
+
+
+def diagonalize(hamiltonian: ndarray, dt):
+    """Eigenvalues (n_dt, d), eigenvectors (n_dt, d, d) and cumulative propagators (n_dt+1, d, d) of
+    a piecewise-constant Hamiltonian of shape (n_dt, d, d)."""
+    H = _lib.as_c128(hamiltonian)
+    if H.ndim != 3 or H.shape[-1] != H.shape[-2]:
+        raise ValueError(f'Expected hamiltonian of shape (n_dt, d, d), not {H.shape}')
+    dt = _lib.as_f64(dt)
+    G, d = H.shape[0], H.shape[1]
+    if dt.shape != (G,):
+        raise ValueError(f'Expected dt of shape ({G},), not {dt.shape}')
+    eigvals = np.empty((G, d), dtype=np.float64)
+    eigvecs = np.empty((G, d, d), dtype=np.complex128)
+    propagators = np.empty((G + 1, d, d), dtype=np.complex128)
+    ctx = _lib.context()
+    _lib.check(ctx, _lib.lib().ffb_diagonalize(ctx, G, d, 0, _lib.ptr(H), None, _lib.ptr(dt),
+                                               _lib.ptr(eigvals), _lib.ptr(eigvecs),
+                                               _lib.ptr(propagators)))
+    return eigvals, eigvecs, propagators
+
+
+def _diagonalize_from_coeffs(c_opers, c_coeffs, dt):
+    """PulseSequence.diagonalize without materialising H on the host (``pulse_sequence.py:577-586``)."""
+    c_opers = _lib.as_c128(c_opers)
+    c_coeffs = _lib.as_f64(c_coeffs)
+    dt = _lib.as_f64(dt)
+    n_cops, d = c_opers.shape[0], c_opers.shape[-1]
+    G = dt.shape[0]
+    eigvals = np.empty((G, d), dtype=np.float64)
+    eigvecs = np.empty((G, d, d), dtype=np.complex128)
+    propagators = np.empty((G + 1, d, d), dtype=np.complex128)
+    ctx = _lib.context()
+    _lib.check(ctx, _lib.lib().ffb_diagonalize(ctx, G, d, n_cops, _lib.ptr(c_opers),
+                                               _lib.ptr(c_coeffs), _lib.ptr(dt), _lib.ptr(eigvals),
+                                               _lib.ptr(eigvecs), _lib.ptr(propagators)))
+    return eigvals, eigvecs, propagators
+
+
+def calculate_control_matrix_from_scratch(eigvals, eigvecs, propagators, omega, basis, n_opers,
+                                          n_coeffs, dt, t=None, show_progressbar: bool = False,
+                                          cache_intermediates: bool = False,
+                                          out: Optional[ndarray] = None):
+    r"""Control matrix :math:`\tilde{\mathcal{B}}_{\alpha k}(\omega)` of shape
+    (n_nops, n_basis, n_omega) without knowledge of more atomic pulses."""
+    if cache_intermediates:
+        raise NotImplementedError(
+            'cache_intermediates=True returns (n_dt, n_omega, d, d)-sized arrays which the fused '
+            'kernel exists to avoid; not available in filter_functions_b200 (SURVEY.md 8f rank 3)')
+    eigvals = _lib.as_f64(eigvals)
+    eigvecs = _lib.as_c128(eigvecs)
+    propagators = _lib.as_c128(propagators)
+    omega = _lib.as_f64(np.asanyarray(omega))
+    basis_arr = _lib.as_c128(np.asarray(basis))
+    n_opers = _lib.as_c128(n_opers)
+    n_coeffs = _lib.as_f64(n_coeffs)
+    dt = _lib.as_f64(dt)
+    if t is None:
+        t = np.concatenate(([0], dt.cumsum()))
+    t = _lib.as_f64(t)
+    G, d = eigvals.shape
+    n_nops, n_basis, n_omega = len(n_opers), len(basis_arr), len(omega)
+    if eigvecs.shape != (G, d, d) or propagators.shape != (G + 1, d, d):
+        raise ValueError('eigvals, eigvecs and propagators have inconsistent shapes')
+    if n_coeffs.shape != (n_nops, G) or dt.shape != (G,) or t.shape != (G + 1,):
+        raise ValueError('n_coeffs, dt or t do not match the number of segments')
+    result = out
+    direct = (out is not None and out.dtype == np.complex128 and out.flags.c_contiguous
+              and out.shape == (n_nops, n_basis, n_omega))
+    if not direct:
+        result = np.empty((n_nops, n_basis, n_omega), dtype=np.complex128)
+    ctx = _lib.context()
+    if n_omega:
+        _lib.check(ctx, _lib.lib().ffb_control_matrix_from_scratch(
+            ctx, G, d, n_nops, n_basis, n_omega, _lib.ptr(eigvals), _lib.ptr(eigvecs),
+            _lib.ptr(propagators), _lib.ptr(omega), _lib.ptr(basis_arr), _lib.ptr(n_opers),
+            _lib.ptr(n_coeffs), _lib.ptr(dt), _lib.ptr(t), _lib.ptr(result)))
+    if out is not None and not direct:
+        out[:] = result
+        return out
+    return result
+
+
+@util.parse_optional_parameters(which=('total', 'correlations'))
+def calculate_control_matrix_from_atomic(phases, control_matrix_atomic, propagators_liouville,
+                                         show_progressbar: bool = False, which: str = 'total'):
+    r"""Control matrix of a sequence from those of its constituents,
+    :math:`\sum_g e^{i\omega t_{g-1}}\tilde{\mathcal{B}}^{(g)}(\omega)\mathcal{Q}^{(g-1)}`.
+    The memory order of the result mirrors that of ``control_matrix_atomic`` (C, F or neither), as
+    in the reference (``numeric.py:671-676``)."""
+    atomic_in = np.asarray(control_matrix_atomic)
+    if atomic_in.ndim != 4:
+        raise ValueError('Expected control_matrix_atomic.ndim == 4.')
+    c_in, f_in = atomic_in.flags.c_contiguous, atomic_in.flags.f_contiguous
+    atomic = _lib.as_c128(atomic_in)
+    P, n_nops, n_basis, n_omega = atomic.shape
+    phases = _lib.as_c128(np.asarray(phases).reshape(P - 1, n_omega))
+    Q = np.asarray(propagators_liouville)
+    q_complex = np.iscomplexobj(Q)
+    Q = (_lib.as_c128(Q) if q_complex else _lib.as_f64(Q)).reshape(P - 1, n_basis, n_basis)
+    corr = which == 'correlations'
+    out = np.empty((P, n_nops, n_basis, n_omega) if corr else (n_nops, n_basis, n_omega),
+                   dtype=np.complex128)
+    ctx = _lib.context()
+    _lib.check(ctx, _lib.lib().ffb_control_matrix_from_atomic(
+        ctx, P, n_nops, n_basis, n_omega, _lib.ptr(phases), _lib.ptr(atomic), _lib.ptr(Q),
+        int(q_complex), int(corr), _lib.ptr(out)))
+    if c_in:
+        return out
+    if f_in:
+        return np.asfortranarray(out)
+    # neither: the reference hands back an array with omega on the second-to-last memory axis
+    return np.ascontiguousarray(out.swapaxes(-1, -2)).swapaxes(-1, -2)
+
+
+def _filter_function(control_matrix, which, P):
+    B = _lib.as_c128(control_matrix)
+    n_nops, n_basis, n_omega = B.shape[-3:]
+    gen = which == 'generalized'
+    shape = (n_nops, n_nops) + ((n_basis, n_basis) if gen else ()) + (n_omega,)
+    if P is not None:
+        shape = (P, P) + shape
+    F = np.empty(shape, dtype=np.complex128)
+    if F.size:
+        ctx = _lib.context()
+        _lib.check(ctx, _lib.lib().ffb_filter_function(ctx, 1 if P is None else P, n_nops, n_basis,
+                                                       n_omega, _lib.ptr(B), int(gen),
+                                                       _lib.ptr(F)))
+    if P is not None and gen:
+        # kernel layout (g,h,a,b,k,l,o) == reference layout 'ghabklo'
+        pass
+    return F
+
+
+@util.parse_optional_parameters(which=('fidelity', 'generalized'))
+def calculate_filter_function(control_matrix, which: str = 'fidelity') -> ndarray:
+    r"""Filter function :math:`F_{\alpha\beta}(\omega)=\sum_k\tilde{\mathcal B}^*_{\alpha k}
+    \tilde{\mathcal B}_{\beta k}` (or the generalized :math:`F_{\alpha\beta,kl}`)."""
+    control_matrix = np.asarray(control_matrix)
+    if control_matrix.ndim != 3:
+        raise ValueError('Expected control_matrix.ndim == 3.')
+    return _filter_function(control_matrix, which, None)
+
+
+@util.parse_optional_parameters(which=('fidelity', 'generalized'))
+def calculate_pulse_correlation_filter_function(control_matrix, which: str = 'fidelity') -> ndarray:
+    r"""Pulse-correlation filter function :math:`F^{(gg')}_{\alpha\beta}(\omega)` of shape
+    (n_pls, n_pls, n_nops, n_nops, [n_basis, n_basis,] n_omega)."""
+    control_matrix = np.asarray(control_matrix)
+    if control_matrix.ndim != 4:
+        raise ValueError('Expected control_matrix.ndim == 4.')
+    return _filter_function(control_matrix, which, control_matrix.shape[0])
+
+
+def _integrate_against_spectrum(filter_function, spectrum, omega, idx, d):
+    """integrate(Re(F[..., idx, idx, :] S), omega) / (2 pi d) on the GPU
+    (``numeric.py:2318-2320`` with the integrand of ``:259-374``)."""
+    omega = _lib.as_f64(omega)
+    idx = np.asarray(idx)
+    spectrum = util.parse_spectrum(np.asarray(spectrum), omega, idx)
+    F = _lib.as_c128(filter_function)
+    n_nops, n_omega = F.shape[-2], F.shape[-1]
+    lead_shape = F.shape[:-3]
+    n_lead = int(np.prod(lead_shape)) if lead_shape else 1
+    s_complex = np.iscomplexobj(spectrum)
+    S = _lib.as_c128(spectrum) if s_complex else _lib.as_f64(spectrum)
+    n_sel = len(idx)
+    out_shape = lead_shape + ((n_sel, n_sel) if spectrum.ndim == 3 else (n_sel,))
+    out = np.empty(out_shape, dtype=np.float64)
+    idx32 = np.ascontiguousarray(idx, dtype=np.int32)
+    ctx = _lib.context()
+    _lib.check(ctx, _lib.lib().ffb_infidelity(ctx, n_lead, n_nops, n_sel, _lib.ptr(idx32), n_omega,
+                                              _lib.ptr(F), _lib.ptr(S), spectrum.ndim,
+                                              int(s_complex), _lib.ptr(omega), int(d),
+                                              _lib.ptr(out)))
+    return out
+
+
+@util.parse_optional_parameters(which=('total', 'correlations'))
+def infidelity(pulse, spectrum, omega, n_oper_identifiers=None, which: str = 'total',
+               show_progressbar: bool = False, cache_intermediates: bool = False,
+               return_smallness: bool = False, test_convergence: bool = False):
+    r"""Leading-order entanglement infidelity
+    :math:`\mathcal I_{\alpha\beta}=\frac1d\int\frac{d\omega}{2\pi}S_{\alpha\beta}(\omega)
+    F_{\alpha\beta}(\omega)` for each (pair of) noise operator(s); see the reference docstring
+    (``numeric.py:2074-2250``) for the options, which behave identically here."""
+    idx = util.get_indices_from_identifiers(pulse.n_oper_identifiers, n_oper_identifiers)
+
+    if test_convergence:
+        if not callable(spectrum):
+            raise TypeError('Spectrum should be callable when test_convergence == True.')
+        try:
+            omega_IR = omega.get('omega_IR', 2*np.pi/pulse.tau*1e-2)
+        except AttributeError:
+            raise TypeError('omega should be dictionary with parameters '
+                            + 'when test_convergence == True.')
+        omega_UV = omega.get('omega_UV', 2*np.pi/pulse.tau*1e+2)
+        spacing = omega.get('spacing', 'linear')
+        n_min = omega.get('n_min', 100)
+        n_max = omega.get('n_max', 500)
+        n_points = omega.get('n_points', 10)
+        if spacing == 'linear':
+            xspace = np.linspace
+        elif spacing == 'log':
+            xspace = np.geomspace
+        else:
+            raise ValueError("spacing should be either 'linear' or 'log'.")
+        delta_n = (n_max - n_min)//(n_points - 1)
+        n_samples = np.arange(n_min, n_max + delta_n, delta_n)
+        convergence_infids = np.empty((len(n_samples), len(idx)))
+        for i, n in enumerate(n_samples):
+            freqs = xspace(omega_IR, omega_UV, n)
+            convergence_infids[i] = infidelity(pulse, spectrum(freqs), freqs,
+                                               n_oper_identifiers=n_oper_identifiers,
+                                               which='total', show_progressbar=show_progressbar,
+                                               cache_intermediates=False, return_smallness=False,
+                                               test_convergence=False)
+        return n_samples, convergence_infids
+
+    spectrum = np.asarray(spectrum)
+    if which == 'total':
+        if not pulse.basis.istraceless:
+            # Trace tensor enters (numeric.py:2295-2305): F_ab = sum_kl B*_ak T_kl B_bl / d with
+            # T_kl = sum_m tr(C_k C_l C_m C_m) - tr(C_k C_m C_l C_m).  Composed from the device ops:
+            # B' = B T^T (from_atomic with an empty first pulse), then the (0, 1) block of the
+            # pulse-correlation filter function of the pair (B, B').
+            traces = pulse.basis.four_element_traces
+            T = (np.einsum('klmm->kl', traces) - np.einsum('kmlm->kl', traces))
+            B = pulse.get_control_matrix(omega, show_progressbar, cache_intermediates)
+            n_omega = B.shape[-1]
+            stacked = np.stack([np.zeros_like(B), B])
+            Bp = calculate_control_matrix_from_atomic(np.ones((1, n_omega), dtype=complex), stacked,
+                                                      np.ascontiguousarray(T.T)[None])
+            pair = calculate_pulse_correlation_filter_function(np.stack([B, Bp]))
+            filter_function = pair[0, 1]/pulse.d
+        else:
+            filter_function = pulse.get_filter_function(omega, which='fidelity',
+                                                        show_progressbar=show_progressbar,
+                                                        cache_intermediates=cache_intermediates)
+    else:
+        if pulse.is_cached('omega') and not np.array_equal(pulse.omega, omega):
+            raise ValueError('Pulse correlation infidelities requested '
+                             + 'but omega not equal to cached frequencies.')
+        filter_function = pulse.get_pulse_correlation_filter_function()
+
+    infid = _integrate_against_spectrum(filter_function, spectrum, omega, idx, pulse.d)
+
+    if return_smallness:
+        if spectrum.ndim > 2:
+            raise NotImplementedError('Smallness parameter only implemented '
+                                      + 'for uncorrelated noise sources')
+        T1 = util.integrate(spectrum, np.asarray(omega))/(2*np.pi)
+        T2 = (pulse.dt*pulse.n_coeffs[idx]).sum(axis=-1)**2
+        T3 = util.abs2(pulse.n_opers[idx]).sum(axis=(1, 2))
+        xi = np.sqrt((T1*T2*T3).sum())
+        return infid, xi
+
+    return infid

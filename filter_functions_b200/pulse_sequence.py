@@ -1,0 +1,662 @@
+"""``PulseSequence`` and concatenation: the reference's object / cache / sequencing layer for the
+control-matrix -> filter-function -> infidelity path, with every numerical body running on the GPU.
+
+Public names, signatures, cache keys (``_data``, ``_frequency_data``, ``_intermediates``), alias
+lookup, invalidation rules and exception types follow ``pulse_sequence.py`` of the reference
+(v1.2.1; ``:61-1267`` for the class, ``:1340-1483`` / ``:1599-1887`` for concatenation).  Out of scope
+here: ``extend``/``remap``, periodic concatenation, second-order filter
+functions and derivatives.
+"""
+import bisect
+import copy
+from itertools import accumulate, chain, compress, zip_longest
+from types import MappingProxyType
+from typing import Any, Iterable, Optional
+
+import numpy as np
+from numpy import ndarray
+
+from . import _lib, numeric, util
+from .basis import Basis
+from .superoperator import liouville_representation
+
+__all__ = ['PulseSequence', 'concatenate', 'concatenate_without_filter_function']
+
+_DATA_ALIASES = {
+    'eigenvalues': 'eigvals',
+    'eigenvectors': 'eigvecs',
+    'propagators': 'propagators',
+    'total propagator': 'total_propagator',
+    'total propagator liouville': 'total_propagator_liouville',
+}
+_FREQUENCY_DATA_ALIASES = {
+    'frequencies': 'omega',
+    'total phases': 'total_phases',
+    'filter function': 'filter_function',
+    'fidelity filter function': 'filter_function',
+    'generalized filter function': 'filter_function_gen',
+    'pulse correlation filter function': 'filter_function_pc',
+    'fidelity pulse correlation filter function': 'filter_function_pc',
+    'generalized pulse correlation filter function': 'filter_function_pc_gen',
+    'second order filter function': 'filter_function_2',
+    'control matrix': 'control_matrix',
+    'pulse correlation control matrix': 'control_matrix_pc',
+}
+
+
+def _unpack_hamiltonian(H, n_dt: int, name: str):
+    """``[[operator, coefficients, identifier?], ...]`` -> sorted (opers, identifiers, coeffs);
+    validation and default identifiers as the reference's ``_parse_hamiltonian`` (``:1288-1337``)."""
+    if not util.is_sequence_like(H):
+        raise TypeError(f'Expected {name} to be a sequence, not of type {type(H)}!')
+    if not all(util.is_sequence_like(item) for item in H):
+        raise TypeError(f'Expected {name} to be a sequence of sequences but found at least one '
+                        'item of H not a sequence!')
+    opers, coeffs, *rest = zip_longest(*H, fillvalue=None)
+    identifiers = list(rest[0]) if rest else None
+    if not all(util.is_sequence_like(coeff) for coeff in coeffs):
+        raise TypeError(f'Expected coefficients in {name} to be a sequence')
+    prefix = 'A' if name == 'H_c' else 'B'
+    if identifiers is None:
+        identifiers = [f'{prefix}_{i}' for i in range(len(opers))]
+    else:
+        identifiers = [f'{prefix}_{i}' if ident is None else ident
+                       for i, ident in enumerate(identifiers)]
+        if len(set(identifiers)) != len(identifiers):
+            raise ValueError(f'{name} identifiers should be unique')
+    if not all(len(coeff) == n_dt for coeff in coeffs):
+        raise ValueError(f'Expected all coefficients in {name} to be of len(dt) = {n_dt}!')
+    order = np.argsort(identifiers)
+    opers = util.parse_operators(opers, name)
+    return opers[order], np.asarray(identifiers)[order], np.asarray(coeffs)[order]
+
+
+def _merge_equal_segments(pulse):
+    """Join consecutive segments with identical control coefficients (for ``__eq__``)."""
+    same = (np.diff(pulse.c_coeffs) == 0).all(axis=0).nonzero()[0]
+    if not same.size:
+        return pulse.c_coeffs, pulse.n_coeffs, pulse.dt
+    c_coeffs = np.delete(pulse.c_coeffs, same, axis=1)
+    n_coeffs = np.delete(pulse.n_coeffs, same, axis=1)
+    dt = np.delete(pulse.dt, same)
+    for old, new in zip(same, same - np.arange(len(same))):
+        dt[new] += pulse.dt[old]
+    return c_coeffs, n_coeffs, dt
+
+
+class PulseSequence:
+    r"""A piecewise-constant control pulse with its noise operators.
+
+    ``PulseSequence(H_c, H_n, dt, basis=None)`` with ``H_c = [[A_i, a_i(t), 'id'], ...]`` and
+    ``H_n = [[B_j, s_j(t), 'id'], ...]`` exactly as in the reference (``pulse_sequence.py:61-357``).
+    Cached quantities live in three dictionaries with the reference's keys; all of them are NumPy
+    arrays.
+    """
+
+    def __new__(cls, *args, **kwargs):
+        new = super().__new__(cls)
+        new._data = dict()
+        new._frequency_data = dict()
+        new._intermediates = dict()
+        return new
+
+    def __init__(self, H_c, H_n, dt, basis: Optional[Basis] = None):
+        if not util.is_sequence_like(dt):
+            raise TypeError(f'Expected a sequence of time steps, not {type(dt)}')
+        self.dt = np.asarray(dt)
+        if not np.isreal(self.dt).all():
+            raise ValueError('Times dt are not (all) real!')
+        if (self.dt < 0).any():
+            raise ValueError('Time steps are not (all) positive!')
+        self.c_opers, self.c_oper_identifiers, self.c_coeffs = _unpack_hamiltonian(
+            H_c, len(self.dt), 'H_c')
+        self.n_opers, self.n_oper_identifiers, self.n_coeffs = _unpack_hamiltonian(
+            H_n, len(self.dt), 'H_n')
+        if self.c_opers.shape[-2:] != self.n_opers.shape[-2:]:
+            raise ValueError('Control and noise Hamiltonian not same dimension!')
+        self.d = self.c_opers.shape[-1]
+        if basis is None:
+            self.basis = Basis.ggm(self.d)
+        else:
+            if not isinstance(basis, Basis):
+                raise ValueError("Expected basis to be an instance of the "
+                                 + f"'filter_functions.basis.Basis' class, not {type(basis)}!")
+            if basis.shape[1:] != (self.d, self.d):
+                raise ValueError("Expected basis elements to be of shape "
+                                 + f"({self.d}, {self.d}), not {basis.shape[1:]}!")
+            self.basis = basis
+
+    @classmethod
+    def from_arrays(cls, c_opers, c_oper_identifiers, c_coeffs, n_opers, n_oper_identifiers,
+                    n_coeffs, dt, basis=None):
+        """Alternative constructor from already parsed arrays (reference ``:313-357``)."""
+        new = cls.__new__(cls)
+        new.c_opers = np.asanyarray(c_opers)
+        new.c_oper_identifiers = np.asanyarray(c_oper_identifiers)
+        new.c_coeffs = np.asanyarray(c_coeffs)
+        new.n_opers = np.asanyarray(n_opers)
+        new.n_oper_identifiers = np.asanyarray(n_oper_identifiers)
+        new.n_coeffs = np.asanyarray(n_coeffs)
+        new.dt = np.asanyarray(dt)
+        new.d = new.c_opers.shape[-1]
+        new.basis = np.asanyarray(basis).view(Basis) if basis is not None else Basis.ggm(new.d)
+        if not len(new.c_opers) == len(new.c_oper_identifiers) == len(new.c_coeffs):
+            raise ValueError('Control Hamiltonian not same length!')
+        if not len(new.n_opers) == len(new.n_oper_identifiers) == len(new.n_coeffs):
+            raise ValueError('Noise Hamiltonian not same length!')
+        if not len(set(new.c_opers.shape[1:] + new.n_opers.shape[1:])) == 1:
+            raise ValueError('Control and/or noise Hamiltonian not same, square dimension!')
+        if not new.dt.size == new.n_coeffs.shape[1] == new.c_coeffs.shape[1]:
+            raise ValueError('Time steps not same length!')
+        if not new.basis.d == new.d:
+            raise ValueError('Basis dimension not same as Hamiltonian dimension!')
+        return new
+
+    # ---- dunder methods --------------------------------------------------------------------------
+    def __str__(self):
+        return f'{repr(self)}\n\tof dimension {self.d} and duration {self.duration}'
+
+    def __eq__(self, other: object) -> bool:
+        if not isinstance(other, self.__class__):
+            return NotImplemented
+        atol = np.finfo(complex).eps*self.basis.shape[0]
+        mine, theirs = _merge_equal_segments(self), _merge_equal_segments(other)
+        if len(mine[2]) != len(theirs[2]) or not np.allclose(mine[2], theirs[2], 1e-10, atol):
+            return False
+        for kind, coeffs_a, coeffs_b in (('c', mine[0], theirs[0]), ('n', mine[1], theirs[1])):
+            ids_a = getattr(self, f'{kind}_oper_identifiers')
+            ids_b = getattr(other, f'{kind}_oper_identifiers')
+            if len(ids_a) != len(ids_b):
+                return False
+            order_a, order_b = np.argsort(ids_a), np.argsort(ids_b)
+            if not np.array_equal(ids_a[order_a], ids_b[order_b]):
+                return False
+            if not np.array_equal(getattr(self, f'{kind}_opers')[order_a],
+                                  getattr(other, f'{kind}_opers')[order_b]):
+                return False
+            if not np.array_equal(coeffs_a[order_a], coeffs_b[order_b]):
+                return False
+        return bool(self.basis == other.basis)
+
+    __hash__ = None
+
+    def __len__(self) -> int:
+        return len(self.dt)
+
+    def __getitem__(self, key) -> 'PulseSequence':
+        new_dt = np.atleast_1d(self.dt[key])
+        if not new_dt.size:
+            raise IndexError('Cannot create empty PulseSequence')
+        return self.__class__.from_arrays(
+            c_opers=self.c_opers, n_opers=self.n_opers,
+            c_oper_identifiers=self.c_oper_identifiers,
+            n_oper_identifiers=self.n_oper_identifiers,
+            c_coeffs=np.atleast_2d(self.c_coeffs.T[key]).T,
+            n_coeffs=np.atleast_2d(self.n_coeffs.T[key]).T,
+            dt=new_dt, basis=self.basis)
+
+    def __copy__(self) -> 'PulseSequence':
+        copied = self.__class__.__new__(self.__class__)
+        copied.__dict__.update(self.__dict__)
+        copied._data = copy.copy(self._data)
+        copied._frequency_data = copy.copy(self._frequency_data)
+        copied._intermediates = copy.copy(self._intermediates)
+        return copied
+
+    def __matmul__(self, other: 'PulseSequence') -> 'PulseSequence':
+        if not isinstance(other, self.__class__):
+            raise TypeError(f'Incompatible type for concatenation: {type(other)}')
+        return concatenate((self, other))
+
+    def __imatmul__(self, other):
+        raise NotImplementedError
+
+    # ---- cache protocol --------------------------------------------------------------------------
+    def is_cached(self, attr: str) -> bool:
+        alias = attr.lower().replace('_', ' ')
+        if alias in _DATA_ALIASES:
+            return _DATA_ALIASES[alias] in self._data
+        if alias in _FREQUENCY_DATA_ALIASES:
+            return _FREQUENCY_DATA_ALIASES[alias] in self._frequency_data
+        return (attr in self._intermediates or attr in self._frequency_data
+                or attr in self._data)
+
+    @property
+    def t(self) -> ndarray:
+        return self._data.setdefault('t', np.concatenate(([0], self.dt.cumsum())))
+
+    @t.setter
+    def t(self, val):
+        self._data['t'] = val
+
+    @property
+    def tau(self):
+        return self._data.setdefault('tau', self.t[-1] if 't' in self._data else self.dt.sum())
+
+    @tau.setter
+    def tau(self, val):
+        self._data['tau'] = val
+
+    @property
+    def duration(self):
+        return self.tau
+
+    @property
+    def data(self):
+        return MappingProxyType(self._data)
+
+    @property
+    def frequency_data(self):
+        return MappingProxyType(self._frequency_data)
+
+    @property
+    def intermediates(self):
+        return MappingProxyType(self._intermediates)
+
+    def _cached_property(key):  # noqa: N805  (helper used while the class body executes)
+        def getter(self):
+            if key not in self._data:
+                self.diagonalize()
+            return self._data[key]
+
+        def setter(self, value):
+            self._data[key] = value
+        return property(getter, setter)
+
+    eigvals = _cached_property('eigvals')
+    eigvecs = _cached_property('eigvecs')
+    propagators = _cached_property('propagators')
+    total_propagator = _cached_property('total_propagator')
+    del _cached_property
+
+    @property
+    def total_propagator_liouville(self) -> ndarray:
+        if 'total_propagator_liouville' not in self._data:
+            self._data['total_propagator_liouville'] = liouville_representation(
+                self.total_propagator, self.basis)
+        return self._data['total_propagator_liouville']
+
+    @total_propagator_liouville.setter
+    def total_propagator_liouville(self, value) -> None:
+        self._data['total_propagator_liouville'] = value
+
+    @property
+    def omega(self):
+        return self._frequency_data.get('omega', None)
+
+    @omega.setter
+    def omega(self, value) -> None:
+        """Setting different frequencies drops everything that depends on them (``:1158-1169``)."""
+        old = self._frequency_data.get('omega', None)
+        new = np.array(value, copy=True)
+        if not np.array_equal(old, new):
+            self.cleanup('frequency dependent')
+        self._frequency_data['omega'] = new
+
+    @property
+    def nbytes(self) -> int:
+        total = 0
+        for val in chain(self._data.values(), self._frequency_data.values(),
+                         self._intermediates.values()):
+            total += getattr(val, 'nbytes', 0)
+        return total
+
+    @util.parse_optional_parameters(method=('conservative', 'greedy', 'frequency dependent', 'all'))
+    def cleanup(self, method: str = 'conservative') -> None:
+        """Drop cached by-products; the four modes delete what the reference deletes (``:1188``)."""
+        if method == 'all':
+            self._data.clear()
+            self._frequency_data.clear()
+            self._intermediates.clear()
+            return
+        if method == 'frequency dependent':
+            self._frequency_data.clear()
+            self._intermediates.clear()
+            return
+        for key in ('eigvals', 'eigvecs', 'propagators'):
+            self._data.pop(key, None)
+        if method == 'greedy':
+            self._intermediates.clear()
+            for key in ('total_propagator', 'total_propagator_liouville'):
+                self._data.pop(key, None)
+            for key in ('total_phases', 'control_matrix', 'control_matrix_pc'):
+                self._frequency_data.pop(key, None)
+
+    # ---- numerics --------------------------------------------------------------------------------
+    def diagonalize(self) -> None:
+        """Eigen-decompose the control Hamiltonian and cache eigvals / eigvecs / propagators."""
+        if not all(key in self._data for key in ('eigvals', 'eigvecs', 'propagators')):
+            self._data['eigvals'], self._data['eigvecs'], self._data['propagators'] = \
+                numeric._diagonalize_from_coeffs(self.c_opers, self.c_coeffs, self.dt)
+        self._data['total_propagator'] = self._data['propagators'][-1]
+
+    def get_control_matrix(self, omega, show_progressbar: bool = False,
+                           cache_intermediates: bool = False) -> ndarray:
+        """Control matrix (n_nops, n_basis, n_omega) for ``omega``; cached per frequency grid."""
+        self.omega = omega
+        if 'control_matrix' in self._frequency_data:
+            return self._frequency_data['control_matrix']
+        if 'control_matrix_pc' in self._frequency_data:
+            self._frequency_data['control_matrix'] = np.sum(
+                self._frequency_data['control_matrix_pc'], axis=0)
+            return self._frequency_data['control_matrix']
+        self.diagonalize()
+        control_matrix = numeric.calculate_control_matrix_from_scratch(
+            self.eigvals, self.eigvecs, self.propagators, self.omega, self.basis, self.n_opers,
+            self.n_coeffs, self.dt, self.t, show_progressbar=show_progressbar,
+            cache_intermediates=cache_intermediates)
+        self.cache_control_matrix(self.omega, control_matrix)
+        return self._frequency_data['control_matrix']
+
+    def cache_control_matrix(self, omega, control_matrix: Optional[ndarray] = None,
+                             show_progressbar: bool = False,
+                             cache_intermediates: bool = False) -> None:
+        self.omega = omega
+        if control_matrix is None:
+            control_matrix = self.get_control_matrix(self.omega, show_progressbar,
+                                                     cache_intermediates)
+        key = 'control_matrix_pc' if control_matrix.ndim == 4 else 'control_matrix'
+        self._frequency_data[key] = control_matrix
+        self.cache_total_phases(self.omega)
+        if 'total_propagator_liouville' not in self._data:
+            self.total_propagator_liouville = liouville_representation(self.total_propagator,
+                                                                       self.basis)
+
+    def get_pulse_correlation_control_matrix(self) -> ndarray:
+        if 'control_matrix_pc' in self._frequency_data:
+            return self._frequency_data['control_matrix_pc']
+        raise util.CalculationError(
+            "Could not get the pulse correlation control matrix since it "
+            + "was not computed during concatenation. Please run the "
+            + "concatenation again with 'calc_pulse_correlation_FF' set to "
+            + "True.")
+
+    def _cold_pipeline(self, omega) -> None:
+        """Cold cache + fidelity filter function: one fused library call (single upload, all
+        kernels back to back, single download) instead of three round trips."""
+        omega_arr = _lib.as_f64(self.omega)
+        c_opers, c_coeffs = _lib.as_c128(self.c_opers), _lib.as_f64(self.c_coeffs)
+        n_opers, n_coeffs = _lib.as_c128(self.n_opers), _lib.as_f64(self.n_coeffs)
+        dt, t = _lib.as_f64(self.dt), _lib.as_f64(self.t)
+        basis = _lib.as_c128(np.asarray(self.basis))
+        G, d = len(dt), self.d
+        n_cops, n_nops, n_basis, n_omega = len(c_opers), len(n_opers), len(basis), len(omega_arr)
+        eigvals = np.empty((G, d))
+        eigvecs = np.empty((G, d, d), dtype=complex)
+        propagators = np.empty((G + 1, d, d), dtype=complex)
+        B = np.empty((n_nops, n_basis, n_omega), dtype=complex)
+        F = np.empty((n_nops, n_nops, n_omega), dtype=complex)
+        ctx = _lib.context()
+        p = _lib.ptr
+        _lib.check(ctx, _lib.lib().ffb_pulse_filter_function(
+            ctx, G, d, n_cops, n_nops, n_basis, n_omega, p(c_opers), p(c_coeffs), p(n_opers),
+            p(n_coeffs), p(dt), p(t), p(basis), p(omega_arr), None, 0, 0, p(eigvals), p(eigvecs),
+            p(propagators), p(B), p(F), None))
+        self._data.update(eigvals=eigvals, eigvecs=eigvecs, propagators=propagators,
+                          total_propagator=propagators[-1])
+        self.cache_control_matrix(self.omega, B)
+        self._frequency_data['filter_function'] = F
+
+    @util.parse_optional_parameters(which=('fidelity', 'generalized'), order=(1, 2))
+    def get_filter_function(self, omega, which: str = 'fidelity', order: int = 1,
+                            show_progressbar: bool = False, cache_intermediates: bool = False,
+                            cache_second_order_cumulative: bool = False) -> ndarray:
+        r"""First-order filter function :math:`F_{\alpha\beta}(\omega)` (or the generalized
+        :math:`F_{\alpha\beta,kl}(\omega)`), cached per frequency grid (reference ``:691-805``)."""
+        if order == 2:
+            raise NotImplementedError('Second-order filter functions are out of scope of '
+                                      'filter_functions_b200 (SURVEY.md section 2, row 11)')
+        self.omega = omega
+        key = 'filter_function' if which == 'fidelity' else 'filter_function_gen'
+        if key in self._frequency_data:
+            return self._frequency_data[key]
+        cold = not any(k in self._frequency_data for k in ('control_matrix', 'control_matrix_pc'))
+        cold = cold and not any(k in self._data for k in ('eigvals', 'eigvecs', 'propagators'))
+        if cold and which == 'fidelity' and not cache_intermediates and len(self.omega):
+            self._cold_pipeline(self.omega)
+            return self._frequency_data[key]
+        control_matrix = self.get_control_matrix(self.omega, show_progressbar, cache_intermediates)
+        self.cache_filter_function(self.omega, control_matrix=control_matrix, which=which,
+                                   order=order, show_progressbar=show_progressbar,
+                                   cache_intermediates=cache_intermediates)
+        return self._frequency_data[key]
+
+    @util.parse_optional_parameters(which=('fidelity', 'generalized'), order=(1, 2))
+    def cache_filter_function(self, omega, control_matrix: Optional[ndarray] = None,
+                              filter_function: Optional[ndarray] = None, which: str = 'fidelity',
+                              order: int = 1, show_progressbar: bool = False,
+                              cache_intermediates: bool = False,
+                              cache_second_order_cumulative: bool = False) -> None:
+        """Cache the filter function; a 4-d ``control_matrix`` is a pulse-correlation control
+        matrix, in which case the pulse-correlation filter function is cached too (``:807-902``)."""
+        if order == 2:
+            raise NotImplementedError('Second-order filter functions are out of scope of '
+                                      'filter_functions_b200 (SURVEY.md section 2, row 11)')
+        self.omega = omega
+        if filter_function is None:
+            if control_matrix is None:
+                control_matrix = self.get_control_matrix(self.omega, show_progressbar,
+                                                         cache_intermediates)
+            self.cache_control_matrix(self.omega, control_matrix)
+            if control_matrix.ndim == 4:
+                F_pc = numeric.calculate_pulse_correlation_filter_function(control_matrix, which)
+                if which == 'fidelity':
+                    self._frequency_data['filter_function_pc'] = F_pc
+                else:
+                    self._frequency_data['filter_function_pc'] = F_pc.trace(axis1=4, axis2=5)
+                    self._frequency_data['filter_function_pc_gen'] = F_pc
+                filter_function = F_pc.sum(axis=(0, 1))
+            else:
+                filter_function = numeric.calculate_filter_function(control_matrix, which)
+        if which == 'fidelity':
+            self._frequency_data['filter_function'] = filter_function
+        else:
+            self._frequency_data['filter_function'] = filter_function.trace(axis1=2, axis2=3)
+            self._frequency_data['filter_function_gen'] = filter_function
+
+    @util.parse_optional_parameters(which=('fidelity', 'generalized'))
+    def get_pulse_correlation_filter_function(self, which: str = 'fidelity') -> ndarray:
+        key = 'filter_function_pc' if which == 'fidelity' else 'filter_function_pc_gen'
+        if key in self._frequency_data:
+            return self._frequency_data[key]
+        if 'control_matrix_pc' in self._frequency_data:
+            F_pc = numeric.calculate_pulse_correlation_filter_function(
+                self._frequency_data['control_matrix_pc'], which=which)
+            self._frequency_data[key] = F_pc
+            return F_pc
+        raise util.CalculationError(
+            "Could not get the pulse correlation filter function since it "
+            + "was not computed during concatenation. Please run the "
+            + "concatenation again with 'calc_pulse_correlation_FF' set to True.")
+
+    def get_total_phases(self, omega) -> ndarray:
+        self.omega = omega
+        if 'total_phases' not in self._frequency_data:
+            self._frequency_data['total_phases'] = util.cexp(self.omega*self.tau)
+        return self._frequency_data['total_phases']
+
+    def cache_total_phases(self, omega, total_phases: Optional[ndarray] = None) -> None:
+        self.omega = omega
+        if total_phases is None:
+            total_phases = self.get_total_phases(self.omega)
+        self._frequency_data['total_phases'] = total_phases
+
+
+# ------------------------------------------------------------------------------------------------
+# concatenation
+# ------------------------------------------------------------------------------------------------
+def _join_hamiltonians(opers, identifiers, coeffs, kind: str):
+    """Merge the operator lists of several pulses into one Hamiltonian.
+
+    Equal operators (byte-wise) are merged; an identifier used for two different operators gets the
+    pulse position appended; operators missing on some pulse get zero (control) or, if constant
+    elsewhere, that constant (noise) coefficients.  Behaviour of the reference's
+    ``_concatenate_hamiltonian`` (``:1340-1483``), including its error messages.
+    """
+    n_dt = [c.shape[1] for c in coeffs]
+    seg_edges = [0] + list(accumulate(n_dt))
+    pulse_edges = list(accumulate(len(op) for op in opers))
+    flat_opers = np.concatenate(opers, axis=0)
+    flat_ids = np.concatenate(identifiers)
+    flat_coeffs = [c for pulse_coeffs in coeffs for c in pulse_coeffs]
+    oper_hashes = util.hash_array_along_axis(flat_opers, axis=0)
+
+    uniq_hashes, first_idx, inverse = np.unique(oper_hashes, return_index=True,
+                                                return_inverse=True)
+    uniq_hashes = uniq_hashes.tolist()
+    new_ids = flat_ids[first_idx].tolist()
+
+    ids_of_oper, opers_of_id = {}, {}
+    for h, ident in zip(oper_hashes, flat_ids.tolist()):
+        ids_of_oper.setdefault(h, set()).add(ident)
+        opers_of_id.setdefault(ident, set()).add(h)
+    if any(len(v) > 1 for v in ids_of_oper.values()):
+        raise ValueError(f'Trying to concatenate pulses with equal {kind} operators but '
+                         + f'different identifiers. Please choose unique {kind} identifiers!')
+
+    mapping = {p: {ident: ident for ident in identifiers[p]} for p in range(len(pulse_edges))}
+    for ident, hashes in opers_of_id.items():
+        if len(hashes) > 1:
+            for h in hashes:
+                pulse_pos = bisect.bisect(pulse_edges, oper_hashes.index(h))
+                pos = uniq_hashes.index(h)
+                new_ids[pos] = f'{new_ids[pos]}_{pulse_pos}'
+                mapping[pulse_pos][ident] = new_ids[pos]
+
+    order = np.argsort(new_ids)
+    joined = np.full((len(new_ids), seg_edges[-1]), np.nan)
+    for i in range(len(new_ids)):
+        for flat_pos in (inverse == i).nonzero()[0]:
+            pulse_pos = bisect.bisect(pulse_edges, flat_pos)
+            joined[i, seg_edges[pulse_pos]:seg_edges[pulse_pos + 1]] = flat_coeffs[flat_pos]
+
+    missing = np.isnan(joined)
+    if kind == 'noise':
+        for row in missing.any(axis=1).nonzero()[0]:
+            present = joined[row][~missing[row]]
+            if (present == present[0]).all():
+                joined[row, missing[row]] = present[0]
+            else:
+                raise ValueError('Not all pulses have the same noise operators and '
+                                 + 'non-trivial noise sensitivities so I cannot infer them.')
+    else:
+        joined[missing] = 0
+
+    return (flat_opers[first_idx[order]], np.array([new_ids[i] for i in order]), joined[order],
+            mapping)
+
+
+def concatenate_without_filter_function(pulses: Iterable[PulseSequence],
+                                        return_identifier_mappings: bool = False) -> Any:
+    """Concatenate the Hamiltonians only (reference ``:1599-1665``)."""
+    try:
+        pulses = tuple(pulses)
+    except TypeError:
+        raise TypeError(f'Expected pulses to be iterable, not {type(pulses)}')
+    if not all(isinstance(pulse, PulseSequence) for pulse in pulses):
+        raise TypeError('Can only concatenate PulseSequences!')
+    if len(set(pulse.d for pulse in pulses)) != 1:
+        raise ValueError('Trying to concatenate PulseSequence instances with different dimension!')
+    if not util.all_array_equal((pulse.basis for pulse in pulses)):
+        raise ValueError('Trying to concatenate PulseSequence instances with different bases!')
+
+    *control, c_map = _join_hamiltonians(
+        [p.c_opers for p in pulses], [p.c_oper_identifiers for p in pulses],
+        [p.c_coeffs for p in pulses], 'control')
+    *noise, n_map = _join_hamiltonians(
+        [p.n_opers for p in pulses], [p.n_oper_identifiers for p in pulses],
+        [p.n_coeffs for p in pulses], 'noise')
+    dt = np.concatenate(tuple(pulse.dt for pulse in pulses))
+    newpulse = PulseSequence.from_arrays(*control, *noise, dt, pulses[0].basis)
+    newpulse.tau = sum(pulse.tau for pulse in pulses)
+    if return_identifier_mappings:
+        return newpulse, c_map, n_map
+    return newpulse
+
+
+@util.parse_optional_parameters(which=('fidelity', 'generalized'))
+def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool = False,
+                calc_filter_function: Optional[bool] = None,
+                calc_second_order_FF: Optional[bool] = None, which: str = 'fidelity',
+                omega=None, show_progressbar: bool = False) -> PulseSequence:
+    r"""Concatenate pulses left to right (``concatenate((A, B))`` is :math:`B\circ A`) and, when the
+    constituents have cached control matrices (or ``omega`` is given), compute the control matrix of
+    the sequence from them.  Decision logic, caching and errors follow the reference (``:1668-1887``).
+    """
+    if calc_second_order_FF:
+        raise NotImplementedError('Second-order filter functions are out of scope of '
+                                  'filter_functions_b200 (SURVEY.md section 2, row 11)')
+    pulses = tuple(pulses)
+    if len(pulses) == 1:
+        return copy.deepcopy(pulses[0])
+
+    newpulse, _, n_oper_mapping = concatenate_without_filter_function(
+        pulses, return_identifier_mappings=True)
+
+    if all(pls.is_cached('total_propagator') for pls in pulses):
+        newpulse.total_propagator = util.mdot([pls.total_propagator for pls in pulses][::-1])
+
+    if calc_pulse_correlation_FF:
+        calc_filter_function = True
+    if calc_filter_function is False:
+        return newpulse
+
+    # which (renamed) noise operators does each pulse carry?
+    pulse_identifiers = [sorted(mapping.values()) for _, mapping in sorted(n_oper_mapping.items())]
+    unique_identifiers = sorted(set(h for ids in pulse_identifiers for h in ids))
+    n_opers_present = np.array([[ident in ids for ident in unique_identifiers]
+                                for ids in pulse_identifiers], dtype=bool)
+
+    equal_n_opers = (n_opers_present.sum(axis=0) > 1).any()
+    if omega is None:
+        cached_ctrl_mat = [pls.is_cached('control_matrix') for pls in pulses]
+        if any(cached_ctrl_mat):
+            equal_omega = util.all_array_equal(
+                (pls.omega for pls in compress(pulses, cached_ctrl_mat)))
+        else:
+            cached_omega = [pls.is_cached('omega') for pls in pulses]
+            equal_omega = util.all_array_equal(
+                (pls.omega for pls in compress(pulses, cached_omega))) if any(cached_omega) \
+                else False
+        if not equal_omega:
+            if calc_filter_function:
+                raise ValueError("Calculation of filter function forced but not all pulses "
+                                 + "have the same frequencies cached and none were supplied!")
+            if calc_pulse_correlation_FF:
+                raise ValueError("Cannot compute the pulse correlation filter functions; do not "
+                                 + "have the frequencies at which to evaluate.")
+            return newpulse
+        if calc_filter_function is None and (not equal_n_opers or not any(cached_ctrl_mat)):
+            return newpulse
+        source = cached_ctrl_mat if any(cached_ctrl_mat) else cached_omega
+        omega = pulses[int(np.nonzero(source)[0][0])].omega
+
+    if not equal_n_opers:
+        newpulse.cache_filter_function(omega, which=which)
+        return newpulse
+
+    phases = np.array([pls.get_total_phases(omega) for pls in pulses[:-1]]).cumprod(axis=0)
+    propagators_liouville = util.adot([pls.total_propagator_liouville for pls in pulses[:-1]])
+
+    control_matrix_atomic = np.empty(
+        (len(pulses), len(newpulse.n_opers), len(newpulse.basis), len(omega)), dtype=complex)
+    seg_edges = [0] + list(accumulate(len(pls.dt) for pls in pulses))
+    for i, (pls, present) in enumerate(zip(pulses, n_opers_present)):
+        control_matrix_atomic[i, present] = pls.get_control_matrix(omega, show_progressbar)
+        if not present.all():
+            control_matrix_atomic[i, ~present] = numeric.calculate_control_matrix_from_scratch(
+                pls.eigvals, pls.eigvecs, pls.propagators, omega, pls.basis,
+                newpulse.n_opers[~present],
+                newpulse.n_coeffs[~present, seg_edges[i]:seg_edges[i + 1]],
+                pls.dt, t=pls.t, show_progressbar=show_progressbar, cache_intermediates=False)
+
+    if not newpulse.is_cached('total_propagator'):
+        newpulse.total_propagator = util.mdot([pls.total_propagator for pls in pulses][::-1])
+    newpulse.cache_total_phases(omega)
+    newpulse.total_propagator_liouville = liouville_representation(newpulse.total_propagator,
+                                                                   newpulse.basis)
+    control_matrix = numeric.calculate_control_matrix_from_atomic(
+        phases, control_matrix_atomic, propagators_liouville, show_progressbar,
+        which='correlations' if calc_pulse_correlation_FF else 'total')
+    newpulse.cache_filter_function(omega, control_matrix, which=which)
+    return newpulse

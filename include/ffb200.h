@@ -1,0 +1,176 @@
+/* ffb200 -- C ABI of the B200-native control-matrix / filter-function / infidelity engine.
+ *
+ * The reference (qutech/filter_functions v1.2.1) is pure Python and has no FFI seam; the drop-in
+ * boundary is the set of Python signatures of its hot path.  Every entry point below replaces the
+ * BODY of one of those functions and is bound from `filter_functions_b200/_lib.py` with ctypes.
+ * The reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, no C++ or torch types; all arrays are C-contiguous;
+ *   - complex128 is `double[2]` (re, im interleaved), passed as `const double*` / `double*`;
+ *   - `ffb_*`      : pointers are HOST pointers, the call is synchronous (results are in the output
+ *                    buffers on return); host<->device copies happen inside the call;
+ *   - `ffb_dev_*`  : pointers are DEVICE pointers on the context's GPU, the call only enqueues work
+ *                    on the context's stream (see ffb_set_stream / ffb_sync);
+ *   - every function returns 0 on success or a negative FFB_E* code; ffb_last_error(ctx) returns
+ *     the message.  No C++ exception crosses the boundary.  There is no CPU fallback: without a
+ *     usable sm_100 device ffb_init fails with FFB_ENODEVICE.
+ *   - a context is bound to one GPU and must be used from one thread at a time (the reference is
+ *     single-threaded Python, util.py:1103-1109).
+ *
+ * Citations are `file:line` relative to /root/reference/filter_functions.
+ */
+#ifndef FFB200_H
+#define FFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ffb_ctx ffb_ctx;
+
+enum {
+  FFB_OK = 0,
+  FFB_EINVAL = -1,    /* -> ValueError  */
+  FFB_ENODEVICE = -2, /* -> RuntimeError: no CUDA device / wrong architecture */
+  FFB_ECUDA = -3,     /* -> RuntimeError: CUDA runtime error */
+  FFB_ENOMEM = -4,    /* -> MemoryError */
+  FFB_ENOTCONV = -5   /* -> util.CalculationError: eigensolver did not converge */
+};
+
+/* ---- context -------------------------------------------------------------------------------- */
+int ffb_init(ffb_ctx** ctx, int device);
+void ffb_destroy(ffb_ctx* ctx);
+const char* ffb_last_error(const ffb_ctx* ctx);
+const char* ffb_version(void);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all subsequent work. Pass
+ * NULL to go back to the context's own stream. */
+int ffb_set_stream(ffb_ctx* ctx, void* cuda_stream);
+int ffb_sync(ffb_ctx* ctx);
+/* Number of kernels this library has launched on this context since creation. */
+int64_t ffb_launch_count(const ffb_ctx* ctx);
+int ffb_device_info(ffb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+/* Measures the DFMA / DMMA peak of the device with a short register-resident kernel (TFLOP/s).
+ * The FP64 roofline denominator; MEASURED_PEAKS.json only holds HBM and bf16. */
+int ffb_measure_fp64_peak(ffb_ctx* ctx, double* dfma_tflops, double* dmma_tflops);
+
+/* ---- a1: diagonalisation and propagators ------------------------------------------------------
+ * Replaces PulseSequence.diagonalize (pulse_sequence.py:577-586) + numeric.diagonalize
+ * (numeric.py:1886-1935).  H_g = sum_i c_coeffs[i,g] c_opers[i]; batched Hermitian Jacobi, ascending
+ * eigenvalues; P_g = V exp(-i D dt_g) V^dagger; propagators = [1, P_0, P_1 P_0, ...].
+ *   c_opers (n_cops,d,d) c128 | c_coeffs (n_cops,G) f64 | dt (G) f64
+ *   eigvals (G,d) f64 | eigvecs (G,d,d) c128 (columns) | propagators (G+1,d,d) c128
+ * If c_coeffs is NULL, c_opers is taken to be the Hamiltonian itself, shape (G,d,d)
+ * (the numeric.diagonalize(hamiltonian, dt) signature, numeric.py:1886). */
+int ffb_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_opers,
+                    const double* c_coeffs, const double* dt, double* eigvals, double* eigvecs,
+                    double* propagators);
+
+/* ---- a2: first-order control matrix from scratch ----------------------------------------------
+ * Replaces numeric.calculate_control_matrix_from_scratch (numeric.py:707-881).
+ *   eigvals (G,d) | eigvecs (G,d,d) | propagators (G+1,d,d) | omega (n_omega) | basis (n_basis,d,d)
+ *   n_opers (n_nops,d,d) | n_coeffs (n_nops,G) | dt (G) | t (G+1)
+ *   out (n_nops,n_basis,n_omega) c128, omega fastest. */
+int ffb_control_matrix_from_scratch(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis,
+                                    int n_omega, const double* eigvals, const double* eigvecs,
+                                    const double* propagators, const double* omega,
+                                    const double* basis, const double* n_opers,
+                                    const double* n_coeffs, const double* dt, const double* t,
+                                    double* out);
+
+/* ---- a3 / a4: filter functions -----------------------------------------------------------------
+ * Replaces numeric.calculate_filter_function (numeric.py:1413-1467) and
+ * numeric.calculate_pulse_correlation_filter_function (numeric.py:1821-1883).
+ *   B (P,n_nops,n_basis,n_omega) c128 with P = 1 for the plain filter function
+ *   F fidelity    : (P,P,n_nops,n_nops,n_omega)
+ *   F generalized : (P,P,n_nops,n_nops,n_basis,n_basis,n_omega) */
+int ffb_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega, const double* B,
+                        int generalized, double* F);
+
+/* ---- a5: control matrix of a sequence from those of its parts ---------------------------------
+ * Replaces numeric.calculate_control_matrix_from_atomic (numeric.py:621-704).
+ *   phases (P-1,n_omega) c128 | B_atomic (P,n_nops,n_basis,n_omega) c128
+ *   Q_liouville (P-1,n_basis,n_basis) f64, or c128 if q_is_complex
+ *   out (n_nops,n_basis,n_omega), or (P,n_nops,n_basis,n_omega) if correlations != 0 */
+int ffb_control_matrix_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+                                   const double* phases, const double* B_atomic,
+                                   const double* Q_liouville, int q_is_complex, int correlations,
+                                   double* out);
+
+/* ---- a7: infidelity integral --------------------------------------------------------------------
+ * Replaces the integrand + trapezoid of numeric.infidelity (numeric.py:2318-2320, :259-374,
+ * util.py:880-906).  F (n_lead,n_nops,n_nops,n_omega) c128 (n_lead = P*P for pulse correlations,
+ * else 1); idx (n_sel) noise-operator indices; spectrum, already broadcast by the caller, is
+ *   spectrum_ndim 1: (n_omega) | 2: (n_sel,n_omega) | 3: (n_sel,n_sel,n_omega), f64 or c128;
+ * out f64: (n_lead,n_sel) for ndim 1/2, (n_lead,n_sel,n_sel) for ndim 3.
+ * out = trapezoid(Re(F[idx..]*S)) / (2 pi d). */
+int ffb_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* idx, int n_omega,
+                   const double* F, const double* spectrum, int spectrum_ndim,
+                   int spectrum_is_complex, const double* omega, int d, double* out);
+
+/* ---- a8 helper: Liouville representation --------------------------------------------------------
+ * Replaces superoperator.liouville_representation (superoperator.py:51-84):
+ * out[n,i,j] = tr(C_i U_n C_j U_n^dagger); U (n,d,d) c128, basis (n_basis,d,d) c128,
+ * out (n,n_basis,n_basis) c128 (the Python shell keeps the real part for Hermitian bases). */
+int ffb_liouville_representation(ffb_ctx* ctx, int n, int d, int n_basis, const double* U,
+                                 const double* basis, double* out);
+
+/* exp(i * x * scale) element-wise (util.cexp, util.py:136-162); x (n) f64 -> out (n) c128. */
+int ffb_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out);
+
+/* ---- fused pulse pipeline ------------------------------------------------------------------------
+ * What PulseSequence.get_filter_function (pulse_sequence.py:691-805) does on a cold cache, in one
+ * call with one upload and one download: diagonalize -> control matrix -> fidelity filter function
+ * (-> infidelity if spectrum != NULL).  Any output pointer may be NULL to skip its download.
+ * spectrum as in ffb_infidelity with n_sel = n_nops, idx = 0..n_nops-1. */
+int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops, int n_basis,
+                              int n_omega, const double* c_opers, const double* c_coeffs,
+                              const double* n_opers, const double* n_coeffs, const double* dt,
+                              const double* t, const double* basis, const double* omega,
+                              const double* spectrum, int spectrum_ndim, int spectrum_is_complex,
+                              double* eigvals, double* eigvecs, double* propagators,
+                              double* control_matrix, double* filter_function, double* infidelity);
+
+/* ---- device-resident variants (pointers are device pointers; asynchronous on the stream) -------- */
+int ffb_dev_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_opers,
+                        const double* c_coeffs, const double* dt, double* eigvals, double* eigvecs,
+                        double* propagators);
+int ffb_dev_control_matrix_from_scratch(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis,
+                                        int n_omega, const double* eigvals, const double* eigvecs,
+                                        const double* propagators, const double* omega,
+                                        const double* basis, const double* n_opers,
+                                        const double* n_coeffs, const double* dt, const double* t,
+                                        int herm_flags, double* out);
+int ffb_dev_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+                            const double* B, int generalized, double* F);
+int ffb_dev_control_matrix_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+                                       const double* phases, const double* B_atomic,
+                                       const double* Q_liouville, int q_is_complex,
+                                       int correlations, double* out);
+int ffb_dev_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* idx,
+                       int n_omega, const double* F, const double* spectrum, int spectrum_ndim,
+                       int spectrum_is_complex, const double* omega, int d, double* out);
+/* herm_flags for ffb_dev_control_matrix_from_scratch: bit 0 = all noise operators exactly
+ * Hermitian, bit 1 = all basis elements exactly Hermitian (the host entry point checks this itself;
+ * pass 0 if unknown -- always correct, up to 4x more rows). */
+#define FFB_HERM_NOPERS 1
+#define FFB_HERM_BASIS 2
+
+/* Raw device memory for the callers of ffb_dev_* that do not bring their own (e.g. torch). */
+int ffb_dev_alloc(ffb_ctx* ctx, size_t bytes, void** ptr);
+int ffb_dev_free(ffb_ctx* ctx, void* ptr);
+int ffb_memcpy_h2d(ffb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int ffb_memcpy_d2h(ffb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* Kernel-level timing of the control-matrix main kernel: average duration (ms) of the launches of
+ * the dominant kernel recorded with CUDA events on the launching stream since the last reset. */
+int ffb_kernel_timing_enable(ffb_ctx* ctx, int enable);
+int ffb_kernel_timing_read(ffb_ctx* ctx, double* total_ms, int64_t* launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFB200_H */
