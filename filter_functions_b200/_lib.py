@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = {
     'ffb_destroy': (None, [c_void_p]),
     'ffb_last_error': (c_char_p, [c_void_p]),
     'ffb_version': (c_char_p, []),
-    'ffb_set_stream': (c_int, [c_void_p, c_void_p]),
+    'ffb_set_stream': (c_int, [c_void_p, c_void_p, c_int]),
     'ffb_sync': (c_int, [c_void_p]),
     'ffb_launch_count': (c_int64, [c_void_p]),
     'ffb_device_info': (c_int, [c_void_p, _ip, _ip, _ip, POINTER(c_size_t)]),

@@ -161,10 +161,10 @@ const char* ffb_last_error(const ffb_ctx* ctx) {
   return ctx ? ctx->err.c_str() : g_init_error.c_str();
 }
 
-int ffb_set_stream(ffb_ctx* ctx, void* cuda_stream) {
+int ffb_set_stream(ffb_ctx* ctx, void* cuda_stream, int external) {
   if (!ctx) return FFB_EINVAL;
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  ctx->stream = external ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
   return FFB_OK;
 }
 

@@ -24,11 +24,20 @@
 // accumulator tiles per row tile: real and imaginary part of P), K = 4 consecutive segments.  Lane
 // (q = lane % 4, w = lane / 4) owns frequency w of the warp's 8 and segment q of the pass's 4: it
 // generates exactly the B-fragment element the instruction expects, so P never leaves registers and
-// nothing of size (G, n_omega, d, d) is ever materialised.  The exponential is factorised,
-// e^{i (w + Omega) dt} = e^{i w dt} e^{i Omega dt}, with e^{i Omega dt} precomputed per segment and
-// e^{i w dt} recomputed only when dt changes, leaving ONE sincos per (segment, frequency) for the phase
-// instead of 2 d^2 + 2; near the removable singularity (|(w + Omega) dt| < 2^-8, including the exact
-// zero of numeric.py:162-165) a Taylor polynomial replaces the cancelling quotient.
+// nothing of size (G, n_omega, d, d) is ever materialised.
+//
+// Transcendentals.  With x = w + Omega, I(x) = e^{i x dt / 2} * 2 sin(x dt / 2) / x, and the half-angle
+// exponential factorises, e^{i (w + Omega) dt / 2} = e^{i w dt / 2} e^{i Omega dt / 2}: the second factor
+// is precomputed per segment, the first is recomputed only when dt changes, and sin(x dt / 2) is the
+// imaginary part of the product.  That leaves ONE sincos per (segment, frequency) -- the phase
+// e^{i w t_g} -- instead of the 2 d^2 + 2 of the reference.  The product form cancels when
+// |sin(x dt / 2)| is small (near the removable singularity x = 0, which includes the exact-zero rule of
+// numeric.py:162-165); lanes below 2^-10 are re-evaluated directly with the reference's own rounding
+// sequence (x = w + Omega, y = x dt) in a rarely taken warp-uniform fix-up.
+//
+// Software pipelining.  The operands of unit u+1 (a unit = one A column pair plus its constants) are
+// generated in the same basic block as the DMMAs of unit u, so the FP64 pipe always has independent
+// work: first version without it measured 71 % DMMA-pipe activity for d = 4 (profiles/).
 //
 // Measured on B200 (tools/microbench/fp64_peaks.cu, profiles/fp64_peaks_r01.jsonl): DFMA peak 36.95
 // TFLOP/s, DMMA peak 37.14 TFLOP/s, and the two do NOT overlap (one FP64 pipe, 64 lanes/clk/SM); DMMA
@@ -40,15 +49,12 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // math helpers
 // ------------------------------------------------------------------------------------------------
-// sin/cos with a 3-constant Cody-Waite reduction.  fma keeps x - k*pi/2 accurate to ~1e-16 ABSOLUTE
-// for |x| < 1e9, which is what a unit-modulus phase factor needs (CUDA's sincos switches to
-// Payne-Hanek above 1e5 to keep the RELATIVE error near zeros of sin, which is irrelevant here).
-// Verified against sincos() on B200 up to |x| = 1e7: max abs deviation 1.1e-16.
+// sin/cos with a 3-constant Cody-Waite reduction.  fma keeps x - k*pi/2 accurate to ~1e-16 ABSOLUTE,
+// which is what a unit-modulus phase factor needs (CUDA's sincos switches to Payne-Hanek above 1e5
+// to keep the RELATIVE error near zeros of sin, which is irrelevant here).  Branch free.  Verified
+// against sincos() on B200 up to |x| = 1e7 (max abs deviation 1.1e-16); beyond ~1e9 the rounding of
+// the argument itself (ulp(w t) > 1e-7 rad) has destroyed the phase in the reference too.
 __device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
-  if (fabs(x) > 1.0e9) {  // outside the validated range of the fast reduction
-    sincos(x, &sn, &cs);
-    return;
-  }
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer by addition
   double kd = fma(x, 6.36619772367581382433e-01, MAGIC);
   const int q = __double2loint(kd);
@@ -69,10 +75,13 @@ __device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
   pc = fma(pc, r2, -1.38888888888741095749e-03);
   pc = fma(pc, r2, 4.16666666666666019037e-02);
   const double c = fma(r2 * r2, pc, fma(r2, -0.5, 1.0));
+  // quadrant: swap for odd q, flip signs through the sign bit (integer ops, not the FP64 pipe)
   const double ss = (q & 1) ? c : s;
   const double cc = (q & 1) ? s : c;
-  sn = (q & 2) ? -ss : ss;
-  cs = ((q + 1) & 2) ? -cc : cc;
+  const int s_flip = (q & 2) << 30;        // bit 31 of the high word
+  const int c_flip = ((q + 1) & 2) << 30;
+  sn = __hiloint2double(__double2hiint(ss) ^ s_flip, __double2loint(ss));
+  cs = __hiloint2double(__double2hiint(cc) ^ c_flip, __double2loint(cc));
 }
 
 // 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps on the FP64 pipe.
@@ -86,27 +95,24 @@ __device__ __forceinline__ double rcp_nr(double x) {
   return r;
 }
 
-constexpr double SMALL_Y = 0.00390625;  // 2^-8
+constexpr double SQRT2 = 1.41421356237309504880;
+constexpr double SMALL_SIN = 0.0009765625 * SQRT2;  // |sqrt(2) sin(x dt / 2)| below this -> direct evaluation
+constexpr double TINY_OMEGA = 1e-290;               // |w| below this is treated as the exact zero
 
-// J(x) = (e^{i x dt} - 1) / (i x) given num = e^{i x dt} - 1 evaluated elsewhere (cancelling for small
-// |x dt|, hence the polynomial branch; y^6/5040 < 1e-18 below the threshold).
-__device__ __forceinline__ cplx first_order_integral(double x, double dt, double num_re,
-                                                     double num_im) {
-  const double y = x * dt;
-  if (fabs(y) < SMALL_Y) {
-    const double y2 = y * y;
-    const double fr = fma(y2, fma(y2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
-    const double fi = y * fma(y2, fma(y2, 1.0 / 720.0, -1.0 / 24.0), 0.5);
-    return {dt * fr, dt * fi};
-  }
-  const double r = rcp_nr(x);
-  return {num_im * r, -num_re * r};
+// I(x) = (e^{i x dt} - 1) / (i x) evaluated directly with the rounding sequence of numeric.py:156-165
+// (y = x * dt); = dt for x == 0.  Only used by the rare fix-up path.
+__device__ __forceinline__ cplx integral_direct(double x, double dt) {
+  if (x == 0.0) return {dt, 0.0};
+  double sn, cs;
+  sincos_cw(0.5 * (x * dt), sn, cs);
+  const double f = 2.0 * sn / x;
+  return {cs * f, sn * f};
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -215,7 +221,7 @@ transform_kernel(int G, int d, int n_nops, int n_basis, int parts_j, int parts_k
 // prologue 2: the operand stream of the main kernel.
 // Per row block rb and pass (4 consecutive segments) the stream holds 1 + n_pairs units:
 //   diag unit   : A column [MT][32], t[4], dt[4]
-//   pair unit p : A column Re [MT][32], A column Im [MT][32], Omega[4], cos(Omega dt)[4], sin(Omega dt)[4]
+//   pair unit p : A column Re [MT][32], A column Im [MT][32], Omega[4], cos(Omega dt/2)[4], sin(Omega dt/2)[4]
 // An A column holds, for lane l = 4*row_in_tile + q, the coefficient of row 8*mt + row_in_tile and
 // segment 4*pass + q -- exactly the DMMA A-fragment, so the main kernel loads it with one LDS.64.
 // ------------------------------------------------------------------------------------------------
@@ -309,7 +315,7 @@ assemble_kernel(StreamGeom geo, int G, int d, int rows, int n_jrows, int n_krows
           val = Om;
         } else {
           double sn, cs;
-          sincos(Om * dtg, &sn, &cs);
+          sincos(0.5 * (Om * dtg), &sn, &cs);  // e^{i Omega dt / 2}
           val = which == 1 ? cs : sn;
         }
       }
@@ -341,11 +347,119 @@ struct MainParams {
 };
 
 // unit boundary of piece j (in units, 0 .. 1 + n_pairs)
-__device__ __forceinline__ int piece_begin(int j, int n_units, int n_sp) {
+__host__ __device__ __forceinline__ int piece_begin(int j, int n_units, int n_sp) {
   return (int)(((long long)j * n_units) / n_sp);
 }
 __device__ __forceinline__ size_t unit_offset(int u, const MainParams& p) {
   return u == 0 ? 0 : (size_t)p.diag_unit + (size_t)(u - 1) * p.pair_unit;
+}
+
+// Per-lane state of the operand generator.  A lane owns ONE frequency w (of the warp's 8) and, within
+// a pass, ONE segment (q = lane % 4 of the pass's 4).
+struct Gen {
+  double w, inv_w;        // frequency, 1/w (garbage if w_zero)
+  bool w_zero;
+  double ph_re, ph_im;    // e^{i w t_g} of the current pass's segment
+  double dt, dt_prev;     // dt of the current segment / the one (hc, hs, J0) were computed for
+  double hc, hs;          // sqrt(2) e^{i w dt / 2}
+  double j0_re, j0_im;    // I(w) for dt_prev
+};
+
+// values a unit feeds to the tensor pipe: diag uses (a_re, a_im); pair uses all four (S then D)
+struct Vals {
+  double a_re, a_im, b_re, b_im;
+};
+
+// ---- diagonal unit: new segment -> (if dt changed) half-angle exponential and I(w); then the phase.
+// Split in two so that the rarely taken branch does not cut the straight-line region in which the
+// phase evaluation is interleaved with the previous unit's DMMAs.
+__device__ __forceinline__ void gen_diag_slow(Gen& g, const double* unit_consts, int q) {
+  g.dt = unit_consts[4 + q];
+  if (g.dt != g.dt_prev) {  // never taken again on uniform time grids
+    double sn, cs;
+    sincos_cw(0.5 * (g.w * g.dt), sn, cs);
+    g.hc = SQRT2 * cs;
+    g.hs = SQRT2 * sn;
+    const double f = g.hs * g.inv_w;  // sqrt(2) sin(w dt / 2) / w
+    g.j0_re = g.w_zero ? g.dt : g.hc * f;
+    g.j0_im = g.w_zero ? 0.0 : g.hs * f;
+    g.dt_prev = g.dt;
+  }
+}
+__device__ __forceinline__ void gen_diag_fast(Gen& g, const double* unit_consts, int q, Vals& v) {
+  sincos_cw(g.w * unit_consts[q], g.ph_im, g.ph_re);
+  v.a_re = g.ph_re * g.j0_re - g.ph_im * g.j0_im;
+  v.a_im = g.ph_re * g.j0_im + g.ph_im * g.j0_re;
+}
+__device__ __forceinline__ void gen_diag(Gen& g, const double* unit_consts, int q, Vals& v) {
+  gen_diag_slow(g, unit_consts, q);
+  gen_diag_fast(g, unit_consts, q, v);
+}
+
+// ---- pair unit (product form): S = I(w + Om) + I(w - Om), D = i (I(w + Om) - I(w - Om)), times phase.
+// Returns true if this lane needs the direct re-evaluation (cancellation in sin((w +- Om) dt / 2)).
+__device__ __forceinline__ bool gen_pair(const Gen& g, const double* unit_consts, int q, Vals& v) {
+  const double Om = unit_consts[q], Ch = unit_consts[4 + q], Sh = unit_consts[8 + q];
+  const double t1 = g.hc * Ch, t3 = g.hs * Ch;
+  const double zp_re = fma(-g.hs, Sh, t1), zp_im = fma(g.hc, Sh, t3);  // sqrt2 e^{i (w+Om) dt/2}
+  const double zm_re = fma(g.hs, Sh, t1), zm_im = fma(-g.hc, Sh, t3);  // sqrt2 e^{i (w-Om) dt/2}
+  const double fp = zp_im * rcp_nr(g.w + Om);
+  const double fm = zm_im * rcp_nr(g.w - Om);
+  const double jp_re = zp_re * fp, jp_im = zp_im * fp;
+  const double jm_re = zm_re * fm, jm_im = zm_im * fm;
+  const double s_re = jp_re + jm_re, s_im = jp_im + jm_im;
+  const double d_re = jm_im - jp_im, d_im = jp_re - jm_re;
+  v.a_re = g.ph_re * s_re - g.ph_im * s_im;
+  v.a_im = g.ph_re * s_im + g.ph_im * s_re;
+  v.b_re = g.ph_re * d_re - g.ph_im * d_im;
+  v.b_im = g.ph_re * d_im + g.ph_im * d_re;
+  return fabs(zp_im) < SMALL_SIN || fabs(zm_im) < SMALL_SIN;
+}
+
+// rare path: at least one lane of the warp sits on the removable singularity.  Everything goes through
+// registers (by value) so that the per-lane generator state never has its address taken.
+struct Vals4 {
+  double a_re, a_im, b_re, b_im;
+};
+__device__ __noinline__ Vals4 fix_pair(double w, double dt, double ph_re, double ph_im, double Om) {
+  const cplx jp = integral_direct(w + Om, dt);
+  const cplx jm = integral_direct(w - Om, dt);
+  const double s_re = jp.re + jm.re, s_im = jp.im + jm.im;
+  const double d_re = jm.im - jp.im, d_im = jp.re - jm.re;
+  Vals4 r;
+  r.a_re = ph_re * s_re - ph_im * s_im;
+  r.a_im = ph_re * s_im + ph_im * s_re;
+  r.b_re = ph_re * d_re - ph_im * d_im;
+  r.b_im = ph_re * d_im + ph_im * d_re;
+  return r;
+}
+
+template <int MT>
+__device__ __forceinline__ void mma_diag(double (&acc_re)[MT][2], double (&acc_im)[MT][2],
+                                         const double* unit, int lane, const Vals& v) {
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const double a = unit[mt * 32 + lane];
+    dmma884(acc_re[mt][0], acc_re[mt][1], a, v.a_re);
+    dmma884(acc_im[mt][0], acc_im[mt][1], a, v.a_im);
+  }
+}
+
+template <int MT>
+__device__ __forceinline__ void mma_pair(double (&acc_re)[MT][2], double (&acc_im)[MT][2],
+                                         const double* unit, int lane, const Vals& v) {
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const double a = unit[mt * 32 + lane];
+    dmma884(acc_re[mt][0], acc_re[mt][1], a, v.a_re);
+    dmma884(acc_im[mt][0], acc_im[mt][1], a, v.a_im);
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const double a = unit[(MT + mt) * 32 + lane];
+    dmma884(acc_re[mt][0], acc_re[mt][1], a, v.b_re);
+    dmma884(acc_im[mt][0], acc_im[mt][1], a, v.b_im);
+  }
 }
 
 template <int MT, int NW>
@@ -360,8 +474,20 @@ ctrlmat_main_kernel(const MainParams p) {
   const int pass_end = min(p.n_pass, pass_begin + p.passes_per_chunk);
   const int n_units = 1 + p.n_pairs;
 
-  const int w_idx = (blockIdx.x * NW + warp) * 8 + (lane >> 2);
-  const double w = w_idx < p.n_omega ? p.omega[w_idx] : 0.0;
+  Gen g;
+  {
+    const int w_idx = (blockIdx.x * NW + warp) * 8 + (lane >> 2);
+    g.w = w_idx < p.n_omega ? p.omega[w_idx] : 1.0;
+    g.w_zero = fabs(g.w) < TINY_OMEGA;
+    g.inv_w = g.w_zero ? 0.0 : 1.0 / g.w;
+    g.dt_prev = -1.0;
+    g.dt = 0.0;
+    g.hc = SQRT2;
+    g.hs = 0.0;
+    g.j0_re = g.j0_im = 0.0;
+    g.ph_re = 1.0;
+    g.ph_im = 0.0;
+  }
 
   double acc_re[MT][2], acc_im[MT][2];
 #pragma unroll
@@ -372,121 +498,209 @@ ctrlmat_main_kernel(const MainParams p) {
 
   const double* gstream = p.stream + (size_t)rb * p.rb_doubles;
 
-  // ---- stage schedule: stage i of this chunk covers [stage_src(i), +stage_len(i)) doubles
+  // ---- stage schedule: stage i of this chunk covers `len` doubles from `src`, holding `units` units
   const int n_passes = pass_end - pass_begin;
   const int n_stages = p.n_sp == 1 ? (n_passes + p.pps - 1) / p.pps : n_passes * p.n_sp;
-  auto stage_range = [&](int i, size_t& src, int& len) {
+  auto stage_range = [&](int i, size_t& src, int& len, int& units) {
     if (p.n_sp == 1) {
       const int p0 = pass_begin + i * p.pps;
       const int p1 = min(pass_end, p0 + p.pps);
       src = (size_t)p0 * p.pass_doubles;
       len = (int)((size_t)(p1 - p0) * p.pass_doubles);
+      units = (p1 - p0) * n_units;
     } else {
       const int pass = pass_begin + i / p.n_sp;
       const int piece = i % p.n_sp;
-      const size_t o0 = unit_offset(piece_begin(piece, n_units, p.n_sp), p);
-      const size_t o1 = piece + 1 == p.n_sp ? p.pass_doubles
-                                            : unit_offset(piece_begin(piece + 1, n_units, p.n_sp), p);
+      const int u0 = piece_begin(piece, n_units, p.n_sp);
+      const int u1 = piece + 1 == p.n_sp ? n_units : piece_begin(piece + 1, n_units, p.n_sp);
+      const size_t o0 = unit_offset(u0, p);
+      const size_t o1 = piece + 1 == p.n_sp ? p.pass_doubles : unit_offset(u1, p);
       src = (size_t)pass * p.pass_doubles + o0;
       len = (int)(o1 - o0);
+      units = u1 - u0;
     }
   };
   auto stage_load = [&](int i, double* buf) {
     size_t src;
-    int len;
-    stage_range(i, src, len);
-    const double* g = gstream + src;
-    for (int e = threadIdx.x * 2; e < len; e += NW * 32 * 2) cp_async16(buf + e, g + e);
+    int len, units;
+    stage_range(i, src, len, units);
+    const double* gsrc = gstream + src;
+    for (int e = threadIdx.x * 2; e < len; e += NW * 32 * 2) cp_async16(buf + e, gsrc + e);
+  };
+  auto stage_units = [&](int i) {
+    size_t src;
+    int len, units;
+    stage_range(i, src, len, units);
+    return units;
   };
 
-  double* buf0 = smem;
-  double* buf1 = smem + p.stage_doubles;
-  if (n_stages > 0) stage_load(0, buf0);
-  cp_async_commit();
-
-  // per-lane state that survives across stages
-  double dt_prev = -1.0, ew_re = 1.0, ew_im = 0.0;  // e^{i w dt}
-  double ph_re = 1.0, ph_im = 0.0, dtg = 0.0;        // phase e^{i w t_g}, dt of the current segment
-
-  for (int s = 0; s < n_stages; ++s) {
-    double* cur = (s & 1) ? buf1 : buf0;
-    if (s + 1 < n_stages) {
-      stage_load(s + 1, (s & 1) ? buf0 : buf1);
+  double* cur_buf = smem;
+  double* nxt_buf = smem + p.stage_doubles;
+  if (n_stages > 0) {
+    stage_load(0, cur_buf);
+    cp_async_commit();
+    if (n_stages > 1) {
+      stage_load(1, nxt_buf);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
+  }
 
-    int u_begin, u_end, n_pass_here;
-    if (p.n_sp == 1) {
-      u_begin = 0;
-      u_end = n_units;
-      n_pass_here = min(p.pps, n_passes - s * p.pps);
-    } else {
-      const int piece = s % p.n_sp;
-      u_begin = piece_begin(piece, n_units, p.n_sp);
-      u_end = piece + 1 == p.n_sp ? n_units : piece_begin(piece + 1, n_units, p.n_sp);
-      n_pass_here = 1;
-    }
-    const double* up = cur;  // walks through the units of the stage
-    for (int ip = 0; ip < n_pass_here; ++ip) {
-      for (int u = u_begin; u < u_end; ++u) {
-        if (u == 0) {
-          // ---- diagonal unit: phase, e^{i w dt}, I_0
-          const double* cst = up + MT * 32;
-          const double tg = cst[q];
-          dtg = cst[4 + q];
-          sincos_cw(w * tg, ph_im, ph_re);
-          if (dtg != dt_prev) {
-            sincos_cw(w * dtg, ew_im, ew_re);
-            dt_prev = dtg;
-          }
-          const cplx J = first_order_integral(w, dtg, ew_re - 1.0, ew_im);
-          const double b_re = ph_re * J.re - ph_im * J.im;
-          const double b_im = ph_re * J.im + ph_im * J.re;
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const double a = up[mt * 32 + lane];
-            dmma884(acc_re[mt][0], acc_re[mt][1], a, b_re);
-            dmma884(acc_im[mt][0], acc_im[mt][1], a, b_im);
-          }
-          up += p.diag_unit;
-        } else {
-          // ---- pair unit: S = I(w + Om) + I(w - Om), D = i (I(w + Om) - I(w - Om))
-          const double* cst = up + 2 * MT * 32;
-          const double Om = cst[q], Ec = cst[4 + q], Es = cst[8 + q];
-          const double t1 = ew_re * Ec, t2 = ew_im * Ec;
-          const double np_re = fma(-ew_im, Es, t1) - 1.0;  // e^{i w dt} e^{+i Om dt} - 1
-          const double np_im = fma(ew_re, Es, t2);
-          const double nm_re = fma(ew_im, Es, t1) - 1.0;   // e^{i w dt} e^{-i Om dt} - 1
-          const double nm_im = fma(-ew_re, Es, t2);
-          const cplx Jp = first_order_integral(w + Om, dtg, np_re, np_im);
-          const cplx Jm = first_order_integral(w - Om, dtg, nm_re, nm_im);
-          const double s_re = Jp.re + Jm.re, s_im = Jp.im + Jm.im;
-          const double d_re = Jm.im - Jp.im, d_im = Jp.re - Jm.re;
-          const double bs_re = ph_re * s_re - ph_im * s_im;
-          const double bs_im = ph_re * s_im + ph_im * s_re;
-          const double bd_re = ph_re * d_re - ph_im * d_im;
-          const double bd_im = ph_re * d_im + ph_im * d_re;
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const double a = up[mt * 32 + lane];
-            dmma884(acc_re[mt][0], acc_re[mt][1], a, bs_re);
-            dmma884(acc_im[mt][0], acc_im[mt][1], a, bs_im);
-          }
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const double a = up[(MT + mt) * 32 + lane];
-            dmma884(acc_re[mt][0], acc_re[mt][1], a, bd_re);
-            dmma884(acc_im[mt][0], acc_im[mt][1], a, bd_im);
-          }
-          up += p.pair_unit;
+  // ---- software-pipelined walk over the units of this chunk.  `v` always holds the operands of the
+  // CURRENT unit; the operands of the next unit are generated in the same basic block as the current
+  // unit's DMMAs.
+  const int total_units = n_passes * n_units;
+  if (p.n_sp == 1 && p.n_pairs >= 1) {
+    // fast path: stages hold whole passes; nested loops with next to no bookkeeping per unit
+    const int n_pairs = p.n_pairs;
+    const int diag_unit = p.diag_unit, pair_unit = p.pair_unit;
+    auto apply_fix = [&](bool fix, const double* consts, Vals& vn) {
+      if (__any_sync(0xffffffffu, fix)) {
+        if (fix) {
+          const Vals4 r = fix_pair(g.w, g.dt, g.ph_re, g.ph_im, consts[q]);
+          vn.a_re = r.a_re;
+          vn.a_im = r.a_im;
+          vn.b_re = r.b_re;
+          vn.b_im = r.b_im;
         }
       }
+    };
+    Vals v = {0.0, 0.0, 0.0, 0.0};
+    if (n_stages > 0) gen_diag(g, cur_buf + MT * 32, q, v);
+    for (int stage = 0; stage < n_stages; ++stage) {
+      const int n_here = min(p.pps, n_passes - stage * p.pps);
+      const bool more_stages = stage + 1 < n_stages;
+      const double* up = cur_buf;
+      for (int ip = 0; ip < n_here; ++ip) {
+        Vals vn;
+        // diagonal unit  ||  operands of pair 0
+        const double* pu = up + diag_unit;
+        {
+          const bool fix = gen_pair(g, pu + 2 * MT * 32, q, vn);
+          mma_diag<MT>(acc_re, acc_im, up, lane, v);
+          apply_fix(fix, pu + 2 * MT * 32, vn);
+          v = vn;
+        }
+        // pair i  ||  operands of pair i + 1
+        for (int pi = 0; pi + 1 < n_pairs; ++pi) {
+          const double* pn = pu + pair_unit;
+          const bool fix = gen_pair(g, pn + 2 * MT * 32, q, vn);
+          mma_pair<MT>(acc_re, acc_im, pu, lane, v);
+          apply_fix(fix, pn + 2 * MT * 32, vn);
+          v = vn;
+          pu = pn;
+        }
+        // last pair  ||  diagonal operands of the next pass (possibly in the next stage's buffer)
+        const double* dn = pu + pair_unit;
+        bool has_next = true;
+        if (ip + 1 == n_here) {
+          if (more_stages) {
+            cp_async_wait<0>();  // the only outstanding group is stage + 1
+            __syncthreads();
+            dn = nxt_buf;
+          } else {
+            has_next = false;
+          }
+        }
+        if (has_next) {
+          gen_diag_slow(g, dn + MT * 32, q);
+          gen_diag_fast(g, dn + MT * 32, q, vn);
+          mma_pair<MT>(acc_re, acc_im, pu, lane, v);
+          v = vn;
+        } else {
+          mma_pair<MT>(acc_re, acc_im, pu, lane, v);
+        }
+        up = dn;
+      }
+      if (more_stages) {
+        __syncthreads();  // everyone is done reading cur_buf
+        if (stage + 2 < n_stages) {
+          stage_load(stage + 2, cur_buf);
+          cp_async_commit();
+        }
+        double* tmp = cur_buf;
+        cur_buf = nxt_buf;
+        nxt_buf = tmp;
+      }
     }
-    __syncthreads();
+  } else {
+    // generic path (a pass is split over several stages, or d == 1): flat walk over the units; unit k
+    // is a diagonal unit iff k % n_units == 0.
+    int stage = 0;
+    int left_in_stage = n_stages > 0 ? stage_units(0) : 0;
+    const double* up = cur_buf;
+    int u = 0;  // unit index within the pass
+    Vals v = {0.0, 0.0, 0.0, 0.0};
+    if (total_units > 0) gen_diag(g, up + MT * 32, q, v);
+
+    for (int k = 0; k < total_units; ++k) {
+      const bool cur_diag = (u == 0);
+      const bool last_in_stage = (left_in_stage == 1);
+      const bool has_next = (k + 1 < total_units);
+      const double* up_next = up + (cur_diag ? p.diag_unit : p.pair_unit);
+      if (last_in_stage && has_next) {
+        cp_async_wait<0>();  // the only outstanding group is stage + 1
+        __syncthreads();
+        up_next = nxt_buf;
+      }
+      const int u_next = (u + 1 == n_units) ? 0 : u + 1;
+      Vals vn = v;
+      // Six straight-line variants (current unit type x next unit type): the generator of the next
+      // unit and the DMMAs of the current one share a basic block so that ptxas interleaves them.
+      if (!has_next) {
+        if (cur_diag) mma_diag<MT>(acc_re, acc_im, up, lane, v);
+        else mma_pair<MT>(acc_re, acc_im, up, lane, v);
+      } else if (u_next == 0) {
+        const double* cn = up_next + MT * 32;
+        gen_diag_slow(g, cn, q);
+        if (cur_diag) {
+          gen_diag_fast(g, cn, q, vn);
+          mma_diag<MT>(acc_re, acc_im, up, lane, v);
+        } else {
+          gen_diag_fast(g, cn, q, vn);
+          mma_pair<MT>(acc_re, acc_im, up, lane, v);
+        }
+      } else {
+        const double* cn = up_next + 2 * MT * 32;
+        bool fix;
+        if (cur_diag) {
+          fix = gen_pair(g, cn, q, vn);
+          mma_diag<MT>(acc_re, acc_im, up, lane, v);
+        } else {
+          fix = gen_pair(g, cn, q, vn);
+          mma_pair<MT>(acc_re, acc_im, up, lane, v);
+        }
+        if (__any_sync(0xffffffffu, fix)) {
+          if (fix) {
+            const Vals4 r = fix_pair(g.w, g.dt, g.ph_re, g.ph_im, cn[q]);
+            vn.a_re = r.a_re;
+            vn.a_im = r.a_im;
+            vn.b_re = r.b_re;
+            vn.b_im = r.b_im;
+          }
+        }
+      }
+      v = vn;
+      if (last_in_stage && has_next) {
+        __syncthreads();  // everyone is done reading cur_buf
+        if (stage + 2 < n_stages) {
+          stage_load(stage + 2, cur_buf);
+          cp_async_commit();
+        }
+        double* tmp = cur_buf;
+        cur_buf = nxt_buf;
+        nxt_buf = tmp;
+        ++stage;
+        left_in_stage = stage_units(stage);
+      } else {
+        --left_in_stage;
+      }
+      up = up_next;
+      u = u_next;
+    }
   }
 
   // ---- epilogue: C fragment (row = lane/4, cols 2q, 2q+1) -> partial[z][row][w]
@@ -578,16 +792,20 @@ int pick_mt(int mt_total) {
   return 12;
 }
 
-#define FFB_DISPATCH_MT(MTV, NWV, CALL)        \
-  switch (MTV) {                               \
-    case 1: { constexpr int MT_ = 1; CALL; } break;   \
-    case 2: { constexpr int MT_ = 2; CALL; } break;   \
-    case 3: { constexpr int MT_ = 3; CALL; } break;   \
-    case 4: { constexpr int MT_ = 4; CALL; } break;   \
-    case 6: { constexpr int MT_ = 6; CALL; } break;   \
-    case 8: { constexpr int MT_ = 8; CALL; } break;   \
-    default: { constexpr int MT_ = 12; CALL; } break; \
+// Row tiles per warp and warps per CTA.  Heavy accumulator tiles (MT >= 8, ~160 registers) run with 4
+// warps per CTA so that two or three INDEPENDENT CTAs share an SM: their barriers and unit boundaries
+// are uncorrelated, which keeps the FP64 pipe fed while one warp does its bookkeeping.
+#define FFB_DISPATCH_MT(MTV, CALL)                                  \
+  switch (MTV) {                                                    \
+    case 1: { constexpr int MT_ = 1, NW_ = 8; CALL; } break;        \
+    case 2: { constexpr int MT_ = 2, NW_ = 8; CALL; } break;        \
+    case 3: { constexpr int MT_ = 3, NW_ = 8; CALL; } break;        \
+    case 4: { constexpr int MT_ = 4, NW_ = 8; CALL; } break;        \
+    case 6: { constexpr int MT_ = 6, NW_ = 8; CALL; } break;        \
+    case 8: { constexpr int MT_ = 8, NW_ = 4; CALL; } break;        \
+    default: { constexpr int MT_ = 12, NW_ = 4; CALL; } break;      \
   }
+inline int warps_per_cta(int MT) { return MT >= 8 ? 4 : 8; }
 
 }  // namespace
 
@@ -606,7 +824,7 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   const int n_jrows = n_nops * parts_j, n_krows = n_basis * parts_k;
   const int rows = n_jrows * n_krows;
   const int MT = pick_mt(ceil_div(rows, 8));
-  constexpr int NW = 8;
+  const int NW = warps_per_cta(MT);
   const StreamGeom geo = make_geom(rows, G, d, MT);
   const int rows_pad = geo.n_rb * MT * 8;
 
@@ -679,26 +897,39 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   const int n_wtiles = ceil_div(n_omega, NW * 8);
   int blocks_per_sm = 1;
   const size_t smem = (size_t)2 * p.stage_doubles * sizeof(double);
-  FFB_DISPATCH_MT(MT, NW, FFB_TRY((occupancy<MT_, NW>(ctx, smem, &blocks_per_sm))));
+  FFB_DISPATCH_MT(MT, FFB_TRY((occupancy<MT_, NW_>(ctx, smem, &blocks_per_sm))));
   blocks_per_sm = std::max(1, blocks_per_sm);
   const long long slots = (long long)ctx->sm_count * blocks_per_sm;
   const long long base_ctas = (long long)n_wtiles * geo.n_rb;
+  // Pick the split S that minimises the makespan estimate waves(S) * (passes per chunk + overhead):
+  // whole waves of CTAs, so the last wave is not left mostly empty (ncu on the first version: 4.24
+  // waves -> 15 % of the SM cycles idle).
   const int min_passes = std::max(p.pps * 2, 8);  // do not cut chunks shorter than this
-  int S = 1;
-  if (base_ctas < 4 * slots) {
-    S = (int)std::min<long long>((4 * slots + base_ctas - 1) / base_ctas,
-                                 std::max(1, geo.n_pass / min_passes));
-    S = std::max(1, S);
+  long long s_cap = (long long)geo.n_pass / min_passes;
+  s_cap = std::min(s_cap, 64 * slots / base_ctas + 1);
+  s_cap = std::min(s_cap, (long long)(((size_t)1 << 30) / ((size_t)rows_pad * n_omega * 16)) + 1);
+  const int S_max = (int)std::max<long long>(1, s_cap);
+  const double overhead_passes = 2.0;
+  int S = 1, ppc = geo.n_pass;
+  double best_cost = 1e300;
+  for (int s = 1; s <= S_max; ++s) {
+    int c = ceil_div(geo.n_pass, s);
+    c = ceil_div(c, p.pps) * p.pps;
+    const int s_eff = ceil_div(geo.n_pass, c);
+    const long long waves = (base_ctas * s_eff + slots - 1) / slots;
+    const double cost = (double)waves * (c + overhead_passes);
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      S = s_eff;
+      ppc = c;
+    }
   }
-  int ppc = ceil_div(geo.n_pass, S);
-  ppc = ceil_div(ppc, p.pps) * p.pps;
-  S = ceil_div(geo.n_pass, ppc);
   p.passes_per_chunk = ppc;
 
   FFB_TRY(partial.alloc(ctx, (size_t)S * rows_pad * n_omega * 16));
   p.partial = partial.as<double>();
 
-  FFB_DISPATCH_MT(MT, NW, FFB_TRY((launch_main<MT_, NW>(ctx, p, n_wtiles, geo.n_rb, S))));
+  FFB_DISPATCH_MT(MT, FFB_TRY((launch_main<MT_, NW_>(ctx, p, n_wtiles, geo.n_rb, S))));
 
   {
     const size_t total = (size_t)n_nops * n_basis * n_omega;

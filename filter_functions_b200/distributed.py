@@ -1,0 +1,164 @@
+"""Frequency-sharded multi-GPU execution: one process per GPU, ``torch.distributed`` for plumbing.
+
+Every quantity on the path depends on a single frequency: control matrix,
+filter function and the concatenation have no cross-omega term, and the infidelity is a sum over
+frequency intervals.  So the omega axis is partitioned into contiguous blocks of trapezoid intervals,
+the tiny per-segment operands are replicated (each rank uploads them itself, no collective), and the
+only exchange on the path is ONE all-reduce of the per-noise-operator partial integrals (<= n_nops^2
+doubles) -- or an all-gather of F(omega) slices when the caller wants the whole filter function.
+The segment axis is a reduction axis and is deliberately not sharded.
+
+Launch with ``torchrun`` (``RANK`` / ``LOCAL_RANK`` / ``WORLD_SIZE`` from the environment); rank r uses
+GPU ``LOCAL_RANK``.  With the ``gloo`` backend the collectives run on CPU tensors, which is how the
+host-side logic is tested without GPUs.
+"""
+import os
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+__all__ = ['frequency_shard', 'init_process_group', 'allreduce_sum', 'allgather_frequency_axis',
+           'infidelity', 'filter_function']
+
+
+def frequency_shard(n_omega: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Half-open index range ``[start, stop)`` of the frequencies rank ``rank`` evaluates.
+
+    The ``n_omega - 1`` trapezoid intervals are split as evenly as possible; a rank owning intervals
+    ``[a, b)`` needs the abscissae ``a .. b`` inclusive, i.e. one halo point shared with its right
+    neighbour.  Ranks beyond the number of intervals get an empty range ``(k, k)``.
+    """
+    if n_omega < 1 or world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError(f'bad shard request: n_omega={n_omega}, rank={rank}, world={world_size}')
+    n_int = n_omega - 1
+    if n_int == 0:
+        return (0, 1) if rank == 0 else (0, 0)
+    base, extra = divmod(n_int, world_size)
+    a = rank*base + min(rank, extra)
+    b = a + base + (1 if rank < extra else 0)
+    if a == b:
+        return (a, a)
+    return (a, b + 1)
+
+
+def owned_frequencies(n_omega: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Range of frequencies rank ``rank`` contributes to a gathered array (no halo duplicates)."""
+    start, stop = frequency_shard(n_omega, rank, world_size)
+    if stop - start == 0:
+        return (start, start)
+    last = True
+    for r in range(rank + 1, world_size):
+        s, e = frequency_shard(n_omega, r, world_size)
+        if e - s > 0:
+            last = False
+            break
+    return (start, stop if last else stop - 1)
+
+
+def init_process_group(backend: Optional[str] = None):
+    """Initialise ``torch.distributed`` from the torchrun environment (idempotent)."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return dist.group.WORLD
+    if backend is None:
+        backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+    if backend == 'nccl':
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29511')
+    dist.init_process_group(backend=backend)
+    return dist.group.WORLD
+
+
+def _world(group):
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def allreduce_sum(arr: np.ndarray, group=None) -> np.ndarray:
+    """Sum a small host array over all ranks (NCCL on the rank's GPU, or gloo on the CPU)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = _world(group)
+    if world == 1:
+        return np.array(arr, copy=True)
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64).copy())
+    if dist.get_backend(group) == 'nccl':
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def allgather_frequency_axis(local: np.ndarray, n_omega: int, group=None) -> np.ndarray:
+    """Assemble an array whose last axis is the (sharded) frequency axis on every rank."""
+    import torch
+    import torch.distributed as dist
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    start, _ = frequency_shard(n_omega, rank, world)
+    o0, o1 = owned_frequencies(n_omega, rank, world)
+    mine = np.ascontiguousarray(local[..., o0 - start:o1 - start])
+    counts = [np.subtract(*owned_frequencies(n_omega, r, world)[::-1]) for r in range(world)]
+    width = max(counts)
+    lead = mine.shape[:-1]
+    is_complex = np.iscomplexobj(mine)
+    buf = np.zeros(lead + (width,), dtype=mine.dtype)
+    buf[..., :mine.shape[-1]] = mine
+    t = torch.from_numpy(buf.view(np.float64) if is_complex else buf)
+    nccl = dist.get_backend(group) == 'nccl'
+    if nccl:
+        t = t.cuda()
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    out = np.empty(lead + (n_omega,), dtype=mine.dtype)
+    pos = 0
+    for r, part in enumerate(parts):
+        a = part.cpu().numpy()
+        if is_complex:
+            a = a.view(np.complex128)
+        out[..., pos:pos + counts[r]] = a[..., :counts[r]]
+        pos += counts[r]
+    return out
+
+
+def infidelity(pulse, spectrum, omega, n_oper_identifiers=None, group=None,
+               _local: Optional[Callable] = None) -> np.ndarray:
+    """Frequency-sharded ``ff.infidelity(pulse, spectrum, omega)``: every rank integrates its block
+    of intervals on its own GPU; one all-reduce combines the partial integrals.  The result is
+    identical on all ranks and equals the single-GPU result up to summation order."""
+    from . import numeric
+    local_fn = numeric.infidelity if _local is None else _local
+    omega = np.asarray(omega, dtype=float)
+    spectrum = np.asarray(spectrum)
+    rank, world = _world(group)
+    start, stop = frequency_shard(len(omega), rank, world)
+    if stop - start >= 2 or (len(omega) == 1 and rank == 0):
+        part = np.asarray(local_fn(pulse, spectrum[..., start:stop], omega[start:stop],
+                                   n_oper_identifiers=n_oper_identifiers))
+    else:
+        part = None
+    if world == 1:
+        return part
+    if part is None:
+        # ranks without intervals contribute zeros of the right shape
+        n_sel = len(pulse.n_oper_identifiers if n_oper_identifiers is None else n_oper_identifiers)
+        part = np.zeros((n_sel, n_sel) if spectrum.ndim == 3 else (n_sel,))
+    return allreduce_sum(part, group).reshape(part.shape)
+
+
+def filter_function(pulse, omega, group=None, _local: Optional[Callable] = None) -> np.ndarray:
+    """Frequency-sharded ``pulse.get_filter_function(omega)`` gathered on every rank."""
+    omega = np.asarray(omega, dtype=float)
+    rank, world = _world(group)
+    start, stop = frequency_shard(len(omega), rank, world)
+    local_fn = (lambda p, w: p.get_filter_function(w)) if _local is None else _local
+    if stop - start > 0:
+        local = np.asarray(local_fn(pulse, omega[start:stop]))
+    else:
+        n = len(pulse.n_opers)
+        local = np.zeros((n, n, 0), dtype=complex)
+    return allgather_frequency_axis(local, len(omega), group)

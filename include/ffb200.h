@@ -46,9 +46,10 @@ int ffb_init(ffb_ctx** ctx, int device);
 void ffb_destroy(ffb_ctx* ctx);
 const char* ffb_last_error(const ffb_ctx* ctx);
 const char* ffb_version(void);
-/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all subsequent work. Pass
- * NULL to go back to the context's own stream. */
-int ffb_set_stream(ffb_ctx* ctx, void* cuda_stream);
+/* external != 0: enqueue all subsequent work on the externally owned cudaStream_t `cuda_stream`
+ * (e.g. torch's current stream; NULL is the legacy default stream).  external == 0: go back to the
+ * context's own non-blocking stream. */
+int ffb_set_stream(ffb_ctx* ctx, void* cuda_stream, int external);
 int ffb_sync(ffb_ctx* ctx);
 /* Number of kernels this library has launched on this context since creation. */
 int64_t ffb_launch_count(const ffb_ctx* ctx);
