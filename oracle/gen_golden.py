@@ -1,0 +1,168 @@
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Runs only in the build container, where /root/reference exists (it is not shipped to the GPU box).
+The reference needs ``opt_einsum`` and ``sparse``; ``oracle/shim`` holds NumPy-backed stand-ins
+(SURVEY.md section 8c).  Usage::
+
+    python oracle/gen_golden.py
+
+Every fixture stores the INPUTS next to the reference's OUTPUTS so that the tests need neither the
+reference nor its random-number stream.  All results come from the reference's public API
+(``ff.PulseSequence``, ``ff.infidelity``, ``ff.concatenate``, ``numeric.*``).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, 'shim'))
+sys.path.insert(0, '/root/reference')
+sys.path.insert(0, '/root/reference/tests')
+
+import filter_functions as ff  # noqa: E402
+from filter_functions import numeric, util  # noqa: E402
+from tests import testutil  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pulse_arrays(pulse):
+    return dict(c_opers=pulse.c_opers, c_ids=np.asarray(pulse.c_oper_identifiers, dtype='U8'),
+                c_coeffs=pulse.c_coeffs, n_opers=pulse.n_opers,
+                n_ids=np.asarray(pulse.n_oper_identifiers, dtype='U8'), n_coeffs=pulse.n_coeffs,
+                dt=pulse.dt, basis=np.asarray(pulse.basis))
+
+
+def seeded_infidelities():
+    """The seeded regression of tests/test_precision.py:495-551 (seed 123456789)."""
+    rng = np.random.default_rng(seed=123456789)
+    spectra = [
+        lambda S0, omega: S0*abs(omega)**0,
+        lambda S0, omega: S0/abs(omega)**0.7,
+        lambda S0, omega: S0*np.exp(-abs(omega)),
+        lambda S0, omega: np.array([S0*abs(omega)**0, S0/abs(omega)**0.7]),
+        lambda S0, omega: np.array([[S0/abs(omega)**0.7, S0/(1 + omega**2) + 1j*S0*omega],
+                                    [S0/(1 + omega**2) - 1j*S0*omega, S0/abs(omega)**0.7]])
+    ]
+    out = {}
+    for d in (2, 3, 4):
+        pulse = testutil.rand_pulse_sequence(d, 10, 2, 3, local_rng=rng)
+        pulse.n_oper_identifiers = np.array(['B_0', 'B_2'])
+        omega = np.geomspace(0.1, 10, 51)
+        S0 = np.abs(rng.standard_normal())
+        for key, val in pulse_arrays(pulse).items():
+            if key != 'n_ids':
+                out[f'd{d}_{key}'] = val
+        out[f'd{d}_omega'] = omega
+        out[f'd{d}_S0'] = S0
+        for i, spec in enumerate(spectra):
+            S = spec(S0, omega)
+            out[f'd{d}_spectrum{i}'] = S
+            out[f'd{d}_infid{i}'] = ff.infidelity(pulse, S, omega,
+                                                   n_oper_identifiers=['B_0', 'B_2'])
+        out[f'd{d}_control_matrix'] = pulse.get_control_matrix(omega)
+        out[f'd{d}_filter_function'] = pulse.get_filter_function(omega)
+    np.savez_compressed(os.path.join(OUT, 'infidelity_seeded.npz'), **out)
+
+
+def random_pulses():
+    """Path results for random pulses of several shapes, incl. non-integer-power-of-two d."""
+    rng = np.random.default_rng(20261017)
+    out = {}
+    cases = [(2, 12, 3, 'Pauli'), (3, 9, 2, 'GGM'), (4, 14, 4, 'Pauli'), (5, 6, 2, 'GGM')]
+    for d, G, n_nops, btype in cases:
+        pulse = testutil.rand_pulse_sequence(d, G, 3, n_nops, btype=btype, local_rng=rng)
+        omega = np.concatenate(([0.0], np.geomspace(1e-3, 40, 60), -np.geomspace(1e-2, 5, 4)))
+        tag = f'd{d}'
+        for key, val in pulse_arrays(pulse).items():
+            out[f'{tag}_{key}'] = val
+        out[f'{tag}_omega'] = omega
+        pulse.diagonalize()
+        out[f'{tag}_eigvals'] = pulse.eigvals
+        out[f'{tag}_propagators'] = pulse.propagators
+        out[f'{tag}_control_matrix'] = pulse.get_control_matrix(omega)
+        out[f'{tag}_filter_function'] = pulse.get_filter_function(omega)
+        if d <= 3:  # (n_nops, n_nops, d^2, d^2, n_omega): keep the fixture small
+            out[f'{tag}_filter_function_gen'] = pulse.get_filter_function(omega, which='generalized')
+        out[f'{tag}_total_phases'] = pulse.get_total_phases(omega)
+        out[f'{tag}_total_propagator_liouville'] = pulse.total_propagator_liouville
+        om = np.geomspace(0.05, 20, 80)
+        S = 1e-3/om**0.7
+        out[f'{tag}_int_omega'] = om
+        out[f'{tag}_int_spectrum'] = S
+        out[f'{tag}_infidelity'] = ff.infidelity(pulse, S, om)
+    np.savez_compressed(os.path.join(OUT, 'random_pulses.npz'), **out)
+
+
+def concatenation():
+    """concatenate() of pulses with cached control matrices, equal and differing noise operators,
+    pulse-correlation filter functions (cf. tests/test_sequencing.py:222-606, :690-799)."""
+    rng = np.random.default_rng(77)
+    out = {}
+    d = 2
+    omega = np.geomspace(1e-2, 30, 70)
+    X, Y, Z = util.paulis[1:]
+    pulses = []
+    for i in range(4):
+        G = int(rng.integers(2, 7))
+        H_c = [[X/2, rng.standard_normal(G), 'X'], [Y/2, rng.standard_normal(G), 'Y']]
+        H_n = [[Z/2, np.ones(G), 'Z'], [X/2, np.full(G, 0.5), 'Xn']]
+        if i == 2:  # one pulse lacks a noise operator with constant sensitivity elsewhere
+            H_n = H_n[:1]
+        pulses.append(ff.PulseSequence(H_c, H_n, 1 - rng.random(G), ff.Basis.pauli(1)))
+    for i, pls in enumerate(pulses):
+        for key, val in pulse_arrays(pls).items():
+            out[f'p{i}_{key}'] = val
+        pls.cache_filter_function(omega)
+    out['omega'] = omega
+    total = ff.concatenate(pulses, calc_pulse_correlation_FF=True)
+    out['n_ids'] = np.asarray(total.n_oper_identifiers, dtype='U8')
+    out['control_matrix'] = total.get_control_matrix(omega)
+    out['control_matrix_pc'] = total.get_pulse_correlation_control_matrix()
+    out['filter_function'] = total.get_filter_function(omega)
+    out['filter_function_pc'] = total.get_pulse_correlation_filter_function()
+    out['total_propagator'] = total.total_propagator
+    S = 1e-2/omega
+    out['infidelity'] = ff.infidelity(total, S, omega)
+    out['infidelity_pc'] = ff.infidelity(total, S, omega, which='correlations')
+    # from scratch on the concatenated pulse
+    scratch = ff.concatenate(pulses, calc_filter_function=False)
+    out['control_matrix_scratch'] = scratch.get_control_matrix(omega)
+    np.savez_compressed(os.path.join(OUT, 'concatenation.npz'), **out)
+
+
+def workloads_small():
+    """Reduced-size instances of BASELINE.json configs 2 and 3 built by the repo's own generators, with
+    the reference's results (so the generators and the engine are pinned on the bench workloads)."""
+    sys.path.insert(0, ROOT)
+    import workloads
+    out = {}
+    for name, kwargs in (('c2', dict(G=64, n_omega=96)), ('c3', dict(G=40, n_omega=64))):
+        wl = workloads.get(name, **kwargs)
+        pulse = ff.PulseSequence(
+            [[op, c, i] for op, c, i in zip(wl.c_opers, wl.c_coeffs, wl.c_ids)],
+            [[op, c, i] for op, c, i in zip(wl.n_opers, wl.n_coeffs, wl.n_ids)],
+            wl.dt, ff.Basis.pauli(int(np.log2(wl.d))))
+        out[f'{name}_n_ids'] = np.asarray(pulse.n_oper_identifiers, dtype='U8')
+        out[f'{name}_control_matrix'] = pulse.get_control_matrix(wl.omega)
+        out[f'{name}_filter_function'] = pulse.get_filter_function(wl.omega)
+        out[f'{name}_infidelity'] = ff.infidelity(pulse, wl.spectrum, wl.omega)
+    wl = workloads.get('c1')
+    pulse = ff.PulseSequence(
+        [[op, c, i] for op, c, i in zip(wl.c_opers, wl.c_coeffs, wl.c_ids)],
+        [[op, c, i] for op, c, i in zip(wl.n_opers, wl.n_coeffs, wl.n_ids)], wl.dt)
+    out['c1_infidelity'] = ff.infidelity(pulse, wl.spectrum, wl.omega)
+    out['c1_filter_function'] = pulse.get_filter_function(wl.omega)
+    np.savez_compressed(os.path.join(OUT, 'workloads_small.npz'), **out)
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    seeded_infidelities()
+    random_pulses()
+    concatenation()
+    workloads_small()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)), 'bytes')

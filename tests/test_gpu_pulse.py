@@ -1,0 +1,338 @@
+"""GPU parity of the public API (PulseSequence, concatenate, infidelity) against the reference's own
+golden vectors, known answers and fixtures.  These read like the reference's tests:
+tests/test_precision.py:75-182 (analytic DD), :495-551 (seeded infidelities), :355-467 / tests/
+test_sequencing.py:222-469, :690-799 (concatenation, pulse correlations), tests/test_core.py:241-470,
+:644-743 (cache semantics, scratch vs atomic)."""
+import os
+from copy import copy
+
+import numpy as np
+import pytest
+
+import ff_oracle as oracle
+from helpers import dd_hamiltonian, nerr, rand_pulse_sequence
+from test_oracle import DD_CASES, GOLDEN, REF_INFIDS, SPECTRA, analytic_dd
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def pulse_from_fixture(ff, g, tag, n_ids=None, basis=None):
+    n_ids = g[f'{tag}_n_ids'] if n_ids is None else n_ids
+    return ff.PulseSequence(
+        [[op, c, str(i)] for op, c, i in zip(g[f'{tag}_c_opers'], g[f'{tag}_c_coeffs'],
+                                             g[f'{tag}_c_ids'])],
+        [[op, c, str(i)] for op, c, i in zip(g[f'{tag}_n_opers'], g[f'{tag}_n_coeffs'], n_ids)],
+        g[f'{tag}_dt'], ff.Basis(g[f'{tag}_basis']) if basis is None else basis)
+
+
+def test_readme_example(engine):
+    """README.md:17-61 of the reference: Hadamard from primitive pulses and by concatenation."""
+    ff = engine
+    X, Y, Z = ff.util.paulis[1:]
+    H_c = [[X/2, [0, np.pi], 'X'], [Y/2, [np.pi/2, 0], 'Y']]
+    H_n = [[Z/2, [1, 1], 'Z']]
+    hadamard = ff.PulseSequence(H_c, H_n, [1, 1])
+    omega = ff.util.get_sample_frequencies(hadamard)
+    F = hadamard.get_filter_function(omega)
+    assert F.shape == (1, 1, 300)
+    infid = ff.infidelity(hadamard, 1e-2/omega, omega)
+    np.testing.assert_allclose(infid, [0.00253303], atol=5e-9)
+    Y2 = ff.PulseSequence([[Y/2, [np.pi/2], 'Y']], [[Z/2, [1], 'Z']], [1])
+    Xp = ff.PulseSequence([[X/2, [np.pi], 'X']], [[Z/2, [1], 'Z']], [1])
+    Y2.cache_filter_function(omega)
+    Xp.cache_filter_function(omega)
+    had2 = Y2 @ Xp
+    assert had2.is_cached('filter function')
+    assert nerr(had2.get_filter_function(omega), F) < TOL
+    assert hadamard == had2
+    g = np.load(os.path.join(GOLDEN, 'workloads_small.npz'))
+    assert nerr(F, g['c1_filter_function']) < TOL
+
+
+def test_seeded_infidelities(engine):
+    """Reference tests/test_precision.py:495-551, same seed, same hard-coded values, atol 1e-12."""
+    ff = engine
+    rng = np.random.default_rng(seed=123456789)
+    count = 0
+    for d in (2, 3, 4):
+        pulse = rand_pulse_sequence(ff, rng, d, 10, 2, 3)
+        pulse.n_oper_identifiers = np.array(['B_0', 'B_2'])
+        omega = np.geomspace(0.1, 10, 51)
+        S0 = np.abs(rng.standard_normal())
+        for spec in SPECTRA:
+            S = spec(S0, omega)
+            infids = ff.infidelity(pulse, S, omega, n_oper_identifiers=['B_0', 'B_2'])
+            np.testing.assert_allclose(infids, REF_INFIDS[count], atol=1e-12, rtol=1e-10)
+            if S.ndim == 3:
+                uncorrelated = ff.infidelity(pulse, S[range(2), range(2)], omega,
+                                             n_oper_identifiers=['B_0', 'B_2'])
+                np.testing.assert_allclose(np.diag(infids), uncorrelated, rtol=1e-12)
+                np.testing.assert_allclose(infids, infids.conj().T, rtol=1e-12, atol=1e-15)
+            count += 1
+    with pytest.raises(TypeError):
+        ff.infidelity(pulse, 2, omega, test_convergence=True)
+    with pytest.raises(TypeError):
+        ff.infidelity(pulse, lambda x: x, 2, test_convergence=True)
+    with pytest.raises(ValueError):
+        ff.infidelity(pulse, S[:1], omega, n_oper_identifiers=['B_0', 'B_2'])
+
+
+def test_seeded_fixture_control_matrices(engine):
+    ff = engine
+    g = np.load(os.path.join(GOLDEN, 'infidelity_seeded.npz'))
+    for d in (2, 3, 4):
+        pulse = pulse_from_fixture(ff, g, f'd{d}', n_ids=[f'n{i}' for i in range(3)])
+        B = pulse.get_control_matrix(g[f'd{d}_omega'])
+        assert nerr(B, g[f'd{d}_control_matrix']) < TOL
+        assert nerr(pulse.get_filter_function(g[f'd{d}_omega']), g[f'd{d}_filter_function']) < TOL
+
+
+@pytest.mark.parametrize('dd_type,formula,n,tau_pi', DD_CASES)
+def test_analytic_dd(engine, dd_type, formula, n, tau_pi):
+    """Filter functions of FID/SE/CPMG/UDD/PDD/CDD sequences against their closed forms; includes
+    negative frequencies and pi-pulse segments of 1e-9 duration (Omega dt = pi with Omega ~ 3e9)."""
+    ff = engine
+    tau = np.pi
+    H_c, dt = dd_hamiltonian(n, tau=tau, tau_pi=tau_pi, dd_type=dd_type)
+    H_n = [[ff.util.paulis[3]/2, np.ones_like(dt)]]
+    pulse = ff.PulseSequence(H_c, H_n, dt)
+    omega = np.logspace(0, 3, 100)
+    omega = np.concatenate([-omega[::-1], omega])
+    F = pulse.get_filter_function(omega)[0, 0]*omega**2
+    np.testing.assert_allclose(F.real, analytic_dd(formula, omega*tau, n), atol=1e-10, rtol=1e-7)
+    assert np.abs(F.imag).max() < 1e-10
+
+
+def test_fid(engine):
+    ff = engine
+    tau = 0.8317
+    pulse = ff.PulseSequence([[ff.util.paulis[1]/2, [0]]], [[ff.util.paulis[3]/2, [1]]], [tau])
+    omega = ff.util.get_sample_frequencies(pulse, 50, spacing='linear')
+    F = pulse.get_filter_function(omega).squeeze()*omega**2
+    np.testing.assert_allclose(F.real, analytic_dd('fid', omega*tau, 0), atol=1e-10, rtol=1e-7)
+
+
+def test_random_pulse_fixture(engine):
+    """Every cached quantity of a cold PulseSequence against the reference's (gauge-invariant ones)."""
+    ff = engine
+    g = np.load(os.path.join(GOLDEN, 'random_pulses.npz'))
+    for d in (2, 3, 4, 5):
+        t = f'd{d}'
+        btype = 'GGM' if d in (3, 5) else 'Pauli'
+        basis = ff.Basis.ggm(d) if btype == 'GGM' else ff.Basis.pauli(int(np.log2(d)))
+        assert nerr(np.asarray(basis), g[f'{t}_basis']) < 1e-15
+        pulse = pulse_from_fixture(ff, g, t, basis=basis)
+        omega = g[f'{t}_omega']
+        F = pulse.get_filter_function(omega)          # cold cache: fused pipeline
+        assert nerr(F, g[f'{t}_filter_function']) < TOL
+        assert nerr(pulse.eigvals, g[f'{t}_eigvals']) < TOL
+        assert nerr(pulse.propagators, g[f'{t}_propagators']) < TOL
+        assert nerr(pulse.total_propagator, g[f'{t}_propagators'][-1]) < TOL
+        B = pulse.get_control_matrix(omega)
+        for j in range(len(B)):
+            assert nerr(B[j], g[f'{t}_control_matrix'][j]) < TOL
+        assert nerr(pulse.get_total_phases(omega), g[f'{t}_total_phases']) < TOL
+        assert nerr(pulse.total_propagator_liouville, g[f'{t}_total_propagator_liouville']) < TOL
+        if d <= 3:
+            Fg = pulse.get_filter_function(omega, which='generalized')
+            assert nerr(Fg, g[f'{t}_filter_function_gen']) < TOL
+            assert nerr(Fg.trace(axis1=2, axis2=3), F) < 1e-12
+        infid = ff.infidelity(pulse, g[f'{t}_int_spectrum'], g[f'{t}_int_omega'])
+        assert nerr(infid, g[f'{t}_infidelity']) < TOL
+        # step-by-step path (warm caches) gives the same as the fused cold path
+        warm = pulse_from_fixture(ff, g, t, basis=basis)
+        warm.diagonalize()
+        assert nerr(warm.get_control_matrix(omega), B) < 1e-13
+        assert nerr(warm.get_filter_function(omega), F) < 1e-13
+
+
+def test_concatenation_fixture(engine):
+    """concatenate() with cached constituents, a missing noise operator on one pulse, pulse
+    correlations: all against the reference's results (tests/test_sequencing.py:507-799)."""
+    ff = engine
+    g = np.load(os.path.join(GOLDEN, 'concatenation.npz'))
+    omega = g['omega']
+    pulses = [pulse_from_fixture(ff, g, f'p{i}', basis=ff.Basis.pauli(1)) for i in range(4)]
+    for pls in pulses:
+        pls.cache_filter_function(omega)
+    total = ff.concatenate(pulses, calc_pulse_correlation_FF=True)
+    assert list(total.n_oper_identifiers) == list(g['n_ids'])
+    assert nerr(total.get_pulse_correlation_control_matrix(), g['control_matrix_pc']) < TOL
+    assert nerr(total.get_control_matrix(omega), g['control_matrix']) < TOL
+    assert nerr(total.get_filter_function(omega), g['filter_function']) < TOL
+    Fpc = total.get_pulse_correlation_filter_function()
+    assert nerr(Fpc, g['filter_function_pc']) < TOL
+    assert nerr(Fpc.sum(axis=(0, 1)), total.get_filter_function(omega)) < 1e-12
+    assert nerr(total.total_propagator, g['total_propagator']) < TOL
+    S = 1e-2/omega
+    assert nerr(ff.infidelity(total, S, omega), g['infidelity']) < TOL
+    infid_pc = ff.infidelity(total, S, omega, which='correlations')
+    assert infid_pc.shape == g['infidelity_pc'].shape and nerr(infid_pc, g['infidelity_pc']) < TOL
+    assert nerr(infid_pc.sum(axis=(0, 1)), g['infidelity']) < TOL
+    with pytest.raises(ValueError):
+        ff.infidelity(total, S[:-1], omega[:-1], which='correlations')
+    # without pulse correlations; and from scratch on the bare concatenated pulse
+    plain = ff.concatenate(pulses)
+    assert plain.is_cached('control_matrix') and not plain.is_cached('control_matrix_pc')
+    assert nerr(plain.get_control_matrix(omega), g['control_matrix']) < TOL
+    bare = ff.concatenate(pulses, calc_filter_function=False)
+    assert not bare.is_cached('control_matrix')
+    assert nerr(bare.get_control_matrix(omega), g['control_matrix_scratch']) < TOL
+    # omega given explicitly forces the calculation on pulses without caches
+    fresh = [pulse_from_fixture(ff, g, f'p{i}', basis=ff.Basis.pauli(1)) for i in range(4)]
+    forced = ff.concatenate(fresh, omega=omega)
+    assert nerr(forced.get_filter_function(omega), g['filter_function']) < TOL
+    with pytest.raises(ValueError):
+        ff.concatenate([pulse_from_fixture(ff, g, f'p{i}', basis=ff.Basis.pauli(1))
+                        for i in range(2)], calc_pulse_correlation_FF=True)
+
+
+@pytest.mark.parametrize('d,btype', [(2, 'Pauli'), (3, 'GGM'), (4, 'Pauli'), (7, 'GGM')])
+def test_scratch_vs_atomic(engine, d, btype):
+    """Reference tests/test_core.py:685-743: splitting a pulse into pieces and concatenating them
+    gives the same control matrix as computing it from scratch (random d, G, 6 noise operators)."""
+    ff = engine
+    rng = np.random.default_rng(1000 + d)
+    G = int(rng.integers(10, 60))
+    pulse = rand_pulse_sequence(ff, rng, d, G, 3, 6 if d < 7 else 3, btype=btype)
+    omega = np.geomspace(1e-2/pulse.tau, 1e2/pulse.tau, 100)*2*np.pi
+    B_scratch = pulse.get_control_matrix(omega)
+    cuts = sorted(set(rng.integers(1, G, 4).tolist()))
+    pieces = [pulse[a:b] for a, b in zip([0] + cuts, cuts + [G])]
+    for piece in pieces:
+        piece.cache_control_matrix(omega)
+    joined = ff.concatenate(pieces)
+    B_atomic = joined.get_control_matrix(omega)
+    assert nerr(B_atomic, B_scratch) < TOL
+    np.testing.assert_allclose(B_atomic, B_scratch, rtol=1e-7, atol=1e-11*np.abs(B_scratch).max())
+    assert nerr(joined.get_filter_function(omega), pulse.get_filter_function(omega)) < TOL
+    assert nerr(joined.total_propagator, pulse.total_propagator) < TOL
+
+
+def test_se_concatenation_is_cpmg(engine):
+    """Two spin echoes are a CPMG-2 sequence (reference tests/test_sequencing.py:222-310)."""
+    ff = engine
+    tau, tau_pi = np.pi, 1e-4
+    Z = ff.util.paulis[3]
+    H_se, dt_se = dd_hamiltonian(1, tau=tau/2, tau_pi=tau_pi, dd_type='cpmg')
+    H_cp, dt_cp = dd_hamiltonian(2, tau=tau, tau_pi=tau_pi, dd_type='cpmg')
+    se = ff.PulseSequence([[H_se[0][0], H_se[0][1], 'X']], [[Z/2, np.ones_like(dt_se), 'Z']], dt_se)
+    cpmg = ff.PulseSequence([[H_cp[0][0], H_cp[0][1], 'X']], [[Z/2, np.ones_like(dt_cp), 'Z']], dt_cp)
+    omega = np.geomspace(1e-2, 1e2, 200)
+    se.cache_filter_function(omega)
+    double = se @ se
+    assert double == cpmg
+    F = cpmg.get_filter_function(omega)
+    np.testing.assert_allclose(double.get_filter_function(omega), F, rtol=1e-9,
+                               atol=1e-12*np.abs(F).max())
+    four = ff.concatenate([se, se, se, se])
+    H4, dt4 = dd_hamiltonian(4, tau=2*tau, tau_pi=tau_pi, dd_type='cpmg')
+    cpmg4 = ff.PulseSequence([[H4[0][0], H4[0][1], 'X']], [[Z/2, np.ones_like(dt4), 'Z']], dt4)
+    assert nerr(four.get_filter_function(omega), cpmg4.get_filter_function(omega)) < 1e-9
+
+
+def test_cache_semantics(engine):
+    """omega as list vs array, cache hits return the same object, omega change invalidates, cleanup
+    modes, control matrix recovered from the pulse-correlation one (tests/test_core.py:241-470)."""
+    ff = engine
+    rng = np.random.default_rng(3)
+    pulse = rand_pulse_sequence(ff, rng, 2, 6, 2, 2)
+    omega = [0.1, 0.5, 1.0, 2.0]
+    F = pulse.get_filter_function(omega)
+    assert pulse.get_filter_function(np.array(omega)) is F
+    for key in ('eigvals', 'eigvecs', 'propagators', 'total_propagator',
+                'total_propagator_liouville', 'omega', 'total_phases', 'control_matrix',
+                'filter_function'):
+        assert pulse.is_cached(key), key
+    B = pulse.get_control_matrix(omega)
+    assert pulse.get_control_matrix(omega) is B
+    Fg = pulse.get_filter_function(omega, which='generalized')
+    assert pulse.is_cached('generalized filter function') and Fg.shape == (2, 2, 4, 4, 4)
+    F2 = pulse.get_filter_function(omega + [3.0])
+    assert F2.shape[-1] == 5 and not pulse.is_cached('filter_function_gen')
+    assert pulse.is_cached('eigvals')
+    pulse.cleanup('greedy')
+    assert not pulse.is_cached('control_matrix') and pulse.is_cached('filter_function')
+    pulse.cleanup('frequency dependent')
+    assert not pulse.is_cached('filter_function') and not pulse.is_cached('omega')
+    # cache_filter_function with an explicit filter function / control matrix
+    pulse.cache_filter_function(omega, filter_function=F)
+    assert pulse.get_filter_function(omega) is F
+    other = copy(pulse)
+    other.cleanup('all')
+    other.cache_control_matrix(omega, B)
+    assert other.get_control_matrix(omega) is B and other.is_cached('total_phases')
+    a, b = rand_pulse_sequence(ff, rng, 2, 3, 2, 2), None
+    b = copy(a)
+    a.cache_control_matrix(omega)
+    b.cache_control_matrix(omega)
+    ab = ff.concatenate([a, b], calc_pulse_correlation_FF=True)
+    pc = ab.get_pulse_correlation_control_matrix()
+    ab._frequency_data.pop('control_matrix', None)
+    assert nerr(ab.get_control_matrix(omega), pc.sum(0)) < 1e-14
+    assert nerr(ab.get_pulse_correlation_filter_function('generalized').trace(axis1=4, axis2=5),
+                ab.get_pulse_correlation_filter_function()) < 1e-12
+
+
+def test_infidelity_options(engine):
+    ff = engine
+    rng = np.random.default_rng(8)
+    pulse = rand_pulse_sequence(ff, rng, 2, 12, 2, 3, btype='Pauli')
+    omega = np.geomspace(0.01, 100, 301)
+    S = 1e-3/omega
+    ids = list(pulse.n_oper_identifiers)
+    full = ff.infidelity(pulse, S, omega)
+    sel = ff.infidelity(pulse, S, omega, n_oper_identifiers=ids[::-2])
+    np.testing.assert_allclose(sel, full[::-2], rtol=1e-12)
+    one = ff.infidelity(pulse, S, omega, n_oper_identifiers=ids[1])
+    np.testing.assert_allclose(one, full[1:2], rtol=1e-12)
+    infid, xi = ff.infidelity(pulse, S, omega, return_smallness=True)
+    T1 = oracle.integrate(S, omega)/(2*np.pi)
+    T2 = (pulse.dt*pulse.n_coeffs).sum(axis=-1)**2
+    T3 = (np.abs(pulse.n_opers)**2).sum(axis=(1, 2))
+    np.testing.assert_allclose(xi, np.sqrt((T1*T2*T3).sum()), rtol=1e-12)
+    with pytest.raises(NotImplementedError):
+        ff.infidelity(pulse, np.ones((3, 3, 301)), omega, return_smallness=True)
+    n, conv = ff.infidelity(pulse, lambda w: 1e-3/w, {'omega_IR': 0.01, 'omega_UV': 100,
+                                                      'spacing': 'log', 'n_min': 50, 'n_max': 150,
+                                                      'n_points': 3}, test_convergence=True)
+    assert list(n) == [50, 100, 150] and conv.shape == (3, 3)
+    ref = oracle.infidelity_from_filter_function(
+        oracle.filter_function(pulse.get_control_matrix(np.geomspace(0.01, 100, 100))),
+        1e-3/np.geomspace(0.01, 100, 100), np.geomspace(0.01, 100, 100), 2)
+    np.testing.assert_allclose(conv[1], ref, rtol=1e-10)
+
+
+def test_non_traceless_basis_infidelity(engine):
+    """Reference tests/test_precision.py:606-629 (trace-tensor branch, numeric.py:2295-2305)."""
+    ff = engine
+    rng = np.random.default_rng(21)
+    d = 2
+    A = rng.standard_normal((4, d, d)) + 1j*rng.standard_normal((4, d, d))
+    A = (A + A.conj().transpose(0, 2, 1))/2
+    # orthonormalise a random Hermitian (non-traceless) basis
+    flat = A.reshape(4, -1)
+    q, _ = np.linalg.qr(flat.T)
+    elems = q.T.reshape(4, d, d)
+    elems = (elems + elems.conj().transpose(0, 2, 1))/2
+    basis = ff.Basis(elems)
+    assert not basis.istraceless
+    pulse = rand_pulse_sequence(ff, rng, d, 8, 2, 2)
+    pulse.basis = basis
+    omega = np.geomspace(0.1, 10, 60)
+    S = 1/omega
+    infid = ff.infidelity(pulse, S, omega)
+    B = pulse.get_control_matrix(omega)
+    T4 = np.einsum('iab,jbc,kcd,lda->ijkl', elems, elems, elems, elems)
+    T = np.einsum('klmm->kl', T4) - np.einsum('kmlm->kl', T4)
+    F = np.einsum('ako,blo,kl->abo', B.conj(), B, T)/d
+    want = oracle.infidelity_from_filter_function(F, S, omega, d)
+    np.testing.assert_allclose(infid, want, rtol=1e-9)
+    # and it agrees with the traceless-basis result (the infidelity is basis independent)
+    ref = rand_pulse_sequence(ff, np.random.default_rng(21), d, 8, 2, 2)
+    ref2 = ff.PulseSequence(list(zip(pulse.c_opers, pulse.c_coeffs, pulse.c_oper_identifiers)),
+                            list(zip(pulse.n_opers, pulse.n_coeffs, pulse.n_oper_identifiers)),
+                            pulse.dt, ff.Basis.pauli(1))
+    np.testing.assert_allclose(infid, ff.infidelity(ref2, S, omega), rtol=1e-7)
+    del ref

@@ -1,0 +1,264 @@
+"""Host-side logic of the drop-in shell that needs no GPU: constructor validation, identifier
+handling, Hamiltonian concatenation, cache bookkeeping, basis constructors, argument parsing and the
+frequency sharding used by the multi-GPU path.  Mirrors reference tests/test_core.py:42-221,
+:1124-1232 and tests/test_sequencing.py:507-606 where the behaviour is host-only."""
+import numpy as np
+import pytest
+
+import ff_oracle as oracle
+import filter_functions_b200 as ff
+from filter_functions_b200 import distributed as ffd
+from filter_functions_b200 import util
+from filter_functions_b200.pulse_sequence import concatenate_without_filter_function
+
+X, Y, Z = util.paulis[1:]
+
+
+def simple_pulse(n_dt=3, ids=('X', 'Y'), n_ids=('Z',)):
+    H_c = [[X/2, np.arange(n_dt) + 1.0, ids[0]], [Y/2, np.ones(n_dt), ids[1]]]
+    H_n = [[Z/2, np.ones(n_dt), n_ids[0]]]
+    return ff.PulseSequence(H_c, H_n, np.full(n_dt, 0.5))
+
+
+def test_constructor_validation():
+    dt = [1.0, 2.0]
+    H_c = [[X/2, [1, 2]]]
+    H_n = [[Z/2, [1, 1]]]
+    with pytest.raises(TypeError):
+        ff.PulseSequence(H_c, H_n, 1.0)
+    with pytest.raises(ValueError):
+        ff.PulseSequence(H_c, H_n, [1.0, -1.0])
+    with pytest.raises(ValueError):
+        ff.PulseSequence(H_c, H_n, [1.0, 1j])
+    with pytest.raises(TypeError):
+        ff.PulseSequence(1, H_n, dt)
+    with pytest.raises(TypeError):
+        ff.PulseSequence([1], H_n, dt)
+    with pytest.raises(TypeError):
+        ff.PulseSequence([[X/2, 3]], H_n, dt)
+    with pytest.raises(ValueError):
+        ff.PulseSequence([[X/2, [1, 2, 3]]], H_n, dt)
+    with pytest.raises(ValueError):
+        ff.PulseSequence([[X/2, [1, 2], 'a'], [Y/2, [1, 2], 'a']], H_n, dt)
+    with pytest.raises(ValueError):
+        ff.PulseSequence(H_c, [[np.eye(3), [1, 1]]], dt)
+    with pytest.raises(ValueError):
+        ff.PulseSequence([[np.ones((2, 3)), [1, 2]]], H_n, dt)
+    with pytest.raises(ValueError):
+        ff.PulseSequence(H_c, H_n, dt, basis=np.eye(2))
+    with pytest.raises(ValueError):
+        ff.PulseSequence(H_c, H_n, dt, basis=ff.Basis.pauli(2))
+    with pytest.raises(TypeError):
+        ff.PulseSequence([[object(), [1, 2]]], H_n, dt)
+
+
+def test_identifiers_and_sorting():
+    pulse = ff.PulseSequence([[Y/2, [1, 2], 'b'], [X/2, [3, 4], 'a']], [[Z/2, [1, 1]], [X/2, [2, 2]]],
+                             [1, 1])
+    assert list(pulse.c_oper_identifiers) == ['a', 'b']
+    np.testing.assert_array_equal(pulse.c_opers[0], X/2)
+    np.testing.assert_array_equal(pulse.c_coeffs, [[3, 4], [1, 2]])
+    assert list(pulse.n_oper_identifiers) == ['B_0', 'B_1']
+    assert pulse.d == 2 and len(pulse) == 2 and pulse.basis.btype == 'GGM'
+    np.testing.assert_allclose(pulse.t, [0, 1, 2])
+    assert pulse.tau == 2 and pulse.duration == 2
+    none_ids = ff.PulseSequence([[X/2, [1, 2], None]], [[Z/2, [1, 1], None]], [1, 1])
+    assert list(none_ids.c_oper_identifiers) == ['A_0'] and list(none_ids.n_oper_identifiers) == ['B_0']
+
+
+def test_from_arrays_validation():
+    p = simple_pulse()
+    args = dict(c_opers=p.c_opers, c_oper_identifiers=p.c_oper_identifiers, c_coeffs=p.c_coeffs,
+                n_opers=p.n_opers, n_oper_identifiers=p.n_oper_identifiers, n_coeffs=p.n_coeffs,
+                dt=p.dt, basis=p.basis)
+    q = ff.PulseSequence.from_arrays(**args)
+    assert q == p
+    for key, bad in (('c_coeffs', p.c_coeffs[:1]), ('n_oper_identifiers', ['a', 'b']),
+                     ('dt', p.dt[:2]), ('n_opers', np.zeros((1, 3, 3))),
+                     ('basis', ff.Basis.pauli(2))):
+        with pytest.raises(ValueError):
+            ff.PulseSequence.from_arrays(**{**args, key: bad})
+
+
+def test_equality_and_slicing():
+    p = simple_pulse()
+    assert p == simple_pulse()
+    assert not (p == simple_pulse(ids=('X', 'W')))
+    assert (p == 1) is False
+    # two equal consecutive segments compare equal to the merged one (pulse_sequence.py:386-390)
+    a = ff.PulseSequence([[X/2, [1, 1]]], [[Z/2, [1, 1]]], [1, 2])
+    b = ff.PulseSequence([[X/2, [1]]], [[Z/2, [1]]], [3])
+    assert a == b
+    s = p[1:]
+    assert len(s) == 2 and np.array_equal(s.c_coeffs, p.c_coeffs[:, 1:])
+    assert len(p[0]) == 1
+    with pytest.raises(IndexError):
+        p[3:]
+
+
+def test_cache_bookkeeping_without_compute():
+    p = simple_pulse()
+    assert not p.is_cached('eigvals') and not p.is_cached('control matrix')
+    p.omega = [1.0, 2.0]
+    assert p.is_cached('frequencies') and isinstance(p.omega, np.ndarray)
+    p._frequency_data['control_matrix'] = np.zeros((1, 4, 2), dtype=complex)
+    p._data['eigvals'] = np.zeros((3, 2))
+    assert p.is_cached('Control Matrix') and p.is_cached('control_matrix')
+    assert p.is_cached('eigenvalues')
+    p.omega = [1.0, 2.0]                      # same frequencies: keeps the cache
+    assert p.is_cached('control_matrix')
+    p.omega = np.array([1.0, 3.0])            # different: drops frequency-dependent data
+    assert not p.is_cached('control_matrix') and p.is_cached('eigvals')
+    assert p.nbytes > 0
+    p.cleanup('conservative')
+    assert not p.is_cached('eigvals') and p.is_cached('omega')
+    p.cleanup('all')
+    assert not p.is_cached('omega')
+    with pytest.raises(ValueError):
+        p.cleanup('everything')
+    with pytest.raises(util.CalculationError):
+        p.get_pulse_correlation_filter_function()
+    with pytest.raises(util.CalculationError):
+        p.get_pulse_correlation_control_matrix()
+    with pytest.raises(NotImplementedError):
+        p.get_filter_function([1.0], order=2)
+    with pytest.raises(ValueError):
+        p.get_filter_function([1.0], which='foo')
+    q = p.__copy__()
+    q._data['x'] = 1
+    assert 'x' not in p.data
+    with pytest.raises(TypeError):
+        p @ 1
+    with pytest.raises(TypeError):
+        p.data['x'] = 1
+
+
+def test_concatenate_hamiltonians():
+    """Operator merging, identifier clashes and inferred noise coefficients, without any numerics
+    (reference pulse_sequence.py:1340-1483, tests/test_sequencing.py:507-606)."""
+    a = ff.PulseSequence([[X/2, [1, 2], 'X']], [[Z/2, [1, 1], 'Z']], [1, 1])
+    b = ff.PulseSequence([[Y/2, [3], 'Y']], [[Z/2, [1], 'Z'], [X/2, [2], 'Xn']], [0.5])
+    c, cmap, nmap = concatenate_without_filter_function([a, b], return_identifier_mappings=True)
+    assert list(c.c_oper_identifiers) == ['X', 'Y'] and list(c.n_oper_identifiers) == ['Xn', 'Z']
+    np.testing.assert_array_equal(c.c_coeffs, [[1, 2, 0], [0, 0, 3]])
+    np.testing.assert_array_equal(c.n_coeffs, [[2, 2, 2], [1, 1, 1]])   # constant inferred
+    np.testing.assert_array_equal(c.dt, [1, 1, 0.5])
+    assert c.tau == 2.5 and cmap[0] == {'X': 'X'} and nmap[1] == {'Z': 'Z', 'Xn': 'Xn'}
+    # same identifier, different operator -> position suffix
+    b2 = ff.PulseSequence([[Y/2, [3], 'X']], [[Z/2, [1], 'Z']], [0.5])
+    c2, cmap2, _ = concatenate_without_filter_function([a, b2], return_identifier_mappings=True)
+    assert sorted(c2.c_oper_identifiers) == ['X_0', 'X_1'] and cmap2[1] == {'X': 'X_1'}
+    # same operator, different identifiers -> error
+    b3 = ff.PulseSequence([[X/2, [3], 'W']], [[Z/2, [1], 'Z']], [0.5])
+    with pytest.raises(ValueError):
+        concatenate_without_filter_function([a, b3])
+    # non-constant sensitivity cannot be inferred
+    a4 = ff.PulseSequence([[X/2, [1, 2], 'X']], [[Z/2, [1, 1], 'Z'], [Y/2, [1, 2], 'Yn']], [1, 1])
+    with pytest.raises(ValueError):
+        concatenate_without_filter_function([a4, b])
+    with pytest.raises(TypeError):
+        concatenate_without_filter_function([a, 1])
+    with pytest.raises(TypeError):
+        concatenate_without_filter_function(1)
+    d3 = ff.PulseSequence([[np.eye(3), [1]]], [[np.eye(3), [1]]], [1])
+    with pytest.raises(ValueError):
+        concatenate_without_filter_function([a, d3])
+    pb = ff.PulseSequence([[X/2, [1], 'X']], [[Z/2, [1], 'Z']], [1],
+                          ff.Basis(np.asarray(ff.Basis.pauli(1))[[0, 2, 1, 3]]))
+    with pytest.raises(ValueError):
+        concatenate_without_filter_function([a, pb])
+    # no cached control matrices and nothing forced: concatenate returns the bare pulse
+    plain = ff.concatenate([a, b])
+    assert not plain.is_cached('control_matrix')
+    with pytest.raises(ValueError):
+        ff.concatenate([a, b], calc_filter_function=True)
+    with pytest.raises(ValueError):
+        ff.concatenate([a, b], which='foo')
+
+
+def test_basis_constructors_match_oracle_and_properties():
+    for n in (1, 2):
+        b = ff.Basis.pauli(n)
+        np.testing.assert_allclose(np.asarray(b), oracle.pauli_basis(n), atol=1e-15)
+        assert b.isherm and b.isorthonorm and b.istraceless and b.iscomplete and b.btype == 'Pauli'
+    for d in (2, 3, 5):
+        b = ff.Basis.ggm(d)
+        np.testing.assert_allclose(np.asarray(b), oracle.ggm_basis(d), atol=1e-15)
+        assert b.isherm and b.isorthonorm and b.istraceless and b.iscomplete and b.btype == 'GGM'
+        M = np.random.default_rng(d).standard_normal((d, d)) + 0j
+        np.testing.assert_allclose(np.einsum('k,kab->ab', b.expand(M), np.asarray(b)), M, atol=1e-14)
+    custom = ff.Basis([np.eye(2), np.array([[0, 1], [0, 0]])])
+    assert not custom.isherm and not custom.iscomplete and custom.btype == 'Custom'
+    with pytest.raises(ValueError):
+        ff.Basis(np.zeros((5, 2, 2)))
+    with pytest.raises(TypeError):
+        ff.Basis(1)
+    assert ff.Basis.pauli(1).four_element_traces.shape == (4, 4, 4, 4)
+
+
+def test_util_parsers():
+    omega = np.linspace(1, 2, 5)
+    assert util.parse_spectrum(np.ones(5), omega, [0, 1]).shape == (5,)
+    assert util.parse_spectrum(np.ones((2, 5)), omega, [0, 1]).shape == (2, 5)
+    with pytest.raises(ValueError):
+        util.parse_spectrum(np.ones((3, 5)), omega, [0, 1])
+    with pytest.raises(ValueError):
+        util.parse_spectrum(np.ones(4), omega, [0])
+    S = np.ones((2, 2, 5), dtype=complex)
+    S[0, 1] += 1j
+    with pytest.raises(ValueError):
+        util.parse_spectrum(S, omega, [0, 1])
+    with pytest.raises(ValueError):
+        util.parse_spectrum(np.ones((1, 1, 1, 5)), omega, [0])
+    np.testing.assert_array_equal(util.get_indices_from_identifiers(['a', 'b', 'c'], ['c', 'a']),
+                                  [2, 0])
+    np.testing.assert_array_equal(util.get_indices_from_identifiers(['a', 'b'], 'b'), [1])
+    np.testing.assert_array_equal(util.get_indices_from_identifiers(['a', 'b'], None), [0, 1])
+    with pytest.raises(ValueError):
+        util.get_indices_from_identifiers(['a'], ['z'])
+    p = simple_pulse()
+    np.testing.assert_allclose(util.get_sample_frequencies(p),
+                               oracle.sample_frequencies(p.tau, p.dt.min()))
+    w = util.get_sample_frequencies(p, 10, 'linear', include_quasistatic=True)
+    assert w[0] == 0 and len(w) == 10
+    with pytest.raises(ValueError):
+        util.get_sample_frequencies(p, spacing='cubic')
+    mats = np.random.default_rng(0).standard_normal((4, 3, 3))
+    np.testing.assert_allclose(util.mdot(mats), mats[0] @ mats[1] @ mats[2] @ mats[3])
+    np.testing.assert_allclose(util.adot(mats)[-1], mats[3] @ mats[2] @ mats[1] @ mats[0])
+    f = np.random.default_rng(1).standard_normal((2, 9))
+    x = np.sort(np.random.default_rng(2).random(9))
+    np.testing.assert_allclose(util.integrate(f, x), oracle.integrate(f, x))
+
+
+def test_infidelity_argument_errors_without_gpu():
+    p = simple_pulse()
+    with pytest.raises(TypeError):
+        ff.infidelity(p, 2, [1.0], test_convergence=True)
+    with pytest.raises(TypeError):
+        ff.infidelity(p, lambda x: x, 2, test_convergence=True)
+    with pytest.raises(ValueError):
+        ff.infidelity(p, lambda x: x, {'spacing': 'cubic'}, test_convergence=True)
+    with pytest.raises(ValueError):
+        ff.infidelity(p, [1.0], [1.0], which='foo')
+    with pytest.raises(ValueError):
+        ff.infidelity(p, [1.0], [1.0], n_oper_identifiers=['nope'])
+
+
+@pytest.mark.parametrize('n_omega,world', [(1, 1), (1, 4), (2, 2), (5, 8), (10, 3), (10001, 8),
+                                           (300, 7), (64, 64)])
+def test_frequency_shard_partition(n_omega, world):
+    """Intervals are partitioned exactly once; every shard has its halo point."""
+    covered = np.zeros(max(n_omega - 1, 0), dtype=int)
+    owned = np.zeros(n_omega, dtype=int)
+    for r in range(world):
+        a, b = ffd.frequency_shard(n_omega, r, world)
+        assert 0 <= a <= b <= n_omega
+        if b - a >= 2:
+            covered[a:b - 1] += 1
+        o0, o1 = ffd.owned_frequencies(n_omega, r, world)
+        owned[o0:o1] += 1
+    assert (covered == 1).all()
+    assert (owned == 1).all()
+    with pytest.raises(ValueError):
+        ffd.frequency_shard(10, 3, 3)
