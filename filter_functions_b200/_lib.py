@@ -8,6 +8,7 @@ box (the ``-m "not gpu"`` tests check that the library loads and exports every d
 import ctypes
 import os
 import threading
+import weakref
 from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
 
 import numpy as np
@@ -45,7 +46,7 @@ EXPORTED_SYMBOLS = {
                                              c_void_p]),
     'ffb_cexp': (c_int, [c_void_p, c_int, c_void_p, c_double, c_void_p]),
     'ffb_pulse_filter_function': (c_int, [c_void_p] + [c_int]*6 + [c_void_p]*9 + [c_int, c_int]
-                                  + [c_void_p]*6),
+                                  + [c_void_p]*8),
     'ffb_dev_diagonalize': (c_int, [c_void_p, c_int, c_int, c_int] + [c_void_p]*6),
     'ffb_dev_control_matrix_from_scratch': (c_int, [c_void_p] + [c_int]*5 + [c_void_p]*9
                                             + [c_int, c_void_p]),
@@ -58,6 +59,8 @@ EXPORTED_SYMBOLS = {
     'ffb_dev_free': (c_int, [c_void_p, c_void_p]),
     'ffb_memcpy_h2d': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     'ffb_memcpy_d2h': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    'ffb_host_alloc': (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
+    'ffb_host_free': (c_int, [c_void_p, c_void_p]),
     'ffb_kernel_timing_enable': (c_int, [c_void_p, c_int]),
     'ffb_kernel_timing_read': (c_int, [c_void_p, _dp, POINTER(c_int64), c_int]),
 }
@@ -121,6 +124,36 @@ def check(ctx, rc):
         from .util import CalculationError
         raise CalculationError(msg)
     raise FFBError(msg)
+
+
+#: result arrays at least this large are allocated in page-locked memory (download at PCIe speed)
+PINNED_THRESHOLD = 256 << 10
+PINNED_LIMIT = 1 << 30
+
+
+def _host_free(ctx, address):
+    try:
+        lib().ffb_host_free(ctx, address)
+    except Exception:  # interpreter shutdown
+        pass
+
+
+def empty(shape, dtype=np.complex128, ctx=None):
+    """``np.empty`` for result arrays of the engine.  Large arrays live in page-locked memory taken
+    from the library's pool, so the device->host copy that fills them runs at full PCIe speed; the
+    block goes back to the pool when the array (and all views of it) are garbage collected."""
+    shape = tuple(int(s) for s in (shape if np.iterable(shape) else (shape,)))
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64))*dtype.itemsize
+    if nbytes < PINNED_THRESHOLD or nbytes > PINNED_LIMIT:
+        return np.empty(shape, dtype=dtype)
+    ctx = context() if ctx is None else ctx
+    address = c_void_p()
+    if lib().ffb_host_alloc(ctx, nbytes, byref(address)) != FFB_OK:
+        return np.empty(shape, dtype=dtype)   # pageable still works, only slower
+    buf = (ctypes.c_char*nbytes).from_address(address.value)
+    weakref.finalize(buf, _host_free, ctx, address.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
 def ptr(arr):

@@ -152,7 +152,8 @@ void ffb_destroy(ffb_ctx* ctx) {
     cudaEventDestroy(ev.first);
     cudaEventDestroy(ev.second);
   }
-  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (auto& kv : ctx->host_free_blocks) cudaFreeHost(kv.second);
+  for (auto& kv : ctx->host_live_blocks) cudaFreeHost(kv.first);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -229,6 +230,45 @@ int ffb_dev_alloc(ffb_ctx* ctx, size_t bytes, void** ptr) {
 int ffb_dev_free(ffb_ctx* ctx, void* ptr) {
   if (!ctx) return FFB_EINVAL;
   ffb_pool_release(ctx, ptr);
+  return FFB_OK;
+}
+
+int ffb_host_alloc(ffb_ctx* ctx, size_t bytes, void** ptr) {
+  if (!ctx || !ptr) return FFB_EINVAL;
+  FFB_CUDA(ctx, cudaSetDevice(ctx->device));
+  bytes = (std::max<size_t>(bytes, 8) + 4095) & ~(size_t)4095;
+  auto it = ctx->host_free_blocks.lower_bound(bytes);
+  if (it != ctx->host_free_blocks.end() && it->first <= 2 * bytes + (1 << 20)) {
+    *ptr = it->second;
+    ctx->host_live_blocks[*ptr] = it->first;
+    ctx->host_free_blocks.erase(it);
+    return FFB_OK;
+  }
+  // keep the amount of page-locked memory bounded: drop cached blocks beyond 4 GiB
+  if (ctx->host_pool_bytes + bytes > ((size_t)4 << 30)) {
+    for (auto& kv : ctx->host_free_blocks) {
+      cudaFreeHost(kv.second);
+      ctx->host_pool_bytes -= kv.first;
+    }
+    ctx->host_free_blocks.clear();
+  }
+  cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return ffb_fail(ctx, FFB_ENOMEM, "page-locked allocation of %zu bytes failed: %s", bytes,
+                    cudaGetErrorString(e));
+  }
+  ctx->host_pool_bytes += bytes;
+  ctx->host_live_blocks[*ptr] = bytes;
+  return FFB_OK;
+}
+
+int ffb_host_free(ffb_ctx* ctx, void* ptr) {
+  if (!ctx) return FFB_EINVAL;
+  auto it = ctx->host_live_blocks.find(ptr);
+  if (it == ctx->host_live_blocks.end()) return FFB_OK;
+  ctx->host_free_blocks.emplace(it->second, ptr);
+  ctx->host_live_blocks.erase(it);
   return FFB_OK;
 }
 
@@ -497,7 +537,8 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
                               const double* spectrum, int spectrum_ndim, int spectrum_is_complex,
                               double* eigvals, double* eigvecs, double* propagators,
                               double* control_matrix, double* filter_function,
-                              double* infidelity) {
+                              double* infidelity, double* total_phases,
+                              double* total_propagator_liouville) {
   FFB_TRY(enter(ctx));
   FFB_REQUIRE(ctx, c_opers && c_coeffs && n_opers && n_coeffs && dt && t && basis && omega,
               "pulse pipeline: null input pointer");
@@ -508,7 +549,7 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
   const int herm = (all_hermitian(n_opers, n_nops, d) ? FFB_HERM_NOPERS : 0) |
                    (all_hermitian(basis, n_basis, d) ? FFB_HERM_BASIS : 0);
   Upload co, cc, no, nc, dts, ts, bs, om, sp;
-  DevBuf ev, V, Q, B, F, I, idx;
+  DevBuf ev, V, Q, B, F, I, idx, ph, liou;
   FFB_TRY(co.put(ctx, c_opers, (size_t)n_cops * dd * 16));
   FFB_TRY(cc.put(ctx, c_coeffs, (size_t)n_cops * G * 8));
   FFB_TRY(no.put(ctx, n_opers, (size_t)n_nops * dd * 16));
@@ -546,6 +587,17 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
     FFB_TRY(I.alloc(ctx, n_inf * 8));
     FFB_TRY(ffbi_infidelity(ctx, 1, n_nops, n_nops, idx.as<int>(), n_omega, F.as<double>(), sp.d(),
                             spectrum_ndim, spectrum_is_complex, om.d(), d, I.as<double>()));
+  }
+  if (total_phases) {
+    FFB_TRY(ph.alloc(ctx, (size_t)n_omega * 16));
+    FFB_TRY(ffbi_cexp(ctx, n_omega, om.d(), t[G], ph.as<double>()));  // tau = t[G] (host value)
+    FFB_TRY(ffb_d2h(ctx, total_phases, ph.p, (size_t)n_omega * 16));
+  }
+  if (total_propagator_liouville) {
+    FFB_TRY(liou.alloc(ctx, (size_t)n_basis * n_basis * 16));
+    FFB_TRY(ffbi_liouville(ctx, 1, d, n_basis, Q.as<double>() + (size_t)G * dd * 2, bs.d(),
+                           liou.as<double>()));
+    FFB_TRY(ffb_d2h(ctx, total_propagator_liouville, liou.p, (size_t)n_basis * n_basis * 16));
   }
   if (eigvals) FFB_TRY(ffb_d2h(ctx, eigvals, ev.p, (size_t)G * d * 8));
   if (eigvecs) FFB_TRY(ffb_d2h(ctx, eigvecs, V.p, (size_t)G * dd * 16));

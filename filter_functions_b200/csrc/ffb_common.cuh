@@ -29,9 +29,10 @@ struct ffb_ctx {
   std::map<void*, size_t> live_blocks;
   size_t pool_bytes = 0;
 
-  // pinned staging for small host<->device transfers
-  void* pinned = nullptr;
-  size_t pinned_bytes = 0;
+  // page-locked host blocks handed out by ffb_host_alloc (same caching scheme as the device pool)
+  std::multimap<size_t, void*> host_free_blocks;
+  std::map<void*, size_t> host_live_blocks;
+  size_t host_pool_bytes = 0;
 
   // timing of the dominant kernel
   bool timing = false;

@@ -37,9 +37,9 @@ def diagonalize(hamiltonian: ndarray, dt):
     G, d = H.shape[0], H.shape[1]
     if dt.shape != (G,):
         raise ValueError(f'Expected dt of shape ({G},), not {dt.shape}')
-    eigvals = np.empty((G, d), dtype=np.float64)
-    eigvecs = np.empty((G, d, d), dtype=np.complex128)
-    propagators = np.empty((G + 1, d, d), dtype=np.complex128)
+    eigvals = _lib.empty((G, d), np.float64)
+    eigvecs = _lib.empty((G, d, d))
+    propagators = _lib.empty((G + 1, d, d))
     ctx = _lib.context()
     _lib.check(ctx, _lib.lib().ffb_diagonalize(ctx, G, d, 0, _lib.ptr(H), None, _lib.ptr(dt),
                                                _lib.ptr(eigvals), _lib.ptr(eigvecs),
@@ -54,9 +54,9 @@ def _diagonalize_from_coeffs(c_opers, c_coeffs, dt):
     dt = _lib.as_f64(dt)
     n_cops, d = c_opers.shape[0], c_opers.shape[-1]
     G = dt.shape[0]
-    eigvals = np.empty((G, d), dtype=np.float64)
-    eigvecs = np.empty((G, d, d), dtype=np.complex128)
-    propagators = np.empty((G + 1, d, d), dtype=np.complex128)
+    eigvals = _lib.empty((G, d), np.float64)
+    eigvecs = _lib.empty((G, d, d))
+    propagators = _lib.empty((G + 1, d, d))
     ctx = _lib.context()
     _lib.check(ctx, _lib.lib().ffb_diagonalize(ctx, G, d, n_cops, _lib.ptr(c_opers),
                                                _lib.ptr(c_coeffs), _lib.ptr(dt), _lib.ptr(eigvals),
@@ -95,7 +95,7 @@ def calculate_control_matrix_from_scratch(eigvals, eigvecs, propagators, omega, 
     direct = (out is not None and out.dtype == np.complex128 and out.flags.c_contiguous
               and out.shape == (n_nops, n_basis, n_omega))
     if not direct:
-        result = np.empty((n_nops, n_basis, n_omega), dtype=np.complex128)
+        result = _lib.empty((n_nops, n_basis, n_omega))
     ctx = _lib.context()
     if n_omega:
         _lib.check(ctx, _lib.lib().ffb_control_matrix_from_scratch(
@@ -126,8 +126,7 @@ def calculate_control_matrix_from_atomic(phases, control_matrix_atomic, propagat
     q_complex = np.iscomplexobj(Q)
     Q = (_lib.as_c128(Q) if q_complex else _lib.as_f64(Q)).reshape(P - 1, n_basis, n_basis)
     corr = which == 'correlations'
-    out = np.empty((P, n_nops, n_basis, n_omega) if corr else (n_nops, n_basis, n_omega),
-                   dtype=np.complex128)
+    out = _lib.empty((P, n_nops, n_basis, n_omega) if corr else (n_nops, n_basis, n_omega))
     ctx = _lib.context()
     _lib.check(ctx, _lib.lib().ffb_control_matrix_from_atomic(
         ctx, P, n_nops, n_basis, n_omega, _lib.ptr(phases), _lib.ptr(atomic), _lib.ptr(Q),
@@ -147,7 +146,7 @@ def _filter_function(control_matrix, which, P):
     shape = (n_nops, n_nops) + ((n_basis, n_basis) if gen else ()) + (n_omega,)
     if P is not None:
         shape = (P, P) + shape
-    F = np.empty(shape, dtype=np.complex128)
+    F = _lib.empty(shape)
     if F.size:
         ctx = _lib.context()
         _lib.check(ctx, _lib.lib().ffb_filter_function(ctx, 1 if P is None else P, n_nops, n_basis,
@@ -245,6 +244,12 @@ def infidelity(pulse, spectrum, omega, n_oper_identifiers=None, which: str = 'to
         return n_samples, convergence_infids
 
     spectrum = np.asarray(spectrum)
+    if (which == 'total' and n_oper_identifiers is None and not cache_intermediates
+            and not return_smallness and len(omega) and pulse.basis.istraceless
+            and pulse._is_cold()):
+        # cold pulse, all noise operators: diagonalisation, control matrix, filter function and the
+        # integral in ONE library call (everything stays on the device in between)
+        return pulse._cold_pipeline(omega, util.parse_spectrum(spectrum, omega, idx))
     if which == 'total':
         if not pulse.basis.istraceless:
             # Trace tensor enters (numeric.py:2295-2305): F_ab = sum_kl B*_ak T_kl B_bl / d with

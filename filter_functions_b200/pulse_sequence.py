@@ -371,9 +371,18 @@ class PulseSequence:
             + "concatenation again with 'calc_pulse_correlation_FF' set to "
             + "True.")
 
-    def _cold_pipeline(self, omega) -> None:
-        """Cold cache + fidelity filter function: one fused library call (single upload, all
-        kernels back to back, single download) instead of three round trips."""
+    def _is_cold(self) -> bool:
+        """Nothing of the path cached yet (so the fused one-call pipeline applies)."""
+        return not (any(k in self._frequency_data for k in ('control_matrix', 'control_matrix_pc',
+                                                            'filter_function'))
+                    or any(k in self._data for k in ('eigvals', 'eigvecs', 'propagators')))
+
+    def _cold_pipeline(self, omega, spectrum=None):
+        """Cold cache + fidelity filter function: ONE library call (single upload, all kernels back
+        to back, single download) instead of one round trip per stage; caches exactly what the
+        step-by-step route caches.  With ``spectrum`` (already broadcast for all noise operators) the
+        infidelity integral runs in the same call and is returned."""
+        self.omega = omega
         omega_arr = _lib.as_f64(self.omega)
         c_opers, c_coeffs = _lib.as_c128(self.c_opers), _lib.as_f64(self.c_coeffs)
         n_opers, n_coeffs = _lib.as_c128(self.n_opers), _lib.as_f64(self.n_coeffs)
@@ -381,21 +390,31 @@ class PulseSequence:
         basis = _lib.as_c128(np.asarray(self.basis))
         G, d = len(dt), self.d
         n_cops, n_nops, n_basis, n_omega = len(c_opers), len(n_opers), len(basis), len(omega_arr)
-        eigvals = np.empty((G, d))
-        eigvecs = np.empty((G, d, d), dtype=complex)
-        propagators = np.empty((G + 1, d, d), dtype=complex)
-        B = np.empty((n_nops, n_basis, n_omega), dtype=complex)
-        F = np.empty((n_nops, n_nops, n_omega), dtype=complex)
+        eigvals = _lib.empty((G, d), np.float64)
+        eigvecs = _lib.empty((G, d, d))
+        propagators = _lib.empty((G + 1, d, d))
+        B = _lib.empty((n_nops, n_basis, n_omega))
+        F = _lib.empty((n_nops, n_nops, n_omega))
+        phases = np.empty(n_omega, dtype=np.complex128)
+        liouville = np.empty((n_basis, n_basis), dtype=np.complex128)
+        S = infid = None
+        s_ndim = s_complex = 0
+        if spectrum is not None:
+            s_ndim, s_complex = spectrum.ndim, int(np.iscomplexobj(spectrum))
+            S = _lib.as_c128(spectrum) if s_complex else _lib.as_f64(spectrum)
+            infid = np.empty((n_nops, n_nops) if s_ndim == 3 else (n_nops,), dtype=np.float64)
         ctx = _lib.context()
         p = _lib.ptr
         _lib.check(ctx, _lib.lib().ffb_pulse_filter_function(
             ctx, G, d, n_cops, n_nops, n_basis, n_omega, p(c_opers), p(c_coeffs), p(n_opers),
-            p(n_coeffs), p(dt), p(t), p(basis), p(omega_arr), None, 0, 0, p(eigvals), p(eigvecs),
-            p(propagators), p(B), p(F), None))
+            p(n_coeffs), p(dt), p(t), p(basis), p(omega_arr), p(S), s_ndim, s_complex, p(eigvals),
+            p(eigvecs), p(propagators), p(B), p(F), p(infid), p(phases), p(liouville)))
         self._data.update(eigvals=eigvals, eigvecs=eigvecs, propagators=propagators,
                           total_propagator=propagators[-1])
-        self.cache_control_matrix(self.omega, B)
-        self._frequency_data['filter_function'] = F
+        self._data['total_propagator_liouville'] = (
+            np.ascontiguousarray(liouville.real) if self.basis.isherm else liouville)
+        self._frequency_data.update(control_matrix=B, total_phases=phases, filter_function=F)
+        return infid
 
     @util.parse_optional_parameters(which=('fidelity', 'generalized'), order=(1, 2))
     def get_filter_function(self, omega, which: str = 'fidelity', order: int = 1,
@@ -410,9 +429,8 @@ class PulseSequence:
         key = 'filter_function' if which == 'fidelity' else 'filter_function_gen'
         if key in self._frequency_data:
             return self._frequency_data[key]
-        cold = not any(k in self._frequency_data for k in ('control_matrix', 'control_matrix_pc'))
-        cold = cold and not any(k in self._data for k in ('eigvals', 'eigvecs', 'propagators'))
-        if cold and which == 'fidelity' and not cache_intermediates and len(self.omega):
+        if (which == 'fidelity' and not cache_intermediates and len(self.omega)
+                and self._is_cold()):
             self._cold_pipeline(self.omega)
             return self._frequency_data[key]
         control_matrix = self.get_control_matrix(self.omega, show_progressbar, cache_intermediates)

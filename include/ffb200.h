@@ -125,15 +125,18 @@ int ffb_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out);
 /* ---- fused pulse pipeline ------------------------------------------------------------------------
  * What PulseSequence.get_filter_function (pulse_sequence.py:691-805) does on a cold cache, in one
  * call with one upload and one download: diagonalize -> control matrix -> fidelity filter function
- * (-> infidelity if spectrum != NULL).  Any output pointer may be NULL to skip its download.
- * spectrum as in ffb_infidelity with n_sel = n_nops, idx = 0..n_nops-1. */
+ * (-> infidelity if spectrum != NULL), plus the two by-products cache_control_matrix keeps
+ * (pulse_sequence.py:674-677): total_phases = exp(i omega tau) (n_omega) c128 and the Liouville
+ * representation of the total propagator (n_basis,n_basis) c128.  Any output pointer may be NULL to
+ * skip it.  spectrum as in ffb_infidelity with n_sel = n_nops, idx = 0..n_nops-1. */
 int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops, int n_basis,
                               int n_omega, const double* c_opers, const double* c_coeffs,
                               const double* n_opers, const double* n_coeffs, const double* dt,
                               const double* t, const double* basis, const double* omega,
                               const double* spectrum, int spectrum_ndim, int spectrum_is_complex,
                               double* eigvals, double* eigvecs, double* propagators,
-                              double* control_matrix, double* filter_function, double* infidelity);
+                              double* control_matrix, double* filter_function, double* infidelity,
+                              double* total_phases, double* total_propagator_liouville);
 
 /* ---- device-resident variants (pointers are device pointers; asynchronous on the stream) -------- */
 int ffb_dev_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_opers,
@@ -165,6 +168,13 @@ int ffb_dev_alloc(ffb_ctx* ctx, size_t bytes, void** ptr);
 int ffb_dev_free(ffb_ctx* ctx, void* ptr);
 int ffb_memcpy_h2d(ffb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int ffb_memcpy_d2h(ffb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* Page-locked host memory from a caching pool.  Result arrays allocated here make the device->host
+ * copies of the host-pointer entry points run at full PCIe speed (the library detects pinned
+ * destinations by itself); pageable buffers work too, just slower.  ffb_host_free returns the block to
+ * the pool. */
+int ffb_host_alloc(ffb_ctx* ctx, size_t bytes, void** ptr);
+int ffb_host_free(ffb_ctx* ctx, void* ptr);
 
 /* Kernel-level timing of the control-matrix main kernel: average duration (ms) of the launches of
  * the dominant kernel recorded with CUDA events on the launching stream since the last reset. */
