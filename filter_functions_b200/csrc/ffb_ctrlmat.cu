@@ -217,6 +217,98 @@ transform_kernel(int G, int d, int n_nops, int n_basis, int parts_j, int parts_k
   }
 }
 
+// Small Hilbert spaces (d <= 4): one THREAD per (segment, operator), everything in registers.  The
+// block-per-segment kernel above spends its time in __syncthreads for 2x2 matrices (66 us for
+// G = 1e4, d = 2 in the first version).
+template <int D>
+__global__ void __launch_bounds__(128)
+transform_small_kernel(int G, int n_nops, int n_basis, int parts_j, int parts_k,
+                       const double2* __restrict__ eigvecs, const double2* __restrict__ propagators,
+                       const double2* __restrict__ n_opers, const double* __restrict__ n_coeffs,
+                       const double2* __restrict__ basis, double2* __restrict__ Bbar,
+                       double2* __restrict__ Cbar) {
+  constexpr int DD = D * D;
+  const int n_ops = n_nops + n_basis;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)G * n_ops) return;
+  const int g = (int)(idx / n_ops), op = (int)(idx % n_ops);
+  const bool is_noise = op < n_nops;
+  double2 W[DD];
+  {
+    double2 V[DD];
+#pragma unroll
+    for (int e = 0; e < DD; ++e) V[e] = eigvecs[(size_t)g * DD + e];
+    if (is_noise) {
+#pragma unroll
+      for (int e = 0; e < DD; ++e) W[e] = V[e];
+    } else {  // W = Q_g^+ V_g
+      double2 Q[DD];
+#pragma unroll
+      for (int e = 0; e < DD; ++e) Q[e] = propagators[(size_t)g * DD + e];
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+#pragma unroll
+        for (int b = 0; b < D; ++b) {
+          double re = 0.0, im = 0.0;
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            const double2 qv = Q[c * D + a], vv = V[c * D + b];  // conj(Q[c][a]) * V[c][b]
+            re += qv.x * vv.x + qv.y * vv.y;
+            im += qv.x * vv.y - qv.y * vv.x;
+          }
+          W[a * D + b] = make_double2(re, im);
+        }
+      }
+    }
+  }
+  const double2* O = is_noise ? n_opers + (size_t)op * DD : basis + (size_t)(op - n_nops) * DD;
+  double2 T[DD];
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+#pragma unroll
+    for (int b = 0; b < D; ++b) {  // T = O W
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double2 o = O[a * D + c], w = W[c * D + b];
+        re += o.x * w.x - o.y * w.y;
+        im += o.x * w.y + o.y * w.x;
+      }
+      T[a * D + b] = make_double2(re, im);
+    }
+  }
+  double2 X[DD];
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+#pragma unroll
+    for (int b = 0; b < D; ++b) {  // X = W^+ T
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double2 w = W[c * D + a], t = T[c * D + b];
+        re += w.x * t.x + w.y * t.y;
+        im += w.x * t.y - w.y * t.x;
+      }
+      X[a * D + b] = make_double2(re, im);
+    }
+  }
+  const int parts = is_noise ? parts_j : parts_k;
+  const double scale = is_noise ? n_coeffs[(size_t)op * G + g] : 1.0;
+  double2* dst = is_noise ? Bbar + ((size_t)g * n_nops * parts_j + (size_t)op * parts_j) * DD
+                          : Cbar + ((size_t)g * n_basis * parts_k + (size_t)(op - n_nops) * parts_k) * DD;
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+#pragma unroll
+    for (int b = 0; b < D; ++b) {
+      const double2 x = X[a * D + b], xt = X[b * D + a];  // xt -> conj below
+      dst[a * D + b] = make_double2(scale * 0.5 * (x.x + xt.x), scale * 0.5 * (x.y - xt.y));
+      if (parts == 2) {
+        dst[DD + a * D + b] = make_double2(scale * 0.5 * (x.y + xt.y), -scale * 0.5 * (x.x - xt.x));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // prologue 2: the operand stream of the main kernel.
 // Per row block rb and pass (4 consecutive segments) the stream holds 1 + n_pairs units:
@@ -387,6 +479,9 @@ __device__ __forceinline__ void gen_diag_slow(Gen& g, const double* unit_consts,
   }
 }
 __device__ __forceinline__ void gen_diag_fast(Gen& g, const double* unit_consts, int q, Vals& v) {
+#ifdef FFB_EXP_NOGEN
+  v.a_re = unit_consts[q]; v.a_im = g.j0_im; return;
+#endif
   sincos_cw(g.w * unit_consts[q], g.ph_im, g.ph_re);
   v.a_re = g.ph_re * g.j0_re - g.ph_im * g.j0_im;
   v.a_im = g.ph_re * g.j0_im + g.ph_im * g.j0_re;
@@ -399,6 +494,9 @@ __device__ __forceinline__ void gen_diag(Gen& g, const double* unit_consts, int 
 // ---- pair unit (product form): S = I(w + Om) + I(w - Om), D = i (I(w + Om) - I(w - Om)), times phase.
 // Returns true if this lane needs the direct re-evaluation (cancellation in sin((w +- Om) dt / 2)).
 __device__ __forceinline__ bool gen_pair(const Gen& g, const double* unit_consts, int q, Vals& v) {
+#ifdef FFB_EXP_NOGEN
+  v.a_re = unit_consts[q]; v.a_im = unit_consts[4 + q]; v.b_re = unit_consts[8 + q]; v.b_im = g.w; return false;
+#endif
   const double Om = unit_consts[q], Ch = unit_consts[4 + q], Sh = unit_consts[8 + q];
   const double t1 = g.hc * Ch, t3 = g.hs * Ch;
   const double zp_re = fma(-g.hs, Sh, t1), zp_im = fma(g.hc, Sh, t3);  // sqrt2 e^{i (w+Om) dt/2}
@@ -463,7 +561,7 @@ __device__ __forceinline__ void mma_pair(double (&acc_re)[MT][2], double (&acc_i
 }
 
 template <int MT, int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, (MT <= 2 ? 3 : MT >= 12 ? 3 : 1))
 ctrlmat_main_kernel(const MainParams p) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
@@ -553,8 +651,9 @@ ctrlmat_main_kernel(const MainParams p) {
   // CURRENT unit; the operands of the next unit are generated in the same basic block as the current
   // unit's DMMAs.
   const int total_units = n_passes * n_units;
-  if (p.n_sp == 1 && p.n_pairs >= 1) {
-    // fast path: stages hold whole passes; nested loops with next to no bookkeeping per unit
+  if (p.n_pairs >= 1) {
+    // fast path: tight loops over runs of pair units; all stage bookkeeping happens only on the unit
+    // that ends a stage (which may be anywhere inside a pass when a pass is split into pieces).
     const int n_pairs = p.n_pairs;
     const int diag_unit = p.diag_unit, pair_unit = p.pair_unit;
     auto apply_fix = [&](bool fix, const double* consts, Vals& vn) {
@@ -568,67 +667,87 @@ ctrlmat_main_kernel(const MainParams p) {
         }
       }
     };
+    int stage = 0;
+    int left = n_stages > 0 ? stage_units(0) : 0;  // units left in the current stage (incl. current)
+    // called before generating the operands of the unit that follows the LAST unit of a stage
+    auto next_stage_ready = [&]() {
+      cp_async_wait<0>();  // the only outstanding group is stage + 1
+      __syncthreads();
+    };
+    // called after the DMMAs of the last unit of a stage
+    auto retire_stage = [&]() {
+      __syncthreads();  // everyone is done reading cur_buf
+      if (stage + 2 < n_stages) {
+        stage_load(stage + 2, cur_buf);
+        cp_async_commit();
+      }
+      double* tmp = cur_buf;
+      cur_buf = nxt_buf;
+      nxt_buf = tmp;
+      ++stage;
+      left = stage_units(stage);
+    };
     Vals v = {0.0, 0.0, 0.0, 0.0};
-    if (n_stages > 0) gen_diag(g, cur_buf + MT * 32, q, v);
-    for (int stage = 0; stage < n_stages; ++stage) {
-      const int n_here = min(p.pps, n_passes - stage * p.pps);
-      const bool more_stages = stage + 1 < n_stages;
-      const double* up = cur_buf;
-      for (int ip = 0; ip < n_here; ++ip) {
-        Vals vn;
-        // diagonal unit  ||  operands of pair 0
-        const double* pu = up + diag_unit;
-        {
-          const bool fix = gen_pair(g, pu + 2 * MT * 32, q, vn);
-          mma_diag<MT>(acc_re, acc_im, up, lane, v);
-          apply_fix(fix, pu + 2 * MT * 32, vn);
-          v = vn;
-        }
-        // pair i  ||  operands of pair i + 1
-        for (int pi = 0; pi + 1 < n_pairs; ++pi) {
-          const double* pn = pu + pair_unit;
+    const double* up = cur_buf;
+    if (n_passes > 0) gen_diag(g, up + MT * 32, q, v);
+    for (int pass = 0; pass < n_passes; ++pass) {
+      Vals vn;
+      // ---- diagonal unit  ||  operands of pair 0
+      {
+        const bool boundary = (left == 1);
+        if (boundary) next_stage_ready();
+        const double* pn = boundary ? nxt_buf : up + diag_unit;
+        const bool fix = gen_pair(g, pn + 2 * MT * 32, q, vn);
+        mma_diag<MT>(acc_re, acc_im, up, lane, v);
+        apply_fix(fix, pn + 2 * MT * 32, vn);
+        v = vn;
+        if (boundary) retire_stage(); else --left;
+        up = pn;
+      }
+      // ---- pair i  ||  operands of pair i + 1
+      int pi = 0;
+      while (pi + 1 < n_pairs) {
+        const int run = min(n_pairs - 1 - pi, left - 1);  // steps that stay inside this stage
+        for (int i = 0; i < run; ++i) {
+          const double* pn = up + pair_unit;
           const bool fix = gen_pair(g, pn + 2 * MT * 32, q, vn);
-          mma_pair<MT>(acc_re, acc_im, pu, lane, v);
+          mma_pair<MT>(acc_re, acc_im, up, lane, v);
           apply_fix(fix, pn + 2 * MT * 32, vn);
           v = vn;
-          pu = pn;
+          up = pn;
         }
-        // last pair  ||  diagonal operands of the next pass (possibly in the next stage's buffer)
-        const double* dn = pu + pair_unit;
-        bool has_next = true;
-        if (ip + 1 == n_here) {
-          if (more_stages) {
-            cp_async_wait<0>();  // the only outstanding group is stage + 1
-            __syncthreads();
-            dn = nxt_buf;
-          } else {
-            has_next = false;
-          }
-        }
-        if (has_next) {
-          gen_diag_slow(g, dn + MT * 32, q);
-          gen_diag_fast(g, dn + MT * 32, q, vn);
-          mma_pair<MT>(acc_re, acc_im, pu, lane, v);
+        pi += run;
+        left -= run;
+        if (pi + 1 < n_pairs) {  // left == 1: the next pair lives in the next stage
+          next_stage_ready();
+          const double* pn = nxt_buf;
+          const bool fix = gen_pair(g, pn + 2 * MT * 32, q, vn);
+          mma_pair<MT>(acc_re, acc_im, up, lane, v);
+          apply_fix(fix, pn + 2 * MT * 32, vn);
           v = vn;
-        } else {
-          mma_pair<MT>(acc_re, acc_im, pu, lane, v);
+          retire_stage();
+          up = pn;
+          ++pi;
         }
-        up = dn;
       }
-      if (more_stages) {
-        __syncthreads();  // everyone is done reading cur_buf
-        if (stage + 2 < n_stages) {
-          stage_load(stage + 2, cur_buf);
-          cp_async_commit();
-        }
-        double* tmp = cur_buf;
-        cur_buf = nxt_buf;
-        nxt_buf = tmp;
+      // ---- last pair  ||  diagonal operands of the next pass
+      if (pass + 1 < n_passes) {
+        const bool boundary = (left == 1);
+        if (boundary) next_stage_ready();
+        const double* dn = boundary ? nxt_buf : up + pair_unit;
+        gen_diag_slow(g, dn + MT * 32, q);
+        gen_diag_fast(g, dn + MT * 32, q, vn);
+        mma_pair<MT>(acc_re, acc_im, up, lane, v);
+        v = vn;
+        if (boundary) retire_stage(); else --left;
+        up = dn;
+      } else {
+        mma_pair<MT>(acc_re, acc_im, up, lane, v);
       }
     }
   } else {
-    // generic path (a pass is split over several stages, or d == 1): flat walk over the units; unit k
-    // is a diagonal unit iff k % n_units == 0.
+    // d == 1 (no pair units): flat walk over the units; unit k is a diagonal unit iff
+    // k % n_units == 0.
     int stage = 0;
     int left_in_stage = n_stages > 0 ? stage_units(0) : 0;
     const double* up = cur_buf;
@@ -792,9 +911,10 @@ int pick_mt(int mt_total) {
   return 12;
 }
 
-// Row tiles per warp and warps per CTA.  Heavy accumulator tiles (MT >= 8, ~160 registers) run with 4
-// warps per CTA so that two or three INDEPENDENT CTAs share an SM: their barriers and unit boundaries
-// are uncorrelated, which keeps the FP64 pipe fed while one warp does its bookkeeping.
+// Row tiles per warp and warps per CTA.  Heavy accumulator tiles (MT >= 8, 130-160 registers) run with
+// 4 warps per CTA (one per scheduler; 6 measured slower because the schedulers are then unevenly
+// loaded) so that three or four INDEPENDENT CTAs share an SM: their barriers and unit boundaries are
+// uncorrelated, which keeps the FP64 pipe fed while one warp does its bookkeeping.
 #define FFB_DISPATCH_MT(MTV, CALL)                                  \
   switch (MTV) {                                                    \
     case 1: { constexpr int MT_ = 1, NW_ = 8; CALL; } break;        \
@@ -833,7 +953,20 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   FFB_TRY(Cbar.alloc(ctx, (size_t)G * n_krows * dd * 16));
   FFB_TRY(stream.alloc(ctx, geo.rb_doubles * geo.n_rb * sizeof(double)));
 
-  {
+  if (d >= 2 && d <= 4) {
+    const long long n_threads = (long long)G * (n_nops + n_basis);
+    const unsigned blocks = (unsigned)((n_threads + 127) / 128);
+    auto args = [&](auto kern) {
+      kern<<<blocks, 128, 0, ctx->stream>>>(
+          G, n_nops, n_basis, parts_j, parts_k, reinterpret_cast<const double2*>(eigvecs),
+          reinterpret_cast<const double2*>(propagators), reinterpret_cast<const double2*>(n_opers),
+          n_coeffs, reinterpret_cast<const double2*>(basis), Bbar.as<double2>(), Cbar.as<double2>());
+    };
+    if (d == 2) args(transform_small_kernel<2>);
+    else if (d == 3) args(transform_small_kernel<3>);
+    else args(transform_small_kernel<4>);
+    FFB_LAUNCHED(ctx);
+  } else {
     const size_t smem = (size_t)8 * dd * sizeof(double);
     FFB_CUDA(ctx, cudaFuncSetAttribute(transform_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -862,16 +995,24 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   p.rb_doubles = geo.rb_doubles;
   p.diag_unit = geo.diag_unit;
   p.pair_unit = geo.pair_unit;
+  // Stage size: small enough that shared memory does not limit the number of resident CTAs below what
+  // the register file allows (independent CTAs decorrelate the warps that share an FP64 pipe), large
+  // enough to amortise the two barriers per stage.
+  int ctas_by_regs = 1;
+  FFB_DISPATCH_MT(MT, FFB_TRY((occupancy<MT_, NW_>(ctx, 0, &ctas_by_regs))));
+  ctas_by_regs = std::max(1, std::min(ctas_by_regs, 8));
+  const size_t stage_budget = std::min<size_t>(STAGE_MAX_BYTES,
+                                               ((size_t)216 * 1024 / ctas_by_regs) / 2);
   const size_t pass_bytes = geo.pass_doubles * sizeof(double);
-  if (pass_bytes <= (size_t)STAGE_MAX_BYTES) {
+  if (pass_bytes <= stage_budget) {
     p.n_sp = 1;
-    p.pps = (int)std::max<size_t>(1, STAGE_TARGET_BYTES / pass_bytes);
+    p.pps = (int)std::max<size_t>(1, std::min<size_t>(stage_budget, STAGE_TARGET_BYTES) / pass_bytes);
     p.pps = std::min(p.pps, 32);
     p.stage_doubles = (int)(p.pps * geo.pass_doubles);
   } else {
     p.pps = 1;
     const int n_units = 1 + geo.n_pairs;
-    int n_sp = (int)ceil_div_sz(pass_bytes, STAGE_TARGET_BYTES);
+    int n_sp = (int)ceil_div_sz(pass_bytes, stage_budget);
     n_sp = std::min(n_sp, n_units);
     // largest piece under this split
     int max_piece = 0;
@@ -884,7 +1025,7 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
         if (u0 == 0) len += geo.diag_unit - geo.pair_unit;
         max_piece = std::max(max_piece, len);
       }
-      if ((size_t)max_piece * sizeof(double) <= (size_t)STAGE_MAX_BYTES || n_sp == n_units) break;
+      if ((size_t)max_piece * sizeof(double) <= stage_budget || n_sp == n_units) break;
       ++n_sp;
     }
     p.n_sp = n_sp;

@@ -72,12 +72,12 @@ ff_generalized_kernel(int P, int n_nops, int n_basis, int n_omega, const double2
 
 // One block per output element: trapezoid of Re(F S) over omega, warp-shuffle + shared reduction in a
 // fixed order (deterministic).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 infidelity_kernel(int n_nops, int n_sel, const int* __restrict__ idx, int n_omega,
                   const double2* __restrict__ F, const double* __restrict__ spectrum,
                   int spectrum_ndim, int spectrum_is_complex, const double* __restrict__ omega,
                   double norm, double* __restrict__ out) {
-  __shared__ double warp_sums[8];
+  __shared__ double warp_sums[32];
   const int o = blockIdx.x;  // output index
   int lead, a, b;
   if (spectrum_ndim == 3) {
@@ -109,7 +109,7 @@ infidelity_kernel(int n_nops, int n_sel, const int* __restrict__ idx, int n_omeg
   __syncthreads();
   if (threadIdx.x == 0) {
     double total = 0.0;
-    for (int i = 0; i < 8; ++i) total += warp_sums[i];
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) total += warp_sums[i];
     out[o] = total / 2.0 / norm;
   }
 }
@@ -151,7 +151,8 @@ int ffbi_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* 
               n_omega, d);
   const int n_out = n_lead * (spectrum_ndim == 3 ? n_sel * n_sel : n_sel);
   const double norm = 2.0 * 3.141592653589793238462643383279502884 * d;
-  infidelity_kernel<<<n_out, 256, 0, ctx->stream>>>(
+  const int threads = n_omega > 4096 ? 1024 : 256;
+  infidelity_kernel<<<n_out, threads, 0, ctx->stream>>>(
       n_nops, n_sel, idx_dev, n_omega, reinterpret_cast<const double2*>(F), spectrum,
       spectrum_ndim, spectrum_is_complex, omega, norm, out);
   FFB_LAUNCHED(ctx);

@@ -52,6 +52,41 @@ __global__ void k_dmma(double* out, double a, double b) {
   if (s == 123.456) out[0] = s;
 }
 
+// The inner loop of the control-matrix kernel without the operand generator: A fragments come from
+// shared memory (one LDS.64 per row tile), two accumulator tiles (Re/Im) per row tile and NT frequency
+// tiles per warp.  Does the LDS-fed DMMA stream reach the register-resident peak?
+template <int MT, int NT>
+__global__ void k_dmma_lds(double* out, double b0, double b1, int units) {
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 2 * MT * 32; i += blockDim.x) sm[i] = 1.0 + i * 1e-6;
+  __syncthreads();
+  double cre[NT][MT][2], cim[NT][MT][2];
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) { cre[n][m][0] = cre[n][m][1] = 0.0; cim[n][m][0] = cim[n][m][1] = 0.0; }
+  for (int u = 0; u < units; ++u) {
+    const double* up = sm + (u & 1) * MT * 32;
+    const double br = b0 + u, bi = b1 - u;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const double a = up[m * 32 + lane];
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        dmma884(cre[n][m][0], cre[n][m][1], a, br + n);
+        dmma884(cim[n][m][0], cim[n][m][1], a, bi + n);
+      }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) s += cre[n][m][0] + cre[n][m][1] + cim[n][m][0] + cim[n][m][1];
+  if (s == 123.456) out[0] = s;
+}
+
 // R DFMA per DMMA, both streams independent.
 template <int R>
 __global__ void k_mixed(double* out, double a, double b) {
@@ -221,6 +256,24 @@ int main() {
       printf("{\"bench\":\"dmma24\",\"threads\":%d,\"blocks_per_sm\":%d,\"ms\":%.4f,\"tflops\":%.3f}\n",
              threads, bps, ms, fl / ms * 1e-9);
     }
+  }
+  {
+    const int units = 4096;
+    auto run = [&](auto kern, int mt, int nt, int threads, int bps, const char* name) {
+      const int grid = sms * bps;
+      const size_t smem = 2 * mt * 32 * sizeof(double);
+      double ms = time_ms([&] { kern<<<grid, threads, smem>>>(out, 1.0000001, 1e-9, units); }, reps);
+      double fl = 2.0 * 256 * 2 * mt * nt * units * (double)grid * (threads / 32);
+      printf("{\"bench\":\"%s\",\"MT\":%d,\"NT\":%d,\"threads\":%d,\"blocks_per_sm\":%d,\"ms\":%.4f,\"tflops\":%.3f}\n",
+             name, mt, nt, threads, bps, ms, fl / ms * 1e-9);
+    };
+    run(k_dmma_lds<12, 1>, 12, 1, 128, 1, "dmma_lds");
+    run(k_dmma_lds<12, 1>, 12, 1, 128, 2, "dmma_lds");
+    run(k_dmma_lds<12, 1>, 12, 1, 256, 1, "dmma_lds");
+    run(k_dmma_lds<6, 2>, 6, 2, 128, 2, "dmma_lds");
+    run(k_dmma_lds<6, 2>, 6, 2, 256, 1, "dmma_lds");
+    run(k_dmma_lds<2, 1>, 2, 1, 256, 3, "dmma_lds");
+    run(k_dmma_lds<2, 4>, 2, 4, 256, 3, "dmma_lds");
   }
   {
     const int threads = 256, grid = sms * 4;
