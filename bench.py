@@ -25,6 +25,12 @@ import sys
 import threading
 import time
 
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the reference arm is the reference's CPU path
+    # on ALL host cores, so undo that before NumPy/OpenBLAS load.
+    for _var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_var] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -260,9 +266,13 @@ def run_b200(args):
         [[op, c, i] for op, c, i in zip(wl.n_opers, wl.n_coeffs, wl.n_ids)],
         wl.dt, ff.Basis(wl.basis, btype='Pauli'))
 
+    # N > 1: the user-facing call takes the GLOBAL grid; distributed.infidelity shards it (this
+    # rank's block is exactly wl.omega above) and all-reduces the partial integrals.
+    wl_global = base.with_omega(omega_global) if world > 1 else wl
+
     def e2e_step():
         pulse.cleanup('all')
-        return ffd.infidelity(pulse, wl.spectrum, wl.omega) if world > 1 else \
+        return ffd.infidelity(pulse, wl_global.spectrum, wl_global.omega) if world > 1 else \
             ff.infidelity(pulse, wl.spectrum, wl.omega)
 
     for _ in range(3):

@@ -11,12 +11,12 @@ NumPy arrays in, NumPy arrays out; the arithmetic runs in hand-written sm_100a C
 """
 from . import basis, numeric, pulse_sequence, superoperator, util
 from .basis import Basis
-from .numeric import infidelity
+from .numeric import error_transfer_matrix, infidelity
 from .pulse_sequence import PulseSequence, concatenate, concatenate_without_filter_function
 from .superoperator import liouville_representation
 
 __all__ = ['Basis', 'PulseSequence', 'basis', 'concatenate', 'concatenate_without_filter_function',
-           'infidelity', 'liouville_representation', 'numeric', 'pulse_sequence', 'superoperator',
-           'util']
+           'error_transfer_matrix', 'infidelity', 'liouville_representation', 'numeric',
+           'pulse_sequence', 'superoperator', 'util']
 
 __version__ = '0.1.0'

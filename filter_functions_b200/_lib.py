@@ -42,6 +42,10 @@ EXPORTED_SYMBOLS = {
                                        + [c_int, c_int, c_void_p]),
     'ffb_infidelity': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                c_int, c_int, c_void_p, c_int, c_void_p]),
+    'ffb_decay_amplitudes': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                     c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'ffb_dev_decay_amplitudes': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                         c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'ffb_liouville_representation': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                              c_void_p]),
     'ffb_cexp': (c_int, [c_void_p, c_int, c_void_p, c_double, c_void_p]),

@@ -330,6 +330,15 @@ int ffb_dev_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const in
                          spectrum_is_complex, omega, d, out);
 }
 
+int ffb_dev_decay_amplitudes(ffb_ctx* ctx, int P, int n_nops, int n_sel, const int* idx,
+                             int n_basis, int n_omega, const double* B, const double* spectrum,
+                             int spectrum_ndim, int spectrum_is_complex, const double* omega,
+                             double* out) {
+  if (!ctx) return FFB_EINVAL;
+  return ffbi_decay_amplitudes(ctx, P, n_nops, n_sel, idx, n_basis, n_omega, B, spectrum,
+                               spectrum_ndim, spectrum_is_complex, omega, out);
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
@@ -494,6 +503,36 @@ int ffb_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* i
   FFB_TRY(res.alloc(ctx, n_out * 8));
   FFB_TRY(ffbi_infidelity(ctx, n_lead, n_nops, n_sel, Id.buf.as<int>(), n_omega, Fd.d(), Sd.d(),
                           spectrum_ndim, spectrum_is_complex, Od.d(), d, res.as<double>()));
+  FFB_TRY(ffb_d2h(ctx, out, res.p, n_out * 8));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_decay_amplitudes(ffb_ctx* ctx, int P, int n_nops, int n_sel, const int* idx, int n_basis,
+                         int n_omega, const double* B, const double* spectrum, int spectrum_ndim,
+                         int spectrum_is_complex, const double* omega, double* out) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, idx && B && spectrum && omega && out, "decay amplitudes: null pointer");
+  FFB_REQUIRE(ctx, spectrum_ndim >= 1 && spectrum_ndim <= 3, "decay amplitudes: spectrum_ndim=%d",
+              spectrum_ndim);
+  FFB_REQUIRE(ctx, P >= 1 && n_nops >= 1 && n_sel >= 1 && n_basis >= 1 && n_omega >= 1,
+              "decay amplitudes: bad shape");
+  for (int i = 0; i < n_sel; ++i)
+    FFB_REQUIRE(ctx, idx[i] >= 0 && idx[i] < n_nops, "decay amplitudes: idx[%d]=%d out of range", i,
+                idx[i]);
+  Upload Bd, Sd, Od, Id;
+  DevBuf res;
+  const size_t n_pairs = spectrum_ndim == 3 ? (size_t)n_sel * n_sel : n_sel;
+  const size_t s_elems = (spectrum_ndim == 1 ? 1 : n_pairs) * n_omega;
+  FFB_TRY(Bd.put(ctx, B, (size_t)P * n_nops * n_basis * n_omega * 16));
+  FFB_TRY(Sd.put(ctx, spectrum, s_elems * (spectrum_is_complex ? 16 : 8)));
+  FFB_TRY(Od.put(ctx, omega, (size_t)n_omega * 8));
+  FFB_TRY(Id.put(ctx, idx, (size_t)n_sel * sizeof(int)));
+  const size_t n_out = (size_t)P * P * n_pairs * n_basis * n_basis;
+  FFB_TRY(res.alloc(ctx, n_out * 8));
+  FFB_TRY(ffbi_decay_amplitudes(ctx, P, n_nops, n_sel, Id.buf.as<int>(), n_basis, n_omega, Bd.d(),
+                                Sd.d(), spectrum_ndim, spectrum_is_complex, Od.d(),
+                                res.as<double>()));
   FFB_TRY(ffb_d2h(ctx, out, res.p, n_out * 8));
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return FFB_OK;

@@ -121,6 +121,10 @@ int ffbi_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
 int ffbi_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* idx_dev,
                     int n_omega, const double* F, const double* spectrum, int spectrum_ndim,
                     int spectrum_is_complex, const double* omega, int d, double* out);
+int ffbi_decay_amplitudes(ffb_ctx* ctx, int P, int n_nops, int n_sel, const int* idx_dev,
+                          int n_basis, int n_omega, const double* B, const double* spectrum,
+                          int spectrum_ndim, int spectrum_is_complex, const double* omega,
+                          double* out);
 int ffbi_liouville(ffb_ctx* ctx, int n, int d, int n_basis, const double* U, const double* basis,
                    double* out);
 int ffbi_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out);

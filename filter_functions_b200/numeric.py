@@ -23,8 +23,9 @@ from numpy import ndarray
 from . import _lib, util
 
 __all__ = ['calculate_control_matrix_from_atomic', 'calculate_control_matrix_from_scratch',
+           'calculate_cumulant_function', 'calculate_decay_amplitudes',
            'calculate_filter_function', 'calculate_pulse_correlation_filter_function',
-           'diagonalize', 'infidelity']
+           'diagonalize', 'error_transfer_matrix', 'infidelity']
 
 
 def diagonalize(hamiltonian: ndarray, dt):
@@ -288,3 +289,157 @@ def infidelity(pulse, spectrum, omega, n_oper_identifiers=None, which: str = 'to
         return infid, xi
 
     return infid
+
+
+# ------------------------------------------------------------------------------------------------
+# decay amplitudes, cumulant function, error transfer matrix
+# ------------------------------------------------------------------------------------------------
+def _decay_amplitudes_from_control_matrix(control_matrix, spectrum, omega, idx) -> ndarray:
+    """trapezoid(Re(conj(B_ak) S_ab B_bl), omega) / (2 pi) on the GPU; the integrand of
+    ``numeric.py:344-347`` / ``:362-371`` is never materialised."""
+    omega = _lib.as_f64(omega)
+    idx = np.asarray(idx)
+    spectrum = util.parse_spectrum(np.asarray(spectrum), omega, idx)
+    B = _lib.as_c128(control_matrix)
+    lead = () if B.ndim == 3 else (B.shape[0], B.shape[0])
+    P = 1 if B.ndim == 3 else B.shape[0]
+    n_nops, n_basis, n_omega = B.shape[-3:]
+    s_complex = np.iscomplexobj(spectrum)
+    S = _lib.as_c128(spectrum) if s_complex else _lib.as_f64(spectrum)
+    n_sel = len(idx)
+    out = np.empty(lead + ((n_sel, n_sel) if spectrum.ndim == 3 else (n_sel,))
+                   + (n_basis, n_basis), dtype=np.float64)
+    idx32 = np.ascontiguousarray(idx, dtype=np.int32)
+    ctx = _lib.context()
+    _lib.check(ctx, _lib.lib().ffb_decay_amplitudes(
+        ctx, P, n_nops, n_sel, _lib.ptr(idx32), n_basis, n_omega, _lib.ptr(B), _lib.ptr(S),
+        spectrum.ndim, int(s_complex), _lib.ptr(omega), _lib.ptr(out)))
+    return out
+
+
+def _decay_amplitudes_from_filter_function(filter_function, spectrum, omega, idx) -> ndarray:
+    """Same integral from a cached generalized filter function ([P, P,] a, b, k, l, omega): the basis
+    axes are moved in front so that the infidelity kernel integrates every (k, l) row."""
+    F = np.asarray(filter_function)
+    n_basis = F.shape[-2]
+    lead = F.shape[:-5]
+    Fm = np.moveaxis(F, (-3, -2), (-5, -4))          # ([P, P,] k, l, a, b, omega)
+    out = _integrate_against_spectrum(Fm, spectrum, omega, idx, 1)
+    # ([P, P,] k, l, a[, b]) -> ([P, P,] a[, b], k, l)
+    n_op_axes = out.ndim - len(lead) - 2
+    out = np.moveaxis(out, (len(lead), len(lead) + 1), (-2, -1))
+    assert out.shape[-2:] == (n_basis, n_basis) and n_op_axes in (1, 2)
+    return np.ascontiguousarray(out)
+
+
+@util.parse_optional_parameters(which=('total', 'correlations'))
+def calculate_decay_amplitudes(pulse, spectrum, omega, n_oper_identifiers=None,
+                               which: str = 'total', show_progressbar: bool = False,
+                               cache_intermediates: bool = False,
+                               memory_parsimonious: bool = False) -> ndarray:
+    r"""Decay amplitudes :math:`\Gamma_{\alpha\beta,kl}=\int\frac{d\omega}{2\pi}
+    \tilde{\mathcal B}^*_{\alpha k}(\omega)S_{\alpha\beta}(\omega)\tilde{\mathcal B}_{\beta l}
+    (\omega)` of shape ([n_pls, n_pls,] n_nops, [n_nops,] n_basis, n_basis) (reference
+    ``numeric.py:1194-1337``).  ``memory_parsimonious`` is accepted for compatibility; the kernel never
+    builds the integrand, so there is nothing to trade."""
+    idx = util.get_indices_from_identifiers(pulse.n_oper_identifiers, n_oper_identifiers)
+    if which == 'total':
+        if pulse.is_cached('filter_function_gen') and not pulse.is_cached('control_matrix'):
+            return _decay_amplitudes_from_filter_function(
+                pulse.get_filter_function(omega, which='generalized'), spectrum, omega, idx)
+        control_matrix = pulse.get_control_matrix(omega, show_progressbar, cache_intermediates)
+    else:
+        if pulse.is_cached('omega') and not np.array_equal(pulse.omega, omega):
+            raise ValueError('Pulse correlation decay amplitudes requested but omega not '
+                             + 'equal to cached frequencies.')
+        if (pulse.is_cached('filter_function_pc_gen')
+                and not pulse.is_cached('control_matrix_pc')):
+            return _decay_amplitudes_from_filter_function(
+                pulse.get_pulse_correlation_filter_function(which='generalized'), spectrum, omega,
+                idx)
+        control_matrix = pulse.get_pulse_correlation_control_matrix()
+    return _decay_amplitudes_from_control_matrix(control_matrix, spectrum, omega, idx)
+
+
+def _contract_with_trace_tensor(decay_amplitudes, basis) -> ndarray:
+    r""":math:`\sum_{kl}\Gamma_{kl}(T_{klji}-T_{kjli}-T_{kilj}+T_{kijl})` with
+    :math:`T_{ijkl}=\mathrm{tr}(C_iC_jC_kC_l)` (reference ``numeric.py:1160-1165``) WITHOUT the
+    n_basis^4 trace tensor: with :math:`D_k=\sum_l\Gamma_{kl}C_l`, :math:`G=\sum_kC_kD_k`,
+    :math:`G'=\sum_kD_kC_k` and the map :math:`\Phi(X)=\sum_kC_kXD_k`,
+
+    .. math:: \mathrm{tr}(GC_jC_i)-\mathrm{tr}(\Phi(C_j)C_i)-\mathrm{tr}(\Phi(C_i)C_j)
+              +\mathrm{tr}(G'C_iC_j).
+
+    O(n_basis^2 d^2 + n_basis d^4) numbers instead of n_basis^4 (69 GB for d = 16)."""
+    C = np.asarray(basis)
+    Gamma = np.asarray(decay_amplitudes)
+    D = np.einsum('...kl,lab->...kab', Gamma, C)
+    G1 = np.einsum('kab,...kbc->...ac', C, D)
+    G2 = np.einsum('...kab,kbc->...ac', D, C)
+    t1 = np.einsum('...jab,iba->...ij', np.einsum('...ac,jcb->...jab', G1, C), C)
+    t4 = np.einsum('...iab,jba->...ij', np.einsum('...ac,icb->...iab', G2, C), C)
+    Phi = np.einsum('kab,...kcd->...adbc', C, D)            # Phi(X)[a,d] = Phi[a,d,b,c] X[b,c]
+    PhiC = np.einsum('...adbc,jbc->...jad', Phi, C)
+    t2 = np.einsum('...jad,ida->...ij', PhiC, C)
+    return t1 - t2 - t2.swapaxes(-1, -2) + t4
+
+
+@util.parse_optional_parameters(which=('total', 'correlations'))
+def calculate_cumulant_function(pulse, spectrum=None, omega=None, n_oper_identifiers=None,
+                                which: str = 'total', second_order: bool = False,
+                                decay_amplitudes: Optional[ndarray] = None,
+                                frequency_shifts: Optional[ndarray] = None,
+                                show_progressbar: bool = False, memory_parsimonious: bool = False,
+                                cache_intermediates: Optional[bool] = None) -> ndarray:
+    r"""Cumulant function :math:`\mathcal K(\tau)` of shape ([[n_pls, n_pls,] n_nops,] n_nops,
+    n_basis, n_basis) (reference ``numeric.py:957-1191``); first order only."""
+    if second_order or frequency_shifts is not None:
+        raise NotImplementedError('Second-order (frequency shift) terms are out of scope of '
+                                  'filter_functions_b200 (SURVEY.md section 2, row 11)')
+    N, d = pulse.basis.shape[:2]
+    if spectrum is None and omega is None and decay_amplitudes is None:
+        raise ValueError('Require either spectrum and frequencies or precomputed '
+                         + 'decay amplitudes (frequency shifts)')
+    if decay_amplitudes is None:
+        decay_amplitudes = calculate_decay_amplitudes(pulse, spectrum, omega, n_oper_identifiers,
+                                                      which, show_progressbar,
+                                                      bool(cache_intermediates),
+                                                      memory_parsimonious)
+    decay_amplitudes = np.asarray(decay_amplitudes)
+
+    if d == 2 and pulse.basis.btype in ('Pauli', 'GGM'):
+        # single qubit (numeric.py:1120-1143): K_ij = Gamma_ij off the diagonal,
+        # K_ii = -sum_{k != i, k > 0} Gamma_kk; the identity row / column vanishes.
+        K = np.zeros(decay_amplitudes.shape, decay_amplitudes.dtype)
+        off = np.zeros((N, N), dtype=bool)
+        off[1:, 1:] = ~np.eye(N - 1, dtype=bool)
+        K[..., off] = decay_amplitudes[..., off]
+        diag = np.einsum('...ii->...i', decay_amplitudes)[..., 1:]
+        for i in range(1, N):
+            K[..., i, i] = -(diag.sum(axis=-1) - diag[..., i - 1])
+        return K
+
+    return -0.5*_contract_with_trace_tensor(decay_amplitudes, pulse.basis).real
+
+
+def error_transfer_matrix(pulse=None, spectrum=None, omega=None, n_oper_identifiers=None,
+                          second_order: bool = False, cumulant_function: Optional[ndarray] = None,
+                          show_progressbar: bool = False, memory_parsimonious: bool = False,
+                          cache_intermediates: Optional[bool] = None) -> ndarray:
+    r"""Error transfer matrix :math:`\langle\tilde{\mathcal U}\rangle=\exp\mathcal K(\tau)` of
+    shape (n_basis, n_basis), summed over all noise operators (reference ``numeric.py:1938-2059``)."""
+    from scipy import linalg as sla
+    if cumulant_function is None:
+        if pulse is None or spectrum is None or omega is None:
+            raise ValueError('Require either precomputed cumulant function '
+                             + 'or pulse, spectrum, and omega as arguments.')
+        cumulant_function = calculate_cumulant_function(
+            pulse, spectrum, omega, n_oper_identifiers, 'total', second_order,
+            show_progressbar=show_progressbar, memory_parsimonious=memory_parsimonious,
+            cache_intermediates=cache_intermediates)
+    try:
+        return sla.expm(cumulant_function.sum(axis=tuple(range(cumulant_function.ndim - 2))))
+    except AttributeError as aerr:
+        raise TypeError(f'cumulant_function invalid type: {type(cumulant_function)}') from aerr
+    except ValueError as verr:
+        raise ValueError(f'cumulant_function invalid shape: {cumulant_function.shape}') from verr

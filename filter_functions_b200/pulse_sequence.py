@@ -503,65 +503,86 @@ class PulseSequence:
 # ------------------------------------------------------------------------------------------------
 # concatenation
 # ------------------------------------------------------------------------------------------------
-def _join_hamiltonians(opers, identifiers, coeffs, kind: str):
+def _oper_hashes(pulse, kind: str):
+    """Hashes of a pulse's control / noise operators, computed once per operator array (the arrays
+    of a ``PulseSequence`` are never modified in place by this package)."""
+    opers = pulse.c_opers if kind == 'control' else pulse.n_opers
+    cache = pulse.__dict__.setdefault('_oper_hash_cache', {})
+    entry = cache.get(kind)
+    if entry is None or entry[0] is not opers:
+        entry = cache[kind] = (opers, tuple(util.hash_array_along_axis(opers, axis=0)))
+    return entry[1]
+
+
+def _join_hamiltonians(pulses, kind: str):
     """Merge the operator lists of several pulses into one Hamiltonian.
 
     Equal operators (byte-wise) are merged; an identifier used for two different operators gets the
     pulse position appended; operators missing on some pulse get zero (control) or, if constant
     elsewhere, that constant (noise) coefficients.  Behaviour of the reference's
-    ``_concatenate_hamiltonian`` (``:1340-1483``), including its error messages.
+    ``_concatenate_hamiltonian`` (``:1340-1483``), including its error messages.  Written for long
+    sequences of recurring gates (randomized benchmarking): hashes are cached per pulse and the
+    bookkeeping is one pass over dictionaries instead of ``np.unique`` + masks.
     """
-    n_dt = [c.shape[1] for c in coeffs]
-    seg_edges = [0] + list(accumulate(n_dt))
-    pulse_edges = list(accumulate(len(op) for op in opers))
-    flat_opers = np.concatenate(opers, axis=0)
-    flat_ids = np.concatenate(identifiers)
-    flat_coeffs = [c for pulse_coeffs in coeffs for c in pulse_coeffs]
-    oper_hashes = util.hash_array_along_axis(flat_opers, axis=0)
-
-    uniq_hashes, first_idx, inverse = np.unique(oper_hashes, return_index=True,
-                                                return_inverse=True)
-    uniq_hashes = uniq_hashes.tolist()
-    new_ids = flat_ids[first_idx].tolist()
-
+    attr = 'c' if kind == 'control' else 'n'
+    per_pulse = [(_oper_hashes(p, kind), getattr(p, f'{attr}_oper_identifiers').tolist(),
+                  getattr(p, f'{attr}_opers'), getattr(p, f'{attr}_coeffs')) for p in pulses]
+    first = {}              # hash -> (pulse position, index within that pulse) of first occurrence
     ids_of_oper, opers_of_id = {}, {}
-    for h, ident in zip(oper_hashes, flat_ids.tolist()):
-        ids_of_oper.setdefault(h, set()).add(ident)
-        opers_of_id.setdefault(ident, set()).add(h)
+    for pos, (hashes, idents, _, _) in enumerate(per_pulse):
+        for loc, (h, ident) in enumerate(zip(hashes, idents)):
+            if h not in first:
+                first[h] = (pos, loc)
+                ids_of_oper[h] = {ident}
+            else:
+                ids_of_oper[h].add(ident)
+            opers_of_id.setdefault(ident, set()).add(h)
     if any(len(v) > 1 for v in ids_of_oper.values()):
         raise ValueError(f'Trying to concatenate pulses with equal {kind} operators but '
                          + f'different identifiers. Please choose unique {kind} identifiers!')
 
-    mapping = {p: {ident: ident for ident in identifiers[p]} for p in range(len(pulse_edges))}
+    row_of = {h: i for i, h in enumerate(first)}
+    new_ids = [per_pulse[pos][1][loc] for pos, loc in first.values()]
+    mapping = {pos: dict(zip(idents, idents)) for pos, (_, idents, _, _) in enumerate(per_pulse)}
     for ident, hashes in opers_of_id.items():
         if len(hashes) > 1:
             for h in hashes:
-                pulse_pos = bisect.bisect(pulse_edges, oper_hashes.index(h))
-                pos = uniq_hashes.index(h)
-                new_ids[pos] = f'{new_ids[pos]}_{pulse_pos}'
-                mapping[pulse_pos][ident] = new_ids[pos]
+                pulse_pos = first[h][0]
+                new_ids[row_of[h]] = f'{ident}_{pulse_pos}'
+                mapping[pulse_pos][ident] = new_ids[row_of[h]]
 
-    order = np.argsort(new_ids)
+    seg_edges = [0] + list(accumulate(entry[3].shape[1] for entry in per_pulse))
     joined = np.full((len(new_ids), seg_edges[-1]), np.nan)
-    for i in range(len(new_ids)):
-        for flat_pos in (inverse == i).nonzero()[0]:
-            pulse_pos = bisect.bisect(pulse_edges, flat_pos)
-            joined[i, seg_edges[pulse_pos]:seg_edges[pulse_pos + 1]] = flat_coeffs[flat_pos]
+    for pos, (hashes, _, _, coeffs) in enumerate(per_pulse):
+        lo, hi = seg_edges[pos], seg_edges[pos + 1]
+        for loc, h in enumerate(hashes):
+            joined[row_of[h], lo:hi] = coeffs[loc]
 
     missing = np.isnan(joined)
-    if kind == 'noise':
-        for row in missing.any(axis=1).nonzero()[0]:
-            present = joined[row][~missing[row]]
-            if (present == present[0]).all():
-                joined[row, missing[row]] = present[0]
-            else:
-                raise ValueError('Not all pulses have the same noise operators and '
-                                 + 'non-trivial noise sensitivities so I cannot infer them.')
-    else:
-        joined[missing] = 0
+    if missing.any():
+        if kind == 'noise':
+            for row in missing.any(axis=1).nonzero()[0]:
+                present = joined[row][~missing[row]]
+                if (present == present[0]).all():
+                    joined[row, missing[row]] = present[0]
+                else:
+                    raise ValueError('Not all pulses have the same noise operators and '
+                                     + 'non-trivial noise sensitivities so I cannot infer them.')
+        else:
+            joined[missing] = 0
 
-    return (flat_opers[first_idx[order]], np.array([new_ids[i] for i in order]), joined[order],
-            mapping)
+    order = np.argsort(new_ids)
+    opers = np.array([per_pulse[pos][2][loc] for pos, loc in first.values()])
+    return opers[order], np.array([new_ids[i] for i in order]), joined[order], mapping
+
+
+def _unique_by_identity(items):
+    seen, out = set(), []
+    for item in items:
+        if id(item) not in seen:
+            seen.add(id(item))
+            out.append(item)
+    return out
 
 
 def concatenate_without_filter_function(pulses: Iterable[PulseSequence],
@@ -575,15 +596,12 @@ def concatenate_without_filter_function(pulses: Iterable[PulseSequence],
         raise TypeError('Can only concatenate PulseSequences!')
     if len(set(pulse.d for pulse in pulses)) != 1:
         raise ValueError('Trying to concatenate PulseSequence instances with different dimension!')
-    if not util.all_array_equal((pulse.basis for pulse in pulses)):
+    bases = _unique_by_identity(pulse.basis for pulse in pulses)
+    if len(bases) > 1 and not util.all_array_equal(bases):
         raise ValueError('Trying to concatenate PulseSequence instances with different bases!')
 
-    *control, c_map = _join_hamiltonians(
-        [p.c_opers for p in pulses], [p.c_oper_identifiers for p in pulses],
-        [p.c_coeffs for p in pulses], 'control')
-    *noise, n_map = _join_hamiltonians(
-        [p.n_opers for p in pulses], [p.n_oper_identifiers for p in pulses],
-        [p.n_coeffs for p in pulses], 'noise')
+    *control, c_map = _join_hamiltonians(pulses, 'control')
+    *noise, n_map = _join_hamiltonians(pulses, 'noise')
     dt = np.concatenate(tuple(pulse.dt for pulse in pulses))
     newpulse = PulseSequence.from_arrays(*control, *noise, dt, pulses[0].basis)
     newpulse.tau = sum(pulse.tau for pulse in pulses)

@@ -112,6 +112,18 @@ int ffb_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* i
                    const double* F, const double* spectrum, int spectrum_ndim,
                    int spectrum_is_complex, const double* omega, int d, double* out);
 
+/* ---- f1: decay amplitudes ---------------------------------------------------
+ * Replaces numeric.calculate_decay_amplitudes (numeric.py:1194-1337) with the integrand of
+ * numeric._get_integrand for a control matrix (numeric.py:259-374, einsum '...ko,...o,...lo->...klo'):
+ *   Gamma^{(gh)}_{ab,kl} = trapezoid_w Re(conj(B^{(g)}_{ak}) S_{ab} B^{(h)}_{bl}) / (2 pi)
+ * B (P,n_nops,n_basis,n_omega) c128 (P = 1: control matrix; P > 1: pulse-correlation control matrix);
+ * idx (n_sel) noise-operator indices; spectrum as in ffb_infidelity;
+ * out f64 (P,P,n_pairs,n_basis,n_basis), n_pairs = n_sel for spectrum_ndim 1/2 (a == b) and n_sel^2
+ * for spectrum_ndim 3.  The integrand (n_basis^2 n_omega values per pair) is never materialised. */
+int ffb_decay_amplitudes(ffb_ctx* ctx, int P, int n_nops, int n_sel, const int* idx, int n_basis,
+                         int n_omega, const double* B, const double* spectrum, int spectrum_ndim,
+                         int spectrum_is_complex, const double* omega, double* out);
+
 /* ---- a8 helper: Liouville representation --------------------------------------------------------
  * Replaces superoperator.liouville_representation (superoperator.py:51-84):
  * out[n,i,j] = tr(C_i U_n C_j U_n^dagger); U (n,d,d) c128, basis (n_basis,d,d) c128,
@@ -157,6 +169,10 @@ int ffb_dev_control_matrix_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_ba
 int ffb_dev_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* idx,
                        int n_omega, const double* F, const double* spectrum, int spectrum_ndim,
                        int spectrum_is_complex, const double* omega, int d, double* out);
+int ffb_dev_decay_amplitudes(ffb_ctx* ctx, int P, int n_nops, int n_sel, const int* idx,
+                             int n_basis, int n_omega, const double* B, const double* spectrum,
+                             int spectrum_ndim, int spectrum_is_complex, const double* omega,
+                             double* out);
 /* herm_flags for ffb_dev_control_matrix_from_scratch: bit 0 = all noise operators exactly
  * Hermitian, bit 1 = all basis elements exactly Hermitian (the host entry point checks this itself;
  * pass 0 if unknown -- always correct, up to 4x more rows). */

@@ -158,11 +158,58 @@ def workloads_small():
     np.savez_compressed(os.path.join(OUT, 'workloads_small.npz'), **out)
 
 
+def decay_amplitudes():
+    """Decay amplitudes, cumulant function and error transfer matrix (numeric.py:957-1337, :1938-2059;
+    cf. tests/test_precision.py:631-727) for the three spectrum shapes, plus the pulse-correlation
+    amplitudes of a concatenated sequence."""
+    rng = np.random.default_rng(314159)
+    out = {}
+    for d, G, n_nops, btype in [(2, 8, 3, 'Pauli'), (3, 7, 2, 'GGM'), (4, 9, 3, 'Pauli')]:
+        pulse = testutil.rand_pulse_sequence(d, G, 2, n_nops, btype=btype, local_rng=rng)
+        omega = np.geomspace(0.05, 30, 73)
+        tag = f'd{d}'
+        for key, val in pulse_arrays(pulse).items():
+            out[f'{tag}_{key}'] = val
+        out[f'{tag}_omega'] = omega
+        S1 = 1e-2/omega**0.7
+        S2 = np.array([S1*(i + 1) for i in range(n_nops)])
+        S3 = np.einsum('a,b,o->abo', np.arange(1, n_nops + 1), np.arange(1, n_nops + 1), S1)
+        S3 = S3 + 1j*np.triu(np.ones((n_nops, n_nops)), 1)[..., None]*omega*1e-3 \
+            - 1j*np.tril(np.ones((n_nops, n_nops)), -1)[..., None]*omega*1e-3
+        for i, S in enumerate((S1, S2, S3)):
+            out[f'{tag}_spectrum{i}'] = S
+            out[f'{tag}_decay_amplitudes{i}'] = numeric.calculate_decay_amplitudes(pulse, S, omega)
+            out[f'{tag}_cumulant_function{i}'] = numeric.calculate_cumulant_function(pulse, S, omega)
+            out[f'{tag}_error_transfer_matrix{i}'] = ff.error_transfer_matrix(pulse, S, omega)
+        # subset of noise operators
+        ids = pulse.n_oper_identifiers[[0, n_nops - 1]]
+        out[f'{tag}_subset_ids'] = np.asarray(ids, dtype='U8')
+        out[f'{tag}_decay_amplitudes_subset'] = numeric.calculate_decay_amplitudes(
+            pulse, S2[[0, n_nops - 1]], omega, n_oper_identifiers=ids)
+        # pulse correlations: the same pulse split in two and concatenated
+        halves = [pulse[:G//2], pulse[G//2:]]
+        for h in halves:
+            h.cache_control_matrix(omega)
+        seq = ff.concatenate(halves, calc_pulse_correlation_FF=True)
+        out[f'{tag}_split'] = np.array(G//2)
+        for i, S in enumerate((S1, S2, S3)):
+            out[f'{tag}_decay_amplitudes_pc{i}'] = numeric.calculate_decay_amplitudes(
+                seq, S, omega, which='correlations')
+        out[f'{tag}_cumulant_function_pc0'] = numeric.calculate_cumulant_function(
+            seq, S1, omega, which='correlations')
+    np.savez_compressed(os.path.join(OUT, 'decay_amplitudes.npz'), **out)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1:       # regenerate only the named fixtures
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     seeded_infidelities()
     random_pulses()
     concatenation()
     workloads_small()
+    decay_amplitudes()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), 'bytes')

@@ -112,6 +112,30 @@ def main():
             record(f'infidelity_{S.ndim}d',
                    nerr(oracle.infidelity_from_filter_function(F, S, om, d),
                         ff.infidelity(pulse, S, om)))
+            if d <= 5:   # dense n_basis^4 trace tensor in the oracle and the stand-in
+                for B_in, which in ((pulse.get_control_matrix(om), 'total'),):
+                    Gam_r = ref_numeric.calculate_decay_amplitudes(pulse, S, om, which=which)
+                    Gam_o = oracle.decay_amplitudes(B_in, S, om)
+                    record(f'decay_amplitudes_{S.ndim}d', nerr(Gam_o, Gam_r))
+                    K_r = ref_numeric.calculate_cumulant_function(pulse, S, om)
+                    K_o = oracle.cumulant_function(Gam_r, my_basis,
+                                                   'Pauli' if btype == 'pauli' else 'GGM')
+                    record(f'cumulant_function_{S.ndim}d', nerr(K_o, K_r))
+                    record(f'error_transfer_matrix_{S.ndim}d',
+                           nerr(oracle.error_transfer_matrix(K_r),
+                                ff.error_transfer_matrix(pulse, S, om)))
+        if d <= 3:
+            # pulse-correlation decay amplitudes of a two-pulse sequence
+            halves = [ff.PulseSequence(list(zip(c_opers, c_coeffs[:, sl])),
+                                       list(zip(n_opers, n_coeffs[:, sl])), dt[sl], basis)
+                      for sl in (slice(0, G//2), slice(G//2, G))]
+            for h in halves:
+                h.cache_control_matrix(om)
+            seq = ff.concatenate(halves, calc_pulse_correlation_FF=True)
+            for S in (S1, S2, S3):
+                Gam_r = ref_numeric.calculate_decay_amplitudes(seq, S, om, which='correlations')
+                Gam_o = oracle.decay_amplitudes(seq.get_pulse_correlation_control_matrix(), S, om)
+                record(f'decay_amplitudes_pc_{S.ndim}d', nerr(Gam_o, Gam_r))
         record('sample_frequencies',
                nerr(oracle.sample_frequencies(pulse.tau, pulse.dt.min()),
                     ref_util.get_sample_frequencies(pulse)))
