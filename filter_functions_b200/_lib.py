@@ -46,6 +46,8 @@ EXPORTED_SYMBOLS = {
                                      c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'ffb_dev_decay_amplitudes': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                          c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'ffb_concatenate_many': (c_int, [c_void_p] + [c_int]*7 + [c_void_p]*7 + [c_int, c_int]
+                             + [c_void_p]*8),
     'ffb_liouville_representation': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                              c_void_p]),
     'ffb_cexp': (c_int, [c_void_p, c_int, c_void_p, c_double, c_void_p]),

@@ -538,6 +538,82 @@ int ffb_decay_amplitudes(ffb_ctx* ctx, int P, int n_nops, int n_sel, const int* 
   return FFB_OK;
 }
 
+int ffb_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int n_lib, int d, int n_nops, int n_basis,
+                         int n_omega, const int* indices, const double* lib_control_matrix,
+                         const double* lib_total_phases, const double* lib_liouville,
+                         const double* lib_propagator, const double* basis, const double* spectrum,
+                         int spectrum_ndim, int spectrum_is_complex, const double* omega,
+                         double* total_propagator, double* total_propagator_liouville,
+                         double* control_matrix, double* filter_function, double* infidelity,
+                         const double* tau, double* total_phases) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, !total_phases || (tau && omega),
+              "concatenate_many: total phases requested without tau and omega");
+  FFB_REQUIRE(ctx, indices && lib_control_matrix && lib_total_phases && lib_liouville &&
+                       lib_propagator, "concatenate_many: null input pointer");
+  FFB_REQUIRE(ctx, n_seq >= 1 && L >= 1 && n_lib >= 1 && d >= 1 && n_nops >= 1 && n_basis >= 1 &&
+                       n_omega >= 1, "concatenate_many: bad shape");
+  FFB_REQUIRE(ctx, !infidelity || (spectrum && omega),
+              "concatenate_many: infidelity requested without spectrum and omega");
+  FFB_REQUIRE(ctx, !total_propagator_liouville || basis,
+              "concatenate_many: Liouville representation requested without basis");
+  for (size_t i = 0; i < (size_t)n_seq * L; ++i)
+    FFB_REQUIRE(ctx, indices[i] < n_lib, "concatenate_many: index %d at position %zu out of range "
+                "[0, %d)", indices[i], i, n_lib);
+  const size_t dd = (size_t)d * d, nn = (size_t)n_basis * n_basis;
+  Upload ix, lb, lp, ll, lu, bs, sp, om;
+  DevBuf U, Lt, B, F, I, iota, ph;
+  if (omega) FFB_TRY(om.put(ctx, omega, (size_t)n_omega * 8));
+  FFB_TRY(ix.put(ctx, indices, (size_t)n_seq * L * sizeof(int)));
+  FFB_TRY(lb.put(ctx, lib_control_matrix, (size_t)n_lib * n_nops * n_basis * n_omega * 16));
+  FFB_TRY(lp.put(ctx, lib_total_phases, (size_t)n_lib * n_omega * 16));
+  FFB_TRY(ll.put(ctx, lib_liouville, (size_t)n_lib * nn * 8));
+  FFB_TRY(lu.put(ctx, lib_propagator, (size_t)n_lib * dd * 16));
+  const size_t b_bytes = (size_t)n_seq * n_nops * n_basis * n_omega * 16;
+  const size_t f_bytes = (size_t)n_seq * n_nops * n_nops * n_omega * 16;
+  const bool need_F = filter_function || infidelity;
+  FFB_TRY(U.alloc(ctx, (size_t)n_seq * dd * 16));
+  FFB_TRY(B.alloc(ctx, b_bytes));
+  if (need_F) FFB_TRY(F.alloc(ctx, f_bytes));
+  FFB_TRY(ffbi_concatenate_many(ctx, n_seq, L, d, n_nops, n_basis, n_omega, ix.buf.as<int>(), lb.d(),
+                                lp.d(), ll.d(), lu.d(), U.as<double>(), B.as<double>(),
+                                need_F ? F.as<double>() : nullptr));
+  size_t n_inf = 0;
+  std::vector<int> sel(n_nops);
+  if (infidelity) {
+    FFB_REQUIRE(ctx, spectrum_ndim >= 1 && spectrum_ndim <= 3, "concatenate_many: spectrum_ndim=%d",
+                spectrum_ndim);
+    const size_t s_elems = (spectrum_ndim == 1 ? 1 : spectrum_ndim == 2 ? (size_t)n_nops
+                                                                         : (size_t)n_nops * n_nops) * n_omega;
+    FFB_TRY(sp.put(ctx, spectrum, s_elems * (spectrum_is_complex ? 16 : 8)));
+    for (int i = 0; i < n_nops; ++i) sel[i] = i;
+    FFB_TRY(iota.alloc(ctx, n_nops * sizeof(int)));
+    FFB_TRY(ffb_h2d(ctx, iota.p, sel.data(), n_nops * sizeof(int)));
+    n_inf = (size_t)n_seq * (spectrum_ndim == 3 ? (size_t)n_nops * n_nops : n_nops);
+    FFB_TRY(I.alloc(ctx, n_inf * 8));
+    FFB_TRY(ffbi_infidelity(ctx, n_seq, n_nops, n_nops, iota.as<int>(), n_omega, F.as<double>(),
+                            sp.d(), spectrum_ndim, spectrum_is_complex, om.d(), d, I.as<double>()));
+  }
+  if (total_propagator_liouville) {
+    FFB_TRY(bs.put(ctx, basis, (size_t)n_basis * dd * 16));
+    FFB_TRY(Lt.alloc(ctx, (size_t)n_seq * nn * 16));
+    FFB_TRY(ffbi_liouville(ctx, n_seq, d, n_basis, U.as<double>(), bs.d(), Lt.as<double>()));
+    FFB_TRY(ffb_d2h(ctx, total_propagator_liouville, Lt.p, (size_t)n_seq * nn * 16));
+  }
+  if (total_phases) {
+    FFB_TRY(ph.alloc(ctx, (size_t)n_seq * n_omega * 16));
+    for (int s = 0; s < n_seq; ++s)  // tau is a host value, as in the cold pulse pipeline
+      FFB_TRY(ffbi_cexp(ctx, n_omega, om.d(), tau[s], ph.as<double>() + (size_t)s * n_omega * 2));
+    FFB_TRY(ffb_d2h(ctx, total_phases, ph.p, (size_t)n_seq * n_omega * 16));
+  }
+  if (total_propagator) FFB_TRY(ffb_d2h(ctx, total_propagator, U.p, (size_t)n_seq * dd * 16));
+  if (control_matrix) FFB_TRY(ffb_d2h(ctx, control_matrix, B.p, b_bytes));
+  if (filter_function) FFB_TRY(ffb_d2h(ctx, filter_function, F.p, f_bytes));
+  if (infidelity) FFB_TRY(ffb_d2h(ctx, infidelity, I.p, n_inf * 8));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
 int ffb_liouville_representation(ffb_ctx* ctx, int n, int d, int n_basis, const double* U,
                                  const double* basis, double* out) {
   FFB_TRY(enter(ctx));

@@ -125,6 +125,10 @@ int ffbi_decay_amplitudes(ffb_ctx* ctx, int P, int n_nops, int n_sel, const int*
                           int n_basis, int n_omega, const double* B, const double* spectrum,
                           int spectrum_ndim, int spectrum_is_complex, const double* omega,
                           double* out);
+int ffbi_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int d, int n_nops, int n_basis,
+                          int n_omega, const int* idx, const double* lib_B, const double* lib_phase,
+                          const double* lib_liouville, const double* lib_U, double* U_total,
+                          double* out_B, double* out_F);
 int ffbi_liouville(ffb_ctx* ctx, int n, int d, int n_basis, const double* U, const double* basis,
                    double* out);
 int ffbi_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out);

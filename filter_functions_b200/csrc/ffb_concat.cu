@@ -158,6 +158,147 @@ __global__ void cexp_kernel(int n, const double* __restrict__ x, double scale,
   out[i] = make_double2(cs, sn);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Batched concatenation: n_seq gate sequences drawn from a library of n_lib
+// pulses with cached control matrices (randomized benchmarking, examples/randomized_benchmarking.py:
+// 70-91 of the reference calls ff.concatenate once per sequence).  seq_scan_kernel forms the running
+// products the reference builds with util.adot / util.mdot (pulse_sequence.py:1745, :1827) for every
+// sequence at once; sequence_batch_kernel is from_atomic_kernel with the constituent's control matrix
+// gathered from the library and the cumulative phase factors (np.cumprod, pulse_sequence.py:1824) kept
+// as a running product in registers.  A negative library index is padding (no gate).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+seq_scan_kernel(int L, int n_basis, int d, const int* __restrict__ idx,
+                const double* __restrict__ lib_liouville, const double2* __restrict__ lib_U,
+                double* __restrict__ Qcum, double2* __restrict__ U_total) {
+  extern __shared__ double sm[];
+  const int s = blockIdx.x;
+  const int nn = n_basis * n_basis, dd = d * d;
+  double* R0 = sm;                 // running Liouville product (ping-pong)
+  double* R1 = R0 + nn;
+  double2* V0 = reinterpret_cast<double2*>(R1 + nn);  // running propagator (ping-pong)
+  double2* V1 = V0 + dd;
+  const int* seq = idx + (size_t)s * L;
+  for (int e = threadIdx.x; e < nn; e += blockDim.x) R0[e] = (e / n_basis == e % n_basis) ? 1.0 : 0.0;
+  for (int e = threadIdx.x; e < dd; e += blockDim.x)
+    V0[e] = make_double2((e / d == e % d) ? 1.0 : 0.0, 0.0);
+  __syncthreads();
+  for (int g = 0; g < L; ++g) {
+    const int c = seq[g];
+    if (c >= 0) {
+      const double* Lc = lib_liouville + (size_t)c * nn;
+      for (int e = threadIdx.x; e < nn; e += blockDim.x) {  // R1 = L_c R0
+        const int i = e / n_basis, j = e % n_basis;
+        double acc = 0.0;
+        for (int k = 0; k < n_basis; ++k) acc += Lc[i * n_basis + k] * R0[k * n_basis + j];
+        R1[e] = acc;
+      }
+      const double2* Uc = lib_U + (size_t)c * dd;
+      for (int e = threadIdx.x; e < dd; e += blockDim.x) {  // V1 = U_c V0
+        const int i = e / d, j = e % d;
+        double re = 0.0, im = 0.0;
+        for (int k = 0; k < d; ++k) {
+          const double2 a = Uc[i * d + k], b = V0[k * d + j];
+          re += a.x * b.x - a.y * b.y;
+          im += a.x * b.y + a.y * b.x;
+        }
+        V1[e] = make_double2(re, im);
+      }
+      __syncthreads();
+      double* tr = R0; R0 = R1; R1 = tr;
+      double2* tv = V0; V0 = V1; V1 = tv;
+    }
+    if (g + 1 < L) {
+      double* dst = Qcum + ((size_t)s * (L - 1) + g) * nn;
+      for (int e = threadIdx.x; e < nn; e += blockDim.x) dst[e] = R0[e];
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < dd; e += blockDim.x) U_total[(size_t)s * dd + e] = V0[e];
+}
+
+template <int LT>
+__global__ void __launch_bounds__(128)
+sequence_batch_kernel(int L, int n_nops, int n_basis, int n_omega, const int* __restrict__ idx,
+                      const double2* __restrict__ lib_B, const double2* __restrict__ lib_phase,
+                      const double* __restrict__ Qcum, double2* __restrict__ out_B) {
+  extern __shared__ double qs[];  // [n_basis][LT]
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = blockIdx.y / n_nops, j = blockIdx.y % n_nops;
+  const int l0 = blockIdx.z * LT;
+  const bool active = w < n_omega;
+  const int* seq = idx + (size_t)s * L;
+  const size_t lib_stride = (size_t)n_nops * n_basis * n_omega;
+  double2 acc[LT];
+#pragma unroll
+  for (int i = 0; i < LT; ++i) acc[i] = make_double2(0.0, 0.0);
+  double2 ph = make_double2(1.0, 0.0);  // product of the total phases of the gates so far
+  bool first = true;                    // no gate applied yet: Q is the identity
+  for (int g = 0; g < L; ++g) {
+    const int c = seq[g];
+    if (c < 0) continue;  // uniform over the block
+    const double2* Bg = lib_B + (size_t)c * lib_stride + (size_t)j * n_basis * n_omega + w;
+    if (first) {
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < LT; ++i)
+          if (l0 + i < n_basis) acc[i] = Bg[(size_t)(l0 + i) * n_omega];
+      }
+      first = false;
+    } else {
+      __syncthreads();
+      const double* Qg = Qcum + ((size_t)s * (L - 1) + g - 1) * n_basis * n_basis;
+      for (int e = threadIdx.x; e < n_basis * LT; e += blockDim.x) {
+        const int k = e / LT, i = e % LT;
+        qs[e] = l0 + i < n_basis ? Qg[(size_t)k * n_basis + l0 + i] : 0.0;
+      }
+      __syncthreads();
+      if (active) {
+        for (int k = 0; k < n_basis; ++k) {
+          const double2 b = Bg[(size_t)k * n_omega];
+          const double xr = ph.x * b.x - ph.y * b.y;
+          const double xi = ph.x * b.y + ph.y * b.x;
+#pragma unroll
+          for (int i = 0; i < LT; ++i) {
+            const double qv = qs[k * LT + i];
+            acc[i].x += xr * qv;
+            acc[i].y += xi * qv;
+          }
+        }
+      }
+    }
+    if (active) {
+      const double2 p2 = lib_phase[(size_t)c * n_omega + w];
+      ph = make_double2(ph.x * p2.x - ph.y * p2.y, ph.x * p2.y + ph.y * p2.x);
+    }
+  }
+  if (active) {
+    double2* dst = out_B + ((size_t)s * n_nops + j) * n_basis * n_omega + w;
+#pragma unroll
+    for (int i = 0; i < LT; ++i)
+      if (l0 + i < n_basis) dst[(size_t)(l0 + i) * n_omega] = acc[i];
+  }
+}
+
+// F[s,a,b,w] = sum_k conj(B[s,a,k,w]) B[s,b,k,w]   (one sequence per blockIdx.y)
+__global__ void __launch_bounds__(128)
+ff_batched_kernel(int n_nops, int n_basis, int n_omega, const double2* __restrict__ B,
+                  double2* __restrict__ F) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_omega) return;
+  const int s = blockIdx.y;
+  const int a = blockIdx.z / n_nops, b = blockIdx.z % n_nops;
+  const double2* Ba = B + ((size_t)s * n_nops + a) * n_basis * n_omega + w;
+  const double2* Bb = B + ((size_t)s * n_nops + b) * n_basis * n_omega + w;
+  double re = 0.0, im = 0.0;
+  for (int k = 0; k < n_basis; ++k) {
+    const double2 x = Ba[(size_t)k * n_omega], y = Bb[(size_t)k * n_omega];
+    re += x.x * y.x + x.y * y.y;
+    im += x.x * y.y - x.y * y.x;
+  }
+  F[(((size_t)s * n_nops + a) * n_nops + b) * n_omega + w] = make_double2(re, im);
+}
+
 template <int LT>
 int launch_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
                        const double* phases, const double* B_atomic, const double* Q,
@@ -220,5 +361,54 @@ int ffbi_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out) {
   cexp_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, x, scale,
                                                          reinterpret_cast<double2*>(out));
   FFB_LAUNCHED(ctx);
+  return FFB_OK;
+}
+
+int ffbi_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int d, int n_nops, int n_basis,
+                          int n_omega, const int* idx, const double* lib_B, const double* lib_phase,
+                          const double* lib_liouville, const double* lib_U, double* U_total,
+                          double* out_B, double* out_F) {
+  FFB_REQUIRE(ctx, n_seq >= 1 && L >= 1 && d >= 1 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
+              "concatenate_many: bad shape (n_seq=%d, L=%d, d=%d, n_nops=%d, n_basis=%d, n_omega=%d)",
+              n_seq, L, d, n_nops, n_basis, n_omega);
+  FFB_REQUIRE(ctx, n_basis <= 64, "concatenate_many: n_basis=%d > 64 is not supported "
+              "(use concatenate per sequence)", n_basis);
+  FFB_REQUIRE(ctx, (long long)n_seq * n_nops <= 65535, "concatenate_many: n_seq * n_nops = %lld "
+              "exceeds 65535; split the batch", (long long)n_seq * n_nops);
+  const int nn = n_basis * n_basis;
+  DevBuf Qcum;
+  FFB_TRY(Qcum.alloc(ctx, (size_t)n_seq * std::max(1, L - 1) * nn * 8));
+  {
+    const size_t smem = (size_t)2 * nn * 8 + (size_t)2 * d * d * 16;
+    FFB_CUDA(ctx, cudaFuncSetAttribute(seq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    seq_scan_kernel<<<n_seq, 128, smem, ctx->stream>>>(
+        L, n_basis, d, idx, lib_liouville, reinterpret_cast<const double2*>(lib_U),
+        Qcum.as<double>(), reinterpret_cast<double2*>(U_total));
+    FFB_LAUNCHED(ctx);
+  }
+  {
+    const int LT = n_basis <= 4 ? 4 : n_basis <= 8 ? 8 : 16;
+    dim3 grid(ceil_div(n_omega, 128), n_seq * n_nops, ceil_div(n_basis, LT));
+    const size_t smem = (size_t)n_basis * LT * 8;
+    auto args = [&](auto kern) {
+      kern<<<grid, 128, smem, ctx->stream>>>(L, n_nops, n_basis, n_omega, idx,
+                                             reinterpret_cast<const double2*>(lib_B),
+                                             reinterpret_cast<const double2*>(lib_phase),
+                                             Qcum.as<double>(), reinterpret_cast<double2*>(out_B));
+    };
+    if (LT == 4) args(sequence_batch_kernel<4>);
+    else if (LT == 8) args(sequence_batch_kernel<8>);
+    else args(sequence_batch_kernel<16>);
+    FFB_LAUNCHED(ctx);
+  }
+  if (out_F) {
+    dim3 grid(ceil_div(n_omega, 128), n_seq, n_nops * n_nops);
+    FFB_REQUIRE(ctx, n_nops * n_nops <= 65535 && n_seq <= 65535, "concatenate_many: grid too large");
+    ff_batched_kernel<<<grid, 128, 0, ctx->stream>>>(n_nops, n_basis, n_omega,
+                                                     reinterpret_cast<const double2*>(out_B),
+                                                     reinterpret_cast<double2*>(out_F));
+    FFB_LAUNCHED(ctx);
+  }
   return FFB_OK;
 }

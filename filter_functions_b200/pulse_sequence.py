@@ -20,7 +20,8 @@ from . import _lib, numeric, util
 from .basis import Basis
 from .superoperator import liouville_representation
 
-__all__ = ['PulseSequence', 'concatenate', 'concatenate_without_filter_function']
+__all__ = ['PulseSequence', 'SequenceBatch', 'concatenate', 'concatenate_many',
+           'concatenate_without_filter_function']
 
 _DATA_ALIASES = {
     'eigenvalues': 'eigvals',
@@ -223,7 +224,9 @@ class PulseSequence:
 
     @property
     def t(self) -> ndarray:
-        return self._data.setdefault('t', np.concatenate(([0], self.dt.cumsum())))
+        if 't' not in self._data:
+            self._data['t'] = np.concatenate(([0], self.dt.cumsum()))
+        return self._data['t']
 
     @t.setter
     def t(self, val):
@@ -231,7 +234,9 @@ class PulseSequence:
 
     @property
     def tau(self):
-        return self._data.setdefault('tau', self.t[-1] if 't' in self._data else self.dt.sum())
+        if 'tau' not in self._data:
+            self._data['tau'] = self.t[-1] if 't' in self._data else self.dt.sum()
+        return self._data['tau']
 
     @tau.setter
     def tau(self, val):
@@ -610,6 +615,17 @@ def concatenate_without_filter_function(pulses: Iterable[PulseSequence],
     return newpulse
 
 
+def _frequency_entry(pls, key: str, omega):
+    """Cached frequency-dependent array ``key`` of ``pls`` if it belongs to the grid ``omega`` (without
+    the copy + comparison the ``omega`` setter makes on every access), else ``None``."""
+    cached = pls._frequency_data.get('omega')
+    if cached is None or key not in pls._frequency_data:
+        return None
+    if cached is omega or (cached.shape == np.shape(omega) and np.array_equal(cached, omega)):
+        return pls._frequency_data[key]
+    return None
+
+
 @util.parse_optional_parameters(which=('fidelity', 'generalized'))
 def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool = False,
                 calc_filter_function: Optional[bool] = None,
@@ -617,7 +633,9 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
                 omega=None, show_progressbar: bool = False) -> PulseSequence:
     r"""Concatenate pulses left to right (``concatenate((A, B))`` is :math:`B\circ A`) and, when the
     constituents have cached control matrices (or ``omega`` is given), compute the control matrix of
-    the sequence from them.  Decision logic, caching and errors follow the reference (``:1668-1887``).
+    the sequence from them.  Decision logic, caching and errors follow the reference (``:1668-1887``);
+    the host side is written for long sequences of recurring gates (per-object work is done once per
+    distinct pulse object, cached arrays are read without re-validating the frequency grid).
     """
     if calc_second_order_FF:
         raise NotImplementedError('Second-order filter functions are out of scope of '
@@ -629,7 +647,7 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
     newpulse, _, n_oper_mapping = concatenate_without_filter_function(
         pulses, return_identifier_mappings=True)
 
-    if all(pls.is_cached('total_propagator') for pls in pulses):
+    if all('total_propagator' in pls._data for pls in pulses):
         newpulse.total_propagator = util.mdot([pls.total_propagator for pls in pulses][::-1])
 
     if calc_pulse_correlation_FF:
@@ -638,22 +656,24 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         return newpulse
 
     # which (renamed) noise operators does each pulse carry?
-    pulse_identifiers = [sorted(mapping.values()) for _, mapping in sorted(n_oper_mapping.items())]
-    unique_identifiers = sorted(set(h for ids in pulse_identifiers for h in ids))
-    n_opers_present = np.array([[ident in ids for ident in unique_identifiers]
-                                for ids in pulse_identifiers], dtype=bool)
+    new_ids = newpulse.n_oper_identifiers.tolist()
+    column = {ident: i for i, ident in enumerate(new_ids)}
+    present_rows = []
+    for pos in range(len(pulses)):
+        row = [False]*len(new_ids)
+        for ident in n_oper_mapping[pos].values():
+            row[column[ident]] = True
+        present_rows.append(row)
+    n_opers_present = np.array(present_rows, dtype=bool)
 
     equal_n_opers = (n_opers_present.sum(axis=0) > 1).any()
+    distinct = _unique_by_identity(pulses)
     if omega is None:
-        cached_ctrl_mat = [pls.is_cached('control_matrix') for pls in pulses]
-        if any(cached_ctrl_mat):
-            equal_omega = util.all_array_equal(
-                (pls.omega for pls in compress(pulses, cached_ctrl_mat)))
-        else:
-            cached_omega = [pls.is_cached('omega') for pls in pulses]
-            equal_omega = util.all_array_equal(
-                (pls.omega for pls in compress(pulses, cached_omega))) if any(cached_omega) \
-                else False
+        with_ctrl = [pls for pls in distinct if 'control_matrix' in pls._frequency_data
+                     or 'control_matrix_pc' in pls._frequency_data]
+        with_omega = with_ctrl or [pls for pls in distinct if 'omega' in pls._frequency_data]
+        grids = _unique_by_identity(pls.omega for pls in with_omega)
+        equal_omega = bool(grids) and (len(grids) == 1 or util.all_array_equal(grids))
         if not equal_omega:
             if calc_filter_function:
                 raise ValueError("Calculation of filter function forced but not all pulses "
@@ -662,31 +682,81 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
                 raise ValueError("Cannot compute the pulse correlation filter functions; do not "
                                  + "have the frequencies at which to evaluate.")
             return newpulse
-        if calc_filter_function is None and (not equal_n_opers or not any(cached_ctrl_mat)):
+        if calc_filter_function is None and (not equal_n_opers or not with_ctrl):
             return newpulse
-        source = cached_ctrl_mat if any(cached_ctrl_mat) else cached_omega
-        omega = pulses[int(np.nonzero(source)[0][0])].omega
+        omega = with_omega[0].omega
 
     if not equal_n_opers:
         newpulse.cache_filter_function(omega, which=which)
         return newpulse
 
-    phases = np.array([pls.get_total_phases(omega) for pls in pulses[:-1]]).cumprod(axis=0)
-    propagators_liouville = util.adot([pls.total_propagator_liouville for pls in pulses[:-1]])
+    # per distinct pulse object: total phases, Liouville propagator, control matrix on this grid
+    slot = {id(pls): i for i, pls in enumerate(distinct)}
+    inverse = [slot[id(pls)] for pls in pulses]
+    lib_phases, lib_liouville, lib_ctrl = [], [], []
+    for pls in distinct:
+        ph = _frequency_entry(pls, 'total_phases', omega)
+        lib_phases.append(pls.get_total_phases(omega) if ph is None else ph)
+        B = _frequency_entry(pls, 'control_matrix', omega)
+        lib_ctrl.append(pls.get_control_matrix(omega, show_progressbar) if B is None else B)
+        lib_liouville.append(pls.total_propagator_liouville)
 
-    control_matrix_atomic = np.empty(
-        (len(pulses), len(newpulse.n_opers), len(newpulse.basis), len(omega)), dtype=complex)
-    seg_edges = [0] + list(accumulate(len(pls.dt) for pls in pulses))
-    for i, (pls, present) in enumerate(zip(pulses, n_opers_present)):
-        control_matrix_atomic[i, present] = pls.get_control_matrix(omega, show_progressbar)
-        if not present.all():
-            control_matrix_atomic[i, ~present] = numeric.calculate_control_matrix_from_scratch(
-                pls.eigvals, pls.eigvecs, pls.propagators, omega, pls.basis,
-                newpulse.n_opers[~present],
-                newpulse.n_coeffs[~present, seg_edges[i]:seg_edges[i + 1]],
-                pls.dt, t=pls.t, show_progressbar=show_progressbar, cache_intermediates=False)
+    n_basis, n_omega = len(newpulse.basis), len(omega)
+    if (n_opers_present.all() and not calc_pulse_correlation_FF and which == 'fidelity'
+            and n_basis <= 64 and n_omega and newpulse.basis.isherm
+            and all(np.isrealobj(liou) for liou in lib_liouville)):
+        # every gate carries every noise operator: the whole tail of this function (running
+        # propagator / phase products, from_atomic, Liouville representation, filter function) is
+        # ONE library call on the distinct pulses plus an index list, as in concatenate_many
+        d = newpulse.d
+        lib_B = _lib.as_c128(np.array(lib_ctrl))
+        lib_ph = _lib.as_c128(np.array(lib_phases))
+        lib_L = _lib.as_f64(np.array(lib_liouville))
+        lib_U = _lib.as_c128(np.array([pls.total_propagator for pls in distinct]))
+        basis = _lib.as_c128(np.asarray(newpulse.basis))
+        index = np.array(inverse, dtype=np.int32)
+        n_nops = lib_B.shape[1]
+        U = np.empty((1, d, d), dtype=np.complex128)
+        liouville = np.empty((1, n_basis, n_basis), dtype=np.complex128)
+        B = _lib.empty((1, n_nops, n_basis, n_omega))
+        F = _lib.empty((1, n_nops, n_nops, n_omega))
+        total_phases = np.empty((1, n_omega), dtype=np.complex128)
+        omega_arr = _lib.as_f64(omega)
+        tau = np.array([newpulse.tau], dtype=np.float64)
+        ctx = _lib.context()
+        p = _lib.ptr
+        _lib.check(ctx, _lib.lib().ffb_concatenate_many(
+            ctx, 1, len(index), len(distinct), d, n_nops, n_basis, n_omega, p(index), p(lib_B),
+            p(lib_ph), p(lib_L), p(lib_U), p(basis), None, 0, 0, p(omega_arr), p(U), p(liouville),
+            p(B), p(F), None, p(tau), p(total_phases)))
+        if 'total_propagator' not in newpulse._data:
+            newpulse.total_propagator = U[0]
+        newpulse._frequency_data['omega'] = np.array(omega, copy=True)
+        newpulse._frequency_data['total_phases'] = total_phases[0]
+        newpulse.total_propagator_liouville = np.ascontiguousarray(liouville[0].real)
+        newpulse._frequency_data['control_matrix'] = B[0]
+        newpulse._frequency_data['filter_function'] = F[0]
+        return newpulse
 
-    if not newpulse.is_cached('total_propagator'):
+    phases = np.array([lib_phases[i] for i in inverse[:-1]]).cumprod(axis=0)
+    propagators_liouville = util.adot([lib_liouville[i] for i in inverse[:-1]])
+
+    if n_opers_present.all():
+        control_matrix_atomic = np.array(lib_ctrl)[inverse]
+    else:
+        control_matrix_atomic = np.empty((len(pulses), len(new_ids), n_basis, n_omega),
+                                         dtype=complex)
+        seg_edges = [0] + list(accumulate(len(pls.dt) for pls in pulses))
+        for i, (pls, present) in enumerate(zip(pulses, n_opers_present)):
+            control_matrix_atomic[i, present] = lib_ctrl[inverse[i]]
+            if not present.all():
+                control_matrix_atomic[i, ~present] = numeric.calculate_control_matrix_from_scratch(
+                    pls.eigvals, pls.eigvecs, pls.propagators, omega, pls.basis,
+                    newpulse.n_opers[~present],
+                    newpulse.n_coeffs[~present, seg_edges[i]:seg_edges[i + 1]],
+                    pls.dt, t=pls.t, show_progressbar=show_progressbar, cache_intermediates=False)
+
+    if 'total_propagator' not in newpulse._data:
         newpulse.total_propagator = util.mdot([pls.total_propagator for pls in pulses][::-1])
     newpulse.cache_total_phases(omega)
     newpulse.total_propagator_liouville = liouville_representation(newpulse.total_propagator,
@@ -696,3 +766,145 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         which='correlations' if calc_pulse_correlation_FF else 'total')
     newpulse.cache_filter_function(omega, control_matrix, which=which)
     return newpulse
+
+
+# ------------------------------------------------------------------------------------------------
+# batched concatenation
+# ------------------------------------------------------------------------------------------------
+class SequenceBatch:
+    """Result of :func:`concatenate_many`: ``n_seq`` gate sequences over one library of pulses, held
+    as stacked arrays (leading axis = sequence) instead of ``n_seq`` ``PulseSequence`` objects.
+
+    Attributes: ``pulses`` (the library), ``indices`` (n_seq, L), ``omega``, ``tau`` (n_seq,),
+    ``total_propagator`` (n_seq, d, d), ``total_propagator_liouville`` (n_seq, n_basis, n_basis),
+    ``control_matrix`` (n_seq, n_nops, n_basis, n_omega) or ``None``, ``filter_function``
+    (n_seq, n_nops, n_nops, n_omega) or ``None``, ``infidelities`` (if a spectrum was given).
+    """
+
+    def __init__(self, pulses, indices, omega):
+        self.pulses = pulses
+        self.indices = indices
+        self.omega = omega
+        self.tau = None
+        self.total_propagator = None
+        self.total_propagator_liouville = None
+        self.control_matrix = None
+        self.filter_function = None
+        self.infidelities = None
+
+    def __len__(self) -> int:
+        return len(self.indices)
+
+    @property
+    def n_oper_identifiers(self):
+        return self.pulses[0].n_oper_identifiers
+
+    def infidelity(self, spectrum, n_oper_identifiers=None) -> ndarray:
+        """``ff.infidelity`` for every sequence: (n_seq, n_sel) or (n_seq, n_sel, n_sel)."""
+        if self.filter_function is None:
+            raise util.CalculationError('concatenate_many was run with calc_filter_function=False')
+        idx = util.get_indices_from_identifiers(self.n_oper_identifiers, n_oper_identifiers)
+        return numeric._integrate_against_spectrum(self.filter_function, np.asarray(spectrum),
+                                                   self.omega, idx, self.pulses[0].d)
+
+    def pulse(self, i: int) -> PulseSequence:
+        """Sequence ``i`` as a full ``PulseSequence`` with everything computed here in its cache."""
+        row = [k for k in self.indices[i] if k >= 0]
+        new = concatenate_without_filter_function([self.pulses[k] for k in row])
+        new.total_propagator = self.total_propagator[i]
+        new.total_propagator_liouville = self.total_propagator_liouville[i]
+        new._frequency_data['omega'] = np.array(self.omega, copy=True)
+        new.cache_total_phases(new.omega)
+        if self.control_matrix is not None:
+            new._frequency_data['control_matrix'] = self.control_matrix[i]
+        if self.filter_function is not None:
+            new._frequency_data['filter_function'] = self.filter_function[i]
+        return new
+
+
+def concatenate_many(pulses, indices, spectrum=None, omega=None, calc_control_matrix: bool = True,
+                     calc_filter_function: bool = True) -> SequenceBatch:
+    r"""Concatenate many sequences of pulses drawn from one library in a single GPU call.
+
+    ``indices[s]`` lists the positions in ``pulses`` of the gates of sequence ``s`` in temporal order
+    (negative entries are padding), i.e. sequence ``s`` is ``concatenate(pulses[indices[s]])``.  All
+    library pulses must carry the same noise operators and have (or be able to compute) control
+    matrices on one frequency grid -- the situation of randomized benchmarking
+    (``examples/randomized_benchmarking.py:70-91`` of the reference loops over ``ff.concatenate``).
+    With ``spectrum`` the infidelities of all sequences are integrated in the same call
+    (``batch.infidelities``).  ``calc_control_matrix=False`` / ``calc_filter_function=False`` skip the
+    download of the respective (large) arrays.
+    """
+    pulses = tuple(pulses)
+    if not pulses or not all(isinstance(pls, PulseSequence) for pls in pulses):
+        raise TypeError('Can only concatenate PulseSequences!')
+    indices = np.ascontiguousarray(np.atleast_2d(np.asarray(indices)), dtype=np.int32)
+    if indices.ndim != 2 or indices.shape[1] == 0:
+        raise ValueError(f'Expected indices of shape (n_seq, L), not {indices.shape}')
+    if indices.max(initial=-1) >= len(pulses):
+        raise ValueError(f'indices refer to pulse {indices.max()} but only {len(pulses)} given')
+    if (indices < 0).all(axis=1).any():
+        raise ValueError('Every sequence needs at least one gate')
+    first = pulses[0]
+    if len(set(pls.d for pls in pulses)) != 1:
+        raise ValueError('Trying to concatenate PulseSequence instances with different dimension!')
+    bases = _unique_by_identity(pls.basis for pls in pulses)
+    if len(bases) > 1 and not util.all_array_equal(bases):
+        raise ValueError('Trying to concatenate PulseSequence instances with different bases!')
+    if not first.basis.isherm:
+        raise ValueError('concatenate_many needs a Hermitian basis (real Liouville propagators)')
+    for pls in pulses[1:]:
+        if (not np.array_equal(pls.n_oper_identifiers, first.n_oper_identifiers)
+                or _oper_hashes(pls, 'noise') != _oper_hashes(first, 'noise')):
+            raise ValueError('concatenate_many requires all pulses to have the same noise operators; '
+                             + 'use concatenate for the general case')
+    if omega is None:
+        grids = _unique_by_identity(pls.omega for pls in pulses)
+        if any(g is None for g in grids) or (len(grids) > 1 and not util.all_array_equal(grids)):
+            raise ValueError('Not all pulses have the same frequencies cached and none were '
+                             + 'supplied!')
+        omega = first.omega
+    omega = _lib.as_f64(omega)
+
+    lib_B = _lib.as_c128(np.array([pls.get_control_matrix(omega) for pls in pulses]))
+    lib_phase = _lib.as_c128(np.array([pls.get_total_phases(omega) for pls in pulses]))
+    lib_liouville = _lib.as_f64(np.array([np.real(pls.total_propagator_liouville)
+                                          for pls in pulses]))
+    lib_U = _lib.as_c128(np.array([pls.total_propagator for pls in pulses]))
+    basis = _lib.as_c128(np.asarray(first.basis))
+    n_lib, n_nops, n_basis, n_omega = lib_B.shape
+    d = first.d
+    n_seq, L = indices.shape
+
+    S = None
+    s_ndim = s_complex = 0
+    if spectrum is not None:
+        spectrum = util.parse_spectrum(np.asarray(spectrum), omega, np.arange(n_nops))
+        s_ndim, s_complex = spectrum.ndim, int(np.iscomplexobj(spectrum))
+        S = _lib.as_c128(spectrum) if s_complex else _lib.as_f64(spectrum)
+
+    batch = SequenceBatch(pulses, indices, omega)
+    taus = np.array([pls.tau for pls in pulses] + [0.0])
+    batch.tau = taus[indices].sum(axis=1)
+    batch.total_propagator = np.empty((n_seq, d, d), dtype=np.complex128)
+    liouville = np.empty((n_seq, n_basis, n_basis), dtype=np.complex128)
+    if calc_control_matrix:
+        batch.control_matrix = _lib.empty((n_seq, n_nops, n_basis, n_omega))
+    if calc_filter_function:
+        batch.filter_function = _lib.empty((n_seq, n_nops, n_nops, n_omega))
+    if S is not None:
+        batch.infidelities = np.empty((n_seq,) + ((n_nops, n_nops) if s_ndim == 3 else (n_nops,)))
+
+    ctx = _lib.context()
+    p = _lib.ptr
+    rows_per_call = max(1, 65535//n_nops)
+    for lo in range(0, n_seq, rows_per_call):
+        hi = min(n_seq, lo + rows_per_call)
+        sub = lambda a: None if a is None else p(a[lo:hi])  # noqa: E731
+        _lib.check(ctx, _lib.lib().ffb_concatenate_many(
+            ctx, hi - lo, L, n_lib, d, n_nops, n_basis, n_omega, p(indices[lo:hi]), p(lib_B),
+            p(lib_phase), p(lib_liouville), p(lib_U), p(basis), p(S), s_ndim, s_complex, p(omega),
+            sub(batch.total_propagator), sub(liouville), sub(batch.control_matrix),
+            sub(batch.filter_function), sub(batch.infidelities), None, None))
+    batch.total_propagator_liouville = np.ascontiguousarray(liouville.real)
+    return batch

@@ -16,7 +16,7 @@ from . import _lib
 __all__ = ['paulis', 'abs2', 'cexp', 'get_sample_frequencies', 'mdot', 'adot', 'integrate',
            'parse_optional_parameters', 'parse_spectrum', 'parse_operators',
            'get_indices_from_identifiers', 'is_sequence_like', 'hash_array_along_axis',
-           'all_array_equal', 'CalculationError']
+           'all_array_equal', 'CalculationError', 'dot_HS', 'oper_equiv']
 
 #: Pauli matrices I, X, Y, Z (reference ``util.py:109-118``)
 paulis = np.array([[[1, 0], [0, 1]], [[0, 1], [1, 0]], [[0, -1j], [1j, 0]], [[1, 0], [0, -1]]],
@@ -162,6 +162,38 @@ def get_sample_frequencies(pulse, n_samples: int = 300, spacing: str = 'log',
     if include_quasistatic:
         return np.insert(omega, 0, 0)
     return omega
+
+
+def dot_HS(U, V, eps=None):
+    """Hilbert-Schmidt inner product tr(U^dagger V), rounded to the precision ``eps`` (default: the
+    rounding error of the product; reference ``util.py:1003-1051``)."""
+    U, V = np.asarray(U), np.asarray(V)
+    if eps is None:
+        try:
+            eps = np.finfo(U.dtype).eps*np.prod(U.shape)*V.shape[-1]*2
+        except ValueError:
+            eps = 0
+    res = np.einsum('...ij,...ij', U.conj(), V)
+    if eps != 0:
+        res = np.around(res, decimals=abs(int(np.log10(eps))))
+    return res if np.imag(res).any() else np.real(res)
+
+
+def oper_equiv(psi, phi, eps=None, normalized: bool = False):
+    """Are ``psi`` and ``phi`` equal up to a global phase?  Returns ``(bool, phase)`` with
+    ``phi = exp(i phase) psi`` (reference ``util.py:941-1000``)."""
+    psi, phi = np.atleast_2d(np.asarray(psi), np.asarray(phi))
+    if eps is None:
+        eps = (max(np.finfo(psi.dtype).eps, np.finfo(phi.dtype).eps)
+               * np.prod(psi.shape)*phi.shape[-1]*2)
+        if not normalized:
+            eps *= (np.prod(psi.shape[-2:])*phi.shape[-1]*2)**2
+    try:
+        inner_product = dot_HS(psi, phi, eps=0)
+    except ValueError as err:
+        raise ValueError('psi and phi have incompatible dimensions!') from err
+    norm = 1 if normalized else np.sqrt(dot_HS(psi, psi, eps=0)*dot_HS(phi, phi, eps=0))
+    return abs(norm - abs(inner_product)) <= eps, np.angle(inner_product)
 
 
 def hash_array_along_axis(arr, axis: int = 0):

@@ -124,6 +124,29 @@ int ffb_decay_amplitudes(ffb_ctx* ctx, int P, int n_nops, int n_sel, const int* 
                          int n_omega, const double* B, const double* spectrum, int spectrum_ndim,
                          int spectrum_is_complex, const double* omega, double* out);
 
+/* ---- f2: batched concatenation -----------------------------------------------
+ * n_seq gate sequences of (up to) L gates each, drawn from a library of n_lib pulses whose control
+ * matrices are cached on one frequency grid: what a loop of ff.concatenate(cliffords[row]) followed by
+ * ff.infidelity does in examples/randomized_benchmarking.py:70-91, in one call (pulse_sequence.py:1745,
+ * :1824-1858 + numeric.py:621-704, :1413-1467, :2318-2320 per sequence).
+ *   indices (n_seq,L) int32, entries in [0,n_lib) or < 0 for padding (no gate)
+ *   lib_control_matrix (n_lib,n_nops,n_basis,n_omega) c128 | lib_total_phases (n_lib,n_omega) c128
+ *   lib_liouville (n_lib,n_basis,n_basis) f64 | lib_propagator (n_lib,d,d) c128 | basis (n_basis,d,d)
+ *   spectrum/omega as in ffb_infidelity with all n_nops operators selected (NULL: no infidelity)
+ *   tau (n_seq) f64: durations of the sequences, only needed for total_phases
+ * Outputs (any may be NULL): total_propagator (n_seq,d,d) c128, total_propagator_liouville
+ * (n_seq,n_basis,n_basis) c128, control_matrix (n_seq,n_nops,n_basis,n_omega) c128, filter_function
+ * (n_seq,n_nops,n_nops,n_omega) c128, infidelity (n_seq,n_nops) or (n_seq,n_nops,n_nops) f64,
+ * total_phases (n_seq,n_omega) c128 = exp(i omega tau) (util.cexp, pulse_sequence.py:1056-1084). */
+int ffb_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int n_lib, int d, int n_nops, int n_basis,
+                         int n_omega, const int* indices, const double* lib_control_matrix,
+                         const double* lib_total_phases, const double* lib_liouville,
+                         const double* lib_propagator, const double* basis, const double* spectrum,
+                         int spectrum_ndim, int spectrum_is_complex, const double* omega,
+                         double* total_propagator, double* total_propagator_liouville,
+                         double* control_matrix, double* filter_function, double* infidelity,
+                         const double* tau, double* total_phases);
+
 /* ---- a8 helper: Liouville representation --------------------------------------------------------
  * Replaces superoperator.liouville_representation (superoperator.py:51-84):
  * out[n,i,j] = tr(C_i U_n C_j U_n^dagger); U (n,d,d) c128, basis (n_basis,d,d) c128,

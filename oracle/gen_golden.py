@@ -200,6 +200,48 @@ def decay_amplitudes():
     np.savez_compressed(os.path.join(OUT, 'decay_amplitudes.npz'), **out)
 
 
+def sequencing_workloads():
+    """BASELINE.json configs 4 and 5 at reduced size, built by workloads.py through the reference's
+    public API: randomized-benchmarking sequences of cached Cliffords (examples/
+    randomized_benchmarking.py) and the QFT concatenated from cached gate pulses (examples/qft.py)."""
+    sys.path.insert(0, ROOT)
+    import workloads
+    out = {}
+    # ---- C4
+    omega = workloads.rb_omega()
+    S = workloads.rb_spectrum(omega)
+    cliffords = workloads.build_cliffords(ff, omega)
+    out['rb_omega'] = omega
+    out['rb_spectrum'] = S
+    out['rb_clifford_infidelity'] = np.array([ff.infidelity(c, S, omega) for c in cliffords])
+    out['rb_clifford_propagators'] = np.array([c.total_propagator for c in cliffords])
+    rows = workloads.rb_sequences(6, 100)
+    out['rb_rows'] = rows
+    seqs = [ff.concatenate([cliffords[k] for k in row]) for row in rows]
+    out['rb_infidelity'] = np.array([ff.infidelity(p, S, omega) for p in seqs])
+    out['rb_filter_function'] = np.array([p.get_filter_function(omega) for p in seqs])
+    out['rb_control_matrix'] = np.array([p.get_control_matrix(omega) for p in seqs])
+    out['rb_total_propagator'] = np.array([p.total_propagator for p in seqs])
+    # ---- C5
+    for N, n_omega in ((2, 60), (3, 40), (4, 24)):
+        omega = np.logspace(-2, 2, n_omega)
+        pulses = workloads.build_qft_pulses(ff, N)
+        for p in pulses:
+            p.cache_control_matrix(omega)
+        qft = ff.concatenate(pulses, omega=omega)
+        B = qft.get_control_matrix(omega)
+        tag = f'qft{N}'
+        out[f'{tag}_omega'] = omega
+        out[f'{tag}_n_ids'] = np.asarray(qft.n_oper_identifiers, dtype='U8')
+        out[f'{tag}_total_propagator'] = qft.total_propagator
+        out[f'{tag}_filter_function'] = qft.get_filter_function(omega)
+        out[f'{tag}_control_matrix'] = B if N < 4 else B[:, ::16]
+        out[f'{tag}_infidelity'] = ff.infidelity(qft, 1e-4/omega, omega)
+        scratch = ff.concatenate(pulses, calc_filter_function=False)
+        out[f'{tag}_filter_function_scratch'] = scratch.get_filter_function(omega)
+    np.savez_compressed(os.path.join(OUT, 'sequencing_workloads.npz'), **out)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1:       # regenerate only the named fixtures
@@ -211,5 +253,6 @@ if __name__ == '__main__':
     concatenation()
     workloads_small()
     decay_amplitudes()
+    sequencing_workloads()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), 'bytes')

@@ -137,3 +137,107 @@ def north_star_d4(G=10_000, n_omega=10_000, seed=3):
 def get(name, **kwargs):
     return {'c1': readme_hadamard, 'c2': single_qubit_grape, 'c3': two_qubit_exchange,
             'd4': north_star_d4}[name](**kwargs)
+
+
+# ------------------------------------------------------------------------------------------------
+# Workloads defined through the public API (BASELINE.json configs 4 and 5).  ``ff`` is the package to
+# build them with: ``filter_functions_b200`` in the tests and the bench, the reference itself in
+# ``oracle/gen_golden.py`` -- the same code drives both.
+# ------------------------------------------------------------------------------------------------
+CLIFFORD_WORDS = [                    # examples/randomized_benchmarking.py:158-183 (X = X2, Y = Y2)
+    'YYYY', 'XX', 'YY', 'YYXX', 'XY', 'XYYY', 'XXXY', 'XXXYYY', 'YX', 'YXXX', 'YYYX', 'YYYXXX',
+    'X', 'XXX', 'Y', 'YYY', 'XYYYXXX', 'XXXYYYX', 'XXY', 'XXYYY', 'YYX', 'YYXXX', 'XYX', 'XYYYX']
+
+
+def rb_omega(T=20.0, m_max=151, n_omega=301):
+    """examples/randomized_benchmarking.py:145."""
+    return np.geomspace(1e-2/(7*m_max*T), 1e2/T, n_omega)*2*np.pi
+
+
+def rb_spectrum(omega, alpha=0.7):
+    """examples/randomized_benchmarking.py:189-194."""
+    eps0 = 2.7241e-4
+    return 4e-11*(2*np.pi*1e-3/omega)**alpha/eps0**2
+
+
+def build_cliffords(ff, omega, T=20.0):
+    """C4: the 24 single-qubit Cliffords from 'naive' X/2 and Y/2 gates with sigma_x noise
+    (examples/randomized_benchmarking.py:95-111, :148-183), control matrices cached on ``omega``."""
+    X2 = ff.PulseSequence([[X/2, [np.pi/2/T], 'X']], [[X/2, [1], 'X']], [T])
+    Y2 = ff.PulseSequence([[Y/2, [np.pi/2/T], 'Y']], [[X/2, [1], 'X']], [T])
+    X2.cache_control_matrix(omega)
+    Y2.cache_control_matrix(omega)
+    gates = {'X': X2, 'Y': Y2}
+    cliffords = []
+    for word in CLIFFORD_WORDS:
+        pulse = gates[word[0]]
+        for letter in word[1:]:
+            pulse = pulse @ gates[letter]
+        cliffords.append(pulse)
+    return cliffords
+
+
+def rb_sequences(n_seq=1000, length=100, seed=4):
+    return np.random.default_rng(seed).integers(0, 24, (n_seq, length))
+
+
+def _embed(op, k, N):
+    """op on qubit k of N (k = 0 is the left-most tensor factor)."""
+    return kron(*[op if i == k else I2 for i in range(N)])
+
+
+def build_qft_pulses(ff, N=4, tau=1.0):
+    """C5: the gate pulses of the N-qubit QFT of examples/qft.py:42-136 with QuTiP objects replaced by
+    Kronecker products: T_I, [H_k, P_{k+1}] for k < N-1, H_{N-1}, T_F."""
+    d = 2**N
+
+    def ident(letters):
+        out = ['I']*N
+        for pos, letter in letters:
+            out[pos] = letter
+        return ''.join(out)
+
+    def R_k(k, theta, phi):
+        Xk, Yk = _embed(X, k, N), _embed(Y, k, N)
+        H_c = [[Xk, [theta/2/tau*np.cos(phi)], ident([(k, 'X')])],
+               [Yk, [theta/2/tau*np.sin(phi)], ident([(k, 'Y')])]]
+        H_n = [[Xk/np.sqrt(d), [1], ident([(k, 'X')])], [Yk/np.sqrt(d), [1], ident([(k, 'Y')])]]
+        return ff.PulseSequence(H_c, H_n, [tau])
+
+    def T_pulse(coeff):
+        H_c = [[_embed(Z, k - 1, N), [coeff(k)], ident([(k - 1, 'Z')])] for k in range(1, N + 1)]
+        H_n = [[_embed(Z, k - 1, N)/np.sqrt(d), [1], ident([(k - 1, 'Z')])]
+               for k in range(1, N + 1)]
+        return ff.PulseSequence(H_c, H_n, [tau])
+
+    def P_n(n):
+        H_c, H_n = [], []
+        for l in range(n + 1, N + 1):
+            ZZ = _embed(Z, n - 1, N) @ _embed(Z, l - 1, N)
+            name = ident([(n - 1, 'Z'), (l - 1, 'Z')])
+            H_c.append([ZZ, [-np.pi/4*2**(n - l)/tau], name])
+            H_n.append([ZZ/np.sqrt(d), [1], name])
+        return ff.PulseSequence(H_c, H_n, [tau])
+
+    def H_k(k):
+        return ff.concatenate([R_k(k, np.pi, 0), R_k(k, np.pi/2, -np.pi/2)])
+
+    pulses = [T_pulse(lambda k: np.pi/4*(1 - 2**(1 - k))/tau)]
+    for n in range(N - 1):
+        pulses.append(H_k(n))
+        pulses.append(P_n(n + 1))
+    pulses.append(H_k(N - 1))
+    pulses.append(T_pulse(lambda k: np.pi/4*(1 - 2**(k - N))/tau))
+    return pulses
+
+
+def qft_matrix(N):
+    d = 2**N
+    j, k = np.meshgrid(np.arange(d), np.arange(d))
+    return np.exp(2j*np.pi*j*k/d)/np.sqrt(d)
+
+
+def bit_reversal(N):
+    d = 2**N
+    perm = [int(format(i, f'0{N}b')[::-1], 2) for i in range(d)]
+    return np.eye(d)[perm]
