@@ -13,11 +13,11 @@ from . import basis, numeric, pulse_sequence, superoperator, util
 from .basis import Basis
 from .numeric import error_transfer_matrix, infidelity
 from .pulse_sequence import (PulseSequence, SequenceBatch, concatenate, concatenate_many,
-                             concatenate_without_filter_function)
+                             concatenate_periodic, concatenate_without_filter_function)
 from .superoperator import liouville_representation
 
 __all__ = ['Basis', 'PulseSequence', 'SequenceBatch', 'basis', 'concatenate', 'concatenate_many',
-           'concatenate_without_filter_function',
+           'concatenate_periodic', 'concatenate_without_filter_function',
            'error_transfer_matrix', 'infidelity', 'liouville_representation', 'numeric',
            'pulse_sequence', 'superoperator', 'util']
 

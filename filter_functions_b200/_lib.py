@@ -37,9 +37,12 @@ EXPORTED_SYMBOLS = {
     'ffb_diagonalize': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]),
     'ffb_control_matrix_from_scratch': (c_int, [c_void_p] + [c_int]*5 + [c_void_p]*10),
+    'ffb_control_matrix_intermediates': (c_int, [c_void_p] + [c_int]*5 + [c_void_p]*17),
     'ffb_filter_function': (c_int, [c_void_p] + [c_int]*4 + [c_void_p, c_int, c_void_p]),
     'ffb_control_matrix_from_atomic': (c_int, [c_void_p] + [c_int]*4 + [c_void_p]*3
                                        + [c_int, c_int, c_void_p]),
+    'ffb_control_matrix_periodic': (c_int, [c_void_p] + [c_int]*4 + [c_void_p]*3
+                                    + [c_int, c_void_p]),
     'ffb_infidelity': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                c_int, c_int, c_void_p, c_int, c_void_p]),
     'ffb_decay_amplitudes': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,

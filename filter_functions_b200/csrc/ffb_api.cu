@@ -438,6 +438,65 @@ int ffb_control_matrix_from_scratch(ffb_ctx* ctx, int G, int d, int n_nops, int 
   return FFB_OK;
 }
 
+int ffb_control_matrix_intermediates(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis,
+                                     int n_omega, const double* eigvals, const double* eigvecs,
+                                     const double* propagators, const double* omega,
+                                     const double* basis, const double* n_opers,
+                                     const double* n_coeffs, const double* dt, const double* t,
+                                     double* out, double* n_opers_transformed,
+                                     double* eigvecs_propagated, double* basis_transformed,
+                                     double* phase_factors, double* first_order_integral,
+                                     double* control_matrix_step,
+                                     double* control_matrix_step_cumulative) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, eigvals && eigvecs && propagators && omega && basis && n_opers && n_coeffs &&
+                       dt && t && out && n_opers_transformed && eigvecs_propagated &&
+                       basis_transformed && phase_factors && first_order_integral &&
+                       control_matrix_step && (G == 1 || control_matrix_step_cumulative),
+              "control matrix intermediates: null pointer");
+  FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
+              "control matrix intermediates: bad shape");
+  const size_t dd = (size_t)d * d;
+  Upload ev, V, Q, om, bs, no, nc, dts, ts;
+  DevBuf B, Bt, Up, Ct, Ph, In, St, Cu;
+  FFB_TRY(ev.put(ctx, eigvals, (size_t)G * d * 8));
+  FFB_TRY(V.put(ctx, eigvecs, (size_t)G * dd * 16));
+  FFB_TRY(Q.put(ctx, propagators, (size_t)G * dd * 16));
+  FFB_TRY(om.put(ctx, omega, (size_t)n_omega * 8));
+  FFB_TRY(bs.put(ctx, basis, (size_t)n_basis * dd * 16));
+  FFB_TRY(no.put(ctx, n_opers, (size_t)n_nops * dd * 16));
+  FFB_TRY(nc.put(ctx, n_coeffs, (size_t)n_nops * G * 8));
+  FFB_TRY(dts.put(ctx, dt, (size_t)G * 8));
+  FFB_TRY(ts.put(ctx, t, (size_t)(G + 1) * 8));
+  const size_t per_step = (size_t)n_nops * n_basis * n_omega * 16;
+  const size_t b_bt = (size_t)n_nops * G * dd * 16, b_up = (size_t)G * dd * 16,
+               b_ct = (size_t)G * n_basis * dd * 16, b_ph = (size_t)G * n_omega * 16,
+               b_in = (size_t)G * n_omega * dd * 16, b_st = (size_t)G * per_step,
+               b_cu = (size_t)(G - 1) * per_step;
+  FFB_TRY(B.alloc(ctx, per_step));
+  FFB_TRY(Bt.alloc(ctx, b_bt));
+  FFB_TRY(Up.alloc(ctx, b_up));
+  FFB_TRY(Ct.alloc(ctx, b_ct));
+  FFB_TRY(Ph.alloc(ctx, b_ph));
+  FFB_TRY(In.alloc(ctx, b_in));
+  FFB_TRY(St.alloc(ctx, b_st));
+  FFB_TRY(Cu.alloc(ctx, b_cu));
+  FFB_TRY(ffbi_control_matrix_intermediates(
+      ctx, G, d, n_nops, n_basis, n_omega, ev.d(), V.d(), Q.d(), om.d(), bs.d(), no.d(), nc.d(),
+      dts.d(), ts.d(), B.as<double>(), Bt.as<double>(), Up.as<double>(), Ct.as<double>(),
+      Ph.as<double>(), In.as<double>(), St.as<double>(), Cu.as<double>()));
+  FFB_TRY(ffb_d2h(ctx, out, B.p, per_step));
+  FFB_TRY(ffb_d2h(ctx, n_opers_transformed, Bt.p, b_bt));
+  FFB_TRY(ffb_d2h(ctx, eigvecs_propagated, Up.p, b_up));
+  FFB_TRY(ffb_d2h(ctx, basis_transformed, Ct.p, b_ct));
+  FFB_TRY(ffb_d2h(ctx, phase_factors, Ph.p, b_ph));
+  FFB_TRY(ffb_d2h(ctx, first_order_integral, In.p, b_in));
+  FFB_TRY(ffb_d2h(ctx, control_matrix_step, St.p, b_st));
+  if (G > 1) FFB_TRY(ffb_d2h(ctx, control_matrix_step_cumulative, Cu.p, b_cu));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
 int ffb_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega, const double* B,
                         int generalized, double* F) {
   FFB_TRY(enter(ctx));
@@ -478,6 +537,27 @@ int ffb_control_matrix_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis,
   FFB_TRY(ffbi_from_atomic(ctx, P, n_nops, n_basis, n_omega, P > 1 ? ph.d() : nullptr, Ba.d(),
                            P > 1 ? Q.d() : nullptr, q_is_complex, correlations, O.as<double>()));
   FFB_TRY(ffb_d2h(ctx, out, O.p, out_bytes));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_control_matrix_periodic(ffb_ctx* ctx, int n_nops, int n_basis, int n_omega, int repeats,
+                                const double* phases, const double* B, const double* L,
+                                int l_is_complex, double* out) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, phases && B && L && out, "periodic control matrix: null pointer");
+  FFB_REQUIRE(ctx, n_nops >= 1 && n_basis >= 1 && n_omega >= 1 && repeats >= 1,
+              "periodic control matrix: bad shape");
+  Upload ph, Bd, Ld;
+  DevBuf O;
+  const size_t b_bytes = (size_t)n_nops * n_basis * n_omega * 16;
+  FFB_TRY(ph.put(ctx, phases, (size_t)n_omega * 16));
+  FFB_TRY(Bd.put(ctx, B, b_bytes));
+  FFB_TRY(Ld.put(ctx, L, (size_t)n_basis * n_basis * (l_is_complex ? 16 : 8)));
+  FFB_TRY(O.alloc(ctx, b_bytes));
+  FFB_TRY(ffbi_control_matrix_periodic(ctx, n_nops, n_basis, n_omega, repeats, ph.d(), Bd.d(),
+                                       Ld.d(), l_is_complex, O.as<double>()));
+  FFB_TRY(ffb_d2h(ctx, out, O.p, b_bytes));
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return FFB_OK;
 }

@@ -129,6 +129,18 @@ int ffbi_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int d, int n_nops, int
                           int n_omega, const int* idx, const double* lib_B, const double* lib_phase,
                           const double* lib_liouville, const double* lib_U, double* U_total,
                           double* out_B, double* out_F);
+int ffbi_control_matrix_intermediates(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis,
+                                      int n_omega, const double* eigvals, const double* eigvecs,
+                                      const double* propagators, const double* omega,
+                                      const double* basis, const double* n_opers,
+                                      const double* n_coeffs, const double* dt, const double* t,
+                                      double* out, double* n_opers_transformed,
+                                      double* eigvecs_propagated, double* basis_transformed,
+                                      double* phase_factors, double* first_order_integral,
+                                      double* step, double* cumulative);
+int ffbi_control_matrix_periodic(ffb_ctx* ctx, int n_nops, int n_basis, int n_omega, int repeats,
+                                 const double* phases, const double* B, const double* L,
+                                 int l_is_complex, double* out);
 int ffbi_liouville(ffb_ctx* ctx, int n, int d, int n_basis, const double* U, const double* basis,
                    double* out);
 int ffbi_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out);

@@ -299,6 +299,100 @@ ff_batched_kernel(int n_nops, int n_basis, int n_omega, const double2* __restric
   F[(((size_t)s * n_nops + a) * n_nops + b) * n_omega + w] = make_double2(re, im);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Periodic repetition: numeric.calculate_control_matrix_periodic
+// (numeric.py:884-954), B_tot(w) = B(w) sum_{g<G} (phi(w) L)^g.  The reference solves a d^2 x d^2 linear
+// system per frequency and falls back to the explicit sum where I - phi L is ill-conditioned.  Here the
+// geometric series is built by binary doubling ON THE ROW VECTORS u_m = B S_m, S_m = sum_{g<m} (phi L)^g:
+//     u_{2m}  = u_m + phi^m (u_m L^m)        u_{m+1} = B + phi (u_m L)
+// (S_m and L commute), i.e. ~2 log2(G) products of the frequency-dependent rows with FIXED matrices L^m
+// -- no per-frequency inverse, no conditioning check, O(n_nops n_basis^2 log G) per frequency.
+//     out[j,l,w] = A[j,l,w] + phi(w)^m sum_k X[j,k,w] Q[k,l]
+// ------------------------------------------------------------------------------------------------
+template <int LT, bool QC>
+__global__ void __launch_bounds__(256)
+periodic_step_kernel(int n_basis, int n_omega, int m, const double2* __restrict__ phases,
+                     const double2* __restrict__ A, const double2* __restrict__ X,
+                     const double* __restrict__ Q, double2* __restrict__ out) {
+  extern __shared__ double qs[];  // [n_basis][LT] (x2 if complex)
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  const int l0 = blockIdx.z * LT;
+  for (int e = threadIdx.x; e < n_basis * LT; e += blockDim.x) {
+    const int k = e / LT, i = e % LT;
+    const bool ok = l0 + i < n_basis;
+    if (QC) {
+      qs[2 * e] = ok ? Q[2 * ((size_t)k * n_basis + l0 + i)] : 0.0;
+      qs[2 * e + 1] = ok ? Q[2 * ((size_t)k * n_basis + l0 + i) + 1] : 0.0;
+    } else {
+      qs[e] = ok ? Q[(size_t)k * n_basis + l0 + i] : 0.0;
+    }
+  }
+  __syncthreads();
+  if (w >= n_omega) return;
+  // phi^m by binary powering of the GIVEN phase factor (as matrix_power does in the reference)
+  double2 ph = make_double2(1.0, 0.0), base = phases[w];
+  for (int e = m; e > 0; e >>= 1) {
+    if (e & 1) ph = make_double2(ph.x * base.x - ph.y * base.y, ph.x * base.y + ph.y * base.x);
+    base = make_double2(base.x * base.x - base.y * base.y, 2.0 * base.x * base.y);
+  }
+  const size_t row0 = (size_t)j * n_basis * n_omega + w;
+  double2 acc[LT];
+#pragma unroll
+  for (int i = 0; i < LT; ++i) acc[i] = make_double2(0.0, 0.0);
+  for (int k = 0; k < n_basis; ++k) {
+    const double2 x = X[row0 + (size_t)k * n_omega];
+#pragma unroll
+    for (int i = 0; i < LT; ++i) {
+      if (QC) {
+        const double qr = qs[2 * (k * LT + i)], qi = qs[2 * (k * LT + i) + 1];
+        acc[i].x += x.x * qr - x.y * qi;
+        acc[i].y += x.x * qi + x.y * qr;
+      } else {
+        const double qv = qs[k * LT + i];
+        acc[i].x += x.x * qv;
+        acc[i].y += x.y * qv;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LT; ++i) {
+    if (l0 + i < n_basis) {
+      const size_t e = row0 + (size_t)(l0 + i) * n_omega;
+      const double2 a = A[e];
+      out[e] = make_double2(a.x + ph.x * acc[i].x - ph.y * acc[i].y,
+                            a.y + ph.x * acc[i].y + ph.y * acc[i].x);
+    }
+  }
+}
+
+// C = A B for n x n matrices (real, or complex if QC); the fixed matrices L^m of the doubling scheme
+template <bool QC>
+__global__ void __launch_bounds__(256)
+small_matmul_kernel(int n, const double* __restrict__ A, const double* __restrict__ B,
+                    double* __restrict__ C) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * n) return;
+  const int i = e / n, j = e % n;
+  double re = 0.0, im = 0.0;
+  for (int k = 0; k < n; ++k) {
+    if (QC) {
+      const double ar = A[2 * (i * n + k)], ai = A[2 * (i * n + k) + 1];
+      const double br = B[2 * (k * n + j)], bi = B[2 * (k * n + j) + 1];
+      re += ar * br - ai * bi;
+      im += ar * bi + ai * br;
+    } else {
+      re += A[i * n + k] * B[k * n + j];
+    }
+  }
+  if (QC) {
+    C[2 * e] = re;
+    C[2 * e + 1] = im;
+  } else {
+    C[e] = re;
+  }
+}
+
 template <int LT>
 int launch_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
                        const double* phases, const double* B_atomic, const double* Q,
@@ -410,5 +504,92 @@ int ffbi_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int d, int n_nops, int
                                                      reinterpret_cast<double2*>(out_F));
     FFB_LAUNCHED(ctx);
   }
+  return FFB_OK;
+}
+
+namespace {
+
+template <int LT>
+int launch_periodic_step(ffb_ctx* ctx, int n_nops, int n_basis, int n_omega, int m,
+                         const double* phases, const double* A, const double* X, const double* Q,
+                         int q_is_complex, double* out) {
+  dim3 grid(ceil_div(n_omega, 256), n_nops, ceil_div(n_basis, LT));
+  const size_t smem = (size_t)n_basis * LT * sizeof(double) * (q_is_complex ? 2 : 1);
+  auto launch = [&](auto kern) -> int {
+    FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, ctx->stream>>>(n_basis, n_omega, m,
+                                           reinterpret_cast<const double2*>(phases),
+                                           reinterpret_cast<const double2*>(A),
+                                           reinterpret_cast<const double2*>(X), Q,
+                                           reinterpret_cast<double2*>(out));
+    FFB_LAUNCHED(ctx);
+    return FFB_OK;
+  };
+  return q_is_complex ? launch(periodic_step_kernel<LT, true>)
+                      : launch(periodic_step_kernel<LT, false>);
+}
+
+int periodic_step(ffb_ctx* ctx, int n_nops, int n_basis, int n_omega, int m, const double* phases,
+                  const double* A, const double* X, const double* Q, int q_is_complex, double* out) {
+  if (n_basis <= 4)
+    return launch_periodic_step<4>(ctx, n_nops, n_basis, n_omega, m, phases, A, X, Q, q_is_complex, out);
+  if (n_basis <= 8)
+    return launch_periodic_step<8>(ctx, n_nops, n_basis, n_omega, m, phases, A, X, Q, q_is_complex, out);
+  return launch_periodic_step<16>(ctx, n_nops, n_basis, n_omega, m, phases, A, X, Q, q_is_complex, out);
+}
+
+}  // namespace
+
+int ffbi_control_matrix_periodic(ffb_ctx* ctx, int n_nops, int n_basis, int n_omega, int repeats,
+                                 const double* phases, const double* B, const double* L,
+                                 int l_is_complex, double* out) {
+  FFB_REQUIRE(ctx, n_nops >= 1 && n_basis >= 1 && n_omega >= 1 && repeats >= 1 && n_nops <= 65535,
+              "periodic control matrix: bad shape (n_nops=%d, n_basis=%d, n_omega=%d, repeats=%d)",
+              n_nops, n_basis, n_omega, repeats);
+  const size_t b_bytes = (size_t)n_nops * n_basis * n_omega * 16;
+  const size_t l_bytes = (size_t)n_basis * n_basis * (l_is_complex ? 16 : 8);
+  if (repeats == 1) {
+    FFB_CUDA(ctx, cudaMemcpyAsync(out, B, b_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return FFB_OK;
+  }
+  DevBuf u0, u1, Lm0, Lm1;
+  FFB_TRY(u0.alloc(ctx, b_bytes));
+  FFB_TRY(u1.alloc(ctx, b_bytes));
+  FFB_TRY(Lm0.alloc(ctx, l_bytes));
+  FFB_TRY(Lm1.alloc(ctx, l_bytes));
+  auto matmul = [&](const double* A_, const double* B_, double* C_) -> int {
+    const unsigned blocks = (unsigned)ceil_div(n_basis * n_basis, 256);
+    if (l_is_complex) small_matmul_kernel<true><<<blocks, 256, 0, ctx->stream>>>(n_basis, A_, B_, C_);
+    else small_matmul_kernel<false><<<blocks, 256, 0, ctx->stream>>>(n_basis, A_, B_, C_);
+    FFB_LAUNCHED(ctx);
+    return FFB_OK;
+  };
+  // u = B S_m and Lm = L^m for m running through the binary prefixes of `repeats`
+  const double* u = B;      // m = 1: S_1 = identity
+  const double* Lm = L;
+  double* u_next = u0.as<double>();
+  double* L_next = Lm0.as<double>();
+  auto flip_u = [&]() { u = u_next; u_next = (u_next == u0.as<double>()) ? u1.as<double>() : u0.as<double>(); };
+  auto flip_L = [&]() { Lm = L_next; L_next = (L_next == Lm0.as<double>()) ? Lm1.as<double>() : Lm0.as<double>(); };
+  int m = 1;
+  int top = 30;
+  while (!((repeats >> top) & 1)) --top;
+  for (int bit = top - 1; bit >= 0; --bit) {
+    // doubling: u_{2m} = u_m + phi^m (u_m L^m)
+    FFB_TRY(periodic_step(ctx, n_nops, n_basis, n_omega, m, phases, u, u, Lm, l_is_complex, u_next));
+    flip_u();
+    FFB_TRY(matmul(Lm, Lm, L_next));
+    flip_L();
+    m *= 2;
+    if ((repeats >> bit) & 1) {
+      // increment: u_{m+1} = B + phi (u_m L)
+      FFB_TRY(periodic_step(ctx, n_nops, n_basis, n_omega, 1, phases, B, u, L, l_is_complex, u_next));
+      flip_u();
+      FFB_TRY(matmul(Lm, L, L_next));
+      flip_L();
+      m += 1;
+    }
+  }
+  FFB_CUDA(ctx, cudaMemcpyAsync(out, u, b_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return FFB_OK;
 }

@@ -23,7 +23,7 @@ from numpy import ndarray
 from . import _lib, util
 
 __all__ = ['calculate_control_matrix_from_atomic', 'calculate_control_matrix_from_scratch',
-           'calculate_cumulant_function', 'calculate_decay_amplitudes',
+           'calculate_control_matrix_periodic', 'calculate_cumulant_function', 'calculate_decay_amplitudes',
            'calculate_filter_function', 'calculate_pulse_correlation_filter_function',
            'diagonalize', 'error_transfer_matrix', 'infidelity']
 
@@ -71,10 +71,6 @@ def calculate_control_matrix_from_scratch(eigvals, eigvecs, propagators, omega, 
                                           out: Optional[ndarray] = None):
     r"""Control matrix :math:`\tilde{\mathcal{B}}_{\alpha k}(\omega)` of shape
     (n_nops, n_basis, n_omega) without knowledge of more atomic pulses."""
-    if cache_intermediates:
-        raise NotImplementedError(
-            'cache_intermediates=True returns (n_dt, n_omega, d, d)-sized arrays which the fused '
-            'kernel exists to avoid; not available in filter_functions_b200 (SURVEY.md 8f rank 3)')
     eigvals = _lib.as_f64(eigvals)
     eigvecs = _lib.as_c128(eigvecs)
     propagators = _lib.as_c128(propagators)
@@ -98,6 +94,30 @@ def calculate_control_matrix_from_scratch(eigvals, eigvecs, propagators, omega, 
     if not direct:
         result = _lib.empty((n_nops, n_basis, n_omega))
     ctx = _lib.context()
+    if cache_intermediates:
+        # materialising variant (numeric.py:828-879): same result plus the (G, n_omega, ...)-sized
+        # by-products the fused kernel never builds
+        inter = dict(
+            n_opers_transformed=_lib.empty((n_nops, G, d, d)),
+            eigvecs_propagated=_lib.empty((G, d, d)),
+            basis_transformed=_lib.empty((G, n_basis, d, d)),
+            phase_factors=_lib.empty((G, n_omega)),
+            first_order_integral=_lib.empty((G, n_omega, d, d)),
+            control_matrix_step=_lib.empty((G, n_nops, n_basis, n_omega)),
+            control_matrix_step_cumulative=_lib.empty((G - 1, n_nops, n_basis, n_omega)))
+        if n_omega:
+            _lib.check(ctx, _lib.lib().ffb_control_matrix_intermediates(
+                ctx, G, d, n_nops, n_basis, n_omega, _lib.ptr(eigvals), _lib.ptr(eigvecs),
+                _lib.ptr(propagators), _lib.ptr(omega), _lib.ptr(basis_arr), _lib.ptr(n_opers),
+                _lib.ptr(n_coeffs), _lib.ptr(dt), _lib.ptr(t), _lib.ptr(result),
+                *(_lib.ptr(inter[key]) for key in (
+                    'n_opers_transformed', 'eigvecs_propagated', 'basis_transformed',
+                    'phase_factors', 'first_order_integral', 'control_matrix_step',
+                    'control_matrix_step_cumulative'))))
+        if out is not None and not direct:
+            out[:] = result
+            result = out
+        return result, inter
     if n_omega:
         _lib.check(ctx, _lib.lib().ffb_control_matrix_from_scratch(
             ctx, G, d, n_nops, n_basis, n_omega, _lib.ptr(eigvals), _lib.ptr(eigvecs),
@@ -138,6 +158,33 @@ def calculate_control_matrix_from_atomic(phases, control_matrix_atomic, propagat
         return np.asfortranarray(out)
     # neither: the reference hands back an array with omega on the second-to-last memory axis
     return np.ascontiguousarray(out.swapaxes(-1, -2)).swapaxes(-1, -2)
+
+
+def calculate_control_matrix_periodic(phases, control_matrix, total_propagator_liouville,
+                                      repeats: int, check_invertible: bool = True) -> ndarray:
+    r"""Control matrix of a pulse repeated ``repeats`` times,
+    :math:`\tilde{\mathcal B}(\omega)\sum_{g<G}(e^{i\omega T}\mathcal Q)^g` (reference
+    ``numeric.py:884-954``).  The geometric series is evaluated by binary doubling on the GPU, which
+    is valid at every frequency, so ``check_invertible`` (the reference's guard around its per-
+    frequency linear solve) is accepted and has nothing to do."""
+    B = _lib.as_c128(control_matrix)
+    if B.ndim != 3:
+        raise ValueError('Expected control_matrix.ndim == 3.')
+    n_nops, n_basis, n_omega = B.shape
+    phases = _lib.as_c128(np.asarray(phases).reshape(n_omega))
+    L = np.asarray(total_propagator_liouville)
+    l_complex = np.iscomplexobj(L)
+    L = (_lib.as_c128(L) if l_complex else _lib.as_f64(L)).reshape(n_basis, n_basis)
+    repeats = int(repeats)
+    if repeats < 1:
+        raise ValueError(f'Expected repeats >= 1, not {repeats}')
+    out = _lib.empty(B.shape)
+    if out.size:
+        ctx = _lib.context()
+        _lib.check(ctx, _lib.lib().ffb_control_matrix_periodic(
+            ctx, n_nops, n_basis, n_omega, repeats, _lib.ptr(phases), _lib.ptr(B), _lib.ptr(L),
+            int(l_complex), _lib.ptr(out)))
+    return out
 
 
 def _filter_function(control_matrix, which, P):

@@ -4,8 +4,7 @@ control-matrix -> filter-function -> infidelity path, with every numerical body 
 Public names, signatures, cache keys (``_data``, ``_frequency_data``, ``_intermediates``), alias
 lookup, invalidation rules and exception types follow ``pulse_sequence.py`` of the reference
 (v1.2.1; ``:61-1267`` for the class, ``:1340-1483`` / ``:1599-1887`` for concatenation).  Out of scope
-here: ``extend``/``remap``, periodic concatenation, second-order filter
-functions and derivatives.
+here: ``extend``/``remap``, second-order filter functions and derivatives.
 """
 import bisect
 import copy
@@ -21,7 +20,7 @@ from .basis import Basis
 from .superoperator import liouville_representation
 
 __all__ = ['PulseSequence', 'SequenceBatch', 'concatenate', 'concatenate_many',
-           'concatenate_without_filter_function']
+           'concatenate_periodic', 'concatenate_without_filter_function']
 
 _DATA_ALIASES = {
     'eigenvalues': 'eigvals',
@@ -350,6 +349,9 @@ class PulseSequence:
             self.eigvals, self.eigvecs, self.propagators, self.omega, self.basis, self.n_opers,
             self.n_coeffs, self.dt, self.t, show_progressbar=show_progressbar,
             cache_intermediates=cache_intermediates)
+        if cache_intermediates:
+            control_matrix, intermediates = control_matrix
+            self._intermediates.update(intermediates)
         self.cache_control_matrix(self.omega, control_matrix)
         return self._frequency_data['control_matrix']
 
@@ -765,6 +767,34 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         phases, control_matrix_atomic, propagators_liouville, show_progressbar,
         which='correlations' if calc_pulse_correlation_FF else 'total')
     newpulse.cache_filter_function(omega, control_matrix, which=which)
+    return newpulse
+
+
+def concatenate_periodic(pulse: PulseSequence, repeats: int,
+                         check_invertible: bool = True) -> PulseSequence:
+    r"""Concatenate ``repeats`` copies of ``pulse``; with a cached control matrix the control matrix of
+    the repeated pulse follows from the geometric series
+    :math:`\tilde{\mathcal B}^{(1)}\sum_{g<G}(e^{i\omega T}\mathcal Q^{(1)})^g` in
+    O(log ``repeats``) GPU passes (reference ``pulse_sequence.py:1890-1977``)."""
+    if not isinstance(pulse, PulseSequence):
+        raise TypeError('Can only concatenate PulseSequences!')
+    repeats = int(repeats)
+    newpulse = PulseSequence.from_arrays(
+        c_opers=pulse.c_opers, c_oper_identifiers=pulse.c_oper_identifiers,
+        c_coeffs=np.tile(pulse.c_coeffs, (1, repeats)), n_opers=pulse.n_opers,
+        n_oper_identifiers=pulse.n_oper_identifiers,
+        n_coeffs=np.tile(pulse.n_coeffs, (1, repeats)), dt=np.tile(pulse.dt, repeats),
+        basis=pulse.basis)
+    newpulse.tau = repeats*pulse.tau
+    if not pulse.is_cached('control_matrix'):
+        return newpulse
+    phases_at = pulse.get_total_phases(pulse.omega)
+    control_matrix_at = pulse.get_control_matrix(pulse.omega)
+    newpulse.total_propagator = np.linalg.matrix_power(pulse.total_propagator, repeats)
+    newpulse.cache_total_phases(pulse.omega)
+    control_matrix_tot = numeric.calculate_control_matrix_periodic(
+        phases_at, control_matrix_at, pulse.total_propagator_liouville, repeats, check_invertible)
+    newpulse.cache_filter_function(pulse.omega, control_matrix_tot)
     return newpulse
 
 

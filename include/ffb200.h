@@ -147,6 +147,35 @@ int ffb_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int n_lib, int d, int n
                          double* control_matrix, double* filter_function, double* infidelity,
                          const double* tau, double* total_phases);
 
+/* ---- f3: control matrix with cached intermediates -----------------------------
+ * cache_intermediates=True of numeric.calculate_control_matrix_from_scratch (numeric.py:828-879): the
+ * control matrix plus the arrays of the `intermediates` dict (keys numeric.py:872-878), all c128:
+ *   n_opers_transformed (n_nops,G,d,d) | eigvecs_propagated (G,d,d) | basis_transformed (G,n_basis,d,d)
+ *   phase_factors (G,n_omega) | first_order_integral (G,n_omega,d,d)
+ *   control_matrix_step (G,n_nops,n_basis,n_omega) | control_matrix_step_cumulative (G-1,n_nops,n_basis,n_omega)
+ * Inputs as in ffb_control_matrix_from_scratch.  Memory grows with G * n_omega (this is the variant the
+ * fused kernel avoids); the call fails with FFB_ENOMEM if the device cannot hold the arrays. */
+int ffb_control_matrix_intermediates(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis,
+                                     int n_omega, const double* eigvals, const double* eigvecs,
+                                     const double* propagators, const double* omega,
+                                     const double* basis, const double* n_opers,
+                                     const double* n_coeffs, const double* dt, const double* t,
+                                     double* out, double* n_opers_transformed,
+                                     double* eigvecs_propagated, double* basis_transformed,
+                                     double* phase_factors, double* first_order_integral,
+                                     double* control_matrix_step,
+                                     double* control_matrix_step_cumulative);
+
+/* ---- f4: periodic repetition ---------------------------------------------------
+ * Replaces numeric.calculate_control_matrix_periodic (numeric.py:884-954):
+ *   out(w) = B(w) sum_{g < repeats} (phases(w) L)^g
+ * phases (n_omega) c128 | B (n_nops,n_basis,n_omega) c128 | L (n_basis,n_basis) f64 (c128 if
+ * l_is_complex) | out (n_nops,n_basis,n_omega) c128.  Binary doubling on the rows of B instead of one
+ * linear solve per frequency; valid for every frequency (no invertibility condition). */
+int ffb_control_matrix_periodic(ffb_ctx* ctx, int n_nops, int n_basis, int n_omega, int repeats,
+                                const double* phases, const double* B, const double* L,
+                                int l_is_complex, double* out);
+
 /* ---- a8 helper: Liouville representation --------------------------------------------------------
  * Replaces superoperator.liouville_representation (superoperator.py:51-84):
  * out[n,i,j] = tr(C_i U_n C_j U_n^dagger); U (n,d,d) c128, basis (n_basis,d,d) c128,

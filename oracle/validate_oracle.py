@@ -74,6 +74,16 @@ def main():
                                                  n_coeffs, dt, t)
         record('control_matrix', nerr(B_o, B_r))
 
+        if d <= 5:
+            B_ri, inter_r = ref_numeric.calculate_control_matrix_from_scratch(
+                ev_r, V_r, Q_r, omega, basis, n_opers, n_coeffs, dt, t, cache_intermediates=True)
+            B_oi, inter_o = oracle.control_matrix_intermediates(ev_r, V_r, Q_r, omega, my_basis,
+                                                                n_opers, n_coeffs, dt, t)
+            record('intermediates_control_matrix', nerr(B_oi, B_ri))
+            assert sorted(inter_r) == sorted(inter_o)
+            for key in inter_r:
+                record('intermediates_' + key, nerr(inter_o[key], inter_r[key]))
+
         for which in ('fidelity', 'generalized'):
             record('filter_function_' + which,
                    nerr(oracle.filter_function(B_r, which),
@@ -93,6 +103,11 @@ def main():
                    nerr(oracle.control_matrix_from_atomic(phases, atomic, Lq, which),
                         ref_numeric.calculate_control_matrix_from_atomic(phases, atomic, Lq,
                                                                          which=which)))
+        for repeats in (1, 2, 7, 64):
+            record('control_matrix_periodic',
+                   nerr(oracle.control_matrix_periodic(phases[0], atomic[0], Lq[0], repeats),
+                        ref_numeric.calculate_control_matrix_periodic(phases[0], atomic[0], Lq[0],
+                                                                      repeats)))
         for which in ('fidelity', 'generalized'):
             record('pc_filter_function_' + which,
                    nerr(oracle.pulse_correlation_filter_function(atomic, which),

@@ -151,8 +151,6 @@ def test_control_matrix_raises(engine):
     _, _, n_opers, n_coeffs, dt, H = _setup(rng, 2, 4, 2)
     ev, V, Q = oracle.diagonalize(H, dt)
     f = engine.numeric.calculate_control_matrix_from_scratch
-    with pytest.raises(NotImplementedError):
-        f(ev, V, Q, [1.0], oracle.pauli_basis(1), n_opers, n_coeffs, dt, cache_intermediates=True)
     with pytest.raises(ValueError):
         f(ev, V, Q[:-1], [1.0], oracle.pauli_basis(1), n_opers, n_coeffs, dt)
 
@@ -271,3 +269,35 @@ def test_liouville_representation(engine, d, btype):
 def test_cexp(engine):
     x = np.random.default_rng(1).standard_normal((7, 13))*1e3
     assert nerr(engine.util.cexp(x), np.exp(1j*x)) < 1e-15
+
+
+@pytest.mark.parametrize('d,G,n_nops,btype,n_omega', [(2, 7, 3, 'pauli', 150), (3, 5, 2, 'ggm', 33),
+                                                      (4, 1, 2, 'pauli', 64), (6, 4, 1, 'ggm', 17)])
+def test_control_matrix_intermediates(engine, d, G, n_nops, btype, n_omega):
+    """cache_intermediates=True (reference numeric.py:828-879, tests/test_core.py:604-642): the control
+    matrix and every entry of the intermediates dict, for fixed input eigenvectors (so nothing is
+    gauge dependent); includes omega = 0 (exact-zero branch of the integral) and negative omega."""
+    rng = np.random.default_rng(1000*d + G)
+    c_opers, c_coeffs, n_opers, n_coeffs, dt, H = _setup(rng, d, G, n_nops)
+    ev, V, Q = oracle.diagonalize(H, dt)
+    basis = oracle.pauli_basis(int(np.log2(d))) if btype == 'pauli' else oracle.ggm_basis(d)
+    omega = np.concatenate(([0.0, -0.3], np.geomspace(1e-3, 30, n_omega - 2)))
+    B, inter = engine.numeric.calculate_control_matrix_from_scratch(
+        ev, V, Q, omega, basis, n_opers, n_coeffs, dt, cache_intermediates=True)
+    B_ref, inter_ref = oracle.control_matrix_intermediates(ev, V, Q, omega, basis, n_opers, n_coeffs,
+                                                           dt)
+    assert nerr(B, B_ref) < TOL
+    assert sorted(inter) == sorted(inter_ref)
+    for key, ref in inter_ref.items():
+        assert inter[key].shape == ref.shape, key
+        assert inter[key].dtype == np.complex128
+        if ref.size:
+            assert nerr(inter[key], ref) < TOL, key
+    # the fused kernel and the materialising kernels agree
+    fused = engine.numeric.calculate_control_matrix_from_scratch(ev, V, Q, omega, basis, n_opers,
+                                                                 n_coeffs, dt)
+    assert nerr(fused, B) < 1e-12
+    out = np.empty_like(B)
+    res, _ = engine.numeric.calculate_control_matrix_from_scratch(
+        ev, V, Q, omega, basis, n_opers, n_coeffs, dt, cache_intermediates=True, out=out)
+    assert res is out and nerr(out, B) == 0

@@ -336,3 +336,30 @@ def test_non_traceless_basis_infidelity(engine):
                             pulse.dt, ff.Basis.pauli(1))
     np.testing.assert_allclose(infid, ff.infidelity(ref2, S, omega), rtol=1e-7)
     del ref
+
+
+def test_pulse_caches_intermediates(engine):
+    """PulseSequence.get_control_matrix(cache_intermediates=True) fills ``_intermediates`` with the
+    reference's keys (pulse_sequence.py:625-634, tests/test_core.py:604-642); cleanup drops them."""
+    ff = engine
+    rng = np.random.default_rng(5)
+    pulse = rand_pulse_sequence(ff, rng, 3, 6, 2, 2)
+    omega = np.geomspace(0.01, 10, 40)
+    B = pulse.get_control_matrix(omega, cache_intermediates=True)
+    keys = {'n_opers_transformed', 'eigvecs_propagated', 'basis_transformed', 'phase_factors',
+            'first_order_integral', 'control_matrix_step', 'control_matrix_step_cumulative'}
+    assert set(pulse.intermediates) == keys
+    assert all(pulse.is_cached(key) for key in keys)
+    assert nerr(pulse.intermediates['control_matrix_step'].sum(axis=0), B) < 1e-12
+    B_ref, inter_ref = oracle.control_matrix_intermediates(
+        pulse.eigvals, pulse.eigvecs, pulse.propagators, omega, np.asarray(pulse.basis),
+        pulse.n_opers, pulse.n_coeffs, pulse.dt)
+    assert nerr(B, B_ref) < TOL
+    for key in keys:
+        assert nerr(pulse.intermediates[key], inter_ref[key]) < TOL, key
+    fresh = rand_pulse_sequence(ff, np.random.default_rng(5), 3, 6, 2, 2)
+    assert nerr(fresh.get_filter_function(omega, cache_intermediates=True),
+                oracle.filter_function(B_ref)) < TOL
+    assert set(fresh.intermediates) == keys
+    fresh.cleanup('greedy')
+    assert not fresh.intermediates
