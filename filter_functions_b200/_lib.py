@@ -51,6 +51,8 @@ EXPORTED_SYMBOLS = {
                                          c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'ffb_concatenate_many': (c_int, [c_void_p] + [c_int]*7 + [c_void_p]*7 + [c_int, c_int]
                              + [c_void_p]*8),
+    'ffb_concatenate_pulses': (c_int, [c_void_p] + [c_int]*5 + [c_void_p]*14 + [c_int, c_int]
+                               + [c_void_p]*2),
     'ffb_liouville_representation': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                              c_void_p]),
     'ffb_cexp': (c_int, [c_void_p, c_int, c_void_p, c_double, c_void_p]),

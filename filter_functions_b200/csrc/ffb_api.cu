@@ -694,6 +694,137 @@ int ffb_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int n_lib, int d, int n
   return FFB_OK;
 }
 
+int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, int n_omega,
+                           const int* row_of, const double* const* cached, const int* G,
+                           const double* const* eigvals, const double* const* eigvecs,
+                           const double* const* propagators, const double* const* dt,
+                           const double* const* t, const double* const* n_coeffs,
+                           const double* n_opers, const double* basis, const double* omega,
+                           const double* phases, const double* liouville, int correlations,
+                           int filter_function_kind, double* control_matrix,
+                           double* filter_function) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, row_of && cached && G && eigvals && eigvecs && propagators && dt && t &&
+                       n_coeffs && n_opers && basis && omega && (P == 1 || (phases && liouville)),
+              "concatenate_pulses: null input pointer");
+  FFB_REQUIRE(ctx, P >= 1 && d >= 1 && d <= 32 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
+              "concatenate_pulses: bad shape");
+  FFB_REQUIRE(ctx, filter_function_kind >= 0 && filter_function_kind <= 2 &&
+                       (filter_function_kind == 0 || filter_function),
+              "concatenate_pulses: filter_function_kind=%d", filter_function_kind);
+  const size_t dd = (size_t)d * d;
+  const size_t row_bytes = (size_t)n_basis * n_omega * 16;
+  const size_t pulse_bytes = (size_t)n_nops * row_bytes;
+  const bool basis_herm = all_hermitian(basis, n_basis, d);
+
+  Upload om, bs, ph, Qd;
+  FFB_TRY(om.put(ctx, omega, (size_t)n_omega * 8));
+  FFB_TRY(bs.put(ctx, basis, (size_t)n_basis * dd * 16));
+  if (P > 1) {
+    FFB_TRY(ph.put(ctx, phases, (size_t)(P - 1) * n_omega * 16));
+    FFB_TRY(Qd.put(ctx, liouville, (size_t)(P - 1) * n_basis * n_basis * 8));
+  }
+  // which = 'total': two pulse slots [accumulator, current pulse], the accumulator is updated in place
+  // (acc <- acc + phi_{p-1} B^{(p)} Q^{(p-1)}, i.e. from_atomic with P = 2; every thread block of the
+  // from_atomic kernels reads exactly the accumulator elements it later writes).  'correlations':
+  // the full (P, ...) stack, since the result has that size anyway.
+  DevBuf stack, scratch, result;
+  const int slots = correlations ? P : std::min(P, 2);
+  FFB_TRY(stack.alloc(ctx, (size_t)slots * pulse_bytes));
+  if (correlations) FFB_TRY(result.alloc(ctx, (size_t)P * pulse_bytes));
+  std::vector<std::vector<double>> keep;  // host staging that must outlive the async uploads
+  std::vector<int> missing;
+  for (int p = 0; p < P; ++p) {
+    const int slot = correlations ? p : std::min(p, 1);
+    char* dst = stack.as<char>() + (size_t)slot * pulse_bytes;
+    const int* rows = row_of + (size_t)p * n_nops;
+    missing.clear();
+    for (int j = 0; j < n_nops; ++j) {
+      if (rows[j] >= 0) {
+        FFB_REQUIRE(ctx, cached[p], "concatenate_pulses: pulse %d has cached rows but no array", p);
+        // consecutive rows of the cached array that map to consecutive merged rows go in one copy
+        int run = 1;
+        while (j + run < n_nops && rows[j + run] == rows[j] + run) ++run;
+        FFB_TRY(ffb_h2d(ctx, dst + (size_t)j * row_bytes,
+                        reinterpret_cast<const char*>(cached[p]) + (size_t)rows[j] * row_bytes,
+                        (size_t)run * row_bytes));
+        j += run - 1;
+      } else {
+        missing.push_back(j);
+      }
+    }
+    if (!missing.empty()) {
+      const int m = (int)missing.size(), Gp = G[p];
+      FFB_REQUIRE(ctx, Gp >= 1 && eigvals[p] && eigvecs[p] && propagators[p] && dt[p] && t[p] &&
+                           n_coeffs[p], "concatenate_pulses: pulse %d lacks its diagonalisation", p);
+      keep.emplace_back((size_t)m * dd * 2);
+      keep.emplace_back((size_t)m * Gp);
+      std::vector<double>& ops = keep[keep.size() - 2];
+      std::vector<double>& cf = keep[keep.size() - 1];
+      for (int i = 0; i < m; ++i) {
+        std::memcpy(ops.data() + (size_t)i * dd * 2, n_opers + (size_t)missing[i] * dd * 2, dd * 16);
+        std::memcpy(cf.data() + (size_t)i * Gp, n_coeffs[p] + (size_t)missing[i] * Gp, (size_t)Gp * 8);
+      }
+      const int herm = (all_hermitian(ops.data(), m, d) ? FFB_HERM_NOPERS : 0) |
+                       (basis_herm ? FFB_HERM_BASIS : 0);
+      Upload ev, V, Qp, no, nc, dts, ts;
+      FFB_TRY(ev.put(ctx, eigvals[p], (size_t)Gp * d * 8));
+      FFB_TRY(V.put(ctx, eigvecs[p], (size_t)Gp * dd * 16));
+      FFB_TRY(Qp.put(ctx, propagators[p], (size_t)Gp * dd * 16));
+      FFB_TRY(no.put(ctx, ops.data(), (size_t)m * dd * 16));
+      FFB_TRY(nc.put(ctx, cf.data(), (size_t)m * Gp * 8));
+      FFB_TRY(dts.put(ctx, dt[p], (size_t)Gp * 8));
+      FFB_TRY(ts.put(ctx, t[p], (size_t)(Gp + 1) * 8));
+      // contiguous run of missing rows at the end/start: write in place, else through scratch
+      const bool contiguous = missing.back() - missing.front() + 1 == m;
+      double* target = reinterpret_cast<double*>(dst + (size_t)missing.front() * row_bytes);
+      if (!contiguous) {
+        FFB_TRY(scratch.alloc(ctx, (size_t)m * row_bytes));
+        target = scratch.as<double>();
+      }
+      FFB_TRY(ffbi_control_matrix(ctx, Gp, d, m, n_basis, n_omega, ev.d(), V.d(), Qp.d(), om.d(),
+                                  bs.d(), no.d(), nc.d(), dts.d(), ts.d(), herm, target));
+      if (!contiguous) {
+        for (int i = 0; i < m; ++i) {
+          int run = 1;
+          while (i + run < m && missing[i + run] == missing[i] + run) ++run;
+          FFB_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)missing[i] * row_bytes,
+                                        scratch.as<char>() + (size_t)i * row_bytes,
+                                        (size_t)run * row_bytes, cudaMemcpyDeviceToDevice,
+                                        ctx->stream));
+          i += run - 1;
+        }
+      }
+    }
+    if (!correlations && p >= 1) {
+      FFB_TRY(ffbi_from_atomic(ctx, 2, n_nops, n_basis, n_omega, ph.d() + (size_t)(p - 1) * n_omega * 2,
+                               stack.as<double>(), Qd.d() + (size_t)(p - 1) * n_basis * n_basis, 0, 0,
+                               stack.as<double>()));
+    }
+  }
+  const double* B_dev = stack.as<double>();
+  if (correlations) {
+    FFB_TRY(ffbi_from_atomic(ctx, P, n_nops, n_basis, n_omega, P > 1 ? ph.d() : nullptr,
+                             stack.as<double>(), P > 1 ? Qd.d() : nullptr, 0, 1,
+                             result.as<double>()));
+    B_dev = result.as<double>();
+  }
+  const int lead = correlations ? P : 1;
+  if (control_matrix) FFB_TRY(ffb_d2h(ctx, control_matrix, B_dev, (size_t)lead * pulse_bytes));
+  DevBuf F;
+  if (filter_function_kind) {
+    const size_t L = (size_t)lead * n_nops;
+    const size_t f_bytes = L * L * (filter_function_kind == 2 ? (size_t)n_basis * n_basis : 1) *
+                           n_omega * 16;
+    FFB_TRY(F.alloc(ctx, f_bytes));
+    FFB_TRY(ffbi_filter_function(ctx, lead, n_nops, n_basis, n_omega, B_dev,
+                                 filter_function_kind == 2, F.as<double>()));
+    FFB_TRY(ffb_d2h(ctx, filter_function, F.p, f_bytes));
+  }
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
 int ffb_liouville_representation(ffb_ctx* ctx, int n, int d, int n_basis, const double* U,
                                  const double* basis, double* out) {
   FFB_TRY(enter(ctx));

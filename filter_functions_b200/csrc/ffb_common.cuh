@@ -118,6 +118,9 @@ int ffbi_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_ome
 int ffbi_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
                      const double* phases, const double* B_atomic, const double* Q, int q_is_complex,
                      int correlations, double* out);
+int ffbi_from_atomic_dmma(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+                          const double* phases, const double* B_atomic, const double* Q,
+                          int correlations, double* out);
 int ffbi_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* idx_dev,
                     int n_omega, const double* F, const double* spectrum, int spectrum_ndim,
                     int spectrum_is_complex, const double* omega, int d, double* out);

@@ -427,6 +427,10 @@ int ffbi_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
               "from_atomic: bad shape (P=%d, n_nops=%d, n_basis=%d, n_omega=%d)", P, n_nops,
               n_basis, n_omega);
   FFB_REQUIRE(ctx, n_nops <= 65535, "from_atomic: too many noise operators (%d)", n_nops);
+  // FP64-bound regime (n_basis / 4 flop per byte): DMMA kernel of ffb_atomic_dmma.cu
+  if (!q_is_complex && n_basis >= 32)
+    return ffbi_from_atomic_dmma(ctx, P, n_nops, n_basis, n_omega, phases, B_atomic, Q,
+                                 correlations, out);
   if (n_basis <= 4)
     return launch_from_atomic<4>(ctx, P, n_nops, n_basis, n_omega, phases, B_atomic, Q,
                                  q_is_complex, correlations, out);

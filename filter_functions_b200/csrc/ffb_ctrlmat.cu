@@ -320,20 +320,32 @@ transform_small_kernel(int G, int n_nops, int n_basis, int parts_j, int parts_k,
 struct StreamGeom {
   int MT;          // row tiles per row block
   int n_rb;        // row blocks
-  int n_pass;      // ceil(G / 4)
-  int n_pairs;     // d (d-1) / 2
+  int n_pass;      // ceil(G / 4); G in transposed mode
+  int n_pairs;     // pair UNITS per pass: d (d-1) / 2; ceil(d (d-1) / 8) in transposed mode
+  int real_pairs;  // d (d-1) / 2
+  int transposed;  // 1: the 4 K-slots of a unit are 4 level pairs of ONE segment (short pulses)
   int diag_unit;   // doubles
   int pair_unit;   // doubles
   size_t pass_doubles;
   size_t rb_doubles;
 };
 
+// Regular layout: the K = 4 slots of a DMMA are 4 consecutive segments, so a pulse of G segments costs
+// ceil(G / 4) (1 + 2 n_pairs) A columns.  For short pulses (gate pulses of one or two segments, the
+// constituents of a concatenation) most of those slots would be padding; the transposed layout puts 4
+// level pairs (m, n) of the SAME segment into the K slots instead: G (1 + 2 ceil(n_pairs / 4)) columns.
+// The main kernel is the same for both -- a lane's slot constants (Omega, e^{i Omega dt / 2}) are
+// per-slot already, and the per-lane segment state (phase, dt) is simply equal across the 4 slots.
 __host__ __device__ inline StreamGeom make_geom(int rows, int G, int d, int MT) {
   StreamGeom s;
   s.MT = MT;
   s.n_rb = ((rows + 7) / 8 + MT - 1) / MT;
-  s.n_pass = (G + 3) / 4;
-  s.n_pairs = d * (d - 1) / 2;
+  s.real_pairs = d * (d - 1) / 2;
+  const long long cost_regular = (long long)((G + 3) / 4) * (1 + 2 * s.real_pairs);
+  const long long cost_transposed = (long long)G * (1 + 2 * ((s.real_pairs + 3) / 4));
+  s.transposed = (s.real_pairs >= 1 && cost_transposed < cost_regular) ? 1 : 0;
+  s.n_pass = s.transposed ? G : (G + 3) / 4;
+  s.n_pairs = s.transposed ? (s.real_pairs + 3) / 4 : s.real_pairs;
   s.diag_unit = MT * 32 + 8;
   s.pair_unit = 2 * MT * 32 + 12;
   s.pass_doubles = (size_t)s.diag_unit + (size_t)s.n_pairs * s.pair_unit;
@@ -371,18 +383,24 @@ assemble_kernel(StreamGeom geo, int G, int d, int rows, int n_jrows, int n_krows
       const int mt = (off / 32) % geo.MT;
       const int l = off % 32;
       const int row = (rb * geo.MT + mt) * 8 + (l >> 2);
-      const int g = pass * 4 + (l & 3);
-      if (row < rows && g < G) {
+      const int slot = l & 3;
+      const int g = geo.transposed ? pass : pass * 4 + slot;
+      // level pair of this K slot (-1: the diagonal term; -2: padding)
+      int pair;
+      if (unit == 0) pair = (geo.transposed && slot != 0) ? -2 : -1;
+      else pair = geo.transposed ? (unit - 1) * 4 + slot : unit - 1;
+      if (pair >= geo.real_pairs) pair = -2;
+      if (row < rows && g < G && pair != -2) {
         const int jr = row / n_krows, kr = row % n_krows;
         const double* Bm = Bbar + ((size_t)g * n_jrows + jr) * 2 * dd;
         const double* Cm = Cbar + ((size_t)g * n_krows + kr) * 2 * dd;
-        if (unit == 0) {
+        if (pair == -1) {
           double acc = 0.0;
           for (int m = 0; m < d; ++m) acc += Bm[2 * (m * d + m)] * Cm[2 * (m * d + m)];
           val = acc;
         } else {
           int m, n;
-          pair_from_index(unit - 1, d, m, n);
+          pair_from_index(pair, d, m, n);
           const cplx b = {Bm[2 * (m * d + n)], Bm[2 * (m * d + n) + 1]};
           const cplx c = {Cm[2 * (n * d + m)], Cm[2 * (n * d + m) + 1]};
           const cplx prod = cmul(b, c);
@@ -392,14 +410,18 @@ assemble_kernel(StreamGeom geo, int G, int d, int rows, int n_jrows, int n_krows
     } else {
       const int c = off - a_doubles;  // constants
       const int which = c / 4;
-      const int g = pass * 4 + (c & 3);
+      const int slot = c & 3;
+      const int g = geo.transposed ? pass : pass * 4 + slot;
       if (unit == 0) {
         if (g < G) val = which == 0 ? t[g] : dt[g];
       } else {
+        // padding slots (A coefficients 0) repeat the constants of the last real pair, so that they
+        // take the removable-singularity fix-up only where that pair takes it anyway
+        const int pair = min(geo.transposed ? (unit - 1) * 4 + slot : unit - 1, geo.real_pairs - 1);
         double Om = 0.0, dtg = 0.0;
         if (g < G) {
           int m, n;
-          pair_from_index(unit - 1, d, m, n);
+          pair_from_index(pair, d, m, n);
           Om = eigvals[(size_t)g * d + m] - eigvals[(size_t)g * d + n];
           dtg = dt[g];
         }

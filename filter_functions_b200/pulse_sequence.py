@@ -8,6 +8,7 @@ here: ``extend``/``remap``, second-order filter functions 
 """
 import bisect
 import copy
+import ctypes
 from itertools import accumulate, chain, compress, zip_longest
 from types import MappingProxyType
 from typing import Any, Iterable, Optional
@@ -743,6 +744,30 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
     phases = np.array([lib_phases[i] for i in inverse[:-1]]).cumprod(axis=0)
     propagators_liouville = util.adot([lib_liouville[i] for i in inverse[:-1]])
 
+    if 'total_propagator' not in newpulse._data:
+        newpulse.total_propagator = util.mdot([pls.total_propagator for pls in pulses][::-1])
+
+    if n_omega and np.isrealobj(propagators_liouville):
+        # general case on the device: the atomic stack (cached rows + from-scratch rows of the noise
+        # operators a pulse does not carry) never exists on the host
+        control_matrix, filter_function = _concatenate_on_device(
+            pulses, newpulse, n_opers_present, [lib_ctrl[i] for i in inverse], omega, phases,
+            propagators_liouville, calc_pulse_correlation_FF, which)
+        newpulse.cache_total_phases(omega)
+        newpulse.total_propagator_liouville = liouville_representation(newpulse.total_propagator,
+                                                                       newpulse.basis)
+        newpulse.cache_control_matrix(omega, control_matrix)
+        if calc_pulse_correlation_FF:
+            if which == 'fidelity':
+                newpulse._frequency_data['filter_function_pc'] = filter_function
+            else:
+                newpulse._frequency_data['filter_function_pc'] = filter_function.trace(axis1=4,
+                                                                                       axis2=5)
+                newpulse._frequency_data['filter_function_pc_gen'] = filter_function
+            filter_function = filter_function.sum(axis=(0, 1))
+        newpulse.cache_filter_function(omega, filter_function=filter_function, which=which)
+        return newpulse
+
     if n_opers_present.all():
         control_matrix_atomic = np.array(lib_ctrl)[inverse]
     else:
@@ -758,8 +783,6 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
                     newpulse.n_coeffs[~present, seg_edges[i]:seg_edges[i + 1]],
                     pls.dt, t=pls.t, show_progressbar=show_progressbar, cache_intermediates=False)
 
-    if 'total_propagator' not in newpulse._data:
-        newpulse.total_propagator = util.mdot([pls.total_propagator for pls in pulses][::-1])
     newpulse.cache_total_phases(omega)
     newpulse.total_propagator_liouville = liouville_representation(newpulse.total_propagator,
                                                                    newpulse.basis)
@@ -768,6 +791,57 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         which='correlations' if calc_pulse_correlation_FF else 'total')
     newpulse.cache_filter_function(omega, control_matrix, which=which)
     return newpulse
+
+
+def _concatenate_on_device(pulses, newpulse, n_opers_present, ctrl, omega, phases, liouville,
+                           correlations: bool, which: str):
+    """Tail of :func:`concatenate` for pulses that do not all carry the same noise operators
+    (reference ``:1822-1866``) through ``ffb_concatenate_pulses``: returns the (pulse-correlation)
+    control matrix and the matching filter function.  ``ctrl[i]`` is pulse i's own control matrix on
+    ``omega``; its rows are, in order, the merged operators ``n_opers_present[i]`` marks."""
+    P, n_nops = n_opers_present.shape
+    n_basis, n_omega, d = len(newpulse.basis), len(omega), newpulse.d
+    row_of = np.where(n_opers_present, np.cumsum(n_opers_present, axis=1) - 1, -1).astype(np.int32)
+    seg_edges = [0] + list(accumulate(len(pls.dt) for pls in pulses))
+    keep = []   # arrays the pointer tables refer to
+
+    def table(arrays):
+        tab = (ctypes.c_void_p*P)()
+        for i, arr in enumerate(arrays):
+            if arr is not None:
+                keep.append(arr)
+                tab[i] = arr.ctypes.data
+        return tab
+
+    cached = table([_lib.as_c128(B) for B in ctrl])
+    need = [not present.all() for present in n_opers_present]
+    for pls, needed in zip(pulses, need):
+        if needed:
+            pls.diagonalize()
+    G = np.array([len(pls.dt) for pls in pulses], dtype=np.int32)
+    eigvals = table([_lib.as_f64(pls.eigvals) if nd else None for pls, nd in zip(pulses, need)])
+    eigvecs = table([_lib.as_c128(pls.eigvecs) if nd else None for pls, nd in zip(pulses, need)])
+    props = table([_lib.as_c128(pls.propagators) if nd else None for pls, nd in zip(pulses, need)])
+    dts = table([_lib.as_f64(pls.dt) if nd else None for pls, nd in zip(pulses, need)])
+    ts = table([_lib.as_f64(pls.t) if nd else None for pls, nd in zip(pulses, need)])
+    coeffs = table([_lib.as_f64(newpulse.n_coeffs[:, seg_edges[i]:seg_edges[i + 1]]) if nd else None
+                    for i, nd in enumerate(need)])
+    n_opers = _lib.as_c128(newpulse.n_opers)
+    basis = _lib.as_c128(np.asarray(newpulse.basis))
+    omega_arr = _lib.as_f64(omega)
+    phases = _lib.as_c128(phases)
+    liouville = _lib.as_f64(liouville)
+    lead = (P,) if correlations else ()
+    B = _lib.empty(lead + (n_nops, n_basis, n_omega))
+    gen = which == 'generalized'
+    F = _lib.empty(lead*2 + (n_nops, n_nops) + ((n_basis, n_basis) if gen else ()) + (n_omega,))
+    ctx = _lib.context()
+    p = _lib.ptr
+    _lib.check(ctx, _lib.lib().ffb_concatenate_pulses(
+        ctx, P, d, n_nops, n_basis, n_omega, p(row_of), cached, p(G), eigvals, eigvecs, props, dts,
+        ts, coeffs, p(n_opers), p(basis), p(omega_arr), p(phases), p(liouville), int(correlations),
+        2 if gen else 1, p(B), p(F)))
+    return B, F
 
 
 def concatenate_periodic(pulse: PulseSequence, repeats: int,

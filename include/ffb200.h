@@ -147,6 +147,34 @@ int ffb_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int n_lib, int d, int n
                          double* control_matrix, double* filter_function, double* infidelity,
                          const double* tau, double* total_phases);
 
+/* ---- a6 with differing noise operators (config 5: QFT from gate pulses) --------------------------
+ * Control matrix of a sequence of P pulses that do NOT all carry the same noise operators, as
+ * ff.concatenate builds it (pulse_sequence.py:1822-1866: rows of cached control matrices are copied into
+ * the atomic stack, rows of operators a pulse does not carry are computed from scratch with the merged
+ * sensitivities, :1843-1851; then calculate_control_matrix_from_atomic, :1858, and the filter function,
+ * :1866).  The atomic stack is assembled and consumed in device memory: cached rows are uploaded,
+ * missing rows are written by the from-scratch kernel, and for the total control matrix only two pulse
+ * slots exist (running sum updated in place).
+ *   row_of (P,n_nops) int32: row of pulse p's cached control matrix holding merged operator j, -1 = missing
+ *   cached[P]: host pointers to (n_cached_p,n_basis,n_omega) c128 (NULL if the pulse has none)
+ *   G[P] and eigvals/eigvecs/propagators/dt/t[P]: the pulses' own diagonalisation, shapes as in
+ *     ffb_control_matrix_from_scratch (t starts at 0 for every pulse); only read for missing rows
+ *   n_coeffs[P] -> (n_nops,G_p) f64 merged noise sensitivities on pulse p's segments
+ *   n_opers (n_nops,d,d) c128 merged | basis (n_basis,d,d) c128 | omega (n_omega) f64
+ *   phases (P-1,n_omega) c128 cumulative | liouville (P-1,n_basis,n_basis) f64 cumulative
+ *   correlations: 0 -> control_matrix (n_nops,n_basis,n_omega); 1 -> (P,n_nops,n_basis,n_omega)
+ *   filter_function_kind: 0 none, 1 fidelity, 2 generalized; shape as ffb_filter_function with
+ *     P = 1 (total) or P (correlations).  control_matrix may be NULL. */
+int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, int n_omega,
+                           const int* row_of, const double* const* cached, const int* G,
+                           const double* const* eigvals, const double* const* eigvecs,
+                           const double* const* propagators, const double* const* dt,
+                           const double* const* t, const double* const* n_coeffs,
+                           const double* n_opers, const double* basis, const double* omega,
+                           const double* phases, const double* liouville, int correlations,
+                           int filter_function_kind, double* control_matrix,
+                           double* filter_function);
+
 /* ---- f3: control matrix with cached intermediates -----------------------------
  * cache_intermediates=True of numeric.calculate_control_matrix_from_scratch (numeric.py:828-879): the
  * control matrix plus the arrays of the `intermediates` dict (keys numeric.py:872-878), all c128:

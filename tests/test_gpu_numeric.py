@@ -94,6 +94,28 @@ def test_control_matrix_special_frequencies(engine):
     assert ret is out and nerr(out, B_o) < TOL
 
 
+@pytest.mark.parametrize('d,G,n_nops,btype', [(3, 1, 2, 'ggm'), (3, 2, 1, 'ggm'), (4, 1, 6, 'pauli'),
+                                              (4, 2, 3, 'pauli'), (4, 3, 2, 'ggm'), (5, 3, 2, 'ggm'),
+                                              (7, 2, 1, 'ggm'), (8, 1, 3, 'pauli'), (16, 1, 2, 'ggm'),
+                                              (16, 2, 3, 'pauli')])
+def test_control_matrix_short_pulses(engine, d, G, n_nops, btype):
+    """Gate pulses of one to three segments (the constituents of a concatenation, config 5) take the
+    transposed operand layout (4 level pairs of one segment per DMMA instead of 4 segments); includes
+    omega = 0, negative and resonant frequencies, for which padding slots must stay finite."""
+    rng = np.random.default_rng(1000 + 37*d + G)
+    _, _, n_opers, n_coeffs, dt, H = _setup(rng, d, G, n_nops)
+    ev, V, Q = oracle.diagonalize(H, dt)
+    basis = oracle.pauli_basis(int(np.log2(d))) if btype == 'pauli' else oracle.ggm_basis(d)
+    res = [ev[0, d - 1] - ev[0, 0], ev[G - 1, 0] - ev[G - 1, d - 1], ev[0, 1] - ev[0, 0]]
+    omega = np.concatenate(([0.0, 1e-12, -2.5], res, np.geomspace(1e-3, 80, 70)))
+    B = engine.numeric.calculate_control_matrix_from_scratch(ev, V, Q, omega, basis, n_opers,
+                                                             n_coeffs, dt)
+    B_o = oracle.control_matrix_from_scratch(ev, V, Q, omega, basis, n_opers, n_coeffs, dt)
+    assert np.isfinite(B).all()
+    for j in range(n_nops):
+        assert nerr(B[j], B_o[j]) < TOL
+
+
 def test_control_matrix_gauge_invariance(engine):
     """Random eigenvector phases must not change the control matrix."""
     rng = np.random.default_rng(11)
@@ -184,7 +206,9 @@ def test_pulse_correlation_filter_function(engine, which):
 
 
 @pytest.mark.parametrize('P,n_nops,n_basis,n_omega', [(2, 1, 4, 301), (5, 3, 16, 200),
-                                                      (3, 2, 9, 64), (4, 2, 64, 100), (1, 2, 4, 10)])
+                                                      (3, 2, 9, 64), (4, 2, 64, 100), (1, 2, 4, 10),
+                                                      (3, 2, 36, 77), (2, 3, 49, 9), (3, 1, 256, 41),
+                                                      (1, 2, 64, 17), (6, 1, 100, 33)])
 @pytest.mark.parametrize('which', ['total', 'correlations'])
 def test_control_matrix_from_atomic(engine, P, n_nops, n_basis, n_omega, which):
     rng = np.random.default_rng(P*n_basis + n_omega)

@@ -11,6 +11,7 @@ import pytest
 
 import ff_oracle as oracle
 from helpers import dd_hamiltonian, nerr, rand_pulse_sequence
+from helpers import rand_herm_traceless as helpers_rand_herm_traceless
 from test_oracle import DD_CASES, GOLDEN, REF_INFIDS, SPECTRA, analytic_dd
 
 pytestmark = pytest.mark.gpu
@@ -208,6 +209,61 @@ def test_scratch_vs_atomic(engine, d, btype):
     np.testing.assert_allclose(B_atomic, B_scratch, rtol=1e-7, atol=1e-11*np.abs(B_scratch).max())
     assert nerr(joined.get_filter_function(omega), pulse.get_filter_function(omega)) < TOL
     assert nerr(joined.total_propagator, pulse.total_propagator) < TOL
+
+
+@pytest.mark.parametrize('d,btype', [(2, 'Pauli'), (3, 'GGM'), (4, 'Pauli'), (6, 'GGM'), (8, 'Pauli')])
+@pytest.mark.parametrize('pc', [False, True])
+def test_concatenate_differing_noise_operators(engine, d, btype, pc):
+    """Pulses that carry different subsets of the noise operators (constant sensitivities, so that the
+    missing ones can be inferred, reference pulse_sequence.py:1464-1481): cached rows are reused,
+    missing rows are computed from scratch in device memory (:1843-1851), and the result equals the
+    control matrix of the concatenated pulse computed from scratch (reference
+    tests/test_sequencing.py:470-606 checks the same for its CNOT/extend examples)."""
+    ff = engine
+    rng = np.random.default_rng(4000 + 10*d + pc)
+    n_all = 5
+    n_opers = helpers_rand_herm_traceless(rng, d, n_all)
+    n_ids = [f'N{i}' for i in range(n_all)]
+    sens = rng.random(n_all) + 0.5
+    subsets = [[0, 1, 2, 3, 4], [1, 3], [0, 4], [2], [0, 1, 2, 3, 4], [3, 4, 0]]
+    basis = ff.Basis.ggm(d) if btype == 'GGM' else ff.Basis.pauli(int(np.log2(d)))
+    pulses = []
+    for i, subset in enumerate(subsets):
+        G = int(rng.integers(1, 6))
+        c_opers = helpers_rand_herm_traceless(rng, d, 2)
+        H_c = [[op, rng.standard_normal(G), f'C{k}'] for k, op in enumerate(c_opers)]
+        H_n = [[n_opers[j], np.full(G, sens[j]), n_ids[j]] for j in subset]
+        pulses.append(ff.PulseSequence(H_c, H_n, 1 - rng.random(G)*0.5, basis))
+    tau = sum(p.tau for p in pulses)
+    omega = np.concatenate(([0.0], np.geomspace(1e-2/tau, 1e2/tau, 83)*2*np.pi))
+    for p in pulses[:4]:   # the rest is computed on demand by concatenate
+        p.cache_control_matrix(omega)
+    joined = ff.concatenate(pulses, omega=omega, calc_pulse_correlation_FF=pc)
+    assert list(joined.n_oper_identifiers) == n_ids
+    whole = ff.concatenate(pulses, calc_filter_function=False)
+    B_scratch = whole.get_control_matrix(omega)
+    B = joined.get_control_matrix(omega)
+    assert B.shape == (n_all, len(basis), len(omega))
+    for j in range(n_all):
+        assert nerr(B[j], B_scratch[j]) < TOL
+    assert nerr(joined.get_filter_function(omega), whole.get_filter_function(omega)) < TOL
+    H = oracle.hamiltonian_from_coeffs(whole.c_opers, whole.c_coeffs)
+    ev, V, Q = oracle.diagonalize(H, whole.dt)
+    B_o = oracle.control_matrix_from_scratch(ev, V, Q, omega, np.asarray(basis), whole.n_opers,
+                                             whole.n_coeffs, whole.dt)
+    assert nerr(B, B_o) < TOL
+    if pc:
+        B_pc = joined.get_pulse_correlation_control_matrix()
+        assert B_pc.shape == (len(pulses),) + B.shape
+        assert nerr(B_pc.sum(axis=0), B_o) < TOL
+        F_pc = joined.get_pulse_correlation_filter_function()
+        assert nerr(F_pc, oracle.pulse_correlation_filter_function(B_pc, 'fidelity')) < TOL
+        assert nerr(F_pc.sum(axis=(0, 1)), oracle.filter_function(B_o)) < TOL
+    if d <= 3:
+        gen = ff.concatenate(pulses, omega=omega, calc_pulse_correlation_FF=pc, which='generalized')
+        F_gen = gen.get_filter_function(omega, 'generalized')
+        assert nerr(F_gen, oracle.filter_function(B_o, 'generalized')) < TOL
+        assert nerr(gen.get_filter_function(omega), oracle.filter_function(B_o)) < TOL
 
 
 def test_se_concatenation_is_cpmg(engine):
