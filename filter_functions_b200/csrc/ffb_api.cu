@@ -1,5 +1,6 @@
 // C ABI of libffb200 (include/ffb200.h): context, memory pool, host-pointer wrappers.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "ffb_common.cuh"
@@ -154,6 +155,9 @@ void ffb_destroy(ffb_ctx* ctx) {
   }
   for (auto& kv : ctx->host_free_blocks) cudaFreeHost(kv.second);
   for (auto& kv : ctx->host_live_blocks) cudaFreeHost(kv.first);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto& ev : ctx->copy_ev)
+    if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -716,6 +720,10 @@ int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, 
   const size_t row_bytes = (size_t)n_basis * n_omega * 16;
   const size_t pulse_bytes = (size_t)n_nops * row_bytes;
   const bool basis_herm = all_hermitian(basis, n_basis, d);
+  for (int p = 0; p < P; ++p)
+    for (int j = 0; j < n_nops; ++j)
+      FFB_REQUIRE(ctx, row_of[(size_t)p * n_nops + j] < 0 || cached[p],
+                  "concatenate_pulses: pulse %d has cached rows but no array", p);
 
   Upload om, bs, ph, Qd;
   FFB_TRY(om.put(ctx, omega, (size_t)n_omega * 8));
@@ -724,35 +732,53 @@ int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, 
     FFB_TRY(ph.put(ctx, phases, (size_t)(P - 1) * n_omega * 16));
     FFB_TRY(Qd.put(ctx, liouville, (size_t)(P - 1) * n_basis * n_basis * 8));
   }
-  // which = 'total': two pulse slots [accumulator, current pulse], the accumulator is updated in place
-  // (acc <- acc + phi_{p-1} B^{(p)} Q^{(p-1)}, i.e. from_atomic with P = 2; every thread block of the
-  // from_atomic kernels reads exactly the accumulator elements it later writes).  'correlations':
-  // the full (P, ...) stack, since the result has that size anyway.
+  // Full stack (P pulse slots) when it takes at most a quarter of the device memory: all from-scratch
+  // fills are enqueued first, the cached rows are uploaded on the copy stream WHILE the fills run, and
+  // one from_atomic launch consumes the stack.  Otherwise (and never for 'correlations', whose result
+  // has the size of the stack anyway) two slots [running sum, current pulse]: the sum is updated in
+  // place pulse by pulse (from_atomic with P = 2; every thread block of the from_atomic kernels reads
+  // exactly the accumulator elements it later writes).
+  bool full_stack = correlations != 0 || (size_t)P * pulse_bytes <= ctx->total_mem / 4;
+  if (const char* e = getenv("FFB_CONCAT_STACK")) full_stack = correlations != 0 || atoi(e) != 0;
+  const int slots = full_stack ? P : std::min(P, 2);
   DevBuf stack, scratch, result;
-  const int slots = correlations ? P : std::min(P, 2);
   FFB_TRY(stack.alloc(ctx, (size_t)slots * pulse_bytes));
-  if (correlations) FFB_TRY(result.alloc(ctx, (size_t)P * pulse_bytes));
+  if (full_stack) FFB_TRY(result.alloc(ctx, (size_t)(correlations ? P : 1) * pulse_bytes));
+  if (full_stack && !ctx->copy_stream) {
+    FFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : ctx->copy_ev) FFB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  if (full_stack) {  // the copy stream must not touch pool memory before earlier work is done with it
+    FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+    FFB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+  }
+  cudaStream_t up_stream = full_stack ? ctx->copy_stream : ctx->stream;
+
+  auto upload_cached = [&](int p, char* dst) -> int {
+    const int* rows = row_of + (size_t)p * n_nops;
+    for (int j = 0; j < n_nops; ++j) {
+      if (rows[j] < 0) continue;
+      // consecutive rows of the cached array that map to consecutive merged rows go in one copy
+      int run = 1;
+      while (j + run < n_nops && rows[j + run] == rows[j] + run) ++run;
+      FFB_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)j * row_bytes,
+                                    reinterpret_cast<const char*>(cached[p]) + (size_t)rows[j] * row_bytes,
+                                    (size_t)run * row_bytes, cudaMemcpyHostToDevice, up_stream));
+      j += run - 1;
+    }
+    return FFB_OK;
+  };
+
   std::vector<std::vector<double>> keep;  // host staging that must outlive the async uploads
   std::vector<int> missing;
   for (int p = 0; p < P; ++p) {
-    const int slot = correlations ? p : std::min(p, 1);
+    const int slot = full_stack ? p : std::min(p, 1);
     char* dst = stack.as<char>() + (size_t)slot * pulse_bytes;
     const int* rows = row_of + (size_t)p * n_nops;
     missing.clear();
-    for (int j = 0; j < n_nops; ++j) {
-      if (rows[j] >= 0) {
-        FFB_REQUIRE(ctx, cached[p], "concatenate_pulses: pulse %d has cached rows but no array", p);
-        // consecutive rows of the cached array that map to consecutive merged rows go in one copy
-        int run = 1;
-        while (j + run < n_nops && rows[j + run] == rows[j] + run) ++run;
-        FFB_TRY(ffb_h2d(ctx, dst + (size_t)j * row_bytes,
-                        reinterpret_cast<const char*>(cached[p]) + (size_t)rows[j] * row_bytes,
-                        (size_t)run * row_bytes));
-        j += run - 1;
-      } else {
-        missing.push_back(j);
-      }
-    }
+    for (int j = 0; j < n_nops; ++j)
+      if (rows[j] < 0) missing.push_back(j);
+    if (!full_stack) FFB_TRY(upload_cached(p, dst));
     if (!missing.empty()) {
       const int m = (int)missing.size(), Gp = G[p];
       FFB_REQUIRE(ctx, Gp >= 1 && eigvals[p] && eigvecs[p] && propagators[p] && dt[p] && t[p] &&
@@ -775,7 +801,7 @@ int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, 
       FFB_TRY(nc.put(ctx, cf.data(), (size_t)m * Gp * 8));
       FFB_TRY(dts.put(ctx, dt[p], (size_t)Gp * 8));
       FFB_TRY(ts.put(ctx, t[p], (size_t)(Gp + 1) * 8));
-      // contiguous run of missing rows at the end/start: write in place, else through scratch
+      // one contiguous run of missing rows is written in place, otherwise through scratch
       const bool contiguous = missing.back() - missing.front() + 1 == m;
       double* target = reinterpret_cast<double*>(dst + (size_t)missing.front() * row_bytes);
       if (!contiguous) {
@@ -796,31 +822,63 @@ int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, 
         }
       }
     }
-    if (!correlations && p >= 1) {
+    if (!full_stack && p >= 1) {
       FFB_TRY(ffbi_from_atomic(ctx, 2, n_nops, n_basis, n_omega, ph.d() + (size_t)(p - 1) * n_omega * 2,
                                stack.as<double>(), Qd.d() + (size_t)(p - 1) * n_basis * n_basis, 0, 0,
                                stack.as<double>()));
     }
   }
   const double* B_dev = stack.as<double>();
-  if (correlations) {
-    FFB_TRY(ffbi_from_atomic(ctx, P, n_nops, n_basis, n_omega, P > 1 ? ph.d() : nullptr,
-                             stack.as<double>(), P > 1 ? Qd.d() : nullptr, 0, 1,
-                             result.as<double>()));
+  if (full_stack) {
+    // cached rows: issued after the fills were enqueued, so that even a pageable source (staged by the
+    // driver while the host thread waits) overlaps them
+    for (int p = 0; p < P; ++p) FFB_TRY(upload_cached(p, stack.as<char>() + (size_t)p * pulse_bytes));
+    FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[1], ctx->copy_stream));
+    FFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1], 0));
     B_dev = result.as<double>();
+    // total control matrix: a few row chunks, each downloaded on the copy stream while the next one
+    // is computed (the download of the whole result takes about as long as computing it)
+    const int n_chunks = (correlations || !control_matrix) ? 1 : std::min(n_nops, 6);
+    for (int c = 0; c < n_chunks; ++c) {
+      const int j0 = (int)((long long)c * n_nops / n_chunks);
+      const int j1 = (int)((long long)(c + 1) * n_nops / n_chunks);
+      FFB_TRY(ffbi_from_atomic_rows(ctx, P, n_nops, j0, j1 - j0, n_basis, n_omega,
+                                    P > 1 ? ph.d() : nullptr, stack.as<double>(),
+                                    P > 1 ? Qd.d() : nullptr, 0, correlations, result.as<double>()));
+      if (n_chunks > 1) {
+        FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+        FFB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+        FFB_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(control_matrix) + (size_t)j0 * row_bytes,
+                                      reinterpret_cast<const char*>(B_dev) + (size_t)j0 * row_bytes,
+                                      (size_t)(j1 - j0) * row_bytes, cudaMemcpyDeviceToHost,
+                                      ctx->copy_stream));
+      }
+    }
+    if (n_chunks > 1) control_matrix = nullptr;  // already on its way
   }
   const int lead = correlations ? P : 1;
-  if (control_matrix) FFB_TRY(ffb_d2h(ctx, control_matrix, B_dev, (size_t)lead * pulse_bytes));
   DevBuf F;
+  size_t f_bytes = 0;
   if (filter_function_kind) {
     const size_t L = (size_t)lead * n_nops;
-    const size_t f_bytes = L * L * (filter_function_kind == 2 ? (size_t)n_basis * n_basis : 1) *
-                           n_omega * 16;
+    f_bytes = L * L * (filter_function_kind == 2 ? (size_t)n_basis * n_basis : 1) * n_omega * 16;
     FFB_TRY(F.alloc(ctx, f_bytes));
+  }
+  if (control_matrix && full_stack && filter_function_kind) {
+    // download the control matrix on the copy stream while the filter function is computed
+    FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+    FFB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+    FFB_CUDA(ctx, cudaMemcpyAsync(control_matrix, B_dev, (size_t)lead * pulse_bytes,
+                                  cudaMemcpyDeviceToHost, ctx->copy_stream));
+  } else if (control_matrix) {
+    FFB_TRY(ffb_d2h(ctx, control_matrix, B_dev, (size_t)lead * pulse_bytes));
+  }
+  if (filter_function_kind) {
     FFB_TRY(ffbi_filter_function(ctx, lead, n_nops, n_basis, n_omega, B_dev,
                                  filter_function_kind == 2, F.as<double>()));
     FFB_TRY(ffb_d2h(ctx, filter_function, F.p, f_bytes));
   }
+  if (full_stack) FFB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return FFB_OK;
 }

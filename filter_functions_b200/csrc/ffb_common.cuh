@@ -23,6 +23,10 @@ struct ffb_ctx {
   cudaStream_t stream = nullptr;  // the stream work is enqueued on (own or external)
   std::string err;
   int64_t launches = 0;
+  // second stream for bulk host<->device copies that overlap kernels (ffb_concatenate_pulses);
+  // ordered against `stream` with the two events
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[2] = {nullptr, nullptr};
 
   // grow-only caching pool: freed blocks are kept and handed out again (best fit)
   std::multimap<size_t, void*> free_blocks;
@@ -118,7 +122,10 @@ int ffbi_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_ome
 int ffbi_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
                      const double* phases, const double* B_atomic, const double* Q, int q_is_complex,
                      int correlations, double* out);
-int ffbi_from_atomic_dmma(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+int ffbi_from_atomic_rows(ffb_ctx* ctx, int P, int n_nops, int j0, int jn, int n_basis, int n_omega,
+                          const double* phases, const double* B_atomic, const double* Q,
+                          int q_is_complex, int correlations, double* out);
+int ffbi_from_atomic_dmma(ffb_ctx* ctx, int P, int n_nops, int n_rows, int n_basis, int n_omega,
                           const double* phases, const double* B_atomic, const double* Q,
                           int correlations, double* out);
 int ffbi_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* idx_dev,

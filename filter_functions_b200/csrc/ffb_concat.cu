@@ -394,10 +394,10 @@ small_matmul_kernel(int n, const double* __restrict__ A, const double* __restric
 }
 
 template <int LT>
-int launch_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+int launch_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_rows, int n_basis, int n_omega,
                        const double* phases, const double* B_atomic, const double* Q,
                        int q_is_complex, int correlations, double* out) {
-  dim3 grid(ceil_div(n_omega, 256), n_nops, ceil_div(n_basis, LT));
+  dim3 grid(ceil_div(n_omega, 256), n_rows, ceil_div(n_basis, LT));
   const size_t smem = (size_t)n_basis * LT * sizeof(double) * (q_is_complex ? 2 : 1);
   if (q_is_complex) {
     auto kern = from_atomic_kernel<LT, true>;
@@ -420,25 +420,38 @@ int launch_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega
 
 }  // namespace
 
-int ffbi_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
-                     const double* phases, const double* B_atomic, const double* Q,
-                     int q_is_complex, int correlations, double* out) {
+// Rows [j0, j0 + jn) of the noise-operator axis only (the strides stay those of the full arrays), so
+// that a caller can pipeline the download of finished rows with the computation of the next ones.
+int ffbi_from_atomic_rows(ffb_ctx* ctx, int P, int n_nops, int j0, int jn, int n_basis, int n_omega,
+                          const double* phases, const double* B_atomic, const double* Q,
+                          int q_is_complex, int correlations, double* out) {
   FFB_REQUIRE(ctx, P >= 1 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
               "from_atomic: bad shape (P=%d, n_nops=%d, n_basis=%d, n_omega=%d)", P, n_nops,
               n_basis, n_omega);
   FFB_REQUIRE(ctx, n_nops <= 65535, "from_atomic: too many noise operators (%d)", n_nops);
+  FFB_REQUIRE(ctx, j0 >= 0 && jn >= 1 && j0 + jn <= n_nops, "from_atomic: bad row range");
+  const size_t off = (size_t)j0 * n_basis * n_omega * 2;
+  B_atomic += off;
+  out += off;
   // FP64-bound regime (n_basis / 4 flop per byte): DMMA kernel of ffb_atomic_dmma.cu
   if (!q_is_complex && n_basis >= 32)
-    return ffbi_from_atomic_dmma(ctx, P, n_nops, n_basis, n_omega, phases, B_atomic, Q,
+    return ffbi_from_atomic_dmma(ctx, P, n_nops, jn, n_basis, n_omega, phases, B_atomic, Q,
                                  correlations, out);
   if (n_basis <= 4)
-    return launch_from_atomic<4>(ctx, P, n_nops, n_basis, n_omega, phases, B_atomic, Q,
+    return launch_from_atomic<4>(ctx, P, n_nops, jn, n_basis, n_omega, phases, B_atomic, Q,
                                  q_is_complex, correlations, out);
   if (n_basis <= 8)
-    return launch_from_atomic<8>(ctx, P, n_nops, n_basis, n_omega, phases, B_atomic, Q,
+    return launch_from_atomic<8>(ctx, P, n_nops, jn, n_basis, n_omega, phases, B_atomic, Q,
                                  q_is_complex, correlations, out);
-  return launch_from_atomic<16>(ctx, P, n_nops, n_basis, n_omega, phases, B_atomic, Q,
+  return launch_from_atomic<16>(ctx, P, n_nops, jn, n_basis, n_omega, phases, B_atomic, Q,
                                 q_is_complex, correlations, out);
+}
+
+int ffbi_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
+                     const double* phases, const double* B_atomic, const double* Q,
+                     int q_is_complex, int correlations, double* out) {
+  return ffbi_from_atomic_rows(ctx, P, n_nops, 0, n_nops, n_basis, n_omega, phases, B_atomic, Q,
+                               q_is_complex, correlations, out);
 }
 
 int ffbi_liouville(ffb_ctx* ctx, int n, int d, int n_basis, const double* U, const double* basis,

@@ -137,7 +137,9 @@ __device__ __forceinline__ void pair_from_index(int p, int d, int& m, int& n) {
 // ------------------------------------------------------------------------------------------------
 // prologue 1: eigenbasis transforms (omega independent, O(G (n_nops + n_basis) d^3))
 //   Bbar[g, jr] = s_j^{(g)} herm-part(V^+ B_j V),   Cbar[g, kr] = herm-part(U^+ C_k U),  U = Q_g^+ V_g
-// one block per segment; operators are transformed one after the other through shared memory.
+// one block per (segment, operator slice): blockIdx.y strides over the operators, so that short pulses
+// with many operators (a one-segment gate with 270 16x16 operators took 1.7 ms in a single block) still
+// fill the machine; operators of a slice are transformed one after the other through shared memory.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 transform_kernel(int G, int d, int n_nops, int n_basis, int parts_j, int parts_k,
@@ -169,7 +171,7 @@ transform_kernel(int G, int d, int n_nops, int n_basis, int parts_j, int parts_k
   }
   __syncthreads();
   const int n_ops = n_nops + n_basis;
-  for (int op = 0; op < n_ops; ++op) {
+  for (int op = blockIdx.y; op < n_ops; op += gridDim.y) {
     const bool is_noise = op < n_nops;
     const double* O = is_noise ? n_opers + (size_t)op * 2 * dd : basis + (size_t)(op - n_nops) * 2 * dd;
     const double* W = is_noise ? V : U;
@@ -992,7 +994,8 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
     const size_t smem = (size_t)8 * dd * sizeof(double);
     FFB_CUDA(ctx, cudaFuncSetAttribute(transform_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    transform_kernel<<<G, 128, smem, ctx->stream>>>(G, d, n_nops, n_basis, parts_j, parts_k, eigvecs,
+    const int slices = std::max(1, std::min(n_nops + n_basis, ceil_div(8 * ctx->sm_count, G)));
+    transform_kernel<<<dim3(G, slices), 128, smem, ctx->stream>>>(G, d, n_nops, n_basis, parts_j, parts_k, eigvecs,
                                                     propagators, n_opers, n_coeffs, basis,
                                                     Bbar.as<double>(), Cbar.as<double>());
     FFB_LAUNCHED(ctx);
