@@ -16,7 +16,8 @@ import numpy as np
 __all__ = ['lib', 'context', 'check', 'library_path', 'FFBError', 'EXPORTED_SYMBOLS']
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-library_path = os.path.join(_HERE, 'csrc', 'libffb200.so')
+#: FFB200_LIBRARY selects another build of the same sources (kernel experiments), never another backend
+library_path = os.environ.get('FFB200_LIBRARY') or os.path.join(_HERE, 'csrc', 'libffb200.so')
 
 FFB_OK, FFB_EINVAL, FFB_ENODEVICE, FFB_ECUDA, FFB_ENOMEM, FFB_ENOTCONV = 0, -1, -2, -3, -4, -5
 

@@ -42,38 +42,58 @@
 // Measured on B200 (tools/microbench/fp64_peaks.cu, profiles/fp64_peaks_r01.jsonl): DFMA peak 36.95
 // TFLOP/s, DMMA peak 37.14 TFLOP/s, and the two do NOT overlap (one FP64 pipe, 64 lanes/clk/SM); DMMA
 // is used because it needs 1/8 of the issue slots and shares the operands through the fragment layout.
+#include <cstdlib>
+
 #include "ffb_common.cuh"
+
+#ifndef FFB_EXP_MODE
+#define FFB_EXP_MODE 0  // kernel experiments only: 1 = generator without the accumulate, 2 = accumulate only
+#endif
 
 namespace {
 
 // ------------------------------------------------------------------------------------------------
 // math helpers
 // ------------------------------------------------------------------------------------------------
-// sin/cos with a 3-constant Cody-Waite reduction.  fma keeps x - k*pi/2 accurate to ~1e-16 ABSOLUTE,
+// sin/cos with a Cody-Waite reduction.  fma keeps x - k*pi/2 accurate to ~1e-16 ABSOLUTE,
 // which is what a unit-modulus phase factor needs (CUDA's sincos switches to Payne-Hanek above 1e5
 // to keep the RELATIVE error near zeros of sin, which is irrelevant here).  Branch free.  Verified
 // against sincos() on B200 up to |x| = 1e7 (max abs deviation 1.1e-16); beyond ~1e9 the rounding of
 // the argument itself (ulp(w t) > 1e-7 rad) has destroyed the phase in the reference too.
+// The constants live in constant memory so that they enter the DFMAs as c[bank][offset] operands: as
+// immediates each one costs two UMOV/IMAD.MOV issue slots per use (ncu: 53 of the 258 instructions per
+// warp and segment of the DFMA kernel), and 16 doubles are too many to pin in registers.
+__constant__ double SC_K[16] = {
+    6.36619772367581382433e-01,   // 0: 2/pi
+    6755399441055744.0,           // 1: 1.5 * 2^52, round-to-nearest-integer by addition
+    1.57079632679489655800e+00,   // 2: pi/2 high
+    6.12323399573676603587e-17,   // 3: pi/2 middle
+    1.58969099521155010221e-10,   // 4..9: sin polynomial
+    -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+    8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11,  // 10..15: cos polynomial
+    2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+
 __device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
-  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer by addition
-  double kd = fma(x, 6.36619772367581382433e-01, MAGIC);
+  double kd = fma(x, SC_K[0], SC_K[1]);
   const int q = __double2loint(kd);
-  kd -= MAGIC;
-  double r = fma(-kd, 1.57079632679489655800e+00, x);
-  r = fma(-kd, 6.12323399573676603587e-17, r);
-  r = fma(-kd, -1.49738490485916983294e-33, r);
+  kd -= SC_K[1];
+  // two-constant Cody-Waite: the third term of pi/2 (1.5e-33 k) is below 1e-17 for |x| < 1e16
+  double r = fma(-kd, SC_K[2], x);
+  r = fma(-kd, SC_K[3], r);
   const double r2 = r * r;
-  double ps = fma(r2, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = fma(ps, r2, 2.75573137070700676789e-06);
-  ps = fma(ps, r2, -1.98412698298579493134e-04);
-  ps = fma(ps, r2, 8.33333333332248946124e-03);
-  ps = fma(ps, r2, -1.66666666666666324348e-01);
+  double ps = fma(r2, SC_K[4], SC_K[5]);
+  ps = fma(ps, r2, SC_K[6]);
+  ps = fma(ps, r2, SC_K[7]);
+  ps = fma(ps, r2, SC_K[8]);
+  ps = fma(ps, r2, SC_K[9]);
   const double s = fma(r * r2, ps, r);
-  double pc = fma(r2, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = fma(pc, r2, -2.75573143513906633035e-07);
-  pc = fma(pc, r2, 2.48015872894767294178e-05);
-  pc = fma(pc, r2, -1.38888888888741095749e-03);
-  pc = fma(pc, r2, 4.16666666666666019037e-02);
+  double pc = fma(r2, SC_K[10], SC_K[11]);
+  pc = fma(pc, r2, SC_K[12]);
+  pc = fma(pc, r2, SC_K[13]);
+  pc = fma(pc, r2, SC_K[14]);
+  pc = fma(pc, r2, SC_K[15]);
   const double c = fma(r2 * r2, pc, fma(r2, -0.5, 1.0));
   // quadrant: swap for odd q, flip signs through the sign bit (integer ops, not the FP64 pipe)
   const double ss = (q & 1) ? c : s;
@@ -96,7 +116,7 @@ __device__ __forceinline__ double rcp_nr(double x) {
 }
 
 constexpr double SQRT2 = 1.41421356237309504880;
-constexpr double SMALL_SIN = 0.0009765625 * SQRT2;  // |sqrt(2) sin(x dt / 2)| below this -> direct evaluation
+// |sqrt(2) sin(x dt / 2)| below 2^-10 sqrt(2) -> direct evaluation (SMALL_SIN_HI, compared on the high word)
 constexpr double TINY_OMEGA = 1e-290;               // |w| below this is treated as the exact zero
 
 // I(x) = (e^{i x dt} - 1) / (i x) evaluated directly with the rounding sequence of numeric.py:156-165
@@ -491,7 +511,7 @@ struct Vals {
 // phase evaluation is interleaved with the previous unit's DMMAs.
 __device__ __forceinline__ void gen_diag_slow(Gen& g, const double* unit_consts, int q) {
   g.dt = unit_consts[4 + q];
-  if (g.dt != g.dt_prev) {  // never taken again on uniform time grids
+  if (__double_as_longlong(g.dt) != __double_as_longlong(g.dt_prev)) {  // never again on uniform grids
     double sn, cs;
     sincos_cw(0.5 * (g.w * g.dt), sn, cs);
     g.hc = SQRT2 * cs;
@@ -517,11 +537,11 @@ __device__ __forceinline__ void gen_diag(Gen& g, const double* unit_consts, int 
 
 // ---- pair unit (product form): S = I(w + Om) + I(w - Om), D = i (I(w + Om) - I(w - Om)), times phase.
 // Returns true if this lane needs the direct re-evaluation (cancellation in sin((w +- Om) dt / 2)).
-__device__ __forceinline__ bool gen_pair(const Gen& g, const double* unit_consts, int q, Vals& v) {
-#ifdef FFB_EXP_NOGEN
-  v.a_re = unit_consts[q]; v.a_im = unit_consts[4 + q]; v.b_re = unit_consts[8 + q]; v.b_im = g.w; return false;
-#endif
-  const double Om = unit_consts[q], Ch = unit_consts[4 + q], Sh = unit_consts[8 + q];
+// |x| < SMALL_SIN on the high word only (integer pipe: a DSETP would take an FP64-pipe slot)
+__device__ __forceinline__ int abs_hi(double x) { return __double2hiint(x) & 0x7fffffff; }
+constexpr int SMALL_SIN_HI = 0x3F56A09E;  // high word of 2^-10 sqrt(2)
+
+__device__ __forceinline__ bool pair_values(const Gen& g, double Om, double Ch, double Sh, Vals& v) {
   const double t1 = g.hc * Ch, t3 = g.hs * Ch;
   const double zp_re = fma(-g.hs, Sh, t1), zp_im = fma(g.hc, Sh, t3);  // sqrt2 e^{i (w+Om) dt/2}
   const double zm_re = fma(g.hs, Sh, t1), zm_im = fma(-g.hc, Sh, t3);  // sqrt2 e^{i (w-Om) dt/2}
@@ -535,7 +555,14 @@ __device__ __forceinline__ bool gen_pair(const Gen& g, const double* unit_consts
   v.a_im = g.ph_re * s_im + g.ph_im * s_re;
   v.b_re = g.ph_re * d_re - g.ph_im * d_im;
   v.b_im = g.ph_re * d_im + g.ph_im * d_re;
-  return fabs(zp_im) < SMALL_SIN || fabs(zm_im) < SMALL_SIN;
+  return min(abs_hi(zp_im), abs_hi(zm_im)) < SMALL_SIN_HI;
+}
+
+__device__ __forceinline__ bool gen_pair(const Gen& g, const double* unit_consts, int q, Vals& v) {
+#ifdef FFB_EXP_NOGEN
+  v.a_re = unit_consts[q]; v.a_im = unit_consts[4 + q]; v.b_re = unit_consts[8 + q]; v.b_im = g.w; return false;
+#endif
+  return pair_values(g, unit_consts[q], unit_consts[4 + q], unit_consts[8 + q], v);
 }
 
 // rare path: at least one lane of the warp sits on the removable singularity.  Everything goes through
@@ -863,6 +890,270 @@ ctrlmat_main_kernel(const MainParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small row counts (rows = n_nops * n_basis <= 16: a single qubit in the Pauli basis, config 2): DFMA
+// variant.  With 12 rows the tensor path pads M to 16 (25 % of the DMMA work is wasted) and the mix of
+// DMMA and the generator's DFMA/DMUL stream costs another ~12 % of the FP64 pipe (measured,
+// profiles/fp64_peaks_r01.jsonl "mixed").  Here a THREAD owns one frequency and walks the segments; the
+// coefficients of a segment are broadcast from shared memory (every lane reads the same address) and
+// the 2 R accumulators live in registers: per (segment, frequency) R (2 + 4 n_pairs) DFMAs with no
+// padding beyond R = 4 ceil(rows / 4), next to the same operand generator.  A warp = 32 frequencies x
+// one contiguous range of segments; the 8 warps of a CTA split the CTA's segment chunk 8 ways (their
+// partial sums are reduced through shared memory in a fixed order), each warp streams its own records
+// through a private double-buffered cp.async pipeline -- no block-wide barrier in the main loop.
+//
+// Stream: one record per segment:  t, dt, diag[R], then per level pair: Omega, cos(Omega dt/2),
+// sin(Omega dt/2), 0, Re[R], Im[R].
+// ------------------------------------------------------------------------------------------------
+struct DfmaParams {
+  const double* stream;
+  const double* omega;
+  double* partial;   // [S][R][n_omega] complex
+  int n_omega;
+  int G;
+  int n_pairs;
+  int rec_doubles;
+  int segs_per_cta;  // segment chunk of one CTA (blockIdx.y)
+  int segs_per_warp; // ceil(segs_per_cta / DFMA_WARPS)
+};
+
+constexpr int DFMA_WARPS = 8;
+constexpr int DFMA_STAGE_SEGS = 8;
+
+__host__ __device__ inline int dfma_rec_doubles(int R, int n_pairs) { return 2 + R + n_pairs * (4 + 2 * R); }
+
+__global__ void __launch_bounds__(256)
+assemble_dfma_kernel(int G, int d, int rows, int R, int n_jrows, int n_krows,
+                     const double* __restrict__ Bbar, const double* __restrict__ Cbar,
+                     const double* __restrict__ eigvals, const double* __restrict__ dt,
+                     const double* __restrict__ t, double* __restrict__ stream) {
+  const int n_pairs = d * (d - 1) / 2;
+  const int rec = dfma_rec_doubles(R, n_pairs);
+  const size_t total = (size_t)G * rec;
+  const int dd = d * d;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx / rec);
+    int off = (int)(idx % rec);
+    double val = 0.0;
+    if (off < 2) {
+      val = off == 0 ? t[g] : dt[g];
+    } else if (off < 2 + R) {
+      const int row = off - 2;
+      if (row < rows) {
+        const double* Bm = Bbar + ((size_t)g * n_jrows + row / n_krows) * 2 * dd;
+        const double* Cm = Cbar + ((size_t)g * n_krows + row % n_krows) * 2 * dd;
+        double acc = 0.0;
+        for (int m = 0; m < d; ++m) acc += Bm[2 * (m * d + m)] * Cm[2 * (m * d + m)];
+        val = acc;
+      }
+    } else {
+      off -= 2 + R;
+      const int pair = off / (4 + 2 * R);
+      off %= 4 + 2 * R;
+      int m, n;
+      pair_from_index(pair, d, m, n);
+      if (off < 4) {
+        const double Om = eigvals[(size_t)g * d + m] - eigvals[(size_t)g * d + n];
+        if (off == 0) {
+          val = Om;
+        } else if (off < 3) {
+          double sn, cs;
+          sincos(0.5 * (Om * dt[g]), &sn, &cs);
+          val = off == 1 ? cs : sn;
+        }
+      } else {
+        const int col = (off - 4) / R, row = (off - 4) % R;
+        if (row < rows) {
+          const double* Bm = Bbar + ((size_t)g * n_jrows + row / n_krows) * 2 * dd;
+          const double* Cm = Cbar + ((size_t)g * n_krows + row % n_krows) * 2 * dd;
+          const cplx b = {Bm[2 * (m * d + n)], Bm[2 * (m * d + n) + 1]};
+          const cplx c = {Cm[2 * (n * d + m)], Cm[2 * (n * d + m) + 1]};
+          const cplx prod = cmul(b, c);
+          val = col == 0 ? prod.re : prod.im;
+        }
+      }
+    }
+    stream[idx] = val;
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(DFMA_WARPS * 32, 2)
+ctrlmat_dfma_kernel(const DfmaParams p) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w_idx = blockIdx.x * 32 + lane;
+  const int rec = p.rec_doubles;
+  double* wbuf = smem + (size_t)warp * 2 * DFMA_STAGE_SEGS * rec;  // this warp's two stage buffers
+
+  Gen g;
+  g.w = w_idx < p.n_omega ? p.omega[w_idx] : 1.0;
+  g.w_zero = fabs(g.w) < TINY_OMEGA;
+  g.inv_w = g.w_zero ? 0.0 : 1.0 / g.w;
+  g.dt_prev = -1.0;
+  g.dt = 0.0;
+  g.hc = SQRT2;
+  g.hs = 0.0;
+  g.j0_re = g.j0_im = 0.0;
+  g.ph_re = 1.0;
+  g.ph_im = 0.0;
+
+  double acc_re[R], acc_im[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc_re[r] = acc_im[r] = 0.0;
+
+  const int seg_begin = min(p.G, blockIdx.y * p.segs_per_cta + warp * p.segs_per_warp);
+  const int seg_end = min(min(p.G, (blockIdx.y + 1) * p.segs_per_cta), seg_begin + p.segs_per_warp);
+  const int n_segs = max(0, seg_end - seg_begin);
+  const int n_stages = (n_segs + DFMA_STAGE_SEGS - 1) / DFMA_STAGE_SEGS;
+  const double* gsrc = p.stream + (size_t)seg_begin * rec;
+  auto stage_load = [&](int st) {
+    const int s0 = st * DFMA_STAGE_SEGS;
+    const int len = min(DFMA_STAGE_SEGS, n_segs - s0) * rec;  // rec is even: whole 16-byte chunks
+    double* dst = wbuf + (st & 1) * DFMA_STAGE_SEGS * rec;
+    const double* src = gsrc + (size_t)s0 * rec;
+    for (int e = lane * 2; e < len; e += 64) cp_async16(dst + e, src + e);
+  };
+  auto dt_update = [&](double dtg) {
+    g.dt = dtg;
+    if (__double_as_longlong(g.dt) != __double_as_longlong(g.dt_prev)) {  // warp-uniform
+      double sn, cs;
+      sincos_cw(0.5 * (g.w * g.dt), sn, cs);
+      g.hc = SQRT2 * cs;
+      g.hs = SQRT2 * sn;
+      const double f = g.hs * g.inv_w;
+      g.j0_re = g.w_zero ? g.dt : g.hc * f;
+      g.j0_im = g.w_zero ? 0.0 : g.hs * f;
+      g.dt_prev = g.dt;
+    }
+  };
+  auto fma_diag = [&](const double* rp, double a_re, double a_im) {
+    const double2* c2 = reinterpret_cast<const double2*>(rp + 2);
+#pragma unroll
+    for (int r = 0; r < R / 2; ++r) {
+      const double2 c = c2[r];
+      acc_re[2 * r] = fma(c.x, a_re, acc_re[2 * r]);
+      acc_im[2 * r] = fma(c.x, a_im, acc_im[2 * r]);
+      acc_re[2 * r + 1] = fma(c.y, a_re, acc_re[2 * r + 1]);
+      acc_im[2 * r + 1] = fma(c.y, a_im, acc_im[2 * r + 1]);
+    }
+  };
+  auto fma_pair = [&](const double* pp, const Vals& v) {
+    const double2* cre = reinterpret_cast<const double2*>(pp + 4);
+    const double2* cim = reinterpret_cast<const double2*>(pp + 4 + R);
+#pragma unroll
+    for (int r = 0; r < R / 2; ++r) {
+      const double2 a = cre[r], b = cim[r];
+      acc_re[2 * r] = fma(a.x, v.a_re, fma(b.x, v.b_re, acc_re[2 * r]));
+      acc_im[2 * r] = fma(a.x, v.a_im, fma(b.x, v.b_im, acc_im[2 * r]));
+      acc_re[2 * r + 1] = fma(a.y, v.a_re, fma(b.y, v.b_re, acc_re[2 * r + 1]));
+      acc_im[2 * r + 1] = fma(a.y, v.a_im, fma(b.y, v.b_im, acc_im[2 * r + 1]));
+    }
+  };
+  auto one_segment = [&](const double* rp) {
+    dt_update(rp[1]);
+    sincos_cw(g.w * rp[0], g.ph_im, g.ph_re);
+    fma_diag(rp, g.ph_re * g.j0_re - g.ph_im * g.j0_im, g.ph_re * g.j0_im + g.ph_im * g.j0_re);
+    const double* pp = rp + 2 + R;
+    for (int pi = 0; pi < p.n_pairs; ++pi, pp += 4 + 2 * R) {
+      Vals v;
+      const double Om = pp[0];
+      const bool fix = pair_values(g, Om, pp[1], pp[2], v);
+      if (__any_sync(0xffffffffu, fix)) {
+        if (fix) {
+          const Vals4 rr = fix_pair(g.w, g.dt, g.ph_re, g.ph_im, Om);
+          v.a_re = rr.a_re; v.a_im = rr.a_im; v.b_re = rr.b_re; v.b_im = rr.b_im;
+        }
+      }
+      fma_pair(pp, v);
+    }
+  };
+  // (Generating the next unit's operands next to the current unit's DFMAs, as the tensor-path kernel
+  // does, was measured SLOWER here: 1.33 vs 1.16 ms on config 2 -- the extra live values cost moves.)
+  if (n_stages > 0) {
+    stage_load(0);
+    cp_async_commit();
+  }
+  for (int st = 0; st < n_stages; ++st) {
+    if (st + 1 < n_stages) {
+      stage_load(st + 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    const double* buf = wbuf + (st & 1) * DFMA_STAGE_SEGS * rec;
+    const int ns = min(DFMA_STAGE_SEGS, n_segs - st * DFMA_STAGE_SEGS);
+    // Two segments per iteration: their generator chains (sincos, reciprocals) are independent and sit
+    // in one basic block, which doubles the instruction-level parallelism the FP64 pipe sees (the
+    // chains are latency-bound: generator alone ran at 52 % of the pipe with one segment at a time).
+    int sgm = 0;
+    for (; sgm + 1 < ns; sgm += 2) {
+      const double* ra = buf + sgm * rec;
+      const double* rb = ra + rec;
+      dt_update(ra[1]);
+      const bool same_dt = __double_as_longlong(rb[1]) == __double_as_longlong(ra[1]);
+      if (same_dt && p.n_pairs == 1) {
+        double pa_re, pa_im, pb_re, pb_im;
+        sincos_cw(g.w * ra[0], pa_im, pa_re);
+        sincos_cw(g.w * rb[0], pb_im, pb_re);
+        Vals va, vb;
+        const double* qa = ra + 2 + R;
+        const double* qb = rb + 2 + R;
+        g.ph_re = pa_re; g.ph_im = pa_im;
+        const bool fa = pair_values(g, qa[0], qa[1], qa[2], va);
+        const double da_re = pa_re * g.j0_re - pa_im * g.j0_im, da_im = pa_re * g.j0_im + pa_im * g.j0_re;
+        g.ph_re = pb_re; g.ph_im = pb_im;
+        const bool fb = pair_values(g, qb[0], qb[1], qb[2], vb);
+        const double db_re = pb_re * g.j0_re - pb_im * g.j0_im, db_im = pb_re * g.j0_im + pb_im * g.j0_re;
+        if (__any_sync(0xffffffffu, fa || fb)) {
+          if (fa) {
+            const Vals4 rr = fix_pair(g.w, g.dt, pa_re, pa_im, qa[0]);
+            va.a_re = rr.a_re; va.a_im = rr.a_im; va.b_re = rr.b_re; va.b_im = rr.b_im;
+          }
+          if (fb) {
+            const Vals4 rr = fix_pair(g.w, g.dt, pb_re, pb_im, qb[0]);
+            vb.a_re = rr.a_re; vb.a_im = rr.a_im; vb.b_re = rr.b_re; vb.b_im = rr.b_im;
+          }
+        }
+        fma_diag(ra, da_re, da_im);
+        fma_pair(qa, va);
+        fma_diag(rb, db_re, db_im);
+        fma_pair(qb, vb);
+      } else {
+        one_segment(ra);
+        one_segment(rb);
+      }
+    }
+    if (sgm < ns) one_segment(buf + sgm * rec);
+    __syncwarp();  // all lanes are done with this buffer before it is refilled
+  }
+
+  // ---- reduce the 8 warps' partial sums (fixed order) and write partial[z][row][w]
+  __syncthreads();  // every warp is done with its stage buffers: reuse them
+  double* red = smem;  // [DFMA_WARPS][2 R][32]
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    red[((size_t)warp * 2 * R + 2 * r) * 32 + lane] = acc_re[r];
+    red[((size_t)warp * 2 * R + 2 * r + 1) * 32 + lane] = acc_im[r];
+  }
+  __syncthreads();
+  if (w_idx < p.n_omega) {
+    double2* out = reinterpret_cast<double2*>(p.partial) + (size_t)blockIdx.y * R * p.n_omega;
+    for (int row = warp; row < R; row += DFMA_WARPS) {
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int wi = 0; wi < DFMA_WARPS; ++wi) {
+        re += red[((size_t)wi * 2 * R + 2 * row) * 32 + lane];
+        im += red[((size_t)wi * 2 * R + 2 * row + 1) * 32 + lane];
+      }
+      out[(size_t)row * p.n_omega + w_idx] = make_double2(re, im);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // finalize: sum the split-K partials and undo the Hermitian/anti-Hermitian row expansion
 //   out[j,k,w] = sum_z sum_{pj,pk} i^{pj+pk} partial[z][(j*parts_j+pj)*n_krows + k*parts_k+pk][w]
 // ------------------------------------------------------------------------------------------------
@@ -971,11 +1262,17 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   const int NW = warps_per_cta(MT);
   const StreamGeom geo = make_geom(rows, G, d, MT);
   const int rows_pad = geo.n_rb * MT * 8;
+  // rows <= 16 and few level pairs: the DFMA variant (thread per frequency), see ctrlmat_dfma_kernel
+  bool use_dfma = rows <= 16 && d >= 2 && d <= 3;
+  if (const char* e = getenv("FFB_CTRLMAT_DFMA")) use_dfma = use_dfma && atoi(e) != 0;
+  const int R = 4 * ceil_div(rows, 4);
+  const int rec = dfma_rec_doubles(R, d * (d - 1) / 2);
 
   DevBuf Bbar, Cbar, stream, partial;
   FFB_TRY(Bbar.alloc(ctx, (size_t)G * n_jrows * dd * 16));
   FFB_TRY(Cbar.alloc(ctx, (size_t)G * n_krows * dd * 16));
-  FFB_TRY(stream.alloc(ctx, geo.rb_doubles * geo.n_rb * sizeof(double)));
+  FFB_TRY(stream.alloc(ctx, use_dfma ? (size_t)G * rec * sizeof(double)
+                                     : geo.rb_doubles * geo.n_rb * sizeof(double)));
 
   if (d >= 2 && d <= 4) {
     const long long n_threads = (long long)G * (n_nops + n_basis);
@@ -999,6 +1296,79 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
                                                     propagators, n_opers, n_coeffs, basis,
                                                     Bbar.as<double>(), Cbar.as<double>());
     FFB_LAUNCHED(ctx);
+  }
+  if (use_dfma) {
+    const size_t total = (size_t)G * rec;
+    const unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total, 256), (size_t)ctx->sm_count * 32);
+    assemble_dfma_kernel<<<blocks, 256, 0, ctx->stream>>>(G, d, rows, R, n_jrows, n_krows,
+                                                          Bbar.as<double>(), Cbar.as<double>(),
+                                                          eigvals, dt, t, stream.as<double>());
+    FFB_LAUNCHED(ctx);
+    DfmaParams q;
+    q.stream = stream.as<double>();
+    q.omega = omega;
+    q.n_omega = n_omega;
+    q.G = G;
+    q.n_pairs = d * (d - 1) / 2;
+    q.rec_doubles = rec;
+    const size_t smem = std::max((size_t)DFMA_WARPS * 2 * DFMA_STAGE_SEGS * rec,
+                                 (size_t)DFMA_WARPS * 2 * R * 32) * sizeof(double);
+    FFB_REQUIRE(ctx, smem <= 200 * 1024, "control matrix: DFMA stage does not fit shared memory");
+    const int n_wt = ceil_div(n_omega, 32);
+    int blocks_per_sm = 1;
+    auto pick = [&](auto kern) -> int {
+      FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FFB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern,
+                                                                   DFMA_WARPS * 32, smem));
+      return FFB_OK;
+    };
+    switch (R) {
+      case 4: FFB_TRY(pick(ctrlmat_dfma_kernel<4>)); break;
+      case 8: FFB_TRY(pick(ctrlmat_dfma_kernel<8>)); break;
+      case 12: FFB_TRY(pick(ctrlmat_dfma_kernel<12>)); break;
+      default: FFB_TRY(pick(ctrlmat_dfma_kernel<16>)); break;
+    }
+    blocks_per_sm = std::max(1, blocks_per_sm);
+    // split the segment axis over CTAs so that whole waves of CTAs are filled (same cost model as below)
+    const long long slots = (long long)ctx->sm_count * blocks_per_sm;
+    const int min_chunk = DFMA_WARPS * 16;  // at least 16 segments per warp
+    long long s_cap = std::max(1, G / min_chunk);
+    s_cap = std::min(s_cap, 64 * slots / n_wt + 1);
+    int S = 1, chunk = G;
+    double best_cost = 1e300;
+    for (int sp = 1; sp <= (int)s_cap; ++sp) {
+      int c = ceil_div(G, sp);
+      c = ceil_div(c, DFMA_WARPS) * DFMA_WARPS;
+      const int s_eff = ceil_div(G, c);
+      const long long waves = ((long long)n_wt * s_eff + slots - 1) / slots;
+      const double cost = (double)waves * (c / DFMA_WARPS + 6.0);
+      if (cost < best_cost * 0.999) {
+        best_cost = cost;
+        S = s_eff;
+        chunk = c;
+      }
+    }
+    q.segs_per_cta = chunk;
+    q.segs_per_warp = ceil_div(chunk, DFMA_WARPS);
+    FFB_TRY(partial.alloc(ctx, (size_t)S * R * n_omega * 16));
+    q.partial = partial.as<double>();
+    dim3 grid(n_wt, S);
+    int slot = -1;
+    FFB_TRY(ffb_time_begin(ctx, &slot));
+    switch (R) {
+      case 4: ctrlmat_dfma_kernel<4><<<grid, DFMA_WARPS * 32, smem, ctx->stream>>>(q); break;
+      case 8: ctrlmat_dfma_kernel<8><<<grid, DFMA_WARPS * 32, smem, ctx->stream>>>(q); break;
+      case 12: ctrlmat_dfma_kernel<12><<<grid, DFMA_WARPS * 32, smem, ctx->stream>>>(q); break;
+      default: ctrlmat_dfma_kernel<16><<<grid, DFMA_WARPS * 32, smem, ctx->stream>>>(q); break;
+    }
+    FFB_LAUNCHED(ctx);
+    FFB_TRY(ffb_time_end(ctx, slot));
+    const size_t total_out = (size_t)n_nops * n_basis * n_omega;
+    const unsigned fblocks = (unsigned)std::min<size_t>(ceil_div_sz(total_out, 256), (size_t)ctx->sm_count * 16);
+    finalize_kernel<<<fblocks, 256, 0, ctx->stream>>>(S, R, n_nops, n_basis, parts_j, parts_k, n_omega,
+                                                      partial.as<double>(), out);
+    FFB_LAUNCHED(ctx);
+    return FFB_OK;
   }
   {
     const size_t total = geo.rb_doubles * geo.n_rb;

@@ -74,15 +74,17 @@ def test_control_matrix_from_scratch(engine, d, G, n_nops, btype, n_omega):
         assert nerr(B[j], B_o[j]) < TOL
 
 
-def test_control_matrix_special_frequencies(engine):
+@pytest.mark.parametrize('d,n_nops', [(3, 2), (2, 3), (3, 1), (2, 1)])
+def test_control_matrix_special_frequencies(engine, d, n_nops):
     """omega = 0 (the exact-zero branch of numeric.py:162-165), negative omega, omega == -Omega_mn
-    (resonance) and tiny omega (series branch), list input, t=None, out=..."""
+    (resonance) and tiny omega (series branch), list input, t=None, out=...; (3, 2) runs on the tensor
+    path, the other shapes (<= 16 rows) on the DFMA variant."""
     rng = np.random.default_rng(5)
-    d, G, n_nops = 3, 12, 2
+    G = 12
     _, _, n_opers, n_coeffs, dt, H = _setup(rng, d, G, n_nops)
     ev, V, Q = oracle.diagonalize(H, dt)
     basis = oracle.ggm_basis(d)
-    res = [ev[3, 1] - ev[3, 0], ev[5, 0] - ev[5, 2], ev[0, 2] - ev[0, 1]]
+    res = [ev[3, 1] - ev[3, 0], ev[5, 0] - ev[5, d - 1], ev[0, d - 1] - ev[0, 1]]
     omega = [0.0, 1e-10, -1e-10, 1e-5, -3.3, 2.0, 1e3, -1e4] + res + [-r for r in res]
     B_o = oracle.control_matrix_from_scratch(ev, V, Q, omega, basis, n_opers, n_coeffs, dt)
     B = engine.numeric.calculate_control_matrix_from_scratch(ev, V, Q, omega, basis, n_opers,
