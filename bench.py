@@ -323,17 +323,28 @@ def run_b200(args):
     kernel_ms = k_ms_max/max(1, k_n.value)
     W = wl.flops_per_seg_omega
     achieved = W*G*n_omega_local/(kernel_ms*1e-3)*1e-12
-    # executed DMMA flops of the Hermitian-pair formulation (csrc/ffb_ctrlmat.cu header)
+    # executed multiply-add flops of the Hermitian-pair formulation (csrc/ffb_ctrlmat.cu header): the
+    # library runs the DFMA variant (thread per frequency) for <= 16 rows and d <= 3, else DMMA tiles
     rows = n_nops*n_basis
-    rows_pad = -(-rows//8)*8
+    use_dfma = rows <= 16 and 2 <= d <= 3 and os.environ.get('FFB_CTRLMAT_DFMA', '1') != '0'
+    if use_dfma:
+        rows_pad = -(-rows//4)*4
+        kernel = 'ctrlmat_dfma_kernel'
+        pipe = ('fp64 DFMA (thread per frequency; 64 lanes/clk/SM, the pipe DMMA shares); the '
+                'operand generator adds ~57 FP64 instructions per seg*omega that are not counted in '
+                'executed_tflops')
+    else:
+        rows_pad = -(-rows//8)*8
+        kernel = 'ctrlmat_main_kernel'
+        pipe = 'fp64 (DMMA.8x8x4; shares the 64 lane/clk/SM FP64 pipe with DFMA)'
     executed = rows_pad*(1 + d*(d - 1))*2*2*G*n_omega_local/(kernel_ms*1e-3)*1e-12
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload)
     roofline = {
-        'bound': 'tensor', 'pipe': 'fp64 (DMMA.8x8x4; shares the 64 lane/clk/SM FP64 pipe with DFMA)',
-        'kernel': 'ctrlmat_main_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+        'bound': 'tensor', 'pipe': pipe,
+        'kernel': kernel, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
         'frac': achieved/peak, 'traffic': traffic,
         'peak_source': 'measured live by ffb_measure_fp64_peak (DFMA %.2f, DMMA %.2f TFLOP/s); '
                        'MEASURED_PEAKS.json has no fp64 entry' % (dfma.value, dmma.value),

@@ -155,6 +155,7 @@ void ffb_destroy(ffb_ctx* ctx) {
   }
   for (auto& kv : ctx->host_free_blocks) cudaFreeHost(kv.second);
   for (auto& kv : ctx->host_live_blocks) cudaFreeHost(kv.first);
+  if (ctx->trig_table) cudaFree(ctx->trig_table);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& ev : ctx->copy_ev)
     if (ev) cudaEventDestroy(ev);

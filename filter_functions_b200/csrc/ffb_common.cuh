@@ -25,6 +25,8 @@ struct ffb_ctx {
   int64_t launches = 0;
   // second stream for bulk host<->device copies that overlap kernels (ffb_concatenate_pulses);
   // ordered against `stream` with the two events
+  // 256-entry table of (sin, cos)(k pi / 128) for the table-driven sincos of the control-matrix kernels
+  double* trig_table = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
 

@@ -46,9 +46,6 @@
 
 #include "ffb_common.cuh"
 
-#ifndef FFB_EXP_MODE
-#define FFB_EXP_MODE 0  // kernel experiments only: 1 = generator without the accumulate, 2 = accumulate only
-#endif
 
 namespace {
 
@@ -102,6 +99,47 @@ __device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
   const int c_flip = ((q + 1) & 2) << 30;
   sn = __hiloint2double(__double2hiint(ss) ^ s_flip, __double2loint(ss));
   cs = __hiloint2double(__double2hiint(cc) ^ c_flip, __double2loint(cc));
+}
+
+// Table-driven variant for the thread-per-frequency kernel: x = k pi/128 + r, |r| <= pi/256, so sin r
+// and cos r need three terms each (remainders r^7/5040 < 1e-17, r^8/40320 < 1e-20) and the quadrant
+// logic disappears into the 256-entry table (sin, cos)(k pi/128) held in shared memory:
+// 15 FP64 operations and one LDS.128 instead of 22 and ~12 integer/select instructions.  On sm_100 an
+// FP64 instruction holds the scheduler's dispatch port for 2 cycles and nothing else issues meanwhile
+// (measured: time = 2 N_fp64 + 16 N_dmma + N_other on every variant of these kernels), so both counts
+// matter.  Same absolute accuracy as sincos_cw (table entries and the reduction are exact to 1 ulp).
+constexpr int TRIG_TABLE_SIZE = 256;
+__constant__ double ST_K[8] = {
+    4.07436654315252084757e+01,   // 0: 128/pi
+    6755399441055744.0,           // 1: 1.5 * 2^52
+    2.45436926061702587187e-02,   // 2: pi/128 high
+    9.56755311833869693105e-19,   // 3: pi/128 low
+    1.0 / 120.0, -1.0 / 6.0, -1.0 / 720.0, 1.0 / 24.0};
+
+__global__ void trig_table_kernel(double2* __restrict__ table) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= TRIG_TABLE_SIZE) return;
+  double sn, cs;
+  sincospi((double)k / 128.0, &sn, &cs);
+  table[k] = make_double2(sn, cs);
+}
+
+__device__ __forceinline__ void sincos_tab(double x, const double2* __restrict__ table_smem,
+                                           double& sn, double& cs) {
+  double kd = fma(x, ST_K[0], ST_K[1]);
+  const int k = __double2loint(kd) & (TRIG_TABLE_SIZE - 1);
+  kd -= ST_K[1];
+  double r = fma(-kd, ST_K[2], x);
+  r = fma(-kd, ST_K[3], r);
+  const double2 sc = table_smem[k];
+  const double r2 = r * r;
+  const double ps = fma(r2, ST_K[4], ST_K[5]);
+  const double s = fma(r * r2, ps, r);
+  double pc = fma(r2, ST_K[6], ST_K[7]);
+  pc = fma(pc, r2, -0.5);
+  const double c = fma(pc, r2, 1.0);
+  sn = fma(sc.x, c, sc.y * s);
+  cs = fma(sc.y, c, -(sc.x * s));
 }
 
 // 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps on the FP64 pipe.
@@ -914,6 +952,8 @@ struct DfmaParams {
   int rec_doubles;
   int segs_per_cta;  // segment chunk of one CTA (blockIdx.y)
   int segs_per_warp; // ceil(segs_per_cta / DFMA_WARPS)
+  const double2* trig_table;  // (sin, cos)(k pi / 128), 256 entries
+  int stage_smem_doubles;     // offset of the table copy in shared memory
 };
 
 constexpr int DFMA_WARPS = 8;
@@ -985,6 +1025,9 @@ ctrlmat_dfma_kernel(const DfmaParams p) {
   const int w_idx = blockIdx.x * 32 + lane;
   const int rec = p.rec_doubles;
   double* wbuf = smem + (size_t)warp * 2 * DFMA_STAGE_SEGS * rec;  // this warp's two stage buffers
+  double2* trig = reinterpret_cast<double2*>(smem + p.stage_smem_doubles);
+  for (int k = threadIdx.x; k < TRIG_TABLE_SIZE; k += DFMA_WARPS * 32) trig[k] = p.trig_table[k];
+  __syncthreads();
 
   Gen g;
   g.w = w_idx < p.n_omega ? p.omega[w_idx] : 1.0;
@@ -1052,7 +1095,7 @@ ctrlmat_dfma_kernel(const DfmaParams p) {
   };
   auto one_segment = [&](const double* rp) {
     dt_update(rp[1]);
-    sincos_cw(g.w * rp[0], g.ph_im, g.ph_re);
+    sincos_tab(g.w * rp[0], trig, g.ph_im, g.ph_re);
     fma_diag(rp, g.ph_re * g.j0_re - g.ph_im * g.j0_im, g.ph_re * g.j0_im + g.ph_im * g.j0_re);
     const double* pp = rp + 2 + R;
     for (int pi = 0; pi < p.n_pairs; ++pi, pp += 4 + 2 * R) {
@@ -1085,48 +1128,10 @@ ctrlmat_dfma_kernel(const DfmaParams p) {
     __syncwarp();
     const double* buf = wbuf + (st & 1) * DFMA_STAGE_SEGS * rec;
     const int ns = min(DFMA_STAGE_SEGS, n_segs - st * DFMA_STAGE_SEGS);
-    // Two segments per iteration: their generator chains (sincos, reciprocals) are independent and sit
-    // in one basic block, which doubles the instruction-level parallelism the FP64 pipe sees (the
-    // chains are latency-bound: generator alone ran at 52 % of the pipe with one segment at a time).
+    // (Generating the operands of two segments per iteration for more instruction-level parallelism
+    // changed nothing: 1.073 vs 1.078 ms -- the kernel is bound by issue slots, not by latency.)
     int sgm = 0;
-    for (; sgm + 1 < ns; sgm += 2) {
-      const double* ra = buf + sgm * rec;
-      const double* rb = ra + rec;
-      dt_update(ra[1]);
-      const bool same_dt = __double_as_longlong(rb[1]) == __double_as_longlong(ra[1]);
-      if (same_dt && p.n_pairs == 1) {
-        double pa_re, pa_im, pb_re, pb_im;
-        sincos_cw(g.w * ra[0], pa_im, pa_re);
-        sincos_cw(g.w * rb[0], pb_im, pb_re);
-        Vals va, vb;
-        const double* qa = ra + 2 + R;
-        const double* qb = rb + 2 + R;
-        g.ph_re = pa_re; g.ph_im = pa_im;
-        const bool fa = pair_values(g, qa[0], qa[1], qa[2], va);
-        const double da_re = pa_re * g.j0_re - pa_im * g.j0_im, da_im = pa_re * g.j0_im + pa_im * g.j0_re;
-        g.ph_re = pb_re; g.ph_im = pb_im;
-        const bool fb = pair_values(g, qb[0], qb[1], qb[2], vb);
-        const double db_re = pb_re * g.j0_re - pb_im * g.j0_im, db_im = pb_re * g.j0_im + pb_im * g.j0_re;
-        if (__any_sync(0xffffffffu, fa || fb)) {
-          if (fa) {
-            const Vals4 rr = fix_pair(g.w, g.dt, pa_re, pa_im, qa[0]);
-            va.a_re = rr.a_re; va.a_im = rr.a_im; va.b_re = rr.b_re; va.b_im = rr.b_im;
-          }
-          if (fb) {
-            const Vals4 rr = fix_pair(g.w, g.dt, pb_re, pb_im, qb[0]);
-            vb.a_re = rr.a_re; vb.a_im = rr.a_im; vb.b_re = rr.b_re; vb.b_im = rr.b_im;
-          }
-        }
-        fma_diag(ra, da_re, da_im);
-        fma_pair(qa, va);
-        fma_diag(rb, db_re, db_im);
-        fma_pair(qb, vb);
-      } else {
-        one_segment(ra);
-        one_segment(rb);
-      }
-    }
-    if (sgm < ns) one_segment(buf + sgm * rec);
+    for (; sgm < ns; ++sgm) one_segment(buf + sgm * rec);
     __syncwarp();  // all lanes are done with this buffer before it is refilled
   }
 
@@ -1311,8 +1316,15 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
     q.G = G;
     q.n_pairs = d * (d - 1) / 2;
     q.rec_doubles = rec;
-    const size_t smem = std::max((size_t)DFMA_WARPS * 2 * DFMA_STAGE_SEGS * rec,
-                                 (size_t)DFMA_WARPS * 2 * R * 32) * sizeof(double);
+    if (!ctx->trig_table) {
+      FFB_CUDA(ctx, cudaMalloc(&ctx->trig_table, TRIG_TABLE_SIZE * sizeof(double2)));
+      trig_table_kernel<<<1, TRIG_TABLE_SIZE, 0, ctx->stream>>>(reinterpret_cast<double2*>(ctx->trig_table));
+      FFB_LAUNCHED(ctx);
+    }
+    q.trig_table = reinterpret_cast<const double2*>(ctx->trig_table);
+    q.stage_smem_doubles = (int)std::max((size_t)DFMA_WARPS * 2 * DFMA_STAGE_SEGS * rec,
+                                         (size_t)DFMA_WARPS * 2 * R * 32);
+    const size_t smem = ((size_t)q.stage_smem_doubles + 2 * TRIG_TABLE_SIZE) * sizeof(double);
     FFB_REQUIRE(ctx, smem <= 200 * 1024, "control matrix: DFMA stage does not fit shared memory");
     const int n_wt = ceil_div(n_omega, 32);
     int blocks_per_sm = 1;
