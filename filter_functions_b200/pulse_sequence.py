@@ -396,7 +396,9 @@ class PulseSequence:
         n_opers, n_coeffs = _lib.as_c128(self.n_opers), _lib.as_f64(self.n_coeffs)
         dt, t = _lib.as_f64(self.dt), _lib.as_f64(self.t)
         basis = _lib.as_c128(np.asarray(self.basis))
-        G, d = len(dt), self.d
+        # ``self.d`` only normalises the infidelity (the reference's tests overwrite it with the size
+        # of a computational subspace, tests/test_precision.py:297); matrix shapes come from the arrays
+        G, d = len(dt), c_opers.shape[-1]
         n_cops, n_nops, n_basis, n_omega = len(c_opers), len(n_opers), len(basis), len(omega_arr)
         eigvals = _lib.empty((G, d), np.float64)
         eigvecs = _lib.empty((G, d, d))
@@ -422,6 +424,8 @@ class PulseSequence:
         self._data['total_propagator_liouville'] = (
             np.ascontiguousarray(liouville.real) if self.basis.isherm else liouville)
         self._frequency_data.update(control_matrix=B, total_phases=phases, filter_function=F)
+        if infid is not None and self.d != d:
+            infid *= d/self.d
         return infid
 
     @util.parse_optional_parameters(which=('fidelity', 'generalized'), order=(1, 2))
@@ -711,7 +715,7 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         # every gate carries every noise operator: the whole tail of this function (running
         # propagator / phase products, from_atomic, Liouville representation, filter function) is
         # ONE library call on the distinct pulses plus an index list, as in concatenate_many
-        d = newpulse.d
+        d = newpulse.c_opers.shape[-1]
         lib_B = _lib.as_c128(np.array(lib_ctrl))
         lib_ph = _lib.as_c128(np.array(lib_phases))
         lib_L = _lib.as_f64(np.array(lib_liouville))
@@ -800,7 +804,7 @@ def _concatenate_on_device(pulses, newpulse, n_opers_present, ctrl, omega, phase
     control matrix and the matching filter function.  ``ctrl[i]`` is pulse i's own control matrix on
     ``omega``; its rows are, in order, the merged operators ``n_opers_present[i]`` marks."""
     P, n_nops = n_opers_present.shape
-    n_basis, n_omega, d = len(newpulse.basis), len(omega), newpulse.d
+    n_basis, n_omega, d = len(newpulse.basis), len(omega), newpulse.c_opers.shape[-1]
     row_of = np.where(n_opers_present, np.cumsum(n_opers_present, axis=1) - 1, -1).astype(np.int32)
     seg_edges = [0] + list(accumulate(len(pls.dt) for pls in pulses))
     keep = []   # arrays the pointer tables refer to
@@ -977,7 +981,7 @@ def concatenate_many(pulses, indices, spectrum=None, omega=None, calc_control_ma
     lib_U = _lib.as_c128(np.array([pls.total_propagator for pls in pulses]))
     basis = _lib.as_c128(np.asarray(first.basis))
     n_lib, n_nops, n_basis, n_omega = lib_B.shape
-    d = first.d
+    d = first.c_opers.shape[-1]   # matrix size; first.d only normalises the infidelity
     n_seq, L = indices.shape
 
     S = None
@@ -1011,4 +1015,6 @@ def concatenate_many(pulses, indices, spectrum=None, omega=None, calc_control_ma
             sub(batch.total_propagator), sub(liouville), sub(batch.control_matrix),
             sub(batch.filter_function), sub(batch.infidelities), None, None))
     batch.total_propagator_liouville = np.ascontiguousarray(liouville.real)
+    if batch.infidelities is not None and first.d != d:
+        batch.infidelities *= d/first.d
     return batch

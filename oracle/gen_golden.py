@@ -242,6 +242,36 @@ def sequencing_workloads():
     np.savez_compressed(os.path.join(OUT, 'sequencing_workloads.npz'), **out)
 
 
+def cnot_gate():
+    """The reference's own experimental fixture: the exchange-coupled singlet-triplet CNOT of
+    examples/data/CNOT.mat (250 segments of 0.2 ns) on the 6-dimensional subspace with the padded
+    two-qubit Pauli basis (15 elements, not complete), as in tests/test_precision.py:184-216 and
+    :274-311 (``cnot.d = 4``; Monte-Carlo infidelities testutil.cnot_infid_fast)."""
+    c_opers = testutil.subspace_opers
+    identifiers = ['eps_12', 'eps_23', 'eps_34', 'b_12', 'b_23', 'b_34']
+    basis = ff.Basis([np.pad(b, 1, 'constant') for b in ff.Basis.pauli(2)[1:]], btype='Pauli')
+    cnot = ff.PulseSequence(list(zip(c_opers, testutil.c_coeffs, identifiers)),
+                            list(zip(c_opers, testutil.n_coeffs, identifiers)), testutil.dt,
+                            basis=basis)
+    cnot.d = 4
+    omega = np.geomspace(1/cnot.tau, 1e2, 250)
+    out = {f'cnot_{k}': v for k, v in pulse_arrays(cnot).items()}
+    out['cnot_omega'] = omega
+    out['cnot_A'] = np.asarray(testutil.A)
+    out['cnot_infid_MC'] = np.asarray(testutil.cnot_infid_fast)
+    cnot.diagonalize()
+    out['cnot_total_propagator'] = cnot.total_propagator
+    out['cnot_eigvals'] = cnot.eigvals
+    out['cnot_control_matrix'] = cnot.get_control_matrix(omega)
+    out['cnot_filter_function'] = cnot.get_filter_function(omega)
+    for i, (A, alpha) in enumerate(zip(testutil.A, (0.0, 0.7))):
+        infid, xi = ff.infidelity(cnot, A/omega**alpha, omega, identifiers[:3],
+                                  return_smallness=True)
+        out[f'cnot_infid_{i}'] = infid
+        out[f'cnot_xi_{i}'] = xi
+    np.savez_compressed(os.path.join(OUT, 'cnot.npz'), **out)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1:       # regenerate only the named fixtures
@@ -254,5 +284,6 @@ if __name__ == '__main__':
     workloads_small()
     decay_amplitudes()
     sequencing_workloads()
+    cnot_gate()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)), 'bytes')

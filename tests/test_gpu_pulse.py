@@ -266,6 +266,45 @@ def test_concatenate_differing_noise_operators(engine, d, btype, pc):
         assert nerr(gen.get_filter_function(omega), oracle.filter_function(B_o)) < TOL
 
 
+def test_cnot_fixture(engine):
+    """Reference tests/test_precision.py:184-216 and :274-311 on its experimental fixture
+    examples/data/CNOT.mat: d = 6 subspace, 250 segments, incomplete (15-element) padded Pauli basis,
+    ``cnot.d = 4`` for the normalisation, infidelities with the smallness parameter, compared with the
+    reference's outputs (tests/golden/cnot.npz) and with its Monte-Carlo numbers (10 %)."""
+    ff = engine
+    g = np.load(os.path.join(GOLDEN, 'cnot.npz'))
+    omega = g['cnot_omega']
+    ids = [str(i) for i in g['cnot_n_ids']]
+    for cold in (True, False):
+        cnot = pulse_from_fixture(ff, g, 'cnot')
+        cnot.d = 4
+        if not cold:   # step-by-step route instead of the fused cold pipeline
+            cnot.diagonalize()
+            assert nerr(cnot.eigvals, g['cnot_eigvals']) < TOL
+            assert nerr(cnot.total_propagator, g['cnot_total_propagator']) < TOL
+            cnot_mat = np.zeros((4, 4))
+            cnot_mat[0, 0] = cnot_mat[1, 1] = cnot_mat[2, 3] = cnot_mat[3, 2] = 1
+            assert ff.util.oper_equiv(cnot.total_propagator[1:5, 1:5], cnot_mat, eps=1e-9)[0]
+            B = cnot.get_control_matrix(omega)
+            for j in range(len(B)):
+                assert nerr(B[j], g['cnot_control_matrix'][j]) < TOL
+        for i, alpha in enumerate((0.0, 0.7)):
+            S = g['cnot_A'][i]/omega**alpha
+            if cold:
+                cnot.cleanup('all')
+                infid_all = ff.infidelity(cnot, S, omega)        # fused path, all operators
+                np.testing.assert_allclose(infid_all[[ids.index(k) for k in ('eps_12', 'eps_23',
+                                                                             'eps_34')]],
+                                           g[f'cnot_infid_{i}'], rtol=1e-9)
+            infid, xi = ff.infidelity(cnot, S, omega, ['eps_12', 'eps_23', 'eps_34'],
+                                      return_smallness=True)
+            np.testing.assert_allclose(infid, g[f'cnot_infid_{i}'], rtol=1e-9)
+            np.testing.assert_allclose(xi, g[f'cnot_xi_{i}'], rtol=1e-12)
+            assert abs(1 - infid.sum()/g['cnot_infid_MC'][i]) < 0.10
+            assert infid.sum() <= xi**2/4
+        assert nerr(cnot.get_filter_function(omega), g['cnot_filter_function']) < TOL
+
+
 def test_se_concatenation_is_cpmg(engine):
     """Two spin echoes are a CPMG-2 sequence (reference tests/test_sequencing.py:222-310)."""
     ff = engine

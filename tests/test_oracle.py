@@ -241,3 +241,32 @@ def test_first_order_integral_against_quadrature():
     dE = np.subtract.outer(eigvals, eigvals)
     numeric_int = np.trapezoid(np.exp(1j*np.multiply.outer(np.add.outer(E, dE), t)), t)
     np.testing.assert_allclose(oracle.first_order_integral(E, eigvals, dt), numeric_int, atol=1e-4)
+
+
+def test_cnot_fixture():
+    """The reference's experimental fixture examples/data/CNOT.mat (exchange-coupled singlet-triplet
+    CNOT, 250 segments, 6-dimensional subspace, padded two-qubit Pauli basis of 15 elements), run
+    through the reference by oracle/gen_golden.py: the oracle reproduces the reference's propagator,
+    control matrix, filter function and infidelities (tests/test_precision.py:184-216, :274-311)."""
+    g = np.load(os.path.join(GOLDEN, 'cnot.npz'))
+    omega = g['cnot_omega']
+    H = oracle.hamiltonian_from_coeffs(g['cnot_c_opers'], g['cnot_c_coeffs'])
+    ev, V, Q = oracle.diagonalize(H, g['cnot_dt'])
+    assert nerr(ev, g['cnot_eigvals']) < 1e-13
+    assert nerr(Q[-1], g['cnot_total_propagator']) < 1e-12
+    B = oracle.control_matrix_from_scratch(ev, V, Q, omega, g['cnot_basis'], g['cnot_n_opers'],
+                                           g['cnot_n_coeffs'], g['cnot_dt'])
+    assert nerr(B, g['cnot_control_matrix']) < 1e-12
+    F = oracle.filter_function(B)
+    assert nerr(F, g['cnot_filter_function']) < 1e-12
+    cnot = np.zeros((4, 4))
+    cnot[0, 0] = cnot[1, 1] = cnot[2, 3] = cnot[3, 2] = 1
+    U = Q[-1][1:5, 1:5]
+    phase = np.trace(cnot.T @ U)
+    assert np.abs(U - cnot*phase/np.abs(phase)).max() < 1e-4   # CNOT up to a global phase
+    assert 1 - np.abs(phase)/4 < 1e-5                          # (optimised gate: 1.4e-5 off)
+    for i, alpha in enumerate((0.0, 0.7)):
+        S = g['cnot_A'][i]/omega**alpha
+        infid = oracle.infidelity_from_filter_function(F, S, omega, 4, idx=np.arange(3))
+        np.testing.assert_allclose(infid, g[f'cnot_infid_{i}'], rtol=1e-10)
+        assert abs(1 - infid.sum()/g['cnot_infid_MC'][i]) < 0.10   # Monte Carlo, as the reference
