@@ -265,8 +265,10 @@ def test_cnot_fixture():
     phase = np.trace(cnot.T @ U)
     assert np.abs(U - cnot*phase/np.abs(phase)).max() < 1e-4   # CNOT up to a global phase
     assert 1 - np.abs(phase)/4 < 1e-5                          # (optimised gate: 1.4e-5 off)
+    ids = [str(k) for k in g['cnot_n_ids']]      # PulseSequence sorts operators by identifier
+    eps = np.array([ids.index(k) for k in ('eps_12', 'eps_23', 'eps_34')])
     for i, alpha in enumerate((0.0, 0.7)):
         S = g['cnot_A'][i]/omega**alpha
-        infid = oracle.infidelity_from_filter_function(F, S, omega, 4, idx=np.arange(3))
+        infid = oracle.infidelity_from_filter_function(F, S, omega, 4, idx=eps)
         np.testing.assert_allclose(infid, g[f'cnot_infid_{i}'], rtol=1e-10)
         assert abs(1 - infid.sum()/g['cnot_infid_MC'][i]) < 0.10   # Monte Carlo, as the reference
