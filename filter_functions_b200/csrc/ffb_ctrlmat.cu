@@ -928,6 +928,147 @@ ctrlmat_main_kernel(const MainParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Statically scheduled variant of ctrlmat_main_kernel for the shapes that dominate config 3 and the
+// north_star target (d = 4: NP = 6 level pairs, one pass per stage or a pass split into two pieces):
+// the walk over the 1 + NP units of a pass is fully unrolled, so the stage boundaries, the unit sizes
+// and the unit kinds are compile-time facts.  In the generic kernel that bookkeeping (run lengths,
+// boundary tests, pointer arithmetic, the v = vn copies) costs ~1.3 issue slots per DMMA, and under the
+// dispatch-port model (an FP64-pipe instruction blocks the scheduler's dispatch for its pipe time, see
+// DESIGN.md 4.1) every one of them is a cycle the tensor pipe idles.
+// Requires pps == 1 and n_sp == NSP with the generic piece boundaries piece_begin(j, 1 + NP, NSP).
+// ------------------------------------------------------------------------------------------------
+template <int MT, int NW, int NP, int NSP>
+__global__ void __launch_bounds__(NW * 32, (MT <= 2 ? 3 : MT >= 12 ? 3 : 1))
+ctrlmat_static_kernel(const MainParams p) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int NU = 1 + NP;
+  constexpr int DIAG_UNIT = MT * 32 + 8, PAIR_UNIT = 2 * MT * 32 + 12;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int q = lane & 3;
+  const int rb = blockIdx.y;
+  const int pass_begin = blockIdx.z * p.passes_per_chunk;
+  const int pass_end = min(p.n_pass, pass_begin + p.passes_per_chunk);
+  const int n_passes = pass_end - pass_begin;
+
+  Gen g;
+  {
+    const int w_idx = (blockIdx.x * NW + warp) * 8 + (lane >> 2);
+    g.w = w_idx < p.n_omega ? p.omega[w_idx] : 1.0;
+    g.w_zero = fabs(g.w) < TINY_OMEGA;
+    g.inv_w = g.w_zero ? 0.0 : 1.0 / g.w;
+    g.dt_prev = -1.0;
+    g.dt = 0.0;
+    g.hc = SQRT2;
+    g.hs = 0.0;
+    g.j0_re = g.j0_im = 0.0;
+    g.ph_re = 1.0;
+    g.ph_im = 0.0;
+  }
+  double acc_re[MT][2], acc_im[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    acc_re[mt][0] = acc_re[mt][1] = 0.0;
+    acc_im[mt][0] = acc_im[mt][1] = 0.0;
+  }
+
+  // stage i = (pass i / NSP, piece i % NSP); piece j holds units [PB(j), PB(j + 1))
+  auto PB = [](int j) constexpr { return (j * NU) / NSP; };
+  auto UOFF = [](int u) constexpr { return u == 0 ? 0 : DIAG_UNIT + (u - 1) * PAIR_UNIT; };
+  const double* gstream = p.stream + (size_t)rb * p.rb_doubles + (size_t)pass_begin * p.pass_doubles;
+  const int n_stages = n_passes * NSP;
+  auto stage_load = [&](int i, double* buf) {
+    const int pass = i / NSP, piece = i % NSP;
+    const int o0 = UOFF(PB(piece));
+    const int o1 = piece + 1 == NSP ? (int)p.pass_doubles : UOFF(PB(piece + 1));
+    const double* gsrc = gstream + (size_t)pass * p.pass_doubles + o0;
+    for (int e = threadIdx.x * 2; e < o1 - o0; e += NW * 32 * 2) cp_async16(buf + e, gsrc + e);
+  };
+  double* cur_buf = smem;
+  double* nxt_buf = smem + p.stage_doubles;
+  if (n_stages > 0) {
+    stage_load(0, cur_buf);
+    cp_async_commit();
+    if (n_stages > 1) {
+      stage_load(1, nxt_buf);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+  }
+  int stage = 0;
+  Vals v = {0.0, 0.0, 0.0, 0.0};
+  const double* up = cur_buf;
+  if (n_passes > 0) gen_diag(g, up + MT * 32, q, v);
+  for (int pass = 0; pass < n_passes; ++pass) {
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      // compile-time facts about unit u
+      int piece = 0;
+#pragma unroll
+      for (int j = 1; j < NSP; ++j) piece += (u >= PB(j)) ? 1 : 0;
+      const bool last_in_piece = (u + 1 == (piece + 1 == NSP ? NU : PB(piece + 1)));
+      const bool last_of_pass = (u + 1 == NU);
+      const bool has_next = !(last_of_pass && pass + 1 == n_passes);
+      Vals vn = v;
+      const double* pn = up + (u == 0 ? DIAG_UNIT : PAIR_UNIT);
+      if (last_in_piece) {
+        if (has_next) {
+          cp_async_wait<0>();  // the only outstanding group is stage + 1
+          __syncthreads();
+        }
+        pn = nxt_buf;
+      }
+      bool fix = false;
+      if (!last_of_pass) {
+        fix = gen_pair(g, pn + 2 * MT * 32, q, vn);
+      } else if (has_next) {
+        gen_diag_slow(g, pn + MT * 32, q);
+        gen_diag_fast(g, pn + MT * 32, q, vn);
+      }
+      if (u == 0) mma_diag<MT>(acc_re, acc_im, up, lane, v);
+      else mma_pair<MT>(acc_re, acc_im, up, lane, v);
+      if (!last_of_pass) {
+        if (__any_sync(0xffffffffu, fix)) {
+          if (fix) {
+            const Vals4 r = fix_pair(g.w, g.dt, g.ph_re, g.ph_im, pn[2 * MT * 32 + q]);
+            vn.a_re = r.a_re;
+            vn.a_im = r.a_im;
+            vn.b_re = r.b_re;
+            vn.b_im = r.b_im;
+          }
+        }
+      }
+      v = vn;
+      if (last_in_piece && has_next) {
+        __syncthreads();  // everyone is done reading cur_buf
+        if (stage + 2 < n_stages) {
+          stage_load(stage + 2, cur_buf);
+          cp_async_commit();
+        }
+        double* tmp = cur_buf;
+        cur_buf = nxt_buf;
+        nxt_buf = tmp;
+        ++stage;
+      }
+      up = pn;
+    }
+  }
+
+  const int w0 = (blockIdx.x * NW + warp) * 8 + 2 * q;
+  double* out = p.partial + (size_t)blockIdx.z * p.rows_pad * p.n_omega * 2;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int row = (rb * MT + mt) * 8 + (lane >> 2);
+    double* dst = out + ((size_t)row * p.n_omega + w0) * 2;
+    if (w0 < p.n_omega) reinterpret_cast<double2*>(dst)[0] = make_double2(acc_re[mt][0], acc_im[mt][0]);
+    if (w0 + 1 < p.n_omega) reinterpret_cast<double2*>(dst)[1] = make_double2(acc_re[mt][1], acc_im[mt][1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Small row counts (rows = n_nops * n_basis <= 16: a single qubit in the Pauli basis, config 2): DFMA
 // variant.  With 12 rows the tensor path pads M to 16 (25 % of the DMMA work is wasted) and the mix of
 // DMMA and the generator's DFMA/DMUL stream costs another ~12 % of the FP64 pipe (measured,
@@ -1214,6 +1355,20 @@ int launch_main(ffb_ctx* ctx, MainParams p, int n_wtiles, int n_rb, int S) {
   return FFB_OK;
 }
 
+template <int MT, int NW, int NP, int NSP>
+int launch_static(ffb_ctx* ctx, MainParams p, int n_wtiles, int n_rb, int S) {
+  auto kern = ctrlmat_static_kernel<MT, NW, NP, NSP>;
+  const size_t smem = (size_t)2 * p.stage_doubles * sizeof(double);
+  FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(n_wtiles, n_rb, S);
+  int slot = -1;
+  FFB_TRY(ffb_time_begin(ctx, &slot));
+  kern<<<grid, NW * 32, smem, ctx->stream>>>(p);
+  FFB_LAUNCHED(ctx);
+  FFB_TRY(ffb_time_end(ctx, slot));
+  return FFB_OK;
+}
+
 template <int MT, int NW>
 int occupancy(ffb_ctx* ctx, size_t smem, int* blocks) {
   auto kern = ctrlmat_main_kernel<MT, NW>;
@@ -1477,7 +1632,20 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   FFB_TRY(partial.alloc(ctx, (size_t)S * rows_pad * n_omega * 16));
   p.partial = partial.as<double>();
 
-  FFB_DISPATCH_MT(MT, FFB_TRY((launch_main<MT_, NW_>(ctx, p, n_wtiles, geo.n_rb, S))));
+  // d = 4 (6 level pairs), one pass per stage or a pass in two pieces: statically scheduled variant
+  bool use_static = geo.n_pairs == 6 && !geo.transposed && p.pps == 1 && p.n_sp <= 2 &&
+                    (MT == 12 || MT == 8 || MT == 6);
+  if (const char* e = getenv("FFB_CTRLMAT_STATIC")) use_static = use_static && atoi(e) != 0;
+  if (use_static) {
+    if (MT == 12 && p.n_sp == 2) FFB_TRY((launch_static<12, 4, 6, 2>(ctx, p, n_wtiles, geo.n_rb, S)));
+    else if (MT == 12) FFB_TRY((launch_static<12, 4, 6, 1>(ctx, p, n_wtiles, geo.n_rb, S)));
+    else if (MT == 8 && p.n_sp == 2) FFB_TRY((launch_static<8, 4, 6, 2>(ctx, p, n_wtiles, geo.n_rb, S)));
+    else if (MT == 8) FFB_TRY((launch_static<8, 4, 6, 1>(ctx, p, n_wtiles, geo.n_rb, S)));
+    else if (p.n_sp == 2) FFB_TRY((launch_static<6, 8, 6, 2>(ctx, p, n_wtiles, geo.n_rb, S)));
+    else FFB_TRY((launch_static<6, 8, 6, 1>(ctx, p, n_wtiles, geo.n_rb, S)));
+  } else {
+    FFB_DISPATCH_MT(MT, FFB_TRY((launch_main<MT_, NW_>(ctx, p, n_wtiles, geo.n_rb, S))));
+  }
 
   {
     const size_t total = (size_t)n_nops * n_basis * n_omega;

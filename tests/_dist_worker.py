@@ -61,6 +61,24 @@ def main():
         F_want = oracle_filter_function(pulse, omega)
         if F.shape != F_want.shape or np.abs(F - F_want).max() > 1e-13*np.abs(F_want).max():
             failures.append(('filter_function', n_omega))
+    # sharded concatenation: every rank concatenates on its own frequency block, F is all-gathered
+    pieces = [pulse[0:3], pulse[3:4], pulse[4:8]]
+
+    def oracle_concatenate(pulses, local_omega):
+        joined = ff.concatenate(pulses, calc_filter_function=False)     # host bookkeeping only
+        n = len(joined.n_opers)
+        if len(local_omega) == 0:
+            return joined, np.zeros((n, n, 0), dtype=complex)
+        return joined, oracle_filter_function(joined, local_omega)
+
+    for n_omega in (1, 2, 5, 64, 131):
+        omega = np.geomspace(0.05, 20, n_omega) if n_omega > 1 else np.array([0.3])
+        joined, F = ffd.concatenate(pieces, omega, _local=oracle_concatenate)
+        F_want = oracle_filter_function(pulse, omega)
+        if F.shape != F_want.shape or np.abs(F - F_want).max() > 1e-12*np.abs(F_want).max():
+            failures.append(('concatenate', n_omega))
+        if abs(joined.tau - pulse.tau) > 1e-12:
+            failures.append(('concatenate tau', n_omega))
     total = ffd.allreduce_sum(np.array([float(rank + 1)]))
     if total[0] != world*(world + 1)/2:
         failures.append(('allreduce', total))
