@@ -183,6 +183,36 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
+// ---- TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (one thread issues a
+// whole stage: no per-thread address arithmetic, no cp.async bookkeeping in the consumer warps)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, void* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(mbar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* mbar, unsigned parity) {
+  unsigned ok = 0;
+  const unsigned addr = smem_u32(mbar);
+  while (!ok) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 __device__ __forceinline__ void pair_from_index(int p, int d, int& m, int& n) {
   m = 0;
   while (p >= d - 1 - m) {
@@ -977,30 +1007,31 @@ ctrlmat_static_kernel(const MainParams p) {
   auto UOFF = [](int u) constexpr { return u == 0 ? 0 : DIAG_UNIT + (u - 1) * PAIR_UNIT; };
   const double* gstream = p.stream + (size_t)rb * p.rb_doubles + (size_t)pass_begin * p.pass_doubles;
   const int n_stages = n_passes * NSP;
-  auto stage_load = [&](int i, double* buf) {
+  // stage i lives in buffer i & 1; its mbarrier completes phase (i >> 1) & 1 when the bytes have landed
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem + 2 * (size_t)p.stage_doubles);
+  auto stage_load = [&](int i) {  // called by thread 0 only
     const int pass = i / NSP, piece = i % NSP;
     const int o0 = UOFF(PB(piece));
     const int o1 = piece + 1 == NSP ? (int)p.pass_doubles : UOFF(PB(piece + 1));
-    const double* gsrc = gstream + (size_t)pass * p.pass_doubles + o0;
-    for (int e = threadIdx.x * 2; e < o1 - o0; e += NW * 32 * 2) cp_async16(buf + e, gsrc + e);
+    const unsigned bytes = (unsigned)(o1 - o0) * 8u;
+    mbar_expect_tx(&mbar[i & 1], bytes);
+    bulk_g2s(smem + (size_t)(i & 1) * p.stage_doubles, gstream + (size_t)pass * p.pass_doubles + o0, bytes,
+             &mbar[i & 1]);
   };
-  double* cur_buf = smem;
-  double* nxt_buf = smem + p.stage_doubles;
-  if (n_stages > 0) {
-    stage_load(0, cur_buf);
-    cp_async_commit();
-    if (n_stages > 1) {
-      stage_load(1, nxt_buf);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_fence_init();
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (n_stages > 0) stage_load(0);
+    if (n_stages > 1) stage_load(1);
+  }
+  if (n_stages > 0) mbar_wait(&mbar[0], 0);
   int stage = 0;
   Vals v = {0.0, 0.0, 0.0, 0.0};
-  const double* up = cur_buf;
+  const double* up = smem;
   if (n_passes > 0) gen_diag(g, up + MT * 32, q, v);
   for (int pass = 0; pass < n_passes; ++pass) {
 #pragma unroll
@@ -1015,11 +1046,8 @@ ctrlmat_static_kernel(const MainParams p) {
       Vals vn = v;
       const double* pn = up + (u == 0 ? DIAG_UNIT : PAIR_UNIT);
       if (last_in_piece) {
-        if (has_next) {
-          cp_async_wait<0>();  // the only outstanding group is stage + 1
-          __syncthreads();
-        }
-        pn = nxt_buf;
+        if (has_next) mbar_wait(&mbar[(stage + 1) & 1], ((stage + 1) >> 1) & 1);  // stage + 1 has landed
+        pn = smem + (size_t)((stage + 1) & 1) * p.stage_doubles;
       }
       bool fix = false;
       if (!last_of_pass) {
@@ -1043,14 +1071,11 @@ ctrlmat_static_kernel(const MainParams p) {
       }
       v = vn;
       if (last_in_piece && has_next) {
-        __syncthreads();  // everyone is done reading cur_buf
-        if (stage + 2 < n_stages) {
-          stage_load(stage + 2, cur_buf);
-          cp_async_commit();
+        __syncthreads();  // everyone is done reading the buffer of `stage`
+        if (threadIdx.x == 0 && stage + 2 < n_stages) {
+          fence_proxy_async();  // order the generic-proxy reads before the async overwrite
+          stage_load(stage + 2);
         }
-        double* tmp = cur_buf;
-        cur_buf = nxt_buf;
-        nxt_buf = tmp;
         ++stage;
       }
       up = pn;
@@ -1358,7 +1383,7 @@ int launch_main(ffb_ctx* ctx, MainParams p, int n_wtiles, int n_rb, int S) {
 template <int MT, int NW, int NP, int NSP>
 int launch_static(ffb_ctx* ctx, MainParams p, int n_wtiles, int n_rb, int S) {
   auto kern = ctrlmat_static_kernel<MT, NW, NP, NSP>;
-  const size_t smem = (size_t)2 * p.stage_doubles * sizeof(double);
+  const size_t smem = (size_t)2 * p.stage_doubles * sizeof(double) + 16;  // + two mbarriers
   FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(n_wtiles, n_rb, S);
   int slot = -1;
