@@ -335,7 +335,13 @@ def run_b200(args):
                 'executed_tflops')
     else:
         rows_pad = -(-rows//8)*8
-        kernel = 'ctrlmat_main_kernel'
+        tiles = rows_pad//8
+        n_rb = -(-tiles//12)
+        mt = next(a for a in (1, 2, 3, 4, 6, 8, 12) if a >= -(-tiles//n_rb))
+        static = (d == 4 and mt in (6, 8, 12) and G >= 4
+                  and os.environ.get('FFB_CTRLMAT_STATIC', '1') != '0')
+        kernel = 'ctrlmat_static_kernel' if static else 'ctrlmat_main_kernel'
+        rows_pad = n_rb*mt*8
         pipe = 'fp64 (DMMA.8x8x4; shares the 64 lane/clk/SM FP64 pipe with DFMA)'
     executed = rows_pad*(1 + d*(d - 1))*2*2*G*n_omega_local/(kernel_ms*1e-3)*1e-12
     traffic = None
