@@ -287,11 +287,10 @@ def run_b200(args):
     sampler.join(timeout=1.0)
 
     d, n_cops, n_nops, n_basis = wl.d, len(wl.c_opers), len(wl.n_opers), len(wl.basis)
+    # inputs of the fused pipeline (ffb_pulse_filter_function): operators, coefficients, dt, t, basis,
+    # omega, spectrum -- one packed upload per step
     h2d = (16*(n_cops + n_nops + n_basis)*d*d + 8*(n_cops + n_nops)*G + 8*G + 8*(G + 1)
-           + 8*n_omega_local                                   # fused pipeline inputs
-           + 16*d*d + 16*n_basis*d*d                           # liouville representation
-           + 8*n_omega_local                                   # total phases
-           + 16*n_nops*n_nops*n_omega_local + 8*wl.spectrum.size + 8*n_omega_local + 4*n_nops)
+           + 8*n_omega_local + wl.spectrum.nbytes)
     d2h = (8*G*d + 16*G*d*d + 16*(G + 1)*d*d + 16*n_nops*n_basis*n_omega_local
            + 16*n_nops*n_nops*n_omega_local + 16*n_basis*n_basis + 16*n_omega_local + 8*n_nops)
 

@@ -172,7 +172,7 @@ def ptr(arr):
     """Raw pointer of a C-contiguous ndarray (``None`` -> NULL)."""
     if arr is None:
         return None
-    return arr.ctypes.data_as(c_void_p)
+    return arr.ctypes.data   # plain integer address: argtypes are c_void_p (no cast object per call)
 
 
 def as_c128(x):

@@ -156,6 +156,7 @@ void ffb_destroy(ffb_ctx* ctx) {
   for (auto& kv : ctx->host_free_blocks) cudaFreeHost(kv.second);
   for (auto& kv : ctx->host_live_blocks) cudaFreeHost(kv.first);
   if (ctx->trig_table) cudaFree(ctx->trig_table);
+  if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& ev : ctx->copy_ev)
     if (ev) cudaEventDestroy(ev);
@@ -379,6 +380,59 @@ int enter(ffb_ctx* ctx) {
   FFB_CUDA(ctx, cudaSetDevice(ctx->device));
   return FFB_OK;
 }
+
+// Several small host arrays -> ONE page-locked staging block -> ONE host-to-device copy.  A pageable
+// cudaMemcpyAsync costs ~10 us of driver time per call and blocks the host for the larger ones; a
+// pulse has 8-9 input arrays of 0.1-500 KB each.  The staging block belongs to the context and is
+// reused by the next call (every host-pointer entry point is synchronous on return).
+struct PackedUpload {
+  static constexpr size_t ALIGN = 256;
+  std::vector<const void*> src;
+  std::vector<size_t> bytes, offset;
+  size_t total = 0;
+  DevBuf dev;
+  int add(const void* host, size_t n) {
+    src.push_back(host);
+    bytes.push_back(n);
+    offset.push_back(total);
+    total += (n + ALIGN - 1) & ~(ALIGN - 1);
+    return (int)src.size() - 1;
+  }
+  int upload(ffb_ctx* ctx) {
+    if (ctx->stage_bytes < total) {
+      if (ctx->stage_host) FFB_CUDA(ctx, cudaFreeHost(ctx->stage_host));
+      ctx->stage_host = nullptr;
+      ctx->stage_bytes = 0;
+      const size_t want = std::max<size_t>(2 * total, (size_t)1 << 20);
+      FFB_CUDA(ctx, cudaHostAlloc(&ctx->stage_host, want, cudaHostAllocDefault));
+      ctx->stage_bytes = want;
+    }
+    char* stage = static_cast<char*>(ctx->stage_host);
+    for (size_t i = 0; i < src.size(); ++i)
+      if (bytes[i]) std::memcpy(stage + offset[i], src[i], bytes[i]);
+    FFB_TRY(dev.alloc(ctx, total));
+    return ffb_h2d(ctx, dev.p, stage, total);
+  }
+  const double* d(int i) const {
+    return reinterpret_cast<const double*>(static_cast<const char*>(dev.p) + offset[i]);
+  }
+};
+
+int ensure_copy_stream(ffb_ctx* ctx) {
+  if (ctx->copy_stream) return FFB_OK;
+  FFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : ctx->copy_ev) FFB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  return FFB_OK;
+}
+
+// the copy stream may read buffers that go back to the pool at scope exit: drain it first (declare
+// AFTER the buffers, so that it is destroyed BEFORE them), also on the error paths
+struct CopyStreamDrain {
+  ffb_ctx* ctx;
+  ~CopyStreamDrain() {
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  }
+};
 
 }  // namespace
 
@@ -746,8 +800,7 @@ int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, 
   FFB_TRY(stack.alloc(ctx, (size_t)slots * pulse_bytes));
   if (full_stack) FFB_TRY(result.alloc(ctx, (size_t)(correlations ? P : 1) * pulse_bytes));
   if (full_stack && !ctx->copy_stream) {
-    FFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (auto& ev : ctx->copy_ev) FFB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    FFB_TRY(ensure_copy_stream(ctx));
   }
   if (full_stack) {  // the copy stream must not touch pool memory before earlier work is done with it
     FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));
@@ -933,16 +986,29 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
   const size_t dd = (size_t)d * d;
   const int herm = (all_hermitian(n_opers, n_nops, d) ? FFB_HERM_NOPERS : 0) |
                    (all_hermitian(basis, n_basis, d) ? FFB_HERM_BASIS : 0);
-  Upload co, cc, no, nc, dts, ts, bs, om, sp;
-  DevBuf ev, V, Q, B, F, I, idx, ph, liou;
-  FFB_TRY(co.put(ctx, c_opers, (size_t)n_cops * dd * 16));
-  FFB_TRY(cc.put(ctx, c_coeffs, (size_t)n_cops * G * 8));
-  FFB_TRY(no.put(ctx, n_opers, (size_t)n_nops * dd * 16));
-  FFB_TRY(nc.put(ctx, n_coeffs, (size_t)n_nops * G * 8));
-  FFB_TRY(dts.put(ctx, dt, (size_t)G * 8));
-  FFB_TRY(ts.put(ctx, t, (size_t)(G + 1) * 8));
-  FFB_TRY(bs.put(ctx, basis, (size_t)n_basis * dd * 16));
-  FFB_TRY(om.put(ctx, omega, (size_t)n_omega * 8));
+  FFB_TRY(ensure_copy_stream(ctx));
+  PackedUpload in;
+  DevBuf ev, V, Q, B, F, I, ph, liou;
+  CopyStreamDrain drain{ctx};
+  const int i_co = in.add(c_opers, (size_t)n_cops * dd * 16);
+  const int i_cc = in.add(c_coeffs, (size_t)n_cops * G * 8);
+  const int i_dt = in.add(dt, (size_t)G * 8);
+  const int i_no = in.add(n_opers, (size_t)n_nops * dd * 16);
+  const int i_nc = in.add(n_coeffs, (size_t)n_nops * G * 8);
+  const int i_ts = in.add(t, (size_t)(G + 1) * 8);
+  const int i_bs = in.add(basis, (size_t)n_basis * dd * 16);
+  const int i_om = in.add(omega, (size_t)n_omega * 8);
+  int i_sp = -1;
+  size_t n_inf = 0;
+  if (infidelity) {
+    FFB_REQUIRE(ctx, spectrum_ndim >= 1 && spectrum_ndim <= 3, "pulse pipeline: spectrum_ndim=%d",
+                spectrum_ndim);
+    const size_t s_elems = (spectrum_ndim == 1 ? 1 : spectrum_ndim == 2 ? (size_t)n_nops
+                                                                         : (size_t)n_nops * n_nops) * n_omega;
+    i_sp = in.add(spectrum, s_elems * (spectrum_is_complex ? 16 : 8));
+    n_inf = spectrum_ndim == 3 ? (size_t)n_nops * n_nops : n_nops;
+  }
+  FFB_TRY(in.upload(ctx));
   FFB_TRY(ev.alloc(ctx, (size_t)G * d * 8));
   FFB_TRY(V.alloc(ctx, (size_t)G * dd * 16));
   FFB_TRY(Q.alloc(ctx, (size_t)(G + 1) * dd * 16));
@@ -950,47 +1016,53 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
   const size_t f_bytes = (size_t)n_nops * n_nops * n_omega * 16;
   FFB_TRY(B.alloc(ctx, b_bytes));
   FFB_TRY(F.alloc(ctx, f_bytes));
-  FFB_TRY(ffbi_diagonalize(ctx, G, d, n_cops, co.d(), cc.d(), dts.d(), ev.as<double>(),
+  cudaStream_t cs = ctx->copy_stream;
+  auto d2h_copy = [&](void* dst, const void* src, size_t bytes) -> int {
+    if (dst && bytes) FFB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, cs));
+    return FFB_OK;
+  };
+
+  // stage 1: everything that does not depend on the control matrix
+  FFB_TRY(ffbi_diagonalize(ctx, G, d, n_cops, in.d(i_co), in.d(i_cc), in.d(i_dt), ev.as<double>(),
                            V.as<double>(), Q.as<double>()));
-  FFB_TRY(ffbi_control_matrix(ctx, G, d, n_nops, n_basis, n_omega, ev.as<double>(), V.as<double>(),
-                              Q.as<double>(), om.d(), bs.d(), no.d(), nc.d(), dts.d(), ts.d(), herm,
-                              B.as<double>()));
-  FFB_TRY(ffbi_filter_function(ctx, 1, n_nops, n_basis, n_omega, B.as<double>(), 0, F.as<double>()));
-  size_t n_inf = 0;
-  if (infidelity) {
-    FFB_REQUIRE(ctx, spectrum_ndim >= 1 && spectrum_ndim <= 3, "pulse pipeline: spectrum_ndim=%d",
-                spectrum_ndim);
-    const size_t s_elems = (spectrum_ndim == 1 ? 1 : spectrum_ndim == 2 ? (size_t)n_nops
-                                                                         : (size_t)n_nops * n_nops) * n_omega;
-    FFB_TRY(sp.put(ctx, spectrum, s_elems * (spectrum_is_complex ? 16 : 8)));
-    std::vector<int> iota(n_nops);
-    for (int i = 0; i < n_nops; ++i) iota[i] = i;
-    FFB_TRY(idx.alloc(ctx, n_nops * sizeof(int)));
-    FFB_TRY(ffb_h2d(ctx, idx.p, iota.data(), n_nops * sizeof(int)));
-    FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // iota goes out of scope below
-    n_inf = spectrum_ndim == 3 ? (size_t)n_nops * n_nops : n_nops;
-    FFB_TRY(I.alloc(ctx, n_inf * 8));
-    FFB_TRY(ffbi_infidelity(ctx, 1, n_nops, n_nops, idx.as<int>(), n_omega, F.as<double>(), sp.d(),
-                            spectrum_ndim, spectrum_is_complex, om.d(), d, I.as<double>()));
-  }
   if (total_phases) {
     FFB_TRY(ph.alloc(ctx, (size_t)n_omega * 16));
-    FFB_TRY(ffbi_cexp(ctx, n_omega, om.d(), t[G], ph.as<double>()));  // tau = t[G] (host value)
-    FFB_TRY(ffb_d2h(ctx, total_phases, ph.p, (size_t)n_omega * 16));
+    FFB_TRY(ffbi_cexp(ctx, n_omega, in.d(i_om), t[G], ph.as<double>()));  // tau = t[G] (host value)
   }
   if (total_propagator_liouville) {
     FFB_TRY(liou.alloc(ctx, (size_t)n_basis * n_basis * 16));
-    FFB_TRY(ffbi_liouville(ctx, 1, d, n_basis, Q.as<double>() + (size_t)G * dd * 2, bs.d(),
+    FFB_TRY(ffbi_liouville(ctx, 1, d, n_basis, Q.as<double>() + (size_t)G * dd * 2, in.d(i_bs),
                            liou.as<double>()));
-    FFB_TRY(ffb_d2h(ctx, total_propagator_liouville, liou.p, (size_t)n_basis * n_basis * 16));
   }
-  if (eigvals) FFB_TRY(ffb_d2h(ctx, eigvals, ev.p, (size_t)G * d * 8));
-  if (eigvecs) FFB_TRY(ffb_d2h(ctx, eigvecs, V.p, (size_t)G * dd * 16));
-  if (propagators) FFB_TRY(ffb_d2h(ctx, propagators, Q.p, (size_t)(G + 1) * dd * 16));
-  if (control_matrix) FFB_TRY(ffb_d2h(ctx, control_matrix, B.p, b_bytes));
+  // ... is downloaded on the copy stream WHILE the control-matrix kernel runs
+  FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+  FFB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->copy_ev[0], 0));
+  FFB_TRY(d2h_copy(eigvals, ev.p, (size_t)G * d * 8));
+  FFB_TRY(d2h_copy(eigvecs, V.p, (size_t)G * dd * 16));
+  FFB_TRY(d2h_copy(propagators, Q.p, (size_t)(G + 1) * dd * 16));
+  if (total_phases) FFB_TRY(d2h_copy(total_phases, ph.p, (size_t)n_omega * 16));
+  if (total_propagator_liouville)
+    FFB_TRY(d2h_copy(total_propagator_liouville, liou.p, (size_t)n_basis * n_basis * 16));
+
+  // stage 2: control matrix; its download overlaps the filter function and the integral
+  FFB_TRY(ffbi_control_matrix(ctx, G, d, n_nops, n_basis, n_omega, ev.as<double>(), V.as<double>(),
+                              Q.as<double>(), in.d(i_om), in.d(i_bs), in.d(i_no), in.d(i_nc),
+                              in.d(i_dt), in.d(i_ts), herm, B.as<double>()));
+  if (control_matrix) {
+    FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[1], ctx->stream));
+    FFB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->copy_ev[1], 0));
+    FFB_TRY(d2h_copy(control_matrix, B.p, b_bytes));
+  }
+  FFB_TRY(ffbi_filter_function(ctx, 1, n_nops, n_basis, n_omega, B.as<double>(), 0, F.as<double>()));
+  if (infidelity) {
+    FFB_TRY(I.alloc(ctx, n_inf * 8));
+    FFB_TRY(ffbi_infidelity(ctx, 1, n_nops, n_nops, nullptr, n_omega, F.as<double>(), in.d(i_sp),
+                            spectrum_ndim, spectrum_is_complex, in.d(i_om), d, I.as<double>()));
+    FFB_TRY(ffb_d2h(ctx, infidelity, I.p, n_inf * 8));
+  }
   if (filter_function) FFB_TRY(ffb_d2h(ctx, filter_function, F.p, f_bytes));
-  if (infidelity) FFB_TRY(ffb_d2h(ctx, infidelity, I.p, n_inf * 8));
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  FFB_CUDA(ctx, cudaStreamSynchronize(cs));
   return FFB_OK;
 }
 

@@ -29,6 +29,9 @@ struct ffb_ctx {
   double* trig_table = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
+  // page-locked staging block: the small host inputs of a call are packed here and uploaded by ONE copy
+  void* stage_host = nullptr;
+  size_t stage_bytes = 0;
 
   // grow-only caching pool: freed blocks are kept and handed out again (best fit)
   std::multimap<size_t, void*> free_blocks;

@@ -1183,14 +1183,46 @@ assemble_dfma_kernel(int G, int d, int rows, int R, int n_jrows, int n_krows,
   }
 }
 
-template <int R>
+// The table-sincos constants enter through the KERNEL PARAMETERS: constant bank 0 can be a direct
+// operand of DFMA/DMUL, whereas a __constant__ array (bank 3) is re-loaded by LDC/LDCU in every
+// iteration (ncu r01c: 33 M of the 676 M warp instructions of config 2) -- and on sm_100 every
+// non-FP64 instruction costs the issue slot of half a DFMA.
+struct TrigConsts {
+  double inv_step, magic, step_hi, step_lo, s5, s3, c6, c4;
+};
+inline TrigConsts trig_consts() {
+  return {4.07436654315252084757e+01, 6755399441055744.0, 2.45436926061702587187e-02,
+          9.56755311833869693105e-19, 1.0 / 120.0, -1.0 / 6.0, -1.0 / 720.0, 1.0 / 24.0};
+}
+__device__ __forceinline__ void sincos_tab_p(double x, const double2* __restrict__ table_smem,
+                                             const TrigConsts& tc, double& sn, double& cs) {
+  double kd = fma(x, tc.inv_step, tc.magic);
+  const int k = __double2loint(kd) & (TRIG_TABLE_SIZE - 1);
+  kd -= tc.magic;
+  double r = fma(-kd, tc.step_hi, x);
+  r = fma(-kd, tc.step_lo, r);
+  const double2 sc = table_smem[k];
+  const double r2 = r * r;
+  const double ps = fma(r2, tc.s5, tc.s3);
+  const double s = fma(r * r2, ps, r);
+  double pc = fma(r2, tc.c6, tc.c4);
+  pc = fma(pc, r2, -0.5);
+  const double c = fma(pc, r2, 1.0);
+  sn = fma(sc.x, c, sc.y * s);
+  cs = fma(sc.y, c, -(sc.x * s));
+}
+
+// NP = number of level pairs d (d - 1) / 2 (compile time: record size and the walk over a record are
+// constants, the pair loop is unrolled).
+template <int R, int NP>
 __global__ void __launch_bounds__(DFMA_WARPS * 32, 2)
-ctrlmat_dfma_kernel(const DfmaParams p) {
+ctrlmat_dfma_kernel(const DfmaParams p, const TrigConsts tc) {
   extern __shared__ __align__(16) double smem[];
+  constexpr int REC = 2 + R + NP * (4 + 2 * R);
+  constexpr int PAIR = 4 + 2 * R;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int w_idx = blockIdx.x * 32 + lane;
-  const int rec = p.rec_doubles;
-  double* wbuf = smem + (size_t)warp * 2 * DFMA_STAGE_SEGS * rec;  // this warp's two stage buffers
+  double* wbuf = smem + (size_t)warp * 2 * DFMA_STAGE_SEGS * REC;  // this warp's two stage buffers
   double2* trig = reinterpret_cast<double2*>(smem + p.stage_smem_doubles);
   for (int k = threadIdx.x; k < TRIG_TABLE_SIZE; k += DFMA_WARPS * 32) trig[k] = p.trig_table[k];
   __syncthreads();
@@ -1215,12 +1247,12 @@ ctrlmat_dfma_kernel(const DfmaParams p) {
   const int seg_end = min(min(p.G, (blockIdx.y + 1) * p.segs_per_cta), seg_begin + p.segs_per_warp);
   const int n_segs = max(0, seg_end - seg_begin);
   const int n_stages = (n_segs + DFMA_STAGE_SEGS - 1) / DFMA_STAGE_SEGS;
-  const double* gsrc = p.stream + (size_t)seg_begin * rec;
+  const double* gsrc = p.stream + (size_t)seg_begin * REC;
   auto stage_load = [&](int st) {
     const int s0 = st * DFMA_STAGE_SEGS;
-    const int len = min(DFMA_STAGE_SEGS, n_segs - s0) * rec;  // rec is even: whole 16-byte chunks
-    double* dst = wbuf + (st & 1) * DFMA_STAGE_SEGS * rec;
-    const double* src = gsrc + (size_t)s0 * rec;
+    const int len = min(DFMA_STAGE_SEGS, n_segs - s0) * REC;  // REC is even: whole 16-byte chunks
+    double* dst = wbuf + (st & 1) * DFMA_STAGE_SEGS * REC;
+    const double* src = gsrc + (size_t)s0 * REC;
     for (int e = lane * 2; e < len; e += 64) cp_async16(dst + e, src + e);
   };
   auto dt_update = [&](double dtg) {
@@ -1259,26 +1291,30 @@ ctrlmat_dfma_kernel(const DfmaParams p) {
       acc_im[2 * r + 1] = fma(a.y, v.a_im, fma(b.y, v.b_im, acc_im[2 * r + 1]));
     }
   };
+  // one segment; the half-angle factors (hc, hs, j0) are valid for its dt
   auto one_segment = [&](const double* rp) {
-    dt_update(rp[1]);
-    sincos_tab(g.w * rp[0], trig, g.ph_im, g.ph_re);
+    sincos_tab_p(g.w * rp[0], trig, tc, g.ph_im, g.ph_re);
     fma_diag(rp, g.ph_re * g.j0_re - g.ph_im * g.j0_im, g.ph_re * g.j0_im + g.ph_im * g.j0_re);
-    const double* pp = rp + 2 + R;
-    for (int pi = 0; pi < p.n_pairs; ++pi, pp += 4 + 2 * R) {
+#pragma unroll
+    for (int pi = 0; pi < NP; ++pi) {
+      const double* pp = rp + 2 + R + pi * PAIR;
       Vals v;
       const double Om = pp[0];
       const bool fix = pair_values(g, Om, pp[1], pp[2], v);
-      if (__any_sync(0xffffffffu, fix)) {
-        if (fix) {
-          const Vals4 rr = fix_pair(g.w, g.dt, g.ph_re, g.ph_im, Om);
-          v.a_re = rr.a_re; v.a_im = rr.a_im; v.b_re = rr.b_re; v.b_im = rr.b_im;
-        }
+      if (__any_sync(0xffffffffu, fix)) {  // rare; taken by the whole warp, so it never diverges
+        const Vals4 rr = fix_pair(g.w, g.dt, g.ph_re, g.ph_im, Om);
+        v.a_re = fix ? rr.a_re : v.a_re;
+        v.a_im = fix ? rr.a_im : v.a_im;
+        v.b_re = fix ? rr.b_re : v.b_re;
+        v.b_im = fix ? rr.b_im : v.b_im;
       }
       fma_pair(pp, v);
     }
   };
   // (Generating the next unit's operands next to the current unit's DFMAs, as the tensor-path kernel
-  // does, was measured SLOWER here: 1.33 vs 1.16 ms on config 2 -- the extra live values cost moves.)
+  // does, was measured SLOWER here: 1.33 vs 1.16 ms on config 2 -- the extra live values cost moves.
+  // Generating the operands of two segments per iteration changed nothing: 1.073 vs 1.078 ms -- the
+  // kernel is bound by issue slots, not by latency.)
   if (n_stages > 0) {
     stage_load(0);
     cp_async_commit();
@@ -1292,12 +1328,21 @@ ctrlmat_dfma_kernel(const DfmaParams p) {
       cp_async_wait<0>();
     }
     __syncwarp();
-    const double* buf = wbuf + (st & 1) * DFMA_STAGE_SEGS * rec;
+    const double* rp = wbuf + (st & 1) * DFMA_STAGE_SEGS * REC;
     const int ns = min(DFMA_STAGE_SEGS, n_segs - st * DFMA_STAGE_SEGS);
-    // (Generating the operands of two segments per iteration for more instruction-level parallelism
-    // changed nothing: 1.073 vs 1.078 ms -- the kernel is bound by issue slots, not by latency.)
-    int sgm = 0;
-    for (; sgm < ns; ++sgm) one_segment(buf + sgm * rec);
+    // dt is tested once per stage, not per segment: on a uniform time grid the half-angle factors never
+    // change after the first segment
+    const double dt_l = rp[(lane < ns ? lane : 0) * REC + 1];
+    const bool same_dt =
+        __all_sync(0xffffffffu, __double_as_longlong(dt_l) == __double_as_longlong(g.dt_prev));
+    if (same_dt) {
+      for (int sgm = 0; sgm < ns; ++sgm, rp += REC) one_segment(rp);
+    } else {
+      for (int sgm = 0; sgm < ns; ++sgm, rp += REC) {
+        dt_update(rp[1]);
+        one_segment(rp);
+      }
+    }
     __syncwarp();  // all lanes are done with this buffer before it is refilled
   }
 
@@ -1514,12 +1559,15 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
                                                                    DFMA_WARPS * 32, smem));
       return FFB_OK;
     };
-    switch (R) {
-      case 4: FFB_TRY(pick(ctrlmat_dfma_kernel<4>)); break;
-      case 8: FFB_TRY(pick(ctrlmat_dfma_kernel<8>)); break;
-      case 12: FFB_TRY(pick(ctrlmat_dfma_kernel<12>)); break;
-      default: FFB_TRY(pick(ctrlmat_dfma_kernel<16>)); break;
-    }
+#define FFB_DFMA_DISPATCH(CALL)                                          \
+  switch (R) {                                                          \
+    case 4: if (d == 2) { CALL(4, 1); } else { CALL(4, 3); } break;     \
+    case 8: if (d == 2) { CALL(8, 1); } else { CALL(8, 3); } break;     \
+    case 12: if (d == 2) { CALL(12, 1); } else { CALL(12, 3); } break;  \
+    default: if (d == 2) { CALL(16, 1); } else { CALL(16, 3); } break;  \
+  }
+#define FFB_DFMA_PICK(R_, NP_) FFB_TRY(pick(ctrlmat_dfma_kernel<R_, NP_>))
+    FFB_DFMA_DISPATCH(FFB_DFMA_PICK)
     blocks_per_sm = std::max(1, blocks_per_sm);
     // split the segment axis over CTAs so that whole waves of CTAs are filled (same cost model as below)
     const long long slots = (long long)ctx->sm_count * blocks_per_sm;
@@ -1547,12 +1595,10 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
     dim3 grid(n_wt, S);
     int slot = -1;
     FFB_TRY(ffb_time_begin(ctx, &slot));
-    switch (R) {
-      case 4: ctrlmat_dfma_kernel<4><<<grid, DFMA_WARPS * 32, smem, ctx->stream>>>(q); break;
-      case 8: ctrlmat_dfma_kernel<8><<<grid, DFMA_WARPS * 32, smem, ctx->stream>>>(q); break;
-      case 12: ctrlmat_dfma_kernel<12><<<grid, DFMA_WARPS * 32, smem, ctx->stream>>>(q); break;
-      default: ctrlmat_dfma_kernel<16><<<grid, DFMA_WARPS * 32, smem, ctx->stream>>>(q); break;
-    }
+    const TrigConsts tc = trig_consts();
+#define FFB_DFMA_LAUNCH(R_, NP_) \
+  ctrlmat_dfma_kernel<R_, NP_><<<grid, DFMA_WARPS * 32, smem, ctx->stream>>>(q, tc)
+    FFB_DFMA_DISPATCH(FFB_DFMA_LAUNCH)
     FFB_LAUNCHED(ctx);
     FFB_TRY(ffb_time_end(ctx, slot));
     const size_t total_out = (size_t)n_nops * n_basis * n_omega;

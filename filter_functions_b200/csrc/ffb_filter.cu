@@ -88,7 +88,8 @@ infidelity_kernel(int n_nops, int n_sel, const int* __restrict__ idx, int n_omeg
     lead = o / n_sel;
     a = b = o % n_sel;
   }
-  const double2* Frow = F + (((size_t)lead * n_nops + idx[a]) * n_nops + idx[b]) * n_omega;
+  const int ia = idx ? idx[a] : a, ib = idx ? idx[b] : b;  // idx == nullptr: all operators, in order
+  const double2* Frow = F + (((size_t)lead * n_nops + ia) * n_nops + ib) * n_omega;
   size_t s_off = 0;
   if (spectrum_ndim == 2) s_off = (size_t)a * n_omega;
   if (spectrum_ndim == 3) s_off = ((size_t)a * n_sel + b) * n_omega;
