@@ -1,4 +1,5 @@
 // C ABI of libffb200 (include/ffb200.h): context, memory pool, host-pointer wrappers.
+#include <chrono>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -978,7 +979,7 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
                               double* infidelity, double* total_phases,
                               double* total_propagator_liouville) {
   FFB_TRY(enter(ctx));
-  FFB_REQUIRE(ctx, c_opers && c_coeffs && n_opers && n_coeffs && dt && t && basis && omega,
+  FFB_REQUIRE(ctx, c_opers && c_coeffs && n_opers && n_coeffs && dt && basis && omega,
               "pulse pipeline: null input pointer");
   FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32 && n_cops >= 1 && n_nops >= 1 && n_basis >= 1 &&
                        n_omega >= 1, "pulse pipeline: bad shape");
@@ -987,6 +988,13 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
   const int herm = (all_hermitian(n_opers, n_nops, d) ? FFB_HERM_NOPERS : 0) |
                    (all_hermitian(basis, n_basis, d) ? FFB_HERM_BASIS : 0);
   FFB_TRY(ensure_copy_stream(ctx));
+  // FFB_TRACE=1: host-side timestamps of the pipeline stages on stderr (where does e2e time go?)
+  static const bool trace = getenv("FFB_TRACE") && atoi(getenv("FFB_TRACE")) != 0;
+  const auto t_enter = std::chrono::steady_clock::now();
+  auto since = [&]() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_enter).count();
+  };
+  double us_packed = 0, us_enqueued = 0, us_main = 0;
   PackedUpload in;
   DevBuf ev, V, Q, B, F, I, ph, liou;
   CopyStreamDrain drain{ctx};
@@ -995,6 +1003,18 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
   const int i_dt = in.add(dt, (size_t)G * 8);
   const int i_no = in.add(n_opers, (size_t)n_nops * dd * 16);
   const int i_nc = in.add(n_coeffs, (size_t)n_nops * G * 8);
+  // t == NULL: t = [0, cumsum(dt)] with the sequential summation of np.cumsum (pulse_sequence.py:540-552)
+  std::vector<double> t_own;
+  if (!t) {
+    t_own.resize((size_t)G + 1);
+    double acc = 0.0;
+    t_own[0] = 0.0;
+    for (int g = 0; g < G; ++g) {
+      acc += dt[g];
+      t_own[(size_t)g + 1] = acc;
+    }
+    t = t_own.data();
+  }
   const int i_ts = in.add(t, (size_t)(G + 1) * 8);
   const int i_bs = in.add(basis, (size_t)n_basis * dd * 16);
   const int i_om = in.add(omega, (size_t)n_omega * 8);
@@ -1009,6 +1029,7 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
     n_inf = spectrum_ndim == 3 ? (size_t)n_nops * n_nops : n_nops;
   }
   FFB_TRY(in.upload(ctx));
+  us_packed = since();
   FFB_TRY(ev.alloc(ctx, (size_t)G * d * 8));
   FFB_TRY(V.alloc(ctx, (size_t)G * dd * 16));
   FFB_TRY(Q.alloc(ctx, (size_t)(G + 1) * dd * 16));
@@ -1044,25 +1065,52 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
   if (total_propagator_liouville)
     FFB_TRY(d2h_copy(total_propagator_liouville, liou.p, (size_t)n_basis * n_basis * 16));
 
-  // stage 2: control matrix; its download overlaps the filter function and the integral
-  FFB_TRY(ffbi_control_matrix(ctx, G, d, n_nops, n_basis, n_omega, ev.as<double>(), V.as<double>(),
-                              Q.as<double>(), in.d(i_om), in.d(i_bs), in.d(i_no), in.d(i_nc),
-                              in.d(i_dt), in.d(i_ts), herm, B.as<double>()));
-  if (control_matrix) {
+  // stage 2: control matrix and filter function in blocks of frequencies; the rows of a finished block
+  // are downloaded (strided 2-D copies) while the next block is computed, so that only the last
+  // block's download is left after the last kernel (PCIe is the tail of this call: config 3 returns
+  // 105 MB, 1.9 ms at 56 GB/s)
+  const size_t out_bytes = (control_matrix ? b_bytes : 0) + (filter_function ? f_bytes : 0);
+  FreqBlocks fb;
+  // measured on B200 (e2e ms with 1 / 2 / 4 / 8 blocks): config 2 (3.4 MB) 1.37 / 1.38 / 1.44 / 1.55,
+  // d4 (21 MB) 17.65 / 17.29 / 17.73 / 18.07, config 3 (105 MB) 18.74 / 18.39 / 17.46 / 17.48 -- a block
+  // pays off from ~10 MB of results per block
+  fb.n_blocks = (int)std::min<size_t>(4, std::max<size_t>(1, out_bytes / ((size_t)10 << 20)));
+  fb.n_blocks = std::max(1, std::min(fb.n_blocks, n_omega / 2048));
+  if (const char* e = getenv("FFB_PIPELINE_BLOCKS")) fb.n_blocks = std::max(1, atoi(e));
+  const size_t pitch = (size_t)n_omega * 16;
+  fb.after_block = [&](int w0, int w1) -> int {
+    const size_t off = (size_t)w0 * 16, width = (size_t)(w1 - w0) * 16;
+    FFB_TRY(ffbi_filter_function_ld(ctx, 1, n_nops, n_basis, w1 - w0, (size_t)n_omega,
+                                    B.as<double>() + 2 * (size_t)w0, F.as<double>() + 2 * (size_t)w0));
     FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[1], ctx->stream));
     FFB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->copy_ev[1], 0));
-    FFB_TRY(d2h_copy(control_matrix, B.p, b_bytes));
-  }
-  FFB_TRY(ffbi_filter_function(ctx, 1, n_nops, n_basis, n_omega, B.as<double>(), 0, F.as<double>()));
+    if (control_matrix)
+      FFB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<char*>(control_matrix) + off, pitch,
+                                      static_cast<const char*>(B.p) + off, pitch, width,
+                                      (size_t)n_nops * n_basis, cudaMemcpyDeviceToHost, cs));
+    if (filter_function)
+      FFB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<char*>(filter_function) + off, pitch,
+                                      static_cast<const char*>(F.p) + off, pitch, width,
+                                      (size_t)n_nops * n_nops, cudaMemcpyDeviceToHost, cs));
+    return FFB_OK;
+  };
+  FFB_TRY(ffbi_control_matrix(ctx, G, d, n_nops, n_basis, n_omega, ev.as<double>(), V.as<double>(),
+                              Q.as<double>(), in.d(i_om), in.d(i_bs), in.d(i_no), in.d(i_nc),
+                              in.d(i_dt), in.d(i_ts), herm, B.as<double>(), &fb));
   if (infidelity) {
     FFB_TRY(I.alloc(ctx, n_inf * 8));
     FFB_TRY(ffbi_infidelity(ctx, 1, n_nops, n_nops, nullptr, n_omega, F.as<double>(), in.d(i_sp),
                             spectrum_ndim, spectrum_is_complex, in.d(i_om), d, I.as<double>()));
     FFB_TRY(ffb_d2h(ctx, infidelity, I.p, n_inf * 8));
   }
-  if (filter_function) FFB_TRY(ffb_d2h(ctx, filter_function, F.p, f_bytes));
+  us_enqueued = since();
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  us_main = since();
   FFB_CUDA(ctx, cudaStreamSynchronize(cs));
+  if (trace)
+    fprintf(stderr, "[ffb trace] pulse pipeline: inputs packed+upload enqueued %.0f us, all work enqueued "
+            "%.0f us, main stream done %.0f us, copy stream done %.0f us\n", us_packed, us_enqueued,
+            us_main, since());
   return FFB_OK;
 }
 

@@ -5,6 +5,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -117,13 +118,24 @@ int ffb_time_end(ffb_ctx* ctx, int slot);
 int ffbi_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_opers,
                      const double* c_coeffs, const double* dt, double* eigvals, double* eigvecs,
                      double* propagators);
+// Optional blocking of the frequency axis of the control-matrix pipeline: the omega-independent
+// prologue runs once, then main kernel + finalize per block of frequencies; after the kernels of a
+// block are enqueued `after_block(w0, w1)` is called, which lets the caller queue the download of the
+// finished block (and its filter function) while the next block is computed.
+struct FreqBlocks {
+  int n_blocks = 1;
+  std::function<int(int, int)> after_block;
+};
 int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int n_omega,
                         const double* eigvals, const double* eigvecs, const double* propagators,
                         const double* omega, const double* basis, const double* n_opers,
                         const double* n_coeffs, const double* dt, const double* t, int herm_flags,
-                        double* out);
+                        double* out, const FreqBlocks* blocks = nullptr);
 int ffbi_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
                          const double* B, int generalized, double* F);
+// same for a block of n_omega frequencies inside arrays whose rows are `ld` frequencies long
+int ffbi_filter_function_ld(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega, size_t ld,
+                            const double* B, double* F);
 int ffbi_from_atomic(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
                      const double* phases, const double* B_atomic, const double* Q, int q_is_complex,
                      int correlations, double* out);

@@ -109,12 +109,7 @@ __device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
 // (measured: time = 2 N_fp64 + 16 N_dmma + N_other on every variant of these kernels), so both counts
 // matter.  Same absolute accuracy as sincos_cw (table entries and the reduction are exact to 1 ulp).
 constexpr int TRIG_TABLE_SIZE = 256;
-__constant__ double ST_K[8] = {
-    4.07436654315252084757e+01,   // 0: 128/pi
-    6755399441055744.0,           // 1: 1.5 * 2^52
-    2.45436926061702587187e-02,   // 2: pi/128 high
-    9.56755311833869693105e-19,   // 3: pi/128 low
-    1.0 / 120.0, -1.0 / 6.0, -1.0 / 720.0, 1.0 / 24.0};
+// (the constants of the reduction and the two polynomials are in TrigConsts, passed as kernel parameters)
 
 __global__ void trig_table_kernel(double2* __restrict__ table) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,24 +117,6 @@ __global__ void trig_table_kernel(double2* __restrict__ table) {
   double sn, cs;
   sincospi((double)k / 128.0, &sn, &cs);
   table[k] = make_double2(sn, cs);
-}
-
-__device__ __forceinline__ void sincos_tab(double x, const double2* __restrict__ table_smem,
-                                           double& sn, double& cs) {
-  double kd = fma(x, ST_K[0], ST_K[1]);
-  const int k = __double2loint(kd) & (TRIG_TABLE_SIZE - 1);
-  kd -= ST_K[1];
-  double r = fma(-kd, ST_K[2], x);
-  r = fma(-kd, ST_K[3], r);
-  const double2 sc = table_smem[k];
-  const double r2 = r * r;
-  const double ps = fma(r2, ST_K[4], ST_K[5]);
-  const double s = fma(r * r2, ps, r);
-  double pc = fma(r2, ST_K[6], ST_K[7]);
-  pc = fma(pc, r2, -0.5);
-  const double c = fma(pc, r2, 1.0);
-  sn = fma(sc.x, c, sc.y * s);
-  cs = fma(sc.y, c, -(sc.x * s));
 }
 
 // 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps on the FP64 pipe.
@@ -1375,7 +1352,7 @@ ctrlmat_dfma_kernel(const DfmaParams p, const TrigConsts tc) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 finalize_kernel(int S, int rows_pad, int n_nops, int n_basis, int parts_j, int parts_k, int n_omega,
-                const double* __restrict__ partial, double* __restrict__ out) {
+                size_t ld_out, const double* __restrict__ partial, double* __restrict__ out) {
   const size_t total = (size_t)n_nops * n_basis * n_omega;
   const int n_krows = n_basis * parts_k;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -1401,7 +1378,7 @@ finalize_kernel(int S, int rows_pad, int n_nops, int n_basis, int parts_j, int p
         }
       }
     }
-    reinterpret_cast<double2*>(out)[idx] = make_double2(re, im);
+    reinterpret_cast<double2*>(out)[(size_t)jk * ld_out + w] = make_double2(re, im);
   }
 }
 
@@ -1478,7 +1455,9 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
                         const double* eigvals, const double* eigvecs, const double* propagators,
                         const double* omega, const double* basis, const double* n_opers,
                         const double* n_coeffs, const double* dt, const double* t, int herm_flags,
-                        double* out) {
+                        double* out_all, const FreqBlocks* blocks) {
+  const double* const omega_all = omega;
+  const int n_omega_all = n_omega;
   FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32, "control matrix: G=%d, d=%d unsupported", G, d);
   FFB_REQUIRE(ctx, n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
               "control matrix: n_nops=%d n_basis=%d n_omega=%d must all be positive", n_nops,
@@ -1534,6 +1513,19 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
                                                           Bbar.as<double>(), Cbar.as<double>(),
                                                           eigvals, dt, t, stream.as<double>());
     FFB_LAUNCHED(ctx);
+  } else {
+    const size_t total = geo.rb_doubles * geo.n_rb;
+    const unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total, 256), (size_t)ctx->sm_count * 32);
+    assemble_kernel<<<blocks, 256, 0, ctx->stream>>>(geo, G, d, rows, n_jrows, n_krows,
+                                                     Bbar.as<double>(), Cbar.as<double>(), eigvals,
+                                                     dt, t, stream.as<double>());
+    FFB_LAUNCHED(ctx);
+  }
+
+  // ---- omega-dependent part, per block of frequencies (one block unless the caller asked for more)
+  const size_t ld_out = (size_t)n_omega_all;
+  auto run_block = [&](const double* omega, int n_omega, double* out) -> int {
+  if (use_dfma) {
     DfmaParams q;
     q.stream = stream.as<double>();
     q.omega = omega;
@@ -1604,17 +1596,9 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
     const size_t total_out = (size_t)n_nops * n_basis * n_omega;
     const unsigned fblocks = (unsigned)std::min<size_t>(ceil_div_sz(total_out, 256), (size_t)ctx->sm_count * 16);
     finalize_kernel<<<fblocks, 256, 0, ctx->stream>>>(S, R, n_nops, n_basis, parts_j, parts_k, n_omega,
-                                                      partial.as<double>(), out);
+                                                      ld_out, partial.as<double>(), out);
     FFB_LAUNCHED(ctx);
     return FFB_OK;
-  }
-  {
-    const size_t total = geo.rb_doubles * geo.n_rb;
-    const unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total, 256), (size_t)ctx->sm_count * 32);
-    assemble_kernel<<<blocks, 256, 0, ctx->stream>>>(geo, G, d, rows, n_jrows, n_krows,
-                                                     Bbar.as<double>(), Cbar.as<double>(), eigvals,
-                                                     dt, t, stream.as<double>());
-    FFB_LAUNCHED(ctx);
   }
 
   MainParams p;
@@ -1722,8 +1706,19 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
     const size_t total = (size_t)n_nops * n_basis * n_omega;
     const unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total, 256), (size_t)ctx->sm_count * 16);
     finalize_kernel<<<blocks, 256, 0, ctx->stream>>>(S, rows_pad, n_nops, n_basis, parts_j, parts_k,
-                                                     n_omega, partial.as<double>(), out);
+                                                     n_omega, ld_out, partial.as<double>(), out);
     FFB_LAUNCHED(ctx);
+  }
+  return FFB_OK;
+  };  // run_block
+
+  // block boundaries on multiples of 64 frequencies (the frequency tiles of all kernel variants)
+  const int n_blocks = blocks ? std::max(1, std::min(blocks->n_blocks, ceil_div(n_omega_all, 64))) : 1;
+  const int per_block = ceil_div(ceil_div(n_omega_all, n_blocks), 64) * 64;
+  for (int w0 = 0; w0 < n_omega_all; w0 += per_block) {
+    const int w1 = std::min(n_omega_all, w0 + per_block);
+    FFB_TRY(run_block(omega_all + w0, w1 - w0, out_all + 2 * (size_t)w0));
+    if (blocks && blocks->after_block) FFB_TRY(blocks->after_block(w0, w1));
   }
   return FFB_OK;
 }

@@ -15,8 +15,8 @@ namespace {
 // Output index (P = n_pulses, l = (g,a), r = (h,b)): (((g*P + h)*n_nops + a)*n_nops + b)*n_omega + w
 template <int RT>
 __global__ void __launch_bounds__(256)
-ff_fidelity_kernel(int P, int n_nops, int n_basis, int n_omega, const double2* __restrict__ B,
-                   double2* __restrict__ F) {
+ff_fidelity_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld,
+                   const double2* __restrict__ B, double2* __restrict__ F) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n_omega) return;
   const int L = P * n_nops;
@@ -25,14 +25,14 @@ ff_fidelity_kernel(int P, int n_nops, int n_basis, int n_omega, const double2* _
   double2 acc[RT];
 #pragma unroll
   for (int i = 0; i < RT; ++i) acc[i] = make_double2(0.0, 0.0);
-  const double2* Bl = B + (size_t)l * n_basis * n_omega + w;
+  const double2* Bl = B + (size_t)l * n_basis * ld + w;  // rows are ld frequencies apart
   for (int k = 0; k < n_basis; ++k) {
-    const double2 x = Bl[(size_t)k * n_omega];
+    const double2 x = Bl[(size_t)k * ld];
 #pragma unroll
     for (int i = 0; i < RT; ++i) {
       const int r = r0 + i;
       if (r < L) {
-        const double2 y = B[((size_t)r * n_basis + k) * n_omega + w];
+        const double2 y = B[((size_t)r * n_basis + k) * ld + w];
         // conj(x) * y
         acc[i].x += x.x * y.x + x.y * y.y;
         acc[i].y += x.x * y.y - x.y * y.x;
@@ -45,7 +45,7 @@ ff_fidelity_kernel(int P, int n_nops, int n_basis, int n_omega, const double2* _
     const int r = r0 + i;
     if (r < L) {
       const int h = r / n_nops, b = r % n_nops;
-      F[((((size_t)g * P + h) * n_nops + a) * n_nops + b) * n_omega + w] = acc[i];
+      F[((((size_t)g * P + h) * n_nops + a) * n_nops + b) * ld + w] = acc[i];
     }
   }
 }
@@ -130,7 +130,7 @@ int ffbi_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_ome
     constexpr int RT = 4;
     dim3 grid(wt, L, ceil_div(L, RT));
     ff_fidelity_kernel<RT><<<grid, 256, 0, ctx->stream>>>(
-        P, n_nops, n_basis, n_omega, reinterpret_cast<const double2*>(B),
+        P, n_nops, n_basis, n_omega, (size_t)n_omega, reinterpret_cast<const double2*>(B),
         reinterpret_cast<double2*>(F));
   } else {
     dim3 grid(wt, L * n_basis, L);
@@ -138,6 +138,22 @@ int ffbi_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_ome
         P, n_nops, n_basis, n_omega, reinterpret_cast<const double2*>(B),
         reinterpret_cast<double2*>(F));
   }
+  FFB_LAUNCHED(ctx);
+  return FFB_OK;
+}
+
+int ffbi_filter_function_ld(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega, size_t ld,
+                            const double* B, double* F) {
+  FFB_REQUIRE(ctx, P >= 1 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1 && ld >= (size_t)n_omega,
+              "filter function: bad shape (P=%d, n_nops=%d, n_basis=%d, n_omega=%d)", P, n_nops,
+              n_basis, n_omega);
+  const int L = P * n_nops;
+  FFB_REQUIRE(ctx, L <= 65535, "filter function: too many rows (%d)", L);
+  constexpr int RT = 4;
+  dim3 grid(ceil_div(n_omega, 256), L, ceil_div(L, RT));
+  ff_fidelity_kernel<RT><<<grid, 256, 0, ctx->stream>>>(
+      P, n_nops, n_basis, n_omega, ld, reinterpret_cast<const double2*>(B),
+      reinterpret_cast<double2*>(F));
   FFB_LAUNCHED(ctx);
   return FFB_OK;
 }

@@ -394,19 +394,18 @@ class PulseSequence:
         omega_arr = _lib.as_f64(self.omega)
         c_opers, c_coeffs = _lib.as_c128(self.c_opers), _lib.as_f64(self.c_coeffs)
         n_opers, n_coeffs = _lib.as_c128(self.n_opers), _lib.as_f64(self.n_coeffs)
-        dt, t = _lib.as_f64(self.dt), _lib.as_f64(self.t)
+        dt = _lib.as_f64(self.dt)
+        # t is only passed if it is cached already; otherwise the library forms [0, cumsum(dt)] itself
+        t = _lib.as_f64(self._data['t']) if 't' in self._data else None
         basis = _lib.as_c128(np.asarray(self.basis))
         # ``self.d`` only normalises the infidelity (the reference's tests overwrite it with the size
         # of a computational subspace, tests/test_precision.py:297); matrix shapes come from the arrays
         G, d = len(dt), c_opers.shape[-1]
         n_cops, n_nops, n_basis, n_omega = len(c_opers), len(n_opers), len(basis), len(omega_arr)
-        eigvals = _lib.empty((G, d), np.float64)
-        eigvecs = _lib.empty((G, d, d))
-        propagators = _lib.empty((G + 1, d, d))
-        B = _lib.empty((n_nops, n_basis, n_omega))
-        F = _lib.empty((n_nops, n_nops, n_omega))
-        phases = np.empty(n_omega, dtype=np.complex128)
-        liouville = np.empty((n_basis, n_basis), dtype=np.complex128)
+        eigvals, eigvecs, propagators, B, F, phases, liouville = _lib.empty_many([
+            ((G, d), np.float64), ((G, d, d), np.complex128), ((G + 1, d, d), np.complex128),
+            ((n_nops, n_basis, n_omega), np.complex128), ((n_nops, n_nops, n_omega), np.complex128),
+            ((n_omega,), np.complex128), ((n_basis, n_basis), np.complex128)])
         S = infid = None
         s_ndim = s_complex = 0
         if spectrum is not None:

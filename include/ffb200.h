@@ -216,11 +216,14 @@ int ffb_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out);
 
 /* ---- fused pulse pipeline ------------------------------------------------------------------------
  * What PulseSequence.get_filter_function (pulse_sequence.py:691-805) does on a cold cache, in one
- * call with one upload and one download: diagonalize -> control matrix -> fidelity filter function
- * (-> infidelity if spectrum != NULL), plus the two by-products cache_control_matrix keeps
+ * call: the inputs are packed into ONE upload; diagonalize -> control matrix -> fidelity filter
+ * function (-> infidelity if spectrum != NULL), plus the two by-products cache_control_matrix keeps
  * (pulse_sequence.py:674-677): total_phases = exp(i omega tau) (n_omega) c128 and the Liouville
- * representation of the total propagator (n_basis,n_basis) c128.  Any output pointer may be NULL to
- * skip it.  spectrum as in ffb_infidelity with n_sel = n_nops, idx = 0..n_nops-1. */
+ * representation of the total propagator (n_basis,n_basis) c128.  The eigensystem, propagators and
+ * by-products are downloaded on a second stream while the control-matrix kernel runs, the control
+ * matrix while the filter function and the integral are computed.  Any output pointer may be NULL
+ * to skip it.  t may be NULL: then t = [0, cumsum(dt)] (sequential sum, as np.cumsum).  spectrum as
+ * in ffb_infidelity with n_sel = n_nops, idx = 0..n_nops-1. */
 int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops, int n_basis,
                               int n_omega, const double* c_opers, const double* c_coeffs,
                               const double* n_opers, const double* n_coeffs, const double* dt,
