@@ -326,12 +326,19 @@ def run_b200(args):
     # library runs the DFMA variant (thread per frequency) for <= 16 rows and d <= 3, else DMMA tiles
     rows = n_nops*n_basis
     use_dfma = rows <= 16 and 2 <= d <= 3 and os.environ.get('FFB_CTRLMAT_DFMA', '1') != '0'
+    n_pairs = d*(d - 1)//2
     if use_dfma:
         rows_pad = -(-rows//4)*4
         kernel = 'ctrlmat_dfma_kernel'
         pipe = ('fp64 DFMA (thread per frequency; 64 lanes/clk/SM, the pipe DMMA shares); the '
-                'operand generator adds ~57 FP64 instructions per seg*omega that are not counted in '
+                'operand generator adds ~52 FP64 instructions per seg*omega that are not counted in '
                 'executed_tflops')
+        # rows of an identity basis element carry no level-pair terms (csrc/ffb_ctrlmat.cu)
+        ident0 = bool((wl.basis[0] == wl.basis[0][0, 0].real*np.eye(d)).all())
+        split = (ident0 and os.environ.get('FFB_DFMA_SPLIT_IDENTITY', '1') != '0'
+                 and ((d == 2 and n_basis == 4 and 2 <= n_nops <= 4)
+                      or (d == 3 and n_basis == 9 and n_nops == 1)))
+        pair_rows = n_nops*(n_basis - 1) if split else rows_pad
     else:
         rows_pad = -(-rows//8)*8
         tiles = rows_pad//8
@@ -342,7 +349,9 @@ def run_b200(args):
         kernel = 'ctrlmat_static_kernel' if static else 'ctrlmat_main_kernel'
         rows_pad = n_rb*mt*8
         pipe = 'fp64 (DMMA.8x8x4; shares the 64 lane/clk/SM FP64 pipe with DFMA)'
-    executed = rows_pad*(1 + d*(d - 1))*2*2*G*n_omega_local/(kernel_ms*1e-3)*1e-12
+        pair_rows = rows_pad
+    # real multiply-adds per seg*omega: 2 per row for the diagonal unit, 4 per row and level pair
+    executed = (2*rows_pad + 4*n_pairs*pair_rows)*2*G*n_omega_local/(kernel_ms*1e-3)*1e-12
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):

@@ -367,6 +367,22 @@ bool all_hermitian(const double* m, int n, int d) {
   return true;
 }
 
+// basis element 0 exactly a real multiple of the identity?
+bool first_is_identity(const double* basis, int d) {
+  const double c = basis[0];
+  for (int r = 0; r < d; ++r)
+    for (int q = 0; q < d; ++q) {
+      if (basis[2 * (r * d + q)] != (r == q ? c : 0.0)) return false;
+      if (basis[2 * (r * d + q) + 1] != 0.0) return false;
+    }
+  return true;
+}
+
+int basis_flags(const double* basis, int n_basis, int d) {
+  return (all_hermitian(basis, n_basis, d) ? FFB_HERM_BASIS : 0) |
+         (n_basis >= 1 && first_is_identity(basis, d) ? FFB_BASIS_IDENTITY0 : 0);
+}
+
 struct Upload {
   DevBuf buf;
   int put(ffb_ctx* ctx, const void* host, size_t bytes) {
@@ -477,7 +493,7 @@ int ffb_control_matrix_from_scratch(ffb_ctx* ctx, int G, int d, int n_nops, int 
               "control matrix: bad shape");
   const size_t dd = (size_t)d * d;
   const int herm = (all_hermitian(n_opers, n_nops, d) ? FFB_HERM_NOPERS : 0) |
-                   (all_hermitian(basis, n_basis, d) ? FFB_HERM_BASIS : 0);
+                   basis_flags(basis, n_basis, d);
   Upload ev, V, Q, om, bs, no, nc, dts, ts;
   DevBuf B;
   FFB_TRY(ev.put(ctx, eigvals, (size_t)G * d * 8));
@@ -986,7 +1002,7 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
   FFB_REQUIRE(ctx, !infidelity || spectrum, "pulse pipeline: infidelity requested without spectrum");
   const size_t dd = (size_t)d * d;
   const int herm = (all_hermitian(n_opers, n_nops, d) ? FFB_HERM_NOPERS : 0) |
-                   (all_hermitian(basis, n_basis, d) ? FFB_HERM_BASIS : 0);
+                   basis_flags(basis, n_basis, d);
   FFB_TRY(ensure_copy_stream(ctx));
   // FFB_TRACE=1: host-side timestamps of the pipeline stages on stderr (where does e2e time go?)
   static const bool trace = getenv("FFB_TRACE") && atoi(getenv("FFB_TRACE")) != 0;

@@ -1083,7 +1083,14 @@ ctrlmat_static_kernel(const MainParams p) {
 // through a private double-buffered cp.async pipeline -- no block-wide barrier in the main loop.
 //
 // Stream: one record per segment:  t, dt, diag[R], then per level pair: Omega, cos(Omega dt/2),
-// sin(Omega dt/2), 0, Re[R], Im[R].
+// sin(Omega dt/2), 0, Re[RFP], Im[RFP]  (RFP = RF rounded up to even).
+//
+// Rows without level-pair terms.  If basis element 0 is a multiple of the identity (Basis.pauli,
+// Basis.ggm), Cbar_0 = U^+ C_0 U = C_0 is diagonal in every eigenbasis: its rows (j, 0) only have the
+// diagonal term (and vanish altogether for traceless noise operators).  The accumulator slots are
+// therefore ordered [RF rows (j, k >= 1) | rows (j, 0) | padding]: the diagonal coefficients cover
+// all R slots, the pair coefficients only the first RF -- for config 2 (3 x 4 rows) 9 instead of 12
+// rows take part in the 4 n_pairs DFMAs per row: 60 instead of 72 DFMAs per (segment, frequency).
 // ------------------------------------------------------------------------------------------------
 struct DfmaParams {
   const double* stream;
@@ -1102,15 +1109,26 @@ struct DfmaParams {
 constexpr int DFMA_WARPS = 8;
 constexpr int DFMA_STAGE_SEGS = 8;
 
-__host__ __device__ inline int dfma_rec_doubles(int R, int n_pairs) { return 2 + R + n_pairs * (4 + 2 * R); }
+__host__ __device__ inline int dfma_rec_doubles(int R, int RF, int n_pairs) {
+  return 2 + R + n_pairs * (4 + 2 * ((RF + 1) & ~1));
+}
+// accumulator slot -> row (j * n_krows + k) of the control matrix, -1 for padding.  split: slots
+// [0, RF) are the rows with k >= 1, slots RF.. the rows with k == 0 (basis element 0 = identity)
+__host__ __device__ inline int dfma_row_of_slot(int slot, int rows, int RF, bool split, int n_jrows,
+                                                int n_krows) {
+  if (!split) return slot < rows ? slot : -1;
+  if (slot < RF) return (slot / (n_krows - 1)) * n_krows + 1 + slot % (n_krows - 1);
+  return slot - RF < n_jrows ? (slot - RF) * n_krows : -1;
+}
 
 __global__ void __launch_bounds__(256)
-assemble_dfma_kernel(int G, int d, int rows, int R, int n_jrows, int n_krows,
+assemble_dfma_kernel(int G, int d, int rows, int R, int RF, int split, int n_jrows, int n_krows,
                      const double* __restrict__ Bbar, const double* __restrict__ Cbar,
                      const double* __restrict__ eigvals, const double* __restrict__ dt,
                      const double* __restrict__ t, double* __restrict__ stream) {
   const int n_pairs = d * (d - 1) / 2;
-  const int rec = dfma_rec_doubles(R, n_pairs);
+  const int RFP = (RF + 1) & ~1;
+  const int rec = dfma_rec_doubles(R, RF, n_pairs);
   const size_t total = (size_t)G * rec;
   const int dd = d * d;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -1121,8 +1139,8 @@ assemble_dfma_kernel(int G, int d, int rows, int R, int n_jrows, int n_krows,
     if (off < 2) {
       val = off == 0 ? t[g] : dt[g];
     } else if (off < 2 + R) {
-      const int row = off - 2;
-      if (row < rows) {
+      const int row = dfma_row_of_slot(off - 2, rows, RF, split != 0, n_jrows, n_krows);
+      if (row >= 0) {
         const double* Bm = Bbar + ((size_t)g * n_jrows + row / n_krows) * 2 * dd;
         const double* Cm = Cbar + ((size_t)g * n_krows + row % n_krows) * 2 * dd;
         double acc = 0.0;
@@ -1131,8 +1149,8 @@ assemble_dfma_kernel(int G, int d, int rows, int R, int n_jrows, int n_krows,
       }
     } else {
       off -= 2 + R;
-      const int pair = off / (4 + 2 * R);
-      off %= 4 + 2 * R;
+      const int pair = off / (4 + 2 * RFP);
+      off %= 4 + 2 * RFP;
       int m, n;
       pair_from_index(pair, d, m, n);
       if (off < 4) {
@@ -1145,8 +1163,9 @@ assemble_dfma_kernel(int G, int d, int rows, int R, int n_jrows, int n_krows,
           val = off == 1 ? cs : sn;
         }
       } else {
-        const int col = (off - 4) / R, row = (off - 4) % R;
-        if (row < rows) {
+        const int col = (off - 4) / RFP, slot = (off - 4) % RFP;
+        const int row = slot < RF ? dfma_row_of_slot(slot, rows, RF, split != 0, n_jrows, n_krows) : -1;
+        if (row >= 0) {
           const double* Bm = Bbar + ((size_t)g * n_jrows + row / n_krows) * 2 * dd;
           const double* Cm = Cbar + ((size_t)g * n_krows + row % n_krows) * 2 * dd;
           const cplx b = {Bm[2 * (m * d + n)], Bm[2 * (m * d + n) + 1]};
@@ -1190,13 +1209,15 @@ __device__ __forceinline__ void sincos_tab_p(double x, const double2* __restrict
 }
 
 // NP = number of level pairs d (d - 1) / 2 (compile time: record size and the walk over a record are
-// constants, the pair loop is unrolled).
-template <int R, int NP>
+// constants, the pair loop is unrolled); RF <= R = number of leading accumulator slots that carry pair
+// coefficients (see "rows without level-pair terms" above).
+template <int R, int RF, int NP>
 __global__ void __launch_bounds__(DFMA_WARPS * 32, 2)
 ctrlmat_dfma_kernel(const DfmaParams p, const TrigConsts tc) {
   extern __shared__ __align__(16) double smem[];
-  constexpr int REC = 2 + R + NP * (4 + 2 * R);
-  constexpr int PAIR = 4 + 2 * R;
+  constexpr int RFP = (RF + 1) & ~1;
+  constexpr int PAIR = 4 + 2 * RFP;
+  constexpr int REC = 2 + R + NP * PAIR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int w_idx = blockIdx.x * 32 + lane;
   double* wbuf = smem + (size_t)warp * 2 * DFMA_STAGE_SEGS * REC;  // this warp's two stage buffers
@@ -1258,14 +1279,19 @@ ctrlmat_dfma_kernel(const DfmaParams p, const TrigConsts tc) {
   };
   auto fma_pair = [&](const double* pp, const Vals& v) {
     const double2* cre = reinterpret_cast<const double2*>(pp + 4);
-    const double2* cim = reinterpret_cast<const double2*>(pp + 4 + R);
+    const double2* cim = reinterpret_cast<const double2*>(pp + 4 + RFP);
 #pragma unroll
-    for (int r = 0; r < R / 2; ++r) {
+    for (int r = 0; r < RF / 2; ++r) {
       const double2 a = cre[r], b = cim[r];
       acc_re[2 * r] = fma(a.x, v.a_re, fma(b.x, v.b_re, acc_re[2 * r]));
       acc_im[2 * r] = fma(a.x, v.a_im, fma(b.x, v.b_im, acc_im[2 * r]));
       acc_re[2 * r + 1] = fma(a.y, v.a_re, fma(b.y, v.b_re, acc_re[2 * r + 1]));
       acc_im[2 * r + 1] = fma(a.y, v.a_im, fma(b.y, v.b_im, acc_im[2 * r + 1]));
+    }
+    if (RF & 1) {  // odd number of pair rows: the last one alone (LDS.64)
+      const double a = pp[4 + RF - 1], b = pp[4 + RFP + RF - 1];
+      acc_re[RF - 1] = fma(a, v.a_re, fma(b, v.b_re, acc_re[RF - 1]));
+      acc_im[RF - 1] = fma(a, v.a_im, fma(b, v.b_im, acc_im[RF - 1]));
     }
   };
   // one segment; the half-angle factors (hc, hs, j0) are valid for its dt
@@ -1352,7 +1378,8 @@ ctrlmat_dfma_kernel(const DfmaParams p, const TrigConsts tc) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 finalize_kernel(int S, int rows_pad, int n_nops, int n_basis, int parts_j, int parts_k, int n_omega,
-                size_t ld_out, const double* __restrict__ partial, double* __restrict__ out) {
+                size_t ld_out, int split_rf, const double* __restrict__ partial,
+                double* __restrict__ out) {
   const size_t total = (size_t)n_nops * n_basis * n_omega;
   const int n_krows = n_basis * parts_k;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -1363,7 +1390,9 @@ finalize_kernel(int S, int rows_pad, int n_nops, int n_basis, int parts_j, int p
     double re = 0.0, im = 0.0;
     for (int pj = 0; pj < parts_j; ++pj) {
       for (int pk = 0; pk < parts_k; ++pk) {
-        const int row = (j * parts_j + pj) * n_krows + k * parts_k + pk;
+        int row = (j * parts_j + pj) * n_krows + k * parts_k + pk;
+        // DFMA kernel with the identity rows split off (parts_j = parts_k = 1): slot of row (j, k)
+        if (split_rf > 0) row = k == 0 ? split_rf + j : j * (n_basis - 1) + k - 1;
         double pr = 0.0, pi = 0.0;
         for (int z = 0; z < S; ++z) {
           const double2 v = reinterpret_cast<const double2*>(
@@ -1475,7 +1504,14 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   bool use_dfma = rows <= 16 && d >= 2 && d <= 3;
   if (const char* e = getenv("FFB_CTRLMAT_DFMA")) use_dfma = use_dfma && atoi(e) != 0;
   const int R = 4 * ceil_div(rows, 4);
-  const int rec = dfma_rec_doubles(R, d * (d - 1) / 2);
+  // rows (j, 0) of an identity basis element carry no pair coefficients (instances that exist:
+  // d = 2 with 2-4 noise operators in a 4-element basis, d = 3 with one in a 9-element basis)
+  bool split = use_dfma && (herm_flags & FFB_BASIS_IDENTITY0) && parts_j == 1 && parts_k == 1 &&
+               ((d == 2 && n_basis == 4 && n_nops >= 2 && n_nops <= 4) ||
+                (d == 3 && n_basis == 9 && n_nops == 1));
+  if (const char* e = getenv("FFB_DFMA_SPLIT_IDENTITY")) split = split && atoi(e) != 0;
+  const int RF = split ? n_nops * (n_basis - 1) : R;
+  const int rec = dfma_rec_doubles(R, RF, d * (d - 1) / 2);
 
   DevBuf Bbar, Cbar, stream, partial;
   FFB_TRY(Bbar.alloc(ctx, (size_t)G * n_jrows * dd * 16));
@@ -1509,7 +1545,7 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   if (use_dfma) {
     const size_t total = (size_t)G * rec;
     const unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total, 256), (size_t)ctx->sm_count * 32);
-    assemble_dfma_kernel<<<blocks, 256, 0, ctx->stream>>>(G, d, rows, R, n_jrows, n_krows,
+    assemble_dfma_kernel<<<blocks, 256, 0, ctx->stream>>>(G, d, rows, R, RF, split ? 1 : 0, n_jrows, n_krows,
                                                           Bbar.as<double>(), Cbar.as<double>(),
                                                           eigvals, dt, t, stream.as<double>());
     FFB_LAUNCHED(ctx);
@@ -1551,14 +1587,21 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
                                                                    DFMA_WARPS * 32, smem));
       return FFB_OK;
     };
-#define FFB_DFMA_DISPATCH(CALL)                                          \
-  switch (R) {                                                          \
-    case 4: if (d == 2) { CALL(4, 1); } else { CALL(4, 3); } break;     \
-    case 8: if (d == 2) { CALL(8, 1); } else { CALL(8, 3); } break;     \
-    case 12: if (d == 2) { CALL(12, 1); } else { CALL(12, 3); } break;  \
-    default: if (d == 2) { CALL(16, 1); } else { CALL(16, 3); } break;  \
+#define FFB_DFMA_DISPATCH(CALL)                                                        \
+  if (split) {                                                                        \
+    if (d == 3) { CALL(12, 8, 3); }                                                   \
+    else if (R == 8) { CALL(8, 6, 1); }                                               \
+    else if (R == 12) { CALL(12, 9, 1); }                                             \
+    else { CALL(16, 12, 1); }                                                         \
+  } else {                                                                            \
+    switch (R) {                                                                      \
+      case 4: if (d == 2) { CALL(4, 4, 1); } else { CALL(4, 4, 3); } break;           \
+      case 8: if (d == 2) { CALL(8, 8, 1); } else { CALL(8, 8, 3); } break;           \
+      case 12: if (d == 2) { CALL(12, 12, 1); } else { CALL(12, 12, 3); } break;      \
+      default: if (d == 2) { CALL(16, 16, 1); } else { CALL(16, 16, 3); } break;      \
+    }                                                                                 \
   }
-#define FFB_DFMA_PICK(R_, NP_) FFB_TRY(pick(ctrlmat_dfma_kernel<R_, NP_>))
+#define FFB_DFMA_PICK(R_, RF_, NP_) FFB_TRY(pick(ctrlmat_dfma_kernel<R_, RF_, NP_>))
     FFB_DFMA_DISPATCH(FFB_DFMA_PICK)
     blocks_per_sm = std::max(1, blocks_per_sm);
     // split the segment axis over CTAs so that whole waves of CTAs are filled (same cost model as below)
@@ -1588,15 +1631,15 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
     int slot = -1;
     FFB_TRY(ffb_time_begin(ctx, &slot));
     const TrigConsts tc = trig_consts();
-#define FFB_DFMA_LAUNCH(R_, NP_) \
-  ctrlmat_dfma_kernel<R_, NP_><<<grid, DFMA_WARPS * 32, smem, ctx->stream>>>(q, tc)
+#define FFB_DFMA_LAUNCH(R_, RF_, NP_) \
+  ctrlmat_dfma_kernel<R_, RF_, NP_><<<grid, DFMA_WARPS * 32, smem, ctx->stream>>>(q, tc)
     FFB_DFMA_DISPATCH(FFB_DFMA_LAUNCH)
     FFB_LAUNCHED(ctx);
     FFB_TRY(ffb_time_end(ctx, slot));
     const size_t total_out = (size_t)n_nops * n_basis * n_omega;
     const unsigned fblocks = (unsigned)std::min<size_t>(ceil_div_sz(total_out, 256), (size_t)ctx->sm_count * 16);
     finalize_kernel<<<fblocks, 256, 0, ctx->stream>>>(S, R, n_nops, n_basis, parts_j, parts_k, n_omega,
-                                                      ld_out, partial.as<double>(), out);
+                                                      ld_out, split ? RF : 0, partial.as<double>(), out);
     FFB_LAUNCHED(ctx);
     return FFB_OK;
   }
@@ -1706,7 +1749,7 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
     const size_t total = (size_t)n_nops * n_basis * n_omega;
     const unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total, 256), (size_t)ctx->sm_count * 16);
     finalize_kernel<<<blocks, 256, 0, ctx->stream>>>(S, rows_pad, n_nops, n_basis, parts_j, parts_k,
-                                                     n_omega, ld_out, partial.as<double>(), out);
+                                                     n_omega, ld_out, 0, partial.as<double>(), out);
     FFB_LAUNCHED(ctx);
   }
   return FFB_OK;

@@ -45,7 +45,9 @@ class DevicePulse:
 
         def herm(m):
             return bool((m == m.conj().swapaxes(-1, -2)).all())
-        self.herm_flags = (1 if herm(n_opers) else 0) | (2 if herm(basis) else 0)
+        b0 = np.asarray(basis[0])
+        ident0 = bool((b0 == b0[0, 0].real*np.eye(self.d)).all())   # exactly c * identity, c real
+        self.herm_flags = (1 if herm(n_opers) else 0) | (2 if herm(basis) else 0) | (4 if ident0 else 0)
 
         up = self._upload
         self.c_opers, self.n_opers, self.basis = up(c_opers), up(n_opers), up(basis)

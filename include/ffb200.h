@@ -257,10 +257,13 @@ int ffb_dev_decay_amplitudes(ffb_ctx* ctx, int P, int n_nops, int n_sel, const i
                              int spectrum_ndim, int spectrum_is_complex, const double* omega,
                              double* out);
 /* herm_flags for ffb_dev_control_matrix_from_scratch: bit 0 = all noise operators exactly
- * Hermitian, bit 1 = all basis elements exactly Hermitian (the host entry point checks this itself;
- * pass 0 if unknown -- always correct, up to 4x more rows). */
+ * Hermitian, bit 1 = all basis elements exactly Hermitian, bit 2 = basis element 0 is exactly a real
+ * multiple of the identity (Basis.pauli, Basis.ggm: its rows of the control matrix only have the
+ * level-diagonal term, sum_g s_j tr(B_j)/sqrt(d) e^{i w t} I(w); the host entry points check all
+ * three themselves; pass 0 if unknown -- always correct, only more work). */
 #define FFB_HERM_NOPERS 1
 #define FFB_HERM_BASIS 2
+#define FFB_BASIS_IDENTITY0 4
 
 /* Raw device memory for the callers of ffb_dev_* that do not bring their own (e.g. torch). */
 int ffb_dev_alloc(ffb_ctx* ctx, size_t bytes, void** ptr);
