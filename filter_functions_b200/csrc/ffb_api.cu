@@ -404,6 +404,7 @@ int enter(ffb_ctx* ctx) {
 // reused by the next call (every host-pointer entry point is synchronous on return).
 struct PackedUpload {
   static constexpr size_t ALIGN = 256;
+  static constexpr size_t PACK_LIMIT = (size_t)512 << 10;  // larger parts are copied from where they lie
   std::vector<const void*> src;
   std::vector<size_t> bytes, offset;
   size_t total = 0;
@@ -425,15 +426,46 @@ struct PackedUpload {
       ctx->stage_bytes = want;
     }
     char* stage = static_cast<char*>(ctx->stage_host);
-    for (size_t i = 0; i < src.size(); ++i)
-      if (bytes[i]) std::memcpy(stage + offset[i], src[i], bytes[i]);
+    char* d0 = nullptr;
     FFB_TRY(dev.alloc(ctx, total));
-    return ffb_h2d(ctx, dev.p, stage, total);
+    d0 = static_cast<char*>(dev.p);
+    // the device block mirrors the staging layout: runs of consecutive small parts travel in one copy
+    // out of the staging block, a large part in its own copy straight from the caller's array (which
+    // is page-locked already when it is one of the library's result arrays)
+    size_t run_begin = 0, run_end = 0;
+    auto flush = [&]() -> int {
+      if (run_end > run_begin) FFB_TRY(ffb_h2d(ctx, d0 + run_begin, stage + run_begin, run_end - run_begin));
+      return FFB_OK;
+    };
+    for (size_t i = 0; i < src.size(); ++i) {
+      if (!bytes[i]) continue;
+      if (bytes[i] <= PACK_LIMIT) {
+        std::memcpy(stage + offset[i], src[i], bytes[i]);
+        if (run_end == run_begin) run_begin = offset[i];
+        run_end = offset[i] + bytes[i];
+      } else {
+        FFB_TRY(flush());
+        run_begin = run_end = 0;
+        FFB_TRY(ffb_h2d(ctx, d0 + offset[i], src[i], bytes[i]));
+      }
+    }
+    return flush();
   }
   const double* d(int i) const {
     return reinterpret_cast<const double*>(static_cast<const char*>(dev.p) + offset[i]);
   }
 };
+
+// number of frequency blocks of a pipeline that returns out_bytes of frequency-dependent results
+// (measured on B200, e2e ms with 1 / 2 / 4 / 8 blocks: config 2 (3.4 MB) 1.37 / 1.38 / 1.44 / 1.55, d4
+// (21 MB) 17.65 / 17.29 / 17.73 / 18.07, config 3 (105 MB) 18.74 / 18.39 / 17.46 / 17.48 -- a block pays
+// off from ~10 MB of results per block)
+int pipeline_blocks(size_t out_bytes, int n_omega) {
+  int n = (int)std::min<size_t>(4, std::max<size_t>(1, out_bytes / ((size_t)10 << 20)));
+  n = std::max(1, std::min(n, n_omega / 2048));
+  if (const char* e = getenv("FFB_PIPELINE_BLOCKS")) n = std::max(1, atoi(e));
+  return n;
+}
 
 int ensure_copy_stream(ffb_ctx* ctx) {
   if (ctx->copy_stream) return FFB_OK;
@@ -494,23 +526,51 @@ int ffb_control_matrix_from_scratch(ffb_ctx* ctx, int G, int d, int n_nops, int 
   const size_t dd = (size_t)d * d;
   const int herm = (all_hermitian(n_opers, n_nops, d) ? FFB_HERM_NOPERS : 0) |
                    basis_flags(basis, n_basis, d);
-  Upload ev, V, Q, om, bs, no, nc, dts, ts;
+  FFB_TRY(ensure_copy_stream(ctx));
+  static const bool trace = getenv("FFB_TRACE") && atoi(getenv("FFB_TRACE")) != 0;
+  const auto t_enter = std::chrono::steady_clock::now();
+  auto since = [&]() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_enter).count();
+  };
+  PackedUpload in;
   DevBuf B;
-  FFB_TRY(ev.put(ctx, eigvals, (size_t)G * d * 8));
-  FFB_TRY(V.put(ctx, eigvecs, (size_t)G * dd * 16));
-  FFB_TRY(Q.put(ctx, propagators, (size_t)G * dd * 16));  // Q_G (the last one) is not needed
-  FFB_TRY(om.put(ctx, omega, (size_t)n_omega * 8));
-  FFB_TRY(bs.put(ctx, basis, (size_t)n_basis * dd * 16));
-  FFB_TRY(no.put(ctx, n_opers, (size_t)n_nops * dd * 16));
-  FFB_TRY(nc.put(ctx, n_coeffs, (size_t)n_nops * G * 8));
-  FFB_TRY(dts.put(ctx, dt, (size_t)G * 8));
-  FFB_TRY(ts.put(ctx, t, (size_t)(G + 1) * 8));
+  CopyStreamDrain drain{ctx};
+  const int i_ev = in.add(eigvals, (size_t)G * d * 8);
+  const int i_V = in.add(eigvecs, (size_t)G * dd * 16);
+  const int i_Q = in.add(propagators, (size_t)G * dd * 16);  // Q_G (the last one) is not needed
+  const int i_om = in.add(omega, (size_t)n_omega * 8);
+  const int i_bs = in.add(basis, (size_t)n_basis * dd * 16);
+  const int i_no = in.add(n_opers, (size_t)n_nops * dd * 16);
+  const int i_nc = in.add(n_coeffs, (size_t)n_nops * G * 8);
+  const int i_dt = in.add(dt, (size_t)G * 8);
+  const int i_ts = in.add(t, (size_t)(G + 1) * 8);
+  FFB_TRY(in.upload(ctx));
   const size_t out_bytes = (size_t)n_nops * n_basis * n_omega * 16;
   FFB_TRY(B.alloc(ctx, out_bytes));
-  FFB_TRY(ffbi_control_matrix(ctx, G, d, n_nops, n_basis, n_omega, ev.d(), V.d(), Q.d(), om.d(),
-                              bs.d(), no.d(), nc.d(), dts.d(), ts.d(), herm, B.as<double>()));
-  FFB_TRY(ffb_d2h(ctx, out, B.p, out_bytes));
+  // the rows of a finished block of frequencies are downloaded while the next block is computed
+  cudaStream_t cs = ctx->copy_stream;
+  const size_t pitch = (size_t)n_omega * 16;
+  FreqBlocks fb;
+  fb.n_blocks = pipeline_blocks(out_bytes, n_omega);
+  fb.after_block = [&](int w0, int w1) -> int {
+    FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[1], ctx->stream));
+    FFB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->copy_ev[1], 0));
+    FFB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<char*>(out) + (size_t)w0 * 16, pitch,
+                                    static_cast<const char*>(B.p) + (size_t)w0 * 16, pitch,
+                                    (size_t)(w1 - w0) * 16, (size_t)n_nops * n_basis,
+                                    cudaMemcpyDeviceToHost, cs));
+    return FFB_OK;
+  };
+  FFB_TRY(ffbi_control_matrix(ctx, G, d, n_nops, n_basis, n_omega, in.d(i_ev), in.d(i_V), in.d(i_Q),
+                              in.d(i_om), in.d(i_bs), in.d(i_no), in.d(i_nc), in.d(i_dt), in.d(i_ts),
+                              herm, B.as<double>(), &fb));
+  const double us_enqueued = since();
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const double us_main = since();
+  FFB_CUDA(ctx, cudaStreamSynchronize(cs));
+  if (trace)
+    fprintf(stderr, "[ffb trace] control matrix: all work enqueued %.0f us, main stream done %.0f us, "
+            "copy stream done %.0f us (%d blocks)\n", us_enqueued, us_main, since(), fb.n_blocks);
   return FFB_OK;
 }
 
@@ -1087,12 +1147,7 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
   // 105 MB, 1.9 ms at 56 GB/s)
   const size_t out_bytes = (control_matrix ? b_bytes : 0) + (filter_function ? f_bytes : 0);
   FreqBlocks fb;
-  // measured on B200 (e2e ms with 1 / 2 / 4 / 8 blocks): config 2 (3.4 MB) 1.37 / 1.38 / 1.44 / 1.55,
-  // d4 (21 MB) 17.65 / 17.29 / 17.73 / 18.07, config 3 (105 MB) 18.74 / 18.39 / 17.46 / 17.48 -- a block
-  // pays off from ~10 MB of results per block
-  fb.n_blocks = (int)std::min<size_t>(4, std::max<size_t>(1, out_bytes / ((size_t)10 << 20)));
-  fb.n_blocks = std::max(1, std::min(fb.n_blocks, n_omega / 2048));
-  if (const char* e = getenv("FFB_PIPELINE_BLOCKS")) fb.n_blocks = std::max(1, atoi(e));
+  fb.n_blocks = pipeline_blocks(out_bytes, n_omega);
   const size_t pitch = (size_t)n_omega * 16;
   fb.after_block = [&](int w0, int w1) -> int {
     const size_t off = (size_t)w0 * 16, width = (size_t)(w1 - w0) * 16;
