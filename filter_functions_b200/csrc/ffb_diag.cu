@@ -180,6 +180,158 @@ diag_kernel(int G, int d, int n_cops, const double* __restrict__ c_opers,
   }
 }
 
+// ---- small matrices (d <= 4): one THREAD per segment, H and V in registers -------------------------
+// The warp-per-segment kernel above spends its time in warp synchronisation and in scalar work that
+// all 32 lanes repeat (hypot, three divisions and two square roots per rotation): 17.5 us for the 1e4
+// 2 x 2 matrices of config 2.  For d <= 4 the whole cyclic Jacobi iteration fits the registers of one
+// thread (fully unrolled, same rotation formulas, same convergence test, same stable ascending
+// order), so a segment costs one thread instead of one warp.
+template <int D>
+__global__ void __launch_bounds__(128)
+diag_small_kernel(int G, int n_cops, const double* __restrict__ c_opers,
+                  const double* __restrict__ c_coeffs, const double* __restrict__ dt,
+                  double* __restrict__ eigvals, double* __restrict__ eigvecs,
+                  double* __restrict__ piecewise, int* __restrict__ not_converged) {
+  constexpr int DD = D * D;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  cplx H[D][D], V[D][D];
+  // ---- H_g (lower triangle is authoritative, as LAPACK's UPLO='L' in numpy.linalg.eigh)
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      cplx h = {0.0, 0.0};
+      if (c_coeffs != nullptr) {
+        for (int i = 0; i < n_cops; ++i) {
+          const double a = c_coeffs[(size_t)i * G + g];
+          h.re += a * c_opers[2 * ((size_t)i * DD + r * D + c)];
+          h.im += a * c_opers[2 * ((size_t)i * DD + r * D + c) + 1];
+        }
+      } else {
+        h.re = c_opers[2 * ((size_t)g * DD + r * D + c)];
+        h.im = c_opers[2 * ((size_t)g * DD + r * D + c) + 1];
+      }
+      H[r][c] = h;
+      V[r][c] = cplx{r == c ? 1.0 : 0.0, 0.0};
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+    H[r][r].im = 0.0;
+#pragma unroll
+    for (int c = r + 1; c < D; ++c) H[r][c] = cconj(H[c][r]);
+  }
+  double norm2 = 0.0;
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) norm2 += H[r][c].re * H[r][c].re + H[r][c].im * H[r][c].im;
+
+  // ---- cyclic Jacobi sweeps
+  bool converged = (D == 1);
+  for (int sweep = 0; sweep < MAX_SWEEPS && !converged; ++sweep) {
+    double off = 0.0;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = r + 1; c < D; ++c) off += H[r][c].re * H[r][c].re + H[r][c].im * H[r][c].im;
+    if (off <= 1e-34 * norm2 || off == 0.0) {
+      converged = true;
+      break;
+    }
+#pragma unroll
+    for (int p = 0; p < D - 1; ++p) {
+#pragma unroll
+      for (int q = p + 1; q < D; ++q) {
+        const cplx h = H[p][q];
+        const double beta = hypot(h.re, h.im);
+        if (beta != 0.0) {
+          const cplx w = {h.re / beta, h.im / beta};
+          const double a = H[p][p].re, b = H[q][q].re;
+          const double tau = (b - a) / (2.0 * beta);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          const double c = 1.0 / sqrt(1.0 + t * t);
+          const double s = t * c;
+          const cplx swc = {s * w.re, -s * w.im};  // s * conj(w)
+          const cplx cwc = {c * w.re, -c * w.im};  // c * conj(w)
+          // columns p, q of H and V
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            cplx xp = H[k][p], xq = H[k][q];
+            cplx a1 = cmul(swc, xq), a2 = cmul(cwc, xq);
+            H[k][p] = cplx{c * xp.re - a1.re, c * xp.im - a1.im};
+            H[k][q] = cplx{s * xp.re + a2.re, s * xp.im + a2.im};
+            xp = V[k][p];
+            xq = V[k][q];
+            a1 = cmul(swc, xq);
+            a2 = cmul(cwc, xq);
+            V[k][p] = cplx{c * xp.re - a1.re, c * xp.im - a1.im};
+            V[k][q] = cplx{s * xp.re + a2.re, s * xp.im + a2.im};
+          }
+          // rows p, q of H
+          const cplx sw = {s * w.re, s * w.im}, cw = {c * w.re, c * w.im};
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            const cplx yp = H[p][k], yq = H[q][k];
+            const cplx a1 = cmul(sw, yq), a2 = cmul(cw, yq);
+            H[p][k] = cplx{c * yp.re - a1.re, c * yp.im - a1.im};
+            H[q][k] = cplx{s * yp.re + a2.re, s * yp.im + a2.im};
+          }
+          H[p][q] = cplx{0.0, 0.0};
+          H[q][p] = cplx{0.0, 0.0};
+          H[p][p].im = 0.0;
+          H[q][q].im = 0.0;
+        }
+      }
+    }
+  }
+  if (!converged) atomicAdd(not_converged, 1);
+
+  // ---- ascending order (stable), as numpy.linalg.eigh returns them: rank of every eigenvalue
+  double ev[D];
+  int rank[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) ev[j] = H[j][j].re;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    int rk = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) rk += (ev[i] < ev[j]) || (ev[i] == ev[j] && i < j);
+    rank[j] = rk;
+  }
+#pragma unroll
+  for (int j = 0; j < D; ++j) {  // column j of V goes to position rank[j] (compile-time register indices)
+    eigvals[(size_t)g * D + rank[j]] = ev[j];
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      eigvecs[2 * ((size_t)g * DD + r * D + rank[j])] = V[r][j].re;
+      eigvecs[2 * ((size_t)g * DD + r * D + rank[j]) + 1] = V[r][j].im;
+    }
+  }
+
+  // ---- P_g = V exp(-i D dt) V^dagger  (order of eigenpairs is irrelevant here)
+  const double dtg = dt[g];
+  double cs[D], sn[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) sincos(-dtg * ev[j], &sn[j], &cs[j]);
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      cplx acc = {0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const cplx vv = cmulc(V[r][j], V[c][j]);
+        acc.re += vv.re * cs[j] - vv.im * sn[j];
+        acc.im += vv.re * sn[j] + vv.im * cs[j];
+      }
+      piecewise[2 * ((size_t)g * DD + r * D + c)] = acc.re;
+      piecewise[2 * ((size_t)g * DD + r * D + c) + 1] = acc.im;
+    }
+  }
+}
+
 // ---- parallel scan of Q_{g+1} = P_g Q_g -----------------------------------------------------------
 // phase A: warp c forms the running products inside chunk c: local[g+1] = P_g ... P_{c*L}, written to
 //          propagators[g+1]; the chunk total goes to totals[c].
@@ -438,7 +590,20 @@ int ffbi_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_ope
   FFB_TRY(flag.alloc(ctx, sizeof(int)));
   FFB_CUDA(ctx, cudaMemsetAsync(flag.p, 0, sizeof(int), ctx->stream));
 
-  {
+  static const bool small_ok = !(getenv("FFB_DIAG_SMALL") && atoi(getenv("FFB_DIAG_SMALL")) == 0);
+  if (d >= 2 && d <= 4 && small_ok) {
+    const unsigned nb = (unsigned)ceil_div(G, 128);
+    if (d == 2)
+      diag_small_kernel<2><<<nb, 128, 0, ctx->stream>>>(G, n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs,
+                                                        piecewise.as<double>(), flag.as<int>());
+    else if (d == 3)
+      diag_small_kernel<3><<<nb, 128, 0, ctx->stream>>>(G, n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs,
+                                                        piecewise.as<double>(), flag.as<int>());
+    else
+      diag_small_kernel<4><<<nb, 128, 0, ctx->stream>>>(G, n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs,
+                                                        piecewise.as<double>(), flag.as<int>());
+    FFB_LAUNCHED(ctx);
+  } else {
     const size_t smem = (size_t)DIAG_WARPS * (4 * dd + 2 * d) * sizeof(double);
     FFB_CUDA(ctx, cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
