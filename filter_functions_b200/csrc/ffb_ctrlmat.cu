@@ -287,18 +287,16 @@ transform_kernel(int G, int d, int n_nops, int n_basis, int parts_j, int parts_k
 // Small Hilbert spaces (d <= 4): one THREAD per (segment, operator), everything in registers.  The
 // block-per-segment kernel above spends its time in __syncthreads for 2x2 matrices (66 us for
 // G = 1e4, d = 2 in the first version).
+// transform of ONE operator of ONE segment: op < n_nops -> s_op V^+ B_op V, else U^+ C_{op - n_nops} U with
+// U = Q_g^+ V_g; the Hermitian part (and, if parts == 2, the anti-Hermitian part / i) go to dst
 template <int D>
-__global__ void __launch_bounds__(128)
-transform_small_kernel(int G, int n_nops, int n_basis, int parts_j, int parts_k,
-                       const double2* __restrict__ eigvecs, const double2* __restrict__ propagators,
-                       const double2* __restrict__ n_opers, const double* __restrict__ n_coeffs,
-                       const double2* __restrict__ basis, double2* __restrict__ Bbar,
-                       double2* __restrict__ Cbar) {
+__device__ __forceinline__ void transform_small_one(int G, int g, int op, int n_nops, int parts,
+                                                    const double2* __restrict__ eigvecs,
+                                                    const double2* __restrict__ propagators,
+                                                    const double2* __restrict__ n_opers,
+                                                    const double* __restrict__ n_coeffs,
+                                                    const double2* __restrict__ basis, double2* dst) {
   constexpr int DD = D * D;
-  const int n_ops = n_nops + n_basis;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)G * n_ops) return;
-  const int g = (int)(idx / n_ops), op = (int)(idx % n_ops);
   const bool is_noise = op < n_nops;
   double2 W[DD];
   {
@@ -359,10 +357,7 @@ transform_small_kernel(int G, int n_nops, int n_basis, int parts_j, int parts_k,
       X[a * D + b] = make_double2(re, im);
     }
   }
-  const int parts = is_noise ? parts_j : parts_k;
   const double scale = is_noise ? n_coeffs[(size_t)op * G + g] : 1.0;
-  double2* dst = is_noise ? Bbar + ((size_t)g * n_nops * parts_j + (size_t)op * parts_j) * DD
-                          : Cbar + ((size_t)g * n_basis * parts_k + (size_t)(op - n_nops) * parts_k) * DD;
 #pragma unroll
   for (int a = 0; a < D; ++a) {
 #pragma unroll
@@ -374,6 +369,25 @@ transform_small_kernel(int G, int n_nops, int n_basis, int parts_j, int parts_k,
       }
     }
   }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128)
+transform_small_kernel(int G, int n_nops, int n_basis, int parts_j, int parts_k,
+                       const double2* __restrict__ eigvecs, const double2* __restrict__ propagators,
+                       const double2* __restrict__ n_opers, const double* __restrict__ n_coeffs,
+                       const double2* __restrict__ basis, double2* __restrict__ Bbar,
+                       double2* __restrict__ Cbar) {
+  constexpr int DD = D * D;
+  const int n_ops = n_nops + n_basis;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)G * n_ops) return;
+  const int g = (int)(idx / n_ops), op = (int)(idx % n_ops);
+  const bool is_noise = op < n_nops;
+  double2* dst = is_noise ? Bbar + ((size_t)g * n_nops * parts_j + (size_t)op * parts_j) * DD
+                          : Cbar + ((size_t)g * n_basis * parts_k + (size_t)(op - n_nops) * parts_k) * DD;
+  transform_small_one<D>(G, g, op, n_nops, is_noise ? parts_j : parts_k, eigvecs, propagators, n_opers,
+                         n_coeffs, basis, dst);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1121,61 +1135,102 @@ __host__ __device__ inline int dfma_row_of_slot(int slot, int rows, int RF, bool
   return slot - RF < n_jrows ? (slot - RF) * n_krows : -1;
 }
 
+// element `off` of the record of a segment; Bseg / Cseg = the segment's transformed noise operators
+// [n_jrows][d*d] and basis elements [n_krows][d*d] (complex, interleaved), ev = its eigenvalues
+__device__ __forceinline__ double dfma_record_value(int off, int d, int rows, int R, int RF, bool split,
+                                                    int n_jrows, int n_krows, const double* Bseg,
+                                                    const double* Cseg, const double* ev, double tg,
+                                                    double dtg) {
+  const int dd = d * d;
+  const int RFP = (RF + 1) & ~1;
+  if (off < 2) return off == 0 ? tg : dtg;
+  if (off < 2 + R) {
+    const int row = dfma_row_of_slot(off - 2, rows, RF, split, n_jrows, n_krows);
+    if (row < 0) return 0.0;
+    const double* Bm = Bseg + (size_t)(row / n_krows) * 2 * dd;
+    const double* Cm = Cseg + (size_t)(row % n_krows) * 2 * dd;
+    double acc = 0.0;
+    for (int m = 0; m < d; ++m) acc += Bm[2 * (m * d + m)] * Cm[2 * (m * d + m)];
+    return acc;
+  }
+  off -= 2 + R;
+  const int pair = off / (4 + 2 * RFP);
+  off %= 4 + 2 * RFP;
+  int m, n;
+  pair_from_index(pair, d, m, n);
+  if (off < 4) {
+    const double Om = ev[m] - ev[n];
+    if (off == 0) return Om;
+    if (off == 3) return 0.0;
+    double sn, cs;
+    sincos(0.5 * (Om * dtg), &sn, &cs);
+    return off == 1 ? cs : sn;
+  }
+  const int col = (off - 4) / RFP, slot = (off - 4) % RFP;
+  const int row = slot < RF ? dfma_row_of_slot(slot, rows, RF, split, n_jrows, n_krows) : -1;
+  if (row < 0) return 0.0;
+  const double* Bm = Bseg + (size_t)(row / n_krows) * 2 * dd;
+  const double* Cm = Cseg + (size_t)(row % n_krows) * 2 * dd;
+  const cplx b = {Bm[2 * (m * d + n)], Bm[2 * (m * d + n) + 1]};
+  const cplx c = {Cm[2 * (n * d + m)], Cm[2 * (n * d + m) + 1]};
+  const cplx prod = cmul(b, c);
+  return col == 0 ? prod.re : prod.im;
+}
+
 __global__ void __launch_bounds__(256)
 assemble_dfma_kernel(int G, int d, int rows, int R, int RF, int split, int n_jrows, int n_krows,
                      const double* __restrict__ Bbar, const double* __restrict__ Cbar,
                      const double* __restrict__ eigvals, const double* __restrict__ dt,
                      const double* __restrict__ t, double* __restrict__ stream) {
-  const int n_pairs = d * (d - 1) / 2;
-  const int RFP = (RF + 1) & ~1;
-  const int rec = dfma_rec_doubles(R, RF, n_pairs);
+  const int rec = dfma_rec_doubles(R, RF, d * (d - 1) / 2);
   const size_t total = (size_t)G * rec;
   const int dd = d * d;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const int g = (int)(idx / rec);
-    int off = (int)(idx % rec);
-    double val = 0.0;
-    if (off < 2) {
-      val = off == 0 ? t[g] : dt[g];
-    } else if (off < 2 + R) {
-      const int row = dfma_row_of_slot(off - 2, rows, RF, split != 0, n_jrows, n_krows);
-      if (row >= 0) {
-        const double* Bm = Bbar + ((size_t)g * n_jrows + row / n_krows) * 2 * dd;
-        const double* Cm = Cbar + ((size_t)g * n_krows + row % n_krows) * 2 * dd;
-        double acc = 0.0;
-        for (int m = 0; m < d; ++m) acc += Bm[2 * (m * d + m)] * Cm[2 * (m * d + m)];
-        val = acc;
-      }
-    } else {
-      off -= 2 + R;
-      const int pair = off / (4 + 2 * RFP);
-      off %= 4 + 2 * RFP;
-      int m, n;
-      pair_from_index(pair, d, m, n);
-      if (off < 4) {
-        const double Om = eigvals[(size_t)g * d + m] - eigvals[(size_t)g * d + n];
-        if (off == 0) {
-          val = Om;
-        } else if (off < 3) {
-          double sn, cs;
-          sincos(0.5 * (Om * dt[g]), &sn, &cs);
-          val = off == 1 ? cs : sn;
-        }
-      } else {
-        const int col = (off - 4) / RFP, slot = (off - 4) % RFP;
-        const int row = slot < RF ? dfma_row_of_slot(slot, rows, RF, split != 0, n_jrows, n_krows) : -1;
-        if (row >= 0) {
-          const double* Bm = Bbar + ((size_t)g * n_jrows + row / n_krows) * 2 * dd;
-          const double* Cm = Cbar + ((size_t)g * n_krows + row % n_krows) * 2 * dd;
-          const cplx b = {Bm[2 * (m * d + n)], Bm[2 * (m * d + n) + 1]};
-          const cplx c = {Cm[2 * (n * d + m)], Cm[2 * (n * d + m) + 1]};
-          const cplx prod = cmul(b, c);
-          val = col == 0 ? prod.re : prod.im;
-        }
-      }
-    }
-    stream[idx] = val;
+    stream[idx] = dfma_record_value((int)(idx % rec), d, rows, R, RF, split != 0, n_jrows, n_krows,
+                                    Bbar + (size_t)g * n_jrows * 2 * dd,
+                                    Cbar + (size_t)g * n_krows * 2 * dd, eigvals + (size_t)g * d, t[g],
+                                    dt[g]);
+  }
+}
+
+// Fused prologue of the DFMA path (d <= 3): a block transforms the operators of DFMA_PRO_SEGS segments
+// into shared memory (thread per (segment, operator), registers) and writes their records, which are
+// contiguous in the stream -- one launch instead of two, and Bbar / Cbar never touch HBM
+// (transform_small_kernel 5.6 us + assemble_dfma_kernel 10.9 us for config 2).
+constexpr int DFMA_PRO_SEGS = 16;
+template <int D>
+__global__ void __launch_bounds__(128)
+dfma_prologue_kernel(int G, int n_nops, int n_basis, int parts_j, int parts_k, int rows, int R, int RF,
+                     int split, const double2* __restrict__ eigvecs,
+                     const double2* __restrict__ propagators, const double2* __restrict__ n_opers,
+                     const double* __restrict__ n_coeffs, const double2* __restrict__ basis,
+                     const double* __restrict__ eigvals, const double* __restrict__ dt,
+                     const double* __restrict__ t, double* __restrict__ stream) {
+  extern __shared__ __align__(16) double2 xs[];  // [DFMA_PRO_SEGS][n_jrows + n_krows][D*D]
+  constexpr int DD = D * D;
+  const int n_ops = n_nops + n_basis;
+  const int n_jrows = n_nops * parts_j, n_krows = n_basis * parts_k;
+  const int per_seg = (n_jrows + n_krows) * DD;
+  const int seg0 = blockIdx.x * DFMA_PRO_SEGS;
+  const int n_seg = min(DFMA_PRO_SEGS, G - seg0);
+  for (int idx = threadIdx.x; idx < n_seg * n_ops; idx += blockDim.x) {
+    const int sl = idx / n_ops, op = idx % n_ops;
+    const bool is_noise = op < n_nops;
+    double2* dst = xs + (size_t)sl * per_seg +
+                   (is_noise ? op * parts_j : n_jrows + (op - n_nops) * parts_k) * DD;
+    transform_small_one<D>(G, seg0 + sl, op, n_nops, is_noise ? parts_j : parts_k, eigvecs, propagators,
+                           n_opers, n_coeffs, basis, dst);
+  }
+  __syncthreads();
+  const int rec = dfma_rec_doubles(R, RF, D * (D - 1) / 2);
+  double* out = stream + (size_t)seg0 * rec;
+  for (int e = threadIdx.x; e < n_seg * rec; e += blockDim.x) {
+    const int sl = e / rec, g = seg0 + sl;
+    const double* Bseg = reinterpret_cast<const double*>(xs + (size_t)sl * per_seg);
+    out[e] = dfma_record_value(e % rec, D, rows, R, RF, split != 0, n_jrows, n_krows, Bseg,
+                               Bseg + (size_t)n_jrows * 2 * DD, eigvals + (size_t)g * D, t[g], dt[g]);
   }
 }
 
@@ -1513,13 +1568,32 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   const int RF = split ? n_nops * (n_basis - 1) : R;
   const int rec = dfma_rec_doubles(R, RF, d * (d - 1) / 2);
 
+  // DFMA path: transforms and records in one kernel (Bbar / Cbar stay in shared memory)
+  static const bool fused_ok = !(getenv("FFB_DFMA_FUSED_PROLOGUE") && atoi(getenv("FFB_DFMA_FUSED_PROLOGUE")) == 0);
+  const size_t pro_smem = (size_t)DFMA_PRO_SEGS * (n_jrows + n_krows) * dd * 16;
+  const bool fused_prologue = use_dfma && fused_ok && pro_smem <= 160 * 1024;
   DevBuf Bbar, Cbar, stream, partial;
-  FFB_TRY(Bbar.alloc(ctx, (size_t)G * n_jrows * dd * 16));
-  FFB_TRY(Cbar.alloc(ctx, (size_t)G * n_krows * dd * 16));
+  if (!fused_prologue) {
+    FFB_TRY(Bbar.alloc(ctx, (size_t)G * n_jrows * dd * 16));
+    FFB_TRY(Cbar.alloc(ctx, (size_t)G * n_krows * dd * 16));
+  }
   FFB_TRY(stream.alloc(ctx, use_dfma ? (size_t)G * rec * sizeof(double)
                                      : geo.rb_doubles * geo.n_rb * sizeof(double)));
 
-  if (d >= 2 && d <= 4) {
+  if (fused_prologue) {
+    auto launch = [&](auto kern) -> int {
+      FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pro_smem));
+      kern<<<ceil_div(G, DFMA_PRO_SEGS), 128, pro_smem, ctx->stream>>>(
+          G, n_nops, n_basis, parts_j, parts_k, rows, R, RF, split ? 1 : 0,
+          reinterpret_cast<const double2*>(eigvecs), reinterpret_cast<const double2*>(propagators),
+          reinterpret_cast<const double2*>(n_opers), n_coeffs, reinterpret_cast<const double2*>(basis),
+          eigvals, dt, t, stream.as<double>());
+      return FFB_OK;
+    };
+    if (d == 2) FFB_TRY(launch(dfma_prologue_kernel<2>));
+    else FFB_TRY(launch(dfma_prologue_kernel<3>));
+    FFB_LAUNCHED(ctx);
+  } else if (d >= 2 && d <= 4) {
     const long long n_threads = (long long)G * (n_nops + n_basis);
     const unsigned blocks = (unsigned)((n_threads + 127) / 128);
     auto args = [&](auto kern) {
@@ -1542,7 +1616,9 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
                                                     Bbar.as<double>(), Cbar.as<double>());
     FFB_LAUNCHED(ctx);
   }
-  if (use_dfma) {
+  if (fused_prologue) {
+    // records written by dfma_prologue_kernel
+  } else if (use_dfma) {
     const size_t total = (size_t)G * rec;
     const unsigned blocks = (unsigned)std::min<size_t>(ceil_div_sz(total, 256), (size_t)ctx->sm_count * 32);
     assemble_dfma_kernel<<<blocks, 256, 0, ctx->stream>>>(G, d, rows, R, RF, split ? 1 : 0, n_jrows, n_krows,

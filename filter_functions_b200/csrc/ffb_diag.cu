@@ -186,15 +186,16 @@ diag_kernel(int G, int d, int n_cops, const double* __restrict__ c_opers,
 // 2 x 2 matrices of config 2.  For d <= 4 the whole cyclic Jacobi iteration fits the registers of one
 // thread (fully unrolled, same rotation formulas, same convergence test, same stable ascending
 // order), so a segment costs one thread instead of one warp.
+// eigendecomposition of segment g (written to eigvals / eigvecs) and its propagator P (registers)
 template <int D>
-__global__ void __launch_bounds__(128)
-diag_small_kernel(int G, int n_cops, const double* __restrict__ c_opers,
-                  const double* __restrict__ c_coeffs, const double* __restrict__ dt,
-                  double* __restrict__ eigvals, double* __restrict__ eigvecs,
-                  double* __restrict__ piecewise, int* __restrict__ not_converged) {
+__device__ __forceinline__ void diag_small_one(int G, int g, int n_cops,
+                                               const double* __restrict__ c_opers,
+                                               const double* __restrict__ c_coeffs,
+                                               const double* __restrict__ dt,
+                                               double* __restrict__ eigvals,
+                                               double* __restrict__ eigvecs,
+                                               int* __restrict__ not_converged, double2 (&P)[D * D]) {
   constexpr int DD = D * D;
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= G) return;
   cplx H[D][D], V[D][D];
   // ---- H_g (lower triangle is authoritative, as LAPACK's UPLO='L' in numpy.linalg.eigh)
 #pragma unroll
@@ -326,10 +327,24 @@ diag_small_kernel(int G, int n_cops, const double* __restrict__ c_opers,
         acc.re += vv.re * cs[j] - vv.im * sn[j];
         acc.im += vv.re * sn[j] + vv.im * cs[j];
       }
-      piecewise[2 * ((size_t)g * DD + r * D + c)] = acc.re;
-      piecewise[2 * ((size_t)g * DD + r * D + c) + 1] = acc.im;
+      P[r * D + c] = make_double2(acc.re, acc.im);
     }
   }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128)
+diag_small_kernel(int G, int n_cops, const double* __restrict__ c_opers,
+                  const double* __restrict__ c_coeffs, const double* __restrict__ dt,
+                  double* __restrict__ eigvals, double* __restrict__ eigvecs,
+                  double* __restrict__ piecewise, int* __restrict__ not_converged) {
+  constexpr int DD = D * D;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  double2 P[DD];
+  diag_small_one<D>(G, g, n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs, not_converged, P);
+#pragma unroll
+  for (int e = 0; e < DD; ++e) reinterpret_cast<double2*>(piecewise)[(size_t)g * DD + e] = P[e];
 }
 
 // ---- parallel scan of Q_{g+1} = P_g Q_g -----------------------------------------------------------
@@ -474,18 +489,35 @@ __device__ __forceinline__ void matmul_reg(const double2 (&a)[D * D], const doub
   }
 }
 
+// arguments of the fused diagonalisation (in == nullptr: thread g first diagonalises segment g and
+// scans its propagator straight out of registers -- no diag launch, no piecewise array)
+struct DiagArgs {
+  int n_cops;
+  const double* c_opers;
+  const double* c_coeffs;
+  const double* dt;
+  double* eigvals;
+  double* eigvecs;
+  int* not_converged;
+};
+
 template <int D, int NT>
 __global__ void __launch_bounds__(NT)
 scan_block_kernel(int n, const double2* __restrict__ in, double2* __restrict__ local,
-                  double2* __restrict__ totals) {
+                  double2* __restrict__ totals, const DiagArgs da) {
   extern __shared__ double2 sbuf[];  // [2][D*D][NT], element-major so that lanes hit distinct banks
   constexpr int DD = D * D;
   const int i = threadIdx.x;
   const int g = blockIdx.x * NT + i;
   double2 m[DD];
   if (g < n) {
+    if (in != nullptr) {
 #pragma unroll
-    for (int e = 0; e < DD; ++e) m[e] = in[(size_t)g * DD + e];
+      for (int e = 0; e < DD; ++e) m[e] = in[(size_t)g * DD + e];
+    } else {
+      diag_small_one<D>(n, g, da.n_cops, da.c_opers, da.c_coeffs, da.dt, da.eigvals, da.eigvecs,
+                        da.not_converged, m);
+    }
   } else {  // identity padding
 #pragma unroll
     for (int e = 0; e < DD; ++e) m[e] = make_double2((e / D == e % D) ? 1.0 : 0.0, 0.0);
@@ -518,6 +550,59 @@ scan_block_kernel(int n, const double2* __restrict__ in, double2* __restrict__ l
 
 // out[i + shift] = local[i] * incl_totals[block(i) - 1]  (identity for block 0); with shift = 1 the
 // kernel also writes the identity to out[0] (the propagators array starts with Q_0 = 1).
+// Same, but the inclusive product of the block totals is formed HERE: thread 0 of the block multiplies
+// the totals of the source blocks before it (a chain of < SCAN_PREFIX_MAX register matmuls, ~1 us)
+// instead of two more launches for a scan over a few dozen matrices.  blockDim.x == NT.
+constexpr int SCAN_PREFIX_MAX = 96;
+template <int D, int NT>
+__global__ void __launch_bounds__(NT)
+scan_apply_prefix_kernel(int n, int shift, const double2* __restrict__ local,
+                         const double2* __restrict__ totals, double2* __restrict__ out) {
+  constexpr int DD = D * D;
+  __shared__ double2 prefix[DD];
+  __shared__ double2 tot[SCAN_PREFIX_MAX * DD];
+  const int blk = blockIdx.x;
+  const int g = blk * NT + threadIdx.x;
+  // the totals before this block come in with one coalesced load (a chain of dependent global loads
+  // would cost an L2 round trip per matrix), then one thread multiplies them up out of shared memory
+  for (int e = threadIdx.x; e < blk * DD; e += NT) tot[e] = totals[e];
+  __syncthreads();
+  if (threadIdx.x == 0 && blk > 0) {
+    double2 acc[DD], nxt[DD], prod[DD];
+#pragma unroll
+    for (int e = 0; e < DD; ++e) acc[e] = tot[e];
+    for (int b = 1; b < blk; ++b) {  // acc = T_b T_{b-1} ... T_0
+#pragma unroll
+      for (int e = 0; e < DD; ++e) nxt[e] = tot[b * DD + e];
+      matmul_reg<D>(nxt, acc, prod);
+#pragma unroll
+      for (int e = 0; e < DD; ++e) acc[e] = prod[e];
+    }
+#pragma unroll
+    for (int e = 0; e < DD; ++e) prefix[e] = acc[e];
+  }
+  if (g == 0 && shift) {
+#pragma unroll
+    for (int e = 0; e < DD; ++e) out[e] = make_double2((e / D == e % D) ? 1.0 : 0.0, 0.0);
+  }
+  __syncthreads();
+  if (g >= n) return;
+  double2 a[DD], r[DD];
+#pragma unroll
+  for (int e = 0; e < DD; ++e) a[e] = local[(size_t)g * DD + e];
+  if (blk == 0) {
+#pragma unroll
+    for (int e = 0; e < DD; ++e) r[e] = a[e];
+  } else {
+    double2 b[DD];
+#pragma unroll
+    for (int e = 0; e < DD; ++e) b[e] = prefix[e];
+    matmul_reg<D>(a, b, r);
+  }
+#pragma unroll
+  for (int e = 0; e < DD; ++e) out[(size_t)(g + shift) * DD + e] = r[e];
+}
+
 template <int D, int NT>
 __global__ void __launch_bounds__(256)
 scan_apply_small_kernel(int n, int shift, const double2* __restrict__ local,
@@ -548,7 +633,8 @@ scan_apply_small_kernel(int n, int shift, const double2* __restrict__ local,
 
 // inclusive scan of n matrices `in` -> out[i + shift]; recursive over the block totals
 template <int D, int NT>
-int scan_small(ffb_ctx* ctx, int n, const double2* in, double2* out, int shift) {
+int scan_small(ffb_ctx* ctx, int n, const double2* in, double2* out, int shift,
+               const DiagArgs& da = DiagArgs{}) {
   constexpr int DD = D * D;
   const int nb = ceil_div(n, NT);
   DevBuf local, totals, totals_incl;
@@ -557,8 +643,14 @@ int scan_small(ffb_ctx* ctx, int n, const double2* in, double2* out, int shift) 
   const size_t smem = (size_t)2 * DD * NT * sizeof(double2);
   auto kern = scan_block_kernel<D, NT>;
   FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<nb, NT, smem, ctx->stream>>>(n, in, local.as<double2>(), totals.as<double2>());
+  kern<<<nb, NT, smem, ctx->stream>>>(n, in, local.as<double2>(), totals.as<double2>(), da);
   FFB_LAUNCHED(ctx);
+  if (nb <= SCAN_PREFIX_MAX) {  // few blocks: their totals are combined inside the apply kernel
+    scan_apply_prefix_kernel<D, NT><<<nb, NT, 0, ctx->stream>>>(
+        n, shift, local.as<double2>(), totals.as<double2>(), out);
+    FFB_LAUNCHED(ctx);
+    return FFB_OK;
+  }
   if (nb > 1) {
     FFB_TRY(totals_incl.alloc(ctx, (size_t)nb * DD * 16));
     FFB_TRY((scan_small<D, NT>(ctx, nb, totals.as<double2>(), totals_incl.as<double2>(), 0)));
@@ -591,6 +683,14 @@ int ffbi_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_ope
   FFB_CUDA(ctx, cudaMemsetAsync(flag.p, 0, sizeof(int), ctx->stream));
 
   static const bool small_ok = !(getenv("FFB_DIAG_SMALL") && atoi(getenv("FFB_DIAG_SMALL")) == 0);
+  static const bool fuse_ok = !(getenv("FFB_DIAG_FUSED") && atoi(getenv("FFB_DIAG_FUSED")) == 0);
+  if (d >= 2 && d <= 4 && small_ok && fuse_ok) {
+    // diagonalisation fused into the block scan: thread per segment, propagator scanned from registers
+    const DiagArgs da{n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs, flag.as<int>()};
+    if (d == 2) return scan_small<2, 256>(ctx, G, nullptr, (double2*)propagators, 1, da);
+    if (d == 3) return scan_small<3, 128>(ctx, G, nullptr, (double2*)propagators, 1, da);
+    return scan_small<4, 128>(ctx, G, nullptr, (double2*)propagators, 1, da);
+  }
   if (d >= 2 && d <= 4 && small_ok) {
     const unsigned nb = (unsigned)ceil_div(G, 128);
     if (d == 2)
