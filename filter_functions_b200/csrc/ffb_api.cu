@@ -73,6 +73,32 @@ int ffb_d2h(ffb_ctx* ctx, void* dst, const void* src, size_t bytes) {
   return FFB_OK;
 }
 
+int ffb_conv_counter(ffb_ctx* ctx, int** dev) {
+  if (!ctx->conv_dev) {
+    FFB_CUDA(ctx, cudaMalloc(&ctx->conv_dev, sizeof(int)));
+    FFB_CUDA(ctx, cudaMemsetAsync(ctx->conv_dev, 0, sizeof(int), ctx->stream));
+    FFB_CUDA(ctx, cudaHostAlloc(&ctx->conv_host, sizeof(int), cudaHostAllocDefault));
+    *ctx->conv_host = 0;
+  }
+  *dev = ctx->conv_dev;
+  return FFB_OK;
+}
+
+int ffb_conv_fetch(ffb_ctx* ctx) {
+  if (!ctx->conv_dev) return FFB_OK;
+  FFB_CUDA(ctx, cudaMemcpyAsync(ctx->conv_host, ctx->conv_dev, sizeof(int), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_conv_check(ffb_ctx* ctx) {
+  if (!ctx->conv_dev || *ctx->conv_host == 0) return FFB_OK;
+  const int n = *ctx->conv_host;
+  *ctx->conv_host = 0;
+  FFB_CUDA(ctx, cudaMemsetAsync(ctx->conv_dev, 0, sizeof(int), ctx->stream));
+  return ffb_fail(ctx, FFB_ENOTCONV, "diagonalize: the Jacobi iteration did not converge for %d matrices", n);
+}
+
 int ffb_time_begin(ffb_ctx* ctx, int* slot) {
   *slot = -1;
   if (!ctx->timing) return FFB_OK;
@@ -158,6 +184,8 @@ void ffb_destroy(ffb_ctx* ctx) {
   for (auto& kv : ctx->host_live_blocks) cudaFreeHost(kv.first);
   if (ctx->trig_table) cudaFree(ctx->trig_table);
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+  if (ctx->conv_dev) cudaFree(ctx->conv_dev);
+  if (ctx->conv_host) cudaFreeHost(ctx->conv_host);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& ev : ctx->copy_ev)
     if (ev) cudaEventDestroy(ev);
@@ -178,8 +206,9 @@ int ffb_set_stream(ffb_ctx* ctx, void* cuda_stream, int external) {
 
 int ffb_sync(ffb_ctx* ctx) {
   if (!ctx) return FFB_EINVAL;
+  FFB_TRY(ffb_conv_fetch(ctx));  // device-resident callers learn about a non-converged eigensolver here
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return FFB_OK;
+  return ffb_conv_check(ctx);
 }
 
 int64_t ffb_launch_count(const ffb_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -508,8 +537,9 @@ int ffb_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_oper
   FFB_TRY(ffb_d2h(ctx, eigvals, ev.p, (size_t)G * d * 8));
   FFB_TRY(ffb_d2h(ctx, eigvecs, V.p, (size_t)G * dd * 16));
   FFB_TRY(ffb_d2h(ctx, propagators, Q.p, (size_t)(G + 1) * dd * 16));
+  FFB_TRY(ffb_conv_fetch(ctx));
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return FFB_OK;
+  return ffb_conv_check(ctx);
 }
 
 int ffb_control_matrix_from_scratch(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis,
@@ -1174,10 +1204,12 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
                             spectrum_ndim, spectrum_is_complex, in.d(i_om), d, I.as<double>()));
     FFB_TRY(ffb_d2h(ctx, infidelity, I.p, n_inf * 8));
   }
+  FFB_TRY(ffb_conv_fetch(ctx));
   us_enqueued = since();
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   us_main = since();
   FFB_CUDA(ctx, cudaStreamSynchronize(cs));
+  FFB_TRY(ffb_conv_check(ctx));
   if (trace)
     fprintf(stderr, "[ffb trace] pulse pipeline: inputs packed+upload enqueued %.0f us, all work enqueued "
             "%.0f us, main stream done %.0f us, copy stream done %.0f us\n", us_packed, us_enqueued,

@@ -33,6 +33,11 @@ struct ffb_ctx {
   // page-locked staging block: the small host inputs of a call are packed here and uploaded by ONE copy
   void* stage_host = nullptr;
   size_t stage_bytes = 0;
+  // eigensolver convergence: a device counter the Jacobi kernels bump for every matrix that did not
+  // converge (allocated and zeroed once), and its page-locked host mirror; the synchronous entry points
+  // fetch it with their last copies and return FFB_ENOTCONV (numpy.linalg.eigh raises LinAlgError)
+  int* conv_dev = nullptr;
+  int* conv_host = nullptr;
 
   // grow-only caching pool: freed blocks are kept and handed out again (best fit)
   std::multimap<size_t, void*> free_blocks;
@@ -106,6 +111,11 @@ struct DevBuf {
 };
 
 int ffb_h2d(ffb_ctx* ctx, void* dst, const void* src, size_t bytes);
+// convergence counter of the eigensolver: device pointer (created on first use); enqueue its download;
+// after a stream synchronisation: FFB_ENOTCONV (and reset) if any matrix failed to converge
+int ffb_conv_counter(ffb_ctx* ctx, int** dev);
+int ffb_conv_fetch(ffb_ctx* ctx);
+int ffb_conv_check(ffb_ctx* ctx);
 int ffb_d2h(ffb_ctx* ctx, void* dst, const void* src, size_t bytes);
 
 // timing hooks around the dominant kernel

@@ -140,10 +140,14 @@ diag_kernel(int G, int d, int n_cops, const double* __restrict__ c_opers,
       }
     }
   }
-  if (!converged && lane == 0) atomicAdd(not_converged, 1);
+  // (a NaN / Inf entry can "converge" because a rotation sets its pivot to exactly zero)
+  if ((!converged || !isfinite(norm2)) && lane == 0) atomicAdd(not_converged, 1);
 
   // ---- ascending order (stable), as numpy.linalg.eigh returns them
-  if (lane < d) ev[lane] = H[2 * (lane * d + lane)];
+  if (lane < d) {
+    ev[lane] = H[2 * (lane * d + lane)];
+    perm[lane] = lane;  // stays a valid permutation entry even if NaN eigenvalues make ranks collide
+  }
   __syncwarp();
   if (lane < d) {
     const double mine = ev[lane];
@@ -287,7 +291,8 @@ __device__ __forceinline__ void diag_small_one(int G, int g, int n_cops,
       }
     }
   }
-  if (!converged) atomicAdd(not_converged, 1);
+  // (a NaN / Inf entry can "converge" because a rotation sets its pivot to exactly zero)
+  if (!converged || !isfinite(norm2)) atomicAdd(not_converged, 1);
 
   // ---- ascending order (stable), as numpy.linalg.eigh returns them: rank of every eigenvalue
   double ev[D];
@@ -674,34 +679,33 @@ int ffbi_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_ope
   while ((long long)L * L < G && L < 256) L *= 2;
   const int n_chunks = ceil_div(G, L);
 
-  DevBuf piecewise, local, totals, prefix, flag;
-  FFB_TRY(piecewise.alloc(ctx, (size_t)G * dd * 16));
-  FFB_TRY(local.alloc(ctx, (size_t)(G + 1) * dd * 16));
-  FFB_TRY(totals.alloc(ctx, (size_t)n_chunks * dd * 16));
-  FFB_TRY(prefix.alloc(ctx, (size_t)n_chunks * dd * 16));
-  FFB_TRY(flag.alloc(ctx, sizeof(int)));
-  FFB_CUDA(ctx, cudaMemsetAsync(flag.p, 0, sizeof(int), ctx->stream));
-
+  int* conv = nullptr;  // counter of matrices whose Jacobi iteration did not converge (per context)
+  FFB_TRY(ffb_conv_counter(ctx, &conv));
   static const bool small_ok = !(getenv("FFB_DIAG_SMALL") && atoi(getenv("FFB_DIAG_SMALL")) == 0);
   static const bool fuse_ok = !(getenv("FFB_DIAG_FUSED") && atoi(getenv("FFB_DIAG_FUSED")) == 0);
   if (d >= 2 && d <= 4 && small_ok && fuse_ok) {
     // diagonalisation fused into the block scan: thread per segment, propagator scanned from registers
-    const DiagArgs da{n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs, flag.as<int>()};
+    const DiagArgs da{n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs, conv};
     if (d == 2) return scan_small<2, 256>(ctx, G, nullptr, (double2*)propagators, 1, da);
     if (d == 3) return scan_small<3, 128>(ctx, G, nullptr, (double2*)propagators, 1, da);
     return scan_small<4, 128>(ctx, G, nullptr, (double2*)propagators, 1, da);
   }
+  DevBuf piecewise, local, totals, prefix;
+  FFB_TRY(piecewise.alloc(ctx, (size_t)G * dd * 16));
+  FFB_TRY(local.alloc(ctx, (size_t)(G + 1) * dd * 16));
+  FFB_TRY(totals.alloc(ctx, (size_t)n_chunks * dd * 16));
+  FFB_TRY(prefix.alloc(ctx, (size_t)n_chunks * dd * 16));
   if (d >= 2 && d <= 4 && small_ok) {
     const unsigned nb = (unsigned)ceil_div(G, 128);
     if (d == 2)
       diag_small_kernel<2><<<nb, 128, 0, ctx->stream>>>(G, n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs,
-                                                        piecewise.as<double>(), flag.as<int>());
+                                                        piecewise.as<double>(), conv);
     else if (d == 3)
       diag_small_kernel<3><<<nb, 128, 0, ctx->stream>>>(G, n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs,
-                                                        piecewise.as<double>(), flag.as<int>());
+                                                        piecewise.as<double>(), conv);
     else
       diag_small_kernel<4><<<nb, 128, 0, ctx->stream>>>(G, n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs,
-                                                        piecewise.as<double>(), flag.as<int>());
+                                                        piecewise.as<double>(), conv);
     FFB_LAUNCHED(ctx);
   } else {
     const size_t smem = (size_t)DIAG_WARPS * (4 * dd + 2 * d) * sizeof(double);
@@ -709,7 +713,7 @@ int ffbi_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_ope
                                        (int)smem));
     diag_kernel<<<ceil_div(G, DIAG_WARPS), DIAG_WARPS * 32, smem, ctx->stream>>>(
         G, d, n_cops, c_opers, c_coeffs, dt, eigvals, eigvecs, piecewise.as<double>(),
-        flag.as<int>());
+        conv);
     FFB_LAUNCHED(ctx);
   }
   // running product Q_{g+1} = P_g ... P_0

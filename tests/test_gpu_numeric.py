@@ -53,6 +53,23 @@ def test_diagonalize_degenerate_and_zero(engine):
     assert nerr(ev, ev_o) < TOL and nerr(Q, Q_o) < TOL
 
 
+@pytest.mark.parametrize('d', [2, 4, 6])
+def test_diagonalize_reports_non_convergence(engine, d):
+    """numpy.linalg.eigh raises LinAlgError when the iteration does not converge (NaN input); the
+    library counts the matrices whose Jacobi iteration hit the sweep limit and the synchronous entry
+    point raises util.CalculationError.  The next call is unaffected (the counter is reset)."""
+    ff = engine
+    rng = np.random.default_rng(3)
+    H = rand_herm(rng, d, 9)
+    dt = np.full(9, 0.5)
+    bad = H.copy()
+    bad[4, 1, 0] = np.nan
+    with pytest.raises(ff.util.CalculationError):
+        ff.numeric.diagonalize(bad, dt)
+    ev, V, Q = ff.numeric.diagonalize(H, dt)
+    assert nerr(ev, np.linalg.eigvalsh(H)) < TOL
+
+
 @pytest.mark.parametrize('d,G,n_nops,btype,n_omega', [
     (2, 1, 1, 'pauli', 1), (2, 2, 1, 'pauli', 300), (2, 37, 3, 'pauli', 257), (2, 50, 2, 'ggm', 64),
     (3, 21, 2, 'ggm', 100), (4, 40, 6, 'pauli', 203), (4, 9, 3, 'ggm', 77), (5, 6, 2, 'ggm', 50),
