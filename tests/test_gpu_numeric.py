@@ -91,6 +91,36 @@ def test_control_matrix_from_scratch(engine, d, G, n_nops, btype, n_omega):
         assert nerr(B[j], B_o[j]) < TOL
 
 
+@pytest.mark.parametrize('d,n_nops,btype', [(2, 2, 'pauli'), (2, 3, 'pauli'), (2, 4, 'pauli'),
+                                            (3, 1, 'ggm'), (2, 3, 'shuffled'), (2, 3, 'scaled')])
+def test_control_matrix_identity_basis_element(engine, d, n_nops, btype):
+    """Thread-per-frequency kernel with the rows of an identity basis element split off (they carry
+    no level-pair coefficients).  The noise operators here are NOT traceless, so those rows are
+    non-zero: B_j0 = tr(B_j)/sqrt(d) sum_g s_j e^{i w t_g} I(w).  'shuffled' (identity not first) and
+    'scaled' (element 0 = 2 x identity / sqrt(d), still a real multiple) check the exact host test."""
+    rng = np.random.default_rng(1000 + 10*d + n_nops)
+    G, n_omega = 53, 211
+    _, _, n_opers, n_coeffs, dt, H = _setup(rng, d, G, n_nops)
+    n_opers = n_opers + rng.standard_normal(n_nops)[:, None, None]*np.eye(d)   # traces != 0
+    ev, V, Q = oracle.diagonalize(H, dt)
+    basis = oracle.ggm_basis(d) if btype == 'ggm' else oracle.pauli_basis(1)
+    if btype == 'shuffled':
+        basis = basis[[1, 0, 2, 3]]
+    if btype == 'scaled':
+        basis = basis.copy()
+        basis[0] *= 2
+    omega = np.concatenate(([0.0], np.geomspace(1e-3, 60, n_omega - 1)))
+    t = np.concatenate(([0], dt.cumsum()))
+    B = engine.numeric.calculate_control_matrix_from_scratch(ev, V, Q, omega, basis, n_opers,
+                                                             n_coeffs, dt, t)
+    B_o = oracle.control_matrix_from_scratch(ev, V, Q, omega, basis, n_opers, n_coeffs, dt, t)
+    k0 = 1 if btype == 'shuffled' else 0
+    for j in range(n_nops):
+        assert np.abs(B_o[j, k0]).max() > 1e-3*np.abs(B_o[j]).max()    # the identity row matters
+        assert nerr(B[j], B_o[j]) < TOL
+        assert nerr(B[j, k0], B_o[j, k0]) < TOL
+
+
 @pytest.mark.parametrize('d,n_nops', [(3, 2), (2, 3), (3, 1), (2, 1)])
 def test_control_matrix_special_frequencies(engine, d, n_nops):
     """omega = 0 (the exact-zero branch of numeric.py:162-165), negative omega, omega == -Omega_mn
