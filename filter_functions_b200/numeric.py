@@ -472,7 +472,7 @@ def calculate_cumulant_function(pulse, spectrum=None, omega=None, n_oper_identif
 def error_transfer_matrix(pulse=None, spectrum=None, omega=None, n_oper_identifiers=None,
                           second_order: bool = False, cumulant_function: Optional[ndarray] = None,
                           show_progressbar: bool = False, memory_parsimonious: bool = False,
-                          cache_intermediates: Optional[bool] = None) -> ndarray:
+                          cache_intermediates: bool = False) -> ndarray:
     r"""Error transfer matrix :math:`\langle\tilde{\mathcal U}\rangle=\exp\mathcal K(\tau)` of
     shape (n_basis, n_basis), summed over all noise operators (reference ``numeric.py:1938-2059``)."""
     from scipy import linalg as sla
