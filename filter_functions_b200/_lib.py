@@ -180,7 +180,10 @@ def empty_many(specs, ctx=None):
     for n in sizes:
         offsets.append(total)
         total += (n + 255) & ~255
-    if total < PINNED_THRESHOLD or total > PINNED_LIMIT:
+    # (no lower limit here: with the results of a call in ONE pool block the library downloads
+    # neighbours in one asynchronous copy; pageable arrays cost one blocking copy each, which is what
+    # bounds a small pulse -- 8 copies x ~10 us for the README example)
+    if total > PINNED_LIMIT:
         return [empty(sh, dt, ctx) for sh, dt in zip(shapes, dtypes)]
     ctx = context() if ctx is None else ctx
     address = c_void_p()

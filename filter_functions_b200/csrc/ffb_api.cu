@@ -1,4 +1,5 @@
 // C ABI of libffb200 (include/ffb200.h): context, memory pool, host-pointer wrappers.
+#include <algorithm>
 #include <chrono>
 #include <cstdarg>
 #include <cstdlib>
@@ -70,6 +71,27 @@ int ffb_h2d(ffb_ctx* ctx, void* dst, const void* src, size_t bytes) {
 int ffb_d2h(ffb_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (bytes == 0) return FFB_OK;
   FFB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return FFB_OK;
+}
+
+int ffb_func_smem_impl(ffb_ctx* ctx, const void* func, size_t smem) {
+  auto it = ctx->func_smem.find(func);
+  if (it != ctx->func_smem.end() && it->second >= smem) return FFB_OK;
+  FFB_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctx->func_smem[func] = smem;
+  return FFB_OK;
+}
+
+int ffb_occupancy_impl(ffb_ctx* ctx, const void* func, int block_threads, size_t smem, int* blocks) {
+  const auto key = std::make_tuple(func, block_threads, smem);
+  auto it = ctx->occupancy_cache.find(key);
+  if (it != ctx->occupancy_cache.end()) {
+    *blocks = it->second;
+    return FFB_OK;
+  }
+  FFB_TRY(ffb_func_smem_impl(ctx, func, smem));
+  FFB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, func, block_threads, smem));
+  ctx->occupancy_cache[key] = *blocks;
   return FFB_OK;
 }
 
@@ -509,6 +531,105 @@ struct CopyStreamDrain {
   ffb_ctx* ctx;
   ~CopyStreamDrain() {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  }
+};
+
+// The results of one call in ONE device block.  If all result pointers of the caller lie in one
+// page-locked block of the library's own pool (ffb_host_alloc; that is how the Python shell allocates
+// them, _lib.empty_many), the device block MIRRORS that layout, and results that are neighbours there
+// (less than 256 bytes of alignment padding apart) travel in one device-to-host copy: a small pulse
+// is bound by the number of driver calls, not by bytes (config 1: 8 copies -> 2).
+struct OutputBlock {
+  static constexpr size_t ALIGN = 256;
+  struct Item {
+    char* host;
+    size_t bytes, off;
+  };
+  std::vector<Item> items;
+  DevBuf dev;
+  bool mirrored = false;
+  char* host_base = nullptr;
+  int add(void* host, size_t bytes) {
+    items.push_back({static_cast<char*>(host), bytes, 0});
+    return (int)items.size() - 1;
+  }
+  int alloc(ffb_ctx* ctx) {
+    // one pool block that contains every requested result?
+    char* lo = nullptr;
+    char* hi = nullptr;
+    mirrored = true;
+    const void* block = nullptr;
+    for (const Item& it : items) {
+      if (!it.host || !it.bytes) continue;
+      auto ub = ctx->host_live_blocks.upper_bound(it.host);
+      if (ub == ctx->host_live_blocks.begin()) { mirrored = false; break; }
+      --ub;
+      char* b0 = static_cast<char*>(ub->first);
+      if (it.host + it.bytes > b0 + ub->second || (block && block != ub->first) ||
+          (size_t)(it.host - b0) % ALIGN != 0) {
+        mirrored = false;
+        break;
+      }
+      block = ub->first;
+      lo = lo ? std::min(lo, it.host) : it.host;
+      hi = hi ? std::max(hi, it.host + it.bytes) : it.host + it.bytes;
+    }
+    if (!block) mirrored = false;
+    size_t total = 0;
+    if (mirrored) {  // overlap check: sorted by address, no two results may share bytes
+      std::vector<const Item*> order;
+      for (const Item& it : items)
+        if (it.host && it.bytes) order.push_back(&it);
+      std::sort(order.begin(), order.end(), [](const Item* a, const Item* b) { return a->host < b->host; });
+      for (size_t i = 1; i < order.size(); ++i)
+        if (order[i]->host < order[i - 1]->host + order[i - 1]->bytes) mirrored = false;
+    }
+    if (mirrored) {
+      host_base = lo;
+      total = ((size_t)(hi - lo) + ALIGN - 1) & ~(ALIGN - 1);
+      for (Item& it : items)
+        if (it.host && it.bytes) it.off = (size_t)(it.host - lo);
+    }
+    for (Item& it : items) {  // not requested (or no mirroring): packed behind
+      if (mirrored && it.host && it.bytes) continue;
+      it.off = total;
+      total += (it.bytes + ALIGN - 1) & ~(ALIGN - 1);
+    }
+    return dev.alloc(ctx, total);
+  }
+  template <typename T = double>
+  T* d(int i) const {
+    return reinterpret_cast<T*>(static_cast<char*>(dev.p) + items[i].off);
+  }
+  // enqueue the download of the listed results on `stream`
+  int download(ffb_ctx* ctx, std::initializer_list<int> which, cudaStream_t stream) {
+    std::vector<const Item*> order;
+    for (int i : which)
+      if (i >= 0 && items[i].host && items[i].bytes) order.push_back(&items[i]);
+    if (order.empty()) return FFB_OK;
+    if (!mirrored) {
+      for (const Item* it : order)
+        FFB_CUDA(ctx, cudaMemcpyAsync(it->host, static_cast<char*>(dev.p) + it->off, it->bytes,
+                                      cudaMemcpyDeviceToHost, stream));
+      return FFB_OK;
+    }
+    std::sort(order.begin(), order.end(), [](const Item* a, const Item* b) { return a->off < b->off; });
+    size_t r0 = order[0]->off, r1 = r0 + order[0]->bytes;
+    auto flush = [&]() -> int {
+      FFB_CUDA(ctx, cudaMemcpyAsync(host_base + r0, static_cast<char*>(dev.p) + r0, r1 - r0,
+                                    cudaMemcpyDeviceToHost, stream));
+      return FFB_OK;
+    };
+    for (size_t i = 1; i < order.size(); ++i) {
+      if (order[i]->off < r1 + ALIGN) {  // neighbours: only alignment padding in between
+        r1 = order[i]->off + order[i]->bytes;
+      } else {
+        FFB_TRY(flush());
+        r0 = order[i]->off;
+        r1 = r0 + order[i]->bytes;
+      }
+    }
+    return flush();
   }
 };
 
@@ -1101,9 +1222,14 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_enter).count();
   };
   double us_packed = 0, us_enqueued = 0, us_main = 0;
+  std::string marks;
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    char buf[64];
+    snprintf(buf, sizeof(buf), " %s@%.0f", what, since());
+    marks += buf;
+  };
   PackedUpload in;
-  DevBuf ev, V, Q, B, F, I, ph, liou;
-  CopyStreamDrain drain{ctx};
   const int i_co = in.add(c_opers, (size_t)n_cops * dd * 16);
   const int i_cc = in.add(c_coeffs, (size_t)n_cops * G * 8);
   const int i_dt = in.add(dt, (size_t)G * 8);
@@ -1136,84 +1262,95 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
   }
   FFB_TRY(in.upload(ctx));
   us_packed = since();
-  FFB_TRY(ev.alloc(ctx, (size_t)G * d * 8));
-  FFB_TRY(V.alloc(ctx, (size_t)G * dd * 16));
-  FFB_TRY(Q.alloc(ctx, (size_t)(G + 1) * dd * 16));
   const size_t b_bytes = (size_t)n_nops * n_basis * n_omega * 16;
   const size_t f_bytes = (size_t)n_nops * n_nops * n_omega * 16;
-  FFB_TRY(B.alloc(ctx, b_bytes));
-  FFB_TRY(F.alloc(ctx, f_bytes));
+  OutputBlock out;
+  CopyStreamDrain drain{ctx};  // after `out`: destroyed (drained) before its device block is released
+  const int o_ev = out.add(eigvals, (size_t)G * d * 8);
+  const int o_V = out.add(eigvecs, (size_t)G * dd * 16);
+  const int o_Q = out.add(propagators, (size_t)(G + 1) * dd * 16);
+  const int o_ph = total_phases ? out.add(total_phases, (size_t)n_omega * 16) : -1;
+  const int o_li = total_propagator_liouville
+                       ? out.add(total_propagator_liouville, (size_t)n_basis * n_basis * 16) : -1;
+  const int o_B = out.add(control_matrix, b_bytes);
+  const int o_F = out.add(filter_function, f_bytes);
+  const int o_I = infidelity ? out.add(infidelity, n_inf * 8) : -1;
+  FFB_TRY(out.alloc(ctx));
+  mark("alloc");
   cudaStream_t cs = ctx->copy_stream;
-  auto d2h_copy = [&](void* dst, const void* src, size_t bytes) -> int {
-    if (dst && bytes) FFB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, cs));
-    return FFB_OK;
-  };
 
   // stage 1: everything that does not depend on the control matrix
-  FFB_TRY(ffbi_diagonalize(ctx, G, d, n_cops, in.d(i_co), in.d(i_cc), in.d(i_dt), ev.as<double>(),
-                           V.as<double>(), Q.as<double>()));
-  if (total_phases) {
-    FFB_TRY(ph.alloc(ctx, (size_t)n_omega * 16));
-    FFB_TRY(ffbi_cexp(ctx, n_omega, in.d(i_om), t[G], ph.as<double>()));  // tau = t[G] (host value)
-  }
-  if (total_propagator_liouville) {
-    FFB_TRY(liou.alloc(ctx, (size_t)n_basis * n_basis * 16));
-    FFB_TRY(ffbi_liouville(ctx, 1, d, n_basis, Q.as<double>() + (size_t)G * dd * 2, in.d(i_bs),
-                           liou.as<double>()));
-  }
-  // ... is downloaded on the copy stream WHILE the control-matrix kernel runs
-  FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));
-  FFB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->copy_ev[0], 0));
-  FFB_TRY(d2h_copy(eigvals, ev.p, (size_t)G * d * 8));
-  FFB_TRY(d2h_copy(eigvecs, V.p, (size_t)G * dd * 16));
-  FFB_TRY(d2h_copy(propagators, Q.p, (size_t)(G + 1) * dd * 16));
-  if (total_phases) FFB_TRY(d2h_copy(total_phases, ph.p, (size_t)n_omega * 16));
+  FFB_TRY(ffbi_diagonalize(ctx, G, d, n_cops, in.d(i_co), in.d(i_cc), in.d(i_dt), out.d(o_ev),
+                           out.d(o_V), out.d(o_Q)));
+  if (total_phases)
+    FFB_TRY(ffbi_cexp(ctx, n_omega, in.d(i_om), t[G], out.d(o_ph)));  // tau = t[G] (host value)
   if (total_propagator_liouville)
-    FFB_TRY(d2h_copy(total_propagator_liouville, liou.p, (size_t)n_basis * n_basis * 16));
+    FFB_TRY(ffbi_liouville(ctx, 1, d, n_basis, out.d(o_Q) + (size_t)G * dd * 2, in.d(i_bs),
+                           out.d(o_li)));
+  mark("stage1");
+  // ... is downloaded on the copy stream WHILE the control-matrix kernel runs -- unless it is so
+  // little that the two extra driver calls of the hand-over cost more than the overlap saves
+  const size_t early_bytes = (size_t)G * d * 8 + (size_t)(2 * G + 1) * dd * 16 + (size_t)n_omega * 16;
+  const size_t out_bytes = (control_matrix ? b_bytes : 0) + (filter_function ? f_bytes : 0);
+  const bool overlap = early_bytes + out_bytes >= ((size_t)256 << 10);
+  if (overlap) {
+    FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+    FFB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->copy_ev[0], 0));
+    FFB_TRY(out.download(ctx, {o_ev, o_V, o_Q, o_ph, o_li}, cs));
+  }
 
   // stage 2: control matrix and filter function in blocks of frequencies; the rows of a finished block
   // are downloaded (strided 2-D copies) while the next block is computed, so that only the last
   // block's download is left after the last kernel (PCIe is the tail of this call: config 3 returns
   // 105 MB, 1.9 ms at 56 GB/s)
-  const size_t out_bytes = (control_matrix ? b_bytes : 0) + (filter_function ? f_bytes : 0);
   FreqBlocks fb;
   fb.n_blocks = pipeline_blocks(out_bytes, n_omega);
   const size_t pitch = (size_t)n_omega * 16;
   fb.after_block = [&](int w0, int w1) -> int {
     const size_t off = (size_t)w0 * 16, width = (size_t)(w1 - w0) * 16;
     FFB_TRY(ffbi_filter_function_ld(ctx, 1, n_nops, n_basis, w1 - w0, (size_t)n_omega,
-                                    B.as<double>() + 2 * (size_t)w0, F.as<double>() + 2 * (size_t)w0));
+                                    out.d(o_B) + 2 * (size_t)w0, out.d(o_F) + 2 * (size_t)w0));
+    if (fb.n_blocks == 1) return FFB_OK;  // one block: whole arrays, copied below
     FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[1], ctx->stream));
     FFB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->copy_ev[1], 0));
     if (control_matrix)
       FFB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<char*>(control_matrix) + off, pitch,
-                                      static_cast<const char*>(B.p) + off, pitch, width,
+                                      out.d<char>(o_B) + off, pitch, width,
                                       (size_t)n_nops * n_basis, cudaMemcpyDeviceToHost, cs));
     if (filter_function)
       FFB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<char*>(filter_function) + off, pitch,
-                                      static_cast<const char*>(F.p) + off, pitch, width,
+                                      out.d<char>(o_F) + off, pitch, width,
                                       (size_t)n_nops * n_nops, cudaMemcpyDeviceToHost, cs));
     return FFB_OK;
   };
-  FFB_TRY(ffbi_control_matrix(ctx, G, d, n_nops, n_basis, n_omega, ev.as<double>(), V.as<double>(),
-                              Q.as<double>(), in.d(i_om), in.d(i_bs), in.d(i_no), in.d(i_nc),
-                              in.d(i_dt), in.d(i_ts), herm, B.as<double>(), &fb));
-  if (infidelity) {
-    FFB_TRY(I.alloc(ctx, n_inf * 8));
-    FFB_TRY(ffbi_infidelity(ctx, 1, n_nops, n_nops, nullptr, n_omega, F.as<double>(), in.d(i_sp),
-                            spectrum_ndim, spectrum_is_complex, in.d(i_om), d, I.as<double>()));
-    FFB_TRY(ffb_d2h(ctx, infidelity, I.p, n_inf * 8));
+  FFB_TRY(ffbi_control_matrix(ctx, G, d, n_nops, n_basis, n_omega, out.d(o_ev), out.d(o_V),
+                              out.d(o_Q), in.d(i_om), in.d(i_bs), in.d(i_no), in.d(i_nc),
+                              in.d(i_dt), in.d(i_ts), herm, out.d(o_B), &fb));
+  mark("ctrlmat");
+  if (overlap && fb.n_blocks == 1) {  // B and F in one copy while the integral runs
+    FFB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[1], ctx->stream));
+    FFB_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->copy_ev[1], 0));
+    FFB_TRY(out.download(ctx, {o_B, o_F}, cs));
+  }
+  if (infidelity)
+    FFB_TRY(ffbi_infidelity(ctx, 1, n_nops, n_nops, nullptr, n_omega, out.d(o_F), in.d(i_sp),
+                            spectrum_ndim, spectrum_is_complex, in.d(i_om), d, out.d(o_I)));
+  mark("integral");
+  if (overlap) {
+    FFB_TRY(out.download(ctx, {o_I}, ctx->stream));
+  } else {  // small pulse: everything on one stream, as few copies as the layout allows
+    FFB_TRY(out.download(ctx, {o_ev, o_V, o_Q, o_ph, o_li, o_B, o_F, o_I}, ctx->stream));
   }
   FFB_TRY(ffb_conv_fetch(ctx));
   us_enqueued = since();
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   us_main = since();
-  FFB_CUDA(ctx, cudaStreamSynchronize(cs));
+  if (overlap) FFB_CUDA(ctx, cudaStreamSynchronize(cs));
   FFB_TRY(ffb_conv_check(ctx));
   if (trace)
     fprintf(stderr, "[ffb trace] pulse pipeline: inputs packed+upload enqueued %.0f us, all work enqueued "
-            "%.0f us, main stream done %.0f us, copy stream done %.0f us\n", us_packed, us_enqueued,
-            us_main, since());
+            "%.0f us, main stream done %.0f us, copy stream done %.0f us;%s\n", us_packed, us_enqueued,
+            us_main, since(), marks.c_str());
   return FFB_OK;
 }
 

@@ -8,6 +8,7 @@
 #include <functional>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/ffb200.h"
@@ -38,6 +39,10 @@ struct ffb_ctx {
   // fetch it with their last copies and return FFB_ENOTCONV (numpy.linalg.eigh raises LinAlgError)
   int* conv_dev = nullptr;
   int* conv_host = nullptr;
+  // launch bookkeeping that would otherwise cost a driver call per launch: the dynamic shared memory
+  // limit already set for a kernel (grow-only) and occupancy query results
+  std::map<const void*, size_t> func_smem;
+  std::map<std::tuple<const void*, int, size_t>, int> occupancy_cache;
 
   // grow-only caching pool: freed blocks are kept and handed out again (best fit)
   std::multimap<size_t, void*> free_blocks;
@@ -110,6 +115,18 @@ struct DevBuf {
   T* as() const { return static_cast<T*>(p); }
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) / cudaOccupancyMaxActiveBlocksPerMultiprocessor,
+// remembered per context (small pulses are bound by the number of driver calls per library call)
+int ffb_func_smem_impl(ffb_ctx* ctx, const void* func, size_t smem);
+int ffb_occupancy_impl(ffb_ctx* ctx, const void* func, int block_threads, size_t smem, int* blocks);
+template <typename K>
+int ffb_func_smem(ffb_ctx* ctx, K kern, size_t smem) {
+  return ffb_func_smem_impl(ctx, reinterpret_cast<const void*>(kern), smem);
+}
+template <typename K>
+int ffb_occupancy(ffb_ctx* ctx, K kern, int block_threads, size_t smem, int* blocks) {
+  return ffb_occupancy_impl(ctx, reinterpret_cast<const void*>(kern), block_threads, smem, blocks);
+}
 int ffb_h2d(ffb_ctx* ctx, void* dst, const void* src, size_t bytes);
 // convergence counter of the eigensolver: device pointer (created on first use); enqueue its download;
 // after a stream synchronisation: FFB_ENOTCONV (and reset) if any matrix failed to converge

@@ -460,8 +460,7 @@ int ffbi_liouville(ffb_ctx* ctx, int n, int d, int n_basis, const double* U, con
               "liouville: bad shape (n=%d, d=%d, n_basis=%d)", n, d, n_basis);
   dim3 grid(n_basis, n);
   const size_t smem = (size_t)6 * d * d * sizeof(double);
-  FFB_CUDA(ctx, cudaFuncSetAttribute(liouville_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
+  FFB_TRY(ffb_func_smem(ctx, liouville_kernel, smem));
   liouville_kernel<<<grid, 128, smem, ctx->stream>>>(d, n_basis, U, basis, out);
   FFB_LAUNCHED(ctx);
   return FFB_OK;

@@ -1476,7 +1476,7 @@ template <int MT, int NW>
 int launch_main(ffb_ctx* ctx, MainParams p, int n_wtiles, int n_rb, int S) {
   auto kern = ctrlmat_main_kernel<MT, NW>;
   const size_t smem = (size_t)2 * p.stage_doubles * sizeof(double);
-  FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FFB_TRY(ffb_func_smem(ctx, kern, smem));
   dim3 grid(n_wtiles, n_rb, S);
   int slot = -1;
   FFB_TRY(ffb_time_begin(ctx, &slot));
@@ -1490,7 +1490,7 @@ template <int MT, int NW, int NP, int NSP>
 int launch_static(ffb_ctx* ctx, MainParams p, int n_wtiles, int n_rb, int S) {
   auto kern = ctrlmat_static_kernel<MT, NW, NP, NSP>;
   const size_t smem = (size_t)2 * p.stage_doubles * sizeof(double) + 16;  // + two mbarriers
-  FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FFB_TRY(ffb_func_smem(ctx, kern, smem));
   dim3 grid(n_wtiles, n_rb, S);
   int slot = -1;
   FFB_TRY(ffb_time_begin(ctx, &slot));
@@ -1503,9 +1503,7 @@ int launch_static(ffb_ctx* ctx, MainParams p, int n_wtiles, int n_rb, int S) {
 template <int MT, int NW>
 int occupancy(ffb_ctx* ctx, size_t smem, int* blocks) {
   auto kern = ctrlmat_main_kernel<MT, NW>;
-  FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  FFB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, NW * 32, smem));
-  return FFB_OK;
+  return ffb_occupancy(ctx, kern, NW * 32, smem, blocks);
 }
 
 int pick_mt(int mt_total) {
@@ -1582,7 +1580,7 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
 
   if (fused_prologue) {
     auto launch = [&](auto kern) -> int {
-      FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pro_smem));
+      FFB_TRY(ffb_func_smem(ctx, kern, pro_smem));
       kern<<<ceil_div(G, DFMA_PRO_SEGS), 128, pro_smem, ctx->stream>>>(
           G, n_nops, n_basis, parts_j, parts_k, rows, R, RF, split ? 1 : 0,
           reinterpret_cast<const double2*>(eigvecs), reinterpret_cast<const double2*>(propagators),
@@ -1658,10 +1656,7 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
     const int n_wt = ceil_div(n_omega, 32);
     int blocks_per_sm = 1;
     auto pick = [&](auto kern) -> int {
-      FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      FFB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern,
-                                                                   DFMA_WARPS * 32, smem));
-      return FFB_OK;
+      return ffb_occupancy(ctx, kern, DFMA_WARPS * 32, smem, &blocks_per_sm);
     };
 #define FFB_DFMA_DISPATCH(CALL)                                                        \
   if (split) {                                                                        \

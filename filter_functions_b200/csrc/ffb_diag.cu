@@ -647,7 +647,7 @@ int scan_small(ffb_ctx* ctx, int n, const double2* in, double2* out, int shift,
   FFB_TRY(totals.alloc(ctx, (size_t)nb * DD * 16));
   const size_t smem = (size_t)2 * DD * NT * sizeof(double2);
   auto kern = scan_block_kernel<D, NT>;
-  FFB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  FFB_TRY(ffb_func_smem(ctx, kern, smem));
   kern<<<nb, NT, smem, ctx->stream>>>(n, in, local.as<double2>(), totals.as<double2>(), da);
   FFB_LAUNCHED(ctx);
   if (nb <= SCAN_PREFIX_MAX) {  // few blocks: their totals are combined inside the apply kernel

@@ -402,16 +402,20 @@ class PulseSequence:
         # of a computational subspace, tests/test_precision.py:297); matrix shapes come from the arrays
         G, d = len(dt), c_opers.shape[-1]
         n_cops, n_nops, n_basis, n_omega = len(c_opers), len(n_opers), len(basis), len(omega_arr)
-        eigvals, eigvecs, propagators, B, F, phases, liouville = _lib.empty_many([
-            ((G, d), np.float64), ((G, d, d), np.complex128), ((G + 1, d, d), np.complex128),
-            ((n_nops, n_basis, n_omega), np.complex128), ((n_nops, n_nops, n_omega), np.complex128),
-            ((n_omega,), np.complex128), ((n_basis, n_basis), np.complex128)])
         S = infid = None
         s_ndim = s_complex = 0
+        # all results in ONE page-locked block, neighbours in the order the library downloads them
+        specs = [((G, d), np.float64), ((G, d, d), np.complex128), ((G + 1, d, d), np.complex128),
+                 ((n_omega,), np.complex128), ((n_basis, n_basis), np.complex128),
+                 ((n_nops, n_basis, n_omega), np.complex128), ((n_nops, n_nops, n_omega), np.complex128)]
         if spectrum is not None:
             s_ndim, s_complex = spectrum.ndim, int(np.iscomplexobj(spectrum))
             S = _lib.as_c128(spectrum) if s_complex else _lib.as_f64(spectrum)
-            infid = np.empty((n_nops, n_nops) if s_ndim == 3 else (n_nops,), dtype=np.float64)
+            specs.append(((n_nops, n_nops) if s_ndim == 3 else (n_nops,), np.float64))
+        arrays = _lib.empty_many(specs)
+        eigvals, eigvecs, propagators, phases, liouville, B, F = arrays[:7]
+        if spectrum is not None:
+            infid = arrays[7]
         ctx = _lib.context()
         p = _lib.ptr
         _lib.check(ctx, _lib.lib().ffb_pulse_filter_function(

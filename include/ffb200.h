@@ -223,7 +223,10 @@ int ffb_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out);
  * by-products are downloaded on a second stream while the control-matrix kernel runs, the control
  * matrix while the filter function and the integral are computed.  Any output pointer may be NULL
  * to skip it.  t may be NULL: then t = [0, cumsum(dt)] (sequential sum, as np.cumsum).  spectrum as
- * in ffb_infidelity with n_sel = n_nops, idx = 0..n_nops-1. */
+ * in ffb_infidelity with n_sel = n_nops, idx = 0..n_nops-1.
+ * If all result pointers lie in ONE block obtained from ffb_host_alloc, results that are less than 256
+ * bytes apart there are downloaded in one copy; the bytes between them are treated as padding and
+ * overwritten (the Python shell carves its result arrays out of one such block, _lib.empty_many). */
 int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops, int n_basis,
                               int n_omega, const double* c_opers, const double* c_coeffs,
                               const double* n_opers, const double* n_coeffs, const double* dt,
