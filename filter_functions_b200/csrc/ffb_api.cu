@@ -456,6 +456,7 @@ int enter(ffb_ctx* ctx) {
 struct PackedUpload {
   static constexpr size_t ALIGN = 256;
   static constexpr size_t PACK_LIMIT = (size_t)512 << 10;  // larger parts are copied from where they lie
+  static constexpr size_t RUN_BYTES = (size_t)128 << 10;   // a run of packed parts is sent at this size
   std::vector<const void*> src;
   std::vector<size_t> bytes, offset;
   size_t total = 0;
@@ -494,6 +495,10 @@ struct PackedUpload {
         std::memcpy(stage + offset[i], src[i], bytes[i]);
         if (run_end == run_begin) run_begin = offset[i];
         run_end = offset[i] + bytes[i];
+        if (run_end - run_begin >= RUN_BYTES) {  // send what is packed while the rest is being packed
+          FFB_TRY(flush());
+          run_begin = run_end = 0;
+        }
       } else {
         FFB_TRY(flush());
         run_begin = run_end = 0;
