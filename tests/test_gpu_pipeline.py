@@ -94,3 +94,68 @@ def test_piecewise_uniform_time_grid(engine, d, n_nops, G):
     pulse, Q, B, F = _pulse_and_reference(ff, rng, d, G, n_nops, dt, omega, np.ones_like(omega))
     assert nerr(pulse.get_control_matrix(omega), B) < TOL
     assert nerr(pulse.get_filter_function(omega), F) < TOL
+
+
+def _call_pipeline(ff, wl_arrays, outs, spectrum):
+    """ffb_pulse_filter_function through ctypes with caller-owned arrays (``outs``: name -> array or None)."""
+    from filter_functions_b200 import _lib
+    c_opers, c_coeffs, n_opers, n_coeffs, dt, basis, omega = wl_arrays
+    G, d = len(dt), c_opers.shape[-1]
+    p = _lib.ptr
+    ctx = _lib.context()
+    S = np.ascontiguousarray(spectrum, dtype=np.float64)
+    _lib.check(ctx, _lib.lib().ffb_pulse_filter_function(
+        ctx, G, d, len(c_opers), len(n_opers), len(basis), len(omega), p(c_opers), p(c_coeffs),
+        p(n_opers), p(n_coeffs), p(dt), None, p(basis), p(omega), p(S), S.ndim, 0,
+        p(outs.get('eigvals')), p(outs.get('eigvecs')), p(outs.get('propagators')),
+        p(outs.get('control_matrix')), p(outs.get('filter_function')), p(outs.get('infidelity')),
+        p(outs.get('total_phases')), p(outs.get('liouville'))))
+
+
+@pytest.mark.parametrize('layout', ['separate', 'one_numpy_block', 'partial'])
+def test_pipeline_result_layouts(engine, layout):
+    """The C entry point with result arrays that are NOT one block of the library's pool: separate
+    pageable NumPy arrays, views into one ordinary NumPy buffer (adjacent, but not the library's:
+    nothing between them may be touched), and some results not requested (NULL)."""
+    ff = engine
+    rng = np.random.default_rng(11)
+    d, G, n_nops, n_omega = 2, 29, 3, 400
+    dt = 1 - rng.random(G)
+    omega = np.geomspace(1e-2, 30, n_omega)
+    spectrum = 1/omega
+    pulse, Q, B, F = _pulse_and_reference(ff, rng, d, G, n_nops, dt, omega, spectrum)
+    arrays = (np.ascontiguousarray(pulse.c_opers), np.ascontiguousarray(pulse.c_coeffs),
+              np.ascontiguousarray(pulse.n_opers), np.ascontiguousarray(pulse.n_coeffs),
+              np.ascontiguousarray(pulse.dt), np.ascontiguousarray(np.asarray(pulse.basis)), omega)
+    n_basis = 4
+    shapes = dict(eigvals=((G, d), np.float64), eigvecs=((G, d, d), np.complex128),
+                  propagators=((G + 1, d, d), np.complex128),
+                  total_phases=((n_omega,), np.complex128), liouville=((n_basis, n_basis), np.complex128),
+                  control_matrix=((n_nops, n_basis, n_omega), np.complex128),
+                  filter_function=((n_nops, n_nops, n_omega), np.complex128),
+                  infidelity=((n_nops,), np.float64))
+    guard = None
+    if layout == 'one_numpy_block':
+        # views 8 bytes apart in one buffer; the guard words in between must survive
+        sizes = {k: int(np.prod(sh))*np.dtype(dt_).itemsize for k, (sh, dt_) in shapes.items()}
+        buf = np.full(sum(sizes.values()) + 8*(len(sizes) + 1), 0x5A, dtype=np.uint8)
+        outs, off, guard = {}, 8, []
+        for k, (sh, dt_) in shapes.items():
+            outs[k] = buf[off:off + sizes[k]].view(dt_).reshape(sh)
+            guard.append((off + sizes[k], off + sizes[k] + 8))
+            off += sizes[k] + 8
+    else:
+        outs = {k: np.empty(sh, dt_) for k, (sh, dt_) in shapes.items()}
+    if layout == 'partial':
+        for k in ('eigvecs', 'total_phases', 'control_matrix'):
+            outs[k] = None
+    _call_pipeline(ff, arrays, outs, spectrum)
+    assert nerr(outs['propagators'], Q) < TOL
+    assert nerr(outs['filter_function'], F) < TOL
+    if outs['control_matrix'] is not None:
+        assert nerr(outs['control_matrix'], B) < TOL
+    f = np.einsum('aaw->aw', F).real*spectrum
+    ref = 0.5*((f[:, 1:] + f[:, :-1])*np.diff(omega)).sum(-1)/(2*np.pi*d)
+    assert nerr(outs['infidelity'], ref) < TOL
+    if guard is not None:
+        assert (buf[:8] == 0x5A).all() and all((buf[a:b] == 0x5A).all() for a, b in guard)
