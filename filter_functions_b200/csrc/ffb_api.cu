@@ -933,55 +933,51 @@ int ffb_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int n_lib, int d, int n
     FFB_REQUIRE(ctx, indices[i] < n_lib, "concatenate_many: index %d at position %zu out of range "
                 "[0, %d)", indices[i], i, n_lib);
   const size_t dd = (size_t)d * d, nn = (size_t)n_basis * n_basis;
-  Upload ix, lb, lp, ll, lu, bs, sp, om;
-  DevBuf U, Lt, B, F, I, iota, ph;
-  if (omega) FFB_TRY(om.put(ctx, omega, (size_t)n_omega * 8));
-  FFB_TRY(ix.put(ctx, indices, (size_t)n_seq * L * sizeof(int)));
-  FFB_TRY(lb.put(ctx, lib_control_matrix, (size_t)n_lib * n_nops * n_basis * n_omega * 16));
-  FFB_TRY(lp.put(ctx, lib_total_phases, (size_t)n_lib * n_omega * 16));
-  FFB_TRY(ll.put(ctx, lib_liouville, (size_t)n_lib * nn * 8));
-  FFB_TRY(lu.put(ctx, lib_propagator, (size_t)n_lib * dd * 16));
-  const size_t b_bytes = (size_t)n_seq * n_nops * n_basis * n_omega * 16;
-  const size_t f_bytes = (size_t)n_seq * n_nops * n_nops * n_omega * 16;
-  const bool need_F = filter_function || infidelity;
-  FFB_TRY(U.alloc(ctx, (size_t)n_seq * dd * 16));
-  FFB_TRY(B.alloc(ctx, b_bytes));
-  if (need_F) FFB_TRY(F.alloc(ctx, f_bytes));
-  FFB_TRY(ffbi_concatenate_many(ctx, n_seq, L, d, n_nops, n_basis, n_omega, ix.buf.as<int>(), lb.d(),
-                                lp.d(), ll.d(), lu.d(), U.as<double>(), B.as<double>(),
-                                need_F ? F.as<double>() : nullptr));
+  // inputs in one packed upload, results in one (mirrored) device block: a single-sequence call -- the
+  // tail of every ff.concatenate -- is bound by driver calls and blocking copies, not by bytes
+  PackedUpload in;
+  const int i_om = omega ? in.add(omega, (size_t)n_omega * 8) : -1;
+  const int i_ix = in.add(indices, (size_t)n_seq * L * sizeof(int));
+  const int i_lb = in.add(lib_control_matrix, (size_t)n_lib * n_nops * n_basis * n_omega * 16);
+  const int i_lp = in.add(lib_total_phases, (size_t)n_lib * n_omega * 16);
+  const int i_ll = in.add(lib_liouville, (size_t)n_lib * nn * 8);
+  const int i_lu = in.add(lib_propagator, (size_t)n_lib * dd * 16);
+  int i_sp = -1, i_bs = -1;
   size_t n_inf = 0;
-  std::vector<int> sel(n_nops);
   if (infidelity) {
     FFB_REQUIRE(ctx, spectrum_ndim >= 1 && spectrum_ndim <= 3, "concatenate_many: spectrum_ndim=%d",
                 spectrum_ndim);
     const size_t s_elems = (spectrum_ndim == 1 ? 1 : spectrum_ndim == 2 ? (size_t)n_nops
                                                                          : (size_t)n_nops * n_nops) * n_omega;
-    FFB_TRY(sp.put(ctx, spectrum, s_elems * (spectrum_is_complex ? 16 : 8)));
-    for (int i = 0; i < n_nops; ++i) sel[i] = i;
-    FFB_TRY(iota.alloc(ctx, n_nops * sizeof(int)));
-    FFB_TRY(ffb_h2d(ctx, iota.p, sel.data(), n_nops * sizeof(int)));
+    i_sp = in.add(spectrum, s_elems * (spectrum_is_complex ? 16 : 8));
     n_inf = (size_t)n_seq * (spectrum_ndim == 3 ? (size_t)n_nops * n_nops : n_nops);
-    FFB_TRY(I.alloc(ctx, n_inf * 8));
-    FFB_TRY(ffbi_infidelity(ctx, n_seq, n_nops, n_nops, iota.as<int>(), n_omega, F.as<double>(),
-                            sp.d(), spectrum_ndim, spectrum_is_complex, om.d(), d, I.as<double>()));
   }
-  if (total_propagator_liouville) {
-    FFB_TRY(bs.put(ctx, basis, (size_t)n_basis * dd * 16));
-    FFB_TRY(Lt.alloc(ctx, (size_t)n_seq * nn * 16));
-    FFB_TRY(ffbi_liouville(ctx, n_seq, d, n_basis, U.as<double>(), bs.d(), Lt.as<double>()));
-    FFB_TRY(ffb_d2h(ctx, total_propagator_liouville, Lt.p, (size_t)n_seq * nn * 16));
-  }
-  if (total_phases) {
-    FFB_TRY(ph.alloc(ctx, (size_t)n_seq * n_omega * 16));
+  if (total_propagator_liouville) i_bs = in.add(basis, (size_t)n_basis * dd * 16);
+  FFB_TRY(in.upload(ctx));
+  const size_t b_bytes = (size_t)n_seq * n_nops * n_basis * n_omega * 16;
+  const size_t f_bytes = (size_t)n_seq * n_nops * n_nops * n_omega * 16;
+  const bool need_F = filter_function || infidelity;
+  OutputBlock out;
+  const int o_U = out.add(total_propagator, (size_t)n_seq * dd * 16);
+  const int o_L = total_propagator_liouville ? out.add(total_propagator_liouville, (size_t)n_seq * nn * 16) : -1;
+  const int o_ph = total_phases ? out.add(total_phases, (size_t)n_seq * n_omega * 16) : -1;
+  const int o_B = out.add(control_matrix, b_bytes);
+  const int o_F = need_F ? out.add(filter_function, f_bytes) : -1;
+  const int o_I = infidelity ? out.add(infidelity, n_inf * 8) : -1;
+  FFB_TRY(out.alloc(ctx));
+  FFB_TRY(ffbi_concatenate_many(ctx, n_seq, L, d, n_nops, n_basis, n_omega,
+                                reinterpret_cast<const int*>(in.d(i_ix)), in.d(i_lb), in.d(i_lp),
+                                in.d(i_ll), in.d(i_lu), out.d(o_U), out.d(o_B),
+                                need_F ? out.d(o_F) : nullptr));
+  if (infidelity)
+    FFB_TRY(ffbi_infidelity(ctx, n_seq, n_nops, n_nops, nullptr, n_omega, out.d(o_F), in.d(i_sp),
+                            spectrum_ndim, spectrum_is_complex, in.d(i_om), d, out.d(o_I)));
+  if (total_propagator_liouville)
+    FFB_TRY(ffbi_liouville(ctx, n_seq, d, n_basis, out.d(o_U), in.d(i_bs), out.d(o_L)));
+  if (total_phases)
     for (int s = 0; s < n_seq; ++s)  // tau is a host value, as in the cold pulse pipeline
-      FFB_TRY(ffbi_cexp(ctx, n_omega, om.d(), tau[s], ph.as<double>() + (size_t)s * n_omega * 2));
-    FFB_TRY(ffb_d2h(ctx, total_phases, ph.p, (size_t)n_seq * n_omega * 16));
-  }
-  if (total_propagator) FFB_TRY(ffb_d2h(ctx, total_propagator, U.p, (size_t)n_seq * dd * 16));
-  if (control_matrix) FFB_TRY(ffb_d2h(ctx, control_matrix, B.p, b_bytes));
-  if (filter_function) FFB_TRY(ffb_d2h(ctx, filter_function, F.p, f_bytes));
-  if (infidelity) FFB_TRY(ffb_d2h(ctx, infidelity, I.p, n_inf * 8));
+      FFB_TRY(ffbi_cexp(ctx, n_omega, in.d(i_om), tau[s], out.d(o_ph) + (size_t)s * n_omega * 2));
+  FFB_TRY(out.download(ctx, {o_U, o_L, o_ph, o_B, o_F, o_I}, ctx->stream));
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return FFB_OK;
 }

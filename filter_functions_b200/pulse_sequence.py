@@ -726,11 +726,10 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         basis = _lib.as_c128(np.asarray(newpulse.basis))
         index = np.array(inverse, dtype=np.int32)
         n_nops = lib_B.shape[1]
-        U = np.empty((1, d, d), dtype=np.complex128)
-        liouville = np.empty((1, n_basis, n_basis), dtype=np.complex128)
-        B = _lib.empty((1, n_nops, n_basis, n_omega))
-        F = _lib.empty((1, n_nops, n_nops, n_omega))
-        total_phases = np.empty((1, n_omega), dtype=np.complex128)
+        U, liouville, total_phases, B, F = _lib.empty_many([   # one block, one download
+            ((1, d, d), np.complex128), ((1, n_basis, n_basis), np.complex128),
+            ((1, n_omega), np.complex128), ((1, n_nops, n_basis, n_omega), np.complex128),
+            ((1, n_nops, n_nops, n_omega), np.complex128)])
         omega_arr = _lib.as_f64(omega)
         tau = np.array([newpulse.tau], dtype=np.float64)
         ctx = _lib.context()
