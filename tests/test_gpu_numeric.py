@@ -40,6 +40,20 @@ def test_diagonalize(engine, d, G):
     assert (np.diff(ev, axis=1) >= 0).all()
 
 
+@pytest.mark.parametrize('d,G', [(2, 30011), (3, 13007), (4, 12400)])
+def test_diagonalize_many_segments(engine, d, G):
+    """More scan blocks than the apply kernel combines on its own (> 96 blocks of 256 / 128 segments):
+    the block totals go through a second scan level.  Small rotation angles keep the long product
+    well conditioned for the comparison."""
+    rng = np.random.default_rng(d*G)
+    *_, dt, H = _setup(rng, d, G, 2)
+    dt = dt*0.05
+    ev, V, Q = engine.numeric.diagonalize(H, dt)
+    ev_o, V_o, Q_o = oracle.diagonalize(H, dt)
+    assert nerr(ev, ev_o) < TOL
+    assert nerr(Q, Q_o) < TOL
+
+
 def test_diagonalize_degenerate_and_zero(engine):
     """H_c = 0 segments and exactly degenerate spectra (gauge freedom in whole subspaces)."""
     d, G = 4, 6
