@@ -84,3 +84,12 @@ def test_full_size_workloads(engine, name):
     np.testing.assert_allclose(dev.infidelity.cpu().numpy(), full, rtol=1e-12)
     from filter_functions_b200 import _lib
     _lib.check(dev.ctx, _lib.lib().ffb_set_stream(dev.ctx, None, 0))
+    # the step-by-step entry points from host arrays (large eigensystems go up straight from the
+    # caller's arrays, small inputs through the packed staging block) give the same control matrix
+    ev2, V2, Q2 = ff.numeric.diagonalize(H, wl.dt)
+    assert nerr(Q2, Q) < TOL
+    sub = slice(0, len(wl.omega), max(1, len(wl.omega)//700))
+    B_sub = ff.numeric.calculate_control_matrix_from_scratch(
+        pulse.eigvals, pulse.eigvecs, pulse.propagators, wl.omega[sub], wl.basis, wl.n_opers[order],
+        wl.n_coeffs[order], wl.dt, wl.t)
+    assert nerr(B_sub, B[..., sub]) < 1e-12
