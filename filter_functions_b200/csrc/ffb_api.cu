@@ -1346,7 +1346,7 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
   us_enqueued = since();
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   us_main = since();
-  if (overlap) FFB_CUDA(ctx, cudaStreamSynchronize(cs));
+  if (overlap || fb.n_blocks > 1) FFB_CUDA(ctx, cudaStreamSynchronize(cs));  // anything on the copy stream?
   FFB_TRY(ffb_conv_check(ctx));
   if (trace)
     fprintf(stderr, "[ffb trace] pulse pipeline: inputs packed+upload enqueued %.0f us, all work enqueued "
