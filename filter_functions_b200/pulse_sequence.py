@@ -540,11 +540,23 @@ def _join_hamiltonians(pulses, kind: str):
     bookkeeping is one pass over dictionaries instead of ``np.unique`` + masks.
     """
     attr = 'c' if kind == 'control' else 'n'
-    per_pulse = [(_oper_hashes(p, kind), getattr(p, f'{attr}_oper_identifiers').tolist(),
-                  getattr(p, f'{attr}_opers'), getattr(p, f'{attr}_coeffs')) for p in pulses]
+    # one entry per DISTINCT pulse object (a sequence of 100 Cliffords has at most 24)
+    entries, per_pulse = {}, []
+    for p in pulses:
+        entry = entries.get(id(p))
+        if entry is None:
+            entry = entries[id(p)] = (_oper_hashes(p, kind),
+                                      getattr(p, f'{attr}_oper_identifiers').tolist(),
+                                      getattr(p, f'{attr}_opers'), getattr(p, f'{attr}_coeffs'))
+        per_pulse.append(entry)
     first = {}              # hash -> (pulse position, index within that pulse) of first occurrence
     ids_of_oper, opers_of_id = {}, {}
-    for pos, (hashes, idents, _, _) in enumerate(per_pulse):
+    seen = set()
+    for pos, entry in enumerate(per_pulse):
+        if id(entry) in seen:       # a pulse object that occurred before adds nothing new
+            continue
+        seen.add(id(entry))
+        hashes, idents = entry[0], entry[1]
         for loc, (h, ident) in enumerate(zip(hashes, idents)):
             if h not in first:
                 first[h] = (pos, loc)
@@ -566,12 +578,19 @@ def _join_hamiltonians(pulses, kind: str):
                 new_ids[row_of[h]] = f'{ident}_{pulse_pos}'
                 mapping[pulse_pos][ident] = new_ids[row_of[h]]
 
-    seg_edges = [0] + list(accumulate(entry[3].shape[1] for entry in per_pulse))
-    joined = np.full((len(new_ids), seg_edges[-1]), np.nan)
-    for pos, (hashes, _, _, coeffs) in enumerate(per_pulse):
-        lo, hi = seg_edges[pos], seg_edges[pos + 1]
-        for loc, h in enumerate(hashes):
-            joined[row_of[h], lo:hi] = coeffs[loc]
+    hashes0 = per_pulse[0][0]
+    if all(entry[0] == hashes0 for entry in entries.values()):
+        # every pulse carries the same operators in the same order: rows are those of the first pulse
+        joined = np.concatenate([entry[3] for entry in per_pulse], axis=1).astype(float, copy=False)
+    else:
+        # per distinct pulse its block of the joined array (NaN rows for operators it does not carry),
+        # then ONE concatenation along the time axis instead of a slice assignment per pulse and row
+        expanded = {}
+        for entry in entries.values():
+            block = np.full((len(new_ids), entry[3].shape[1]), np.nan)
+            block[[row_of[h] for h in entry[0]]] = entry[3]
+            expanded[id(entry)] = block
+        joined = np.concatenate([expanded[id(entry)] for entry in per_pulse], axis=1)
 
     missing = np.isnan(joined)
     if missing.any():
@@ -625,15 +644,15 @@ def concatenate_without_filter_function(pulses: Iterable[PulseSequence],
     return newpulse
 
 
-def _frequency_entry(pls, key: str, omega):
-    """Cached frequency-dependent array ``key`` of ``pls`` if it belongs to the grid ``omega`` (without
-    the copy + comparison the ``omega`` setter makes on every access), else ``None``."""
+def _frequency_entries(pls, keys, omega):
+    """Cached frequency-dependent arrays ``keys`` of ``pls`` if they belong to the grid ``omega``
+    (one comparison for all of them, and without the copy + comparison the ``omega`` setter makes on
+    every access); ``None`` for what is not cached or belongs to another grid."""
     cached = pls._frequency_data.get('omega')
-    if cached is None or key not in pls._frequency_data:
-        return None
-    if cached is omega or (cached.shape == np.shape(omega) and np.array_equal(cached, omega)):
-        return pls._frequency_data[key]
-    return None
+    if cached is None or not (cached is omega or (cached.shape == np.shape(omega)
+                                                  and np.array_equal(cached, omega))):
+        return (None,)*len(keys)
+    return tuple(pls._frequency_data.get(key) for key in keys)
 
 
 @util.parse_optional_parameters(which=('fidelity', 'generalized'))
@@ -705,9 +724,8 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
     inverse = [slot[id(pls)] for pls in pulses]
     lib_phases, lib_liouville, lib_ctrl = [], [], []
     for pls in distinct:
-        ph = _frequency_entry(pls, 'total_phases', omega)
+        ph, B = _frequency_entries(pls, ('total_phases', 'control_matrix'), omega)
         lib_phases.append(pls.get_total_phases(omega) if ph is None else ph)
-        B = _frequency_entry(pls, 'control_matrix', omega)
         lib_ctrl.append(pls.get_control_matrix(omega, show_progressbar) if B is None else B)
         lib_liouville.append(pls.total_propagator_liouville)
 
