@@ -207,6 +207,7 @@ void ffb_destroy(ffb_ctx* ctx) {
   if (ctx->trig_table) cudaFree(ctx->trig_table);
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
   if (ctx->conv_dev) cudaFree(ctx->conv_dev);
+  if (ctx->infid_scratch) cudaFree(ctx->infid_scratch);
   if (ctx->conv_host) cudaFreeHost(ctx->conv_host);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& ev : ctx->copy_ev)

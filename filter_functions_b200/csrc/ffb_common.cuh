@@ -39,6 +39,8 @@ struct ffb_ctx {
   // fetch it with their last copies and return FFB_ENOTCONV (numpy.linalg.eigh raises LinAlgError)
   int* conv_dev = nullptr;
   int* conv_host = nullptr;
+  // partial sums + ticket counters of the chunked infidelity integral (allocated and zeroed once)
+  void* infid_scratch = nullptr;
   // launch bookkeeping that would otherwise cost a driver call per launch: the dynamic shared memory
   // limit already set for a kernel (grow-only) and occupancy query results
   std::map<const void*, size_t> func_smem;

@@ -7,6 +7,9 @@
 // These stages are HBM/L2-bound streaming reductions: omega is the fastest axis of every array, so a
 // warp reads 32 consecutive complex128 values (512 B) per row and the basis axis is reduced in
 // registers.
+#include <algorithm>
+#include <cstdlib>
+
 #include "ffb_common.cuh"
 
 namespace {
@@ -115,6 +118,71 @@ infidelity_kernel(int n_nops, int n_sel, const int* __restrict__ idx, int n_omeg
   }
 }
 
+// Few outputs on a long frequency grid (one pulse: 3-36 integrals over 1e4-5e4 frequencies): one block
+// per output leaves the machine idle and walks the grid with one block's worth of loads in flight
+// (9 us for config 2).  Here an output is cut into chunks of INFID_CHUNK intervals, one block each; a
+// block writes its partial sum and takes a ticket, and the block that draws the last ticket adds the
+// partial sums up IN CHUNK ORDER (deterministic) and resets the ticket counter for the next launch.
+constexpr int INFID_CHUNK = 1024;
+constexpr int INFID_MAX_CHUNKS = 64;
+constexpr int INFID_MAX_OUT = 64;  // more outputs than this fill the machine with one block each
+__global__ void __launch_bounds__(256)
+infidelity_chunked_kernel(int n_nops, int n_sel, const int* __restrict__ idx, int n_omega,
+                          const double2* __restrict__ F, const double* __restrict__ spectrum,
+                          int spectrum_ndim, int spectrum_is_complex,
+                          const double* __restrict__ omega, double norm, int n_chunks,
+                          double* __restrict__ partial, unsigned* __restrict__ tickets,
+                          double* __restrict__ out) {
+  __shared__ double warp_sums[8];
+  __shared__ bool last;
+  const int o = blockIdx.x, chunk = blockIdx.y;
+  int lead, a, b;
+  if (spectrum_ndim == 3) {
+    lead = o / (n_sel * n_sel);
+    a = (o / n_sel) % n_sel;
+    b = o % n_sel;
+  } else {
+    lead = o / n_sel;
+    a = b = o % n_sel;
+  }
+  const int ia = idx ? idx[a] : a, ib = idx ? idx[b] : b;
+  const double2* Frow = F + (((size_t)lead * n_nops + ia) * n_nops + ib) * n_omega;
+  size_t s_off = 0;
+  if (spectrum_ndim == 2) s_off = (size_t)a * n_omega;
+  if (spectrum_ndim == 3) s_off = ((size_t)a * n_sel + b) * n_omega;
+  auto integrand = [&](int i) -> double {
+    const double2 f = Frow[i];
+    if (spectrum_is_complex) {
+      const double2 s = reinterpret_cast<const double2*>(spectrum)[s_off + i];
+      return f.x * s.x - f.y * s.y;
+    }
+    return f.x * spectrum[s_off + i];
+  };
+  const int per = (n_omega - 1 + n_chunks - 1) / n_chunks;  // intervals per chunk
+  const int i0 = chunk * per, i1 = min(n_omega - 1, i0 + per);
+  double sum = 0.0;
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x)
+    sum += (integrand(i + 1) + integrand(i)) * (omega[i + 1] - omega[i]);
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) total += warp_sums[i];
+    partial[(size_t)o * n_chunks + chunk] = total;
+    __threadfence();
+    last = atomicAdd(&tickets[o], 1u) == (unsigned)(n_chunks - 1);
+    if (last) {
+      __threadfence();
+      double all = 0.0;
+      for (int c = 0; c < n_chunks; ++c)
+        all += reinterpret_cast<volatile double*>(partial)[(size_t)o * n_chunks + c];
+      out[o] = all / 2.0 / norm;
+      tickets[o] = 0;  // ready for the next launch (launches on one stream are ordered)
+    }
+  }
+}
+
 }  // namespace
 
 int ffbi_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega,
@@ -168,6 +236,24 @@ int ffbi_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* 
               n_omega, d);
   const int n_out = n_lead * (spectrum_ndim == 3 ? n_sel * n_sel : n_sel);
   const double norm = 2.0 * 3.141592653589793238462643383279502884 * d;
+  static const bool chunked_ok = !(getenv("FFB_INFIDELITY_CHUNKED") && atoi(getenv("FFB_INFIDELITY_CHUNKED")) == 0);
+  if (chunked_ok && n_out <= INFID_MAX_OUT && n_omega - 1 >= 2 * INFID_CHUNK) {
+    const int n_chunks = std::min(INFID_MAX_CHUNKS, ceil_div(n_omega - 1, INFID_CHUNK));
+    if (!ctx->infid_scratch) {  // partial sums and ticket counters, allocated (and zeroed) once
+      FFB_CUDA(ctx, cudaMalloc(&ctx->infid_scratch,
+                               (size_t)INFID_MAX_OUT * (INFID_MAX_CHUNKS * sizeof(double) + sizeof(unsigned))));
+      FFB_CUDA(ctx, cudaMemsetAsync(ctx->infid_scratch, 0,
+                                    (size_t)INFID_MAX_OUT * (INFID_MAX_CHUNKS * sizeof(double) + sizeof(unsigned)),
+                                    ctx->stream));
+    }
+    double* partial = static_cast<double*>(ctx->infid_scratch);
+    unsigned* tickets = reinterpret_cast<unsigned*>(partial + (size_t)INFID_MAX_OUT * INFID_MAX_CHUNKS);
+    infidelity_chunked_kernel<<<dim3(n_out, n_chunks), 256, 0, ctx->stream>>>(
+        n_nops, n_sel, idx_dev, n_omega, reinterpret_cast<const double2*>(F), spectrum, spectrum_ndim,
+        spectrum_is_complex, omega, norm, n_chunks, partial, tickets, out);
+    FFB_LAUNCHED(ctx);
+    return FFB_OK;
+  }
   const int threads = n_omega > 4096 ? 1024 : 256;
   infidelity_kernel<<<n_out, threads, 0, ctx->stream>>>(
       n_nops, n_sel, idx_dev, n_omega, reinterpret_cast<const double2*>(F), spectrum,

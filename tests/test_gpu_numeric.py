@@ -309,9 +309,13 @@ def test_from_atomic_memory_layout(engine):
             assert nerr(o, ref) < 1e-13
 
 
-def test_infidelity_integral(engine):
+@pytest.mark.parametrize('n_omega', [501, 2049, 2050, 5000, 70001])
+def test_infidelity_integral(engine, n_omega):
+    """501: one block per output; >= 2049 intervals: chunked over several blocks per output with the
+    partial sums added in chunk order (2049 / 2050 straddle the switch, 70001 hits the chunk cap);
+    repeated calls reuse the ticket counters."""
     rng = np.random.default_rng(31)
-    n_nops, n_omega, d = 4, 501, 2
+    n_nops, d = 4, 2
     B = rng.standard_normal((n_nops, 4, n_omega)) + 1j*rng.standard_normal((n_nops, 4, n_omega))
     F = oracle.filter_function(B)
     omega = np.sort(rng.random(n_omega))*10
@@ -322,10 +326,11 @@ def test_infidelity_integral(engine):
     S3[0, 1] += 1j*omega
     S3[1, 0] -= 1j*omega
     f = engine.numeric._integrate_against_spectrum
-    for S in (S1, S2, S3):
+    for S in (S1, S2, S3, S1):
         got = f(F, S, omega, idx, d)
         want = oracle.infidelity_from_filter_function(F, S, omega, d, idx)
         assert got.shape == want.shape and nerr(got, want) < 1e-13
+        assert np.array_equal(got, f(F, S, omega, idx, d))     # deterministic
     # leading pulse-correlation axes
     Fpc = oracle.pulse_correlation_filter_function(np.stack([B, 2*B]))
     got = f(Fpc, S2, omega, idx, d)
