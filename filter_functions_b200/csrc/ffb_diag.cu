@@ -555,9 +555,9 @@ scan_block_kernel(int n, const double2* __restrict__ in, double2* __restrict__ l
 
 // out[i + shift] = local[i] * incl_totals[block(i) - 1]  (identity for block 0); with shift = 1 the
 // kernel also writes the identity to out[0] (the propagators array starts with Q_0 = 1).
-// Same, but the inclusive product of the block totals is formed HERE: thread 0 of the block multiplies
-// the totals of the source blocks before it (a chain of < SCAN_PREFIX_MAX register matmuls, ~1 us)
-// instead of two more launches for a scan over a few dozen matrices.  blockDim.x == NT.
+// Same, but the inclusive product of the block totals is formed HERE (every block multiplies up the
+// totals of the source blocks before it, at most SCAN_PREFIX_MAX of them) instead of two more launches
+// for a scan over a few dozen matrices.  blockDim.x == NT >= SCAN_PREFIX_MAX / 2.
 constexpr int SCAN_PREFIX_MAX = 96;
 template <int D, int NT>
 __global__ void __launch_bounds__(NT)
@@ -569,23 +569,32 @@ scan_apply_prefix_kernel(int n, int shift, const double2* __restrict__ local,
   const int blk = blockIdx.x;
   const int g = blk * NT + threadIdx.x;
   // the totals before this block come in with one coalesced load (a chain of dependent global loads
-  // would cost an L2 round trip per matrix), then one thread multiplies them up out of shared memory
+  // would cost an L2 round trip per matrix), then an ORDERED tree product in shared memory: after the
+  // level with stride s, tot[i] (i a multiple of 2 s) holds T_{i+2s-1} ... T_i -- log2(blk) levels of
+  // one register matmul each instead of a chain of blk - 1 (60 us for 79 4 x 4 totals).
   for (int e = threadIdx.x; e < blk * DD; e += NT) tot[e] = totals[e];
   __syncthreads();
-  if (threadIdx.x == 0 && blk > 0) {
-    double2 acc[DD], nxt[DD], prod[DD];
+  for (int stride = 1; stride < blk; stride <<= 1) {
+    const int i = threadIdx.x * 2 * stride;
+    const bool act = i + stride < blk;
+    double2 prod[DD];
+    if (act) {
+      double2 later[DD], earlier[DD];
 #pragma unroll
-    for (int e = 0; e < DD; ++e) acc[e] = tot[e];
-    for (int b = 1; b < blk; ++b) {  // acc = T_b T_{b-1} ... T_0
-#pragma unroll
-      for (int e = 0; e < DD; ++e) nxt[e] = tot[b * DD + e];
-      matmul_reg<D>(nxt, acc, prod);
-#pragma unroll
-      for (int e = 0; e < DD; ++e) acc[e] = prod[e];
+      for (int e = 0; e < DD; ++e) {
+        later[e] = tot[(i + stride) * DD + e];
+        earlier[e] = tot[i * DD + e];
+      }
+      matmul_reg<D>(later, earlier, prod);
     }
+    __syncthreads();
+    if (act) {
 #pragma unroll
-    for (int e = 0; e < DD; ++e) prefix[e] = acc[e];
+      for (int e = 0; e < DD; ++e) tot[i * DD + e] = prod[e];
+    }
+    __syncthreads();
   }
+  if (threadIdx.x < DD && blk > 0) prefix[threadIdx.x] = tot[threadIdx.x];
   if (g == 0 && shift) {
 #pragma unroll
     for (int e = 0; e < DD; ++e) out[e] = make_double2((e / D == e % D) ? 1.0 : 0.0, 0.0);
