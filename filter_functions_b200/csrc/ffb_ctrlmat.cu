@@ -434,88 +434,113 @@ __host__ __device__ inline StreamGeom make_geom(int rows, int G, int d, int MT) 
   return s;
 }
 
+// One block per (row block, pass).  A thread takes one (row, K slot) of the pass and walks its units
+// (diagonal term, then the level pairs), so the index arithmetic is done once per 1 + 2 n_pairs values
+// instead of once per value (the first version decoded every double of the stream on its own: ~300
+// instructions per value, 143 us for the 100 MB stream of d = 4, G = 1e4), and consecutive threads write
+// consecutive addresses of every A column.  STAGED: the transformed operators of the pass's segments are
+// copied to shared memory first (coalesced); used when they fit, i.e. for small d.
+template <bool STAGED>
 __global__ void __launch_bounds__(256)
 assemble_kernel(StreamGeom geo, int G, int d, int rows, int n_jrows, int n_krows,
-                const double* __restrict__ Bbar, const double* __restrict__ Cbar,
+                const double* __restrict__ Bbar_g, const double* __restrict__ Cbar_g,
                 const double* __restrict__ eigvals, const double* __restrict__ dt,
                 const double* __restrict__ t, double* __restrict__ stream) {
-  // one thread per double of the stream; blockIdx.x = (row block, pass), blockIdx.y strides over the
-  // doubles of that pass -- all index arithmetic in 32 bits (the first version decoded a flat 64-bit
-  // index with three 64-bit divisions per element: 143 us for the 100 MB stream of d = 4, G = 1e4)
+  extern __shared__ __align__(16) double stage[];
   const int dd = d * d;
   const int rb = blockIdx.x / geo.n_pass, pass = blockIdx.x % geo.n_pass;
+  const int segs = geo.transposed ? 1 : 4;
+  const int g0 = geo.transposed ? pass : pass * 4;  // first segment of the pass
+  const double* Bbar = Bbar_g;
+  const double* Cbar = Cbar_g;
+  int g_base = 0;  // segment whose operators sit at index 0 of Bbar / Cbar
+  if (STAGED) {
+    const int n_seg = max(0, min(segs, G - g0));
+    const int nb = n_jrows * 2 * dd, nc = n_krows * 2 * dd;
+    double* Bs = stage;
+    double* Cs = stage + (size_t)segs * nb;
+    for (int e = threadIdx.x; e < n_seg * nb; e += blockDim.x) Bs[e] = Bbar_g[(size_t)g0 * nb + e];
+    for (int e = threadIdx.x; e < n_seg * nc; e += blockDim.x) Cs[e] = Cbar_g[(size_t)g0 * nc + e];
+    __syncthreads();
+    Bbar = Bs;
+    Cbar = Cs;
+    g_base = g0;
+  }
   double* const out = stream + (size_t)rb * geo.rb_doubles + (size_t)pass * geo.pass_doubles;
-  const int pass_doubles = (int)geo.pass_doubles;
-  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < pass_doubles; e += gridDim.y * blockDim.x) {
-    int rem = e;
-    int unit, off;  // unit 0 = diag, 1.. = pairs
-    if (rem < geo.diag_unit) {
-      unit = 0;
-      off = rem;
-    } else {
-      rem -= geo.diag_unit;
-      unit = 1 + rem / geo.pair_unit;
-      off = rem % geo.pair_unit;
+  const int col = geo.MT * 32;  // doubles per A column
+
+  // ---- A columns
+  for (int item = threadIdx.x; item < col; item += blockDim.x) {
+    const int mt = item >> 5, l = item & 31;
+    const int row = (rb * geo.MT + mt) * 8 + (l >> 2);
+    const int slot = l & 3;
+    const int g = geo.transposed ? pass : g0 + slot;
+    const bool live = row < rows && g < G;
+    const double* Bm = nullptr;
+    const double* Cm = nullptr;
+    if (live) {
+      Bm = Bbar + ((size_t)(g - g_base) * n_jrows + row / n_krows) * 2 * dd;
+      Cm = Cbar + ((size_t)(g - g_base) * n_krows + row % n_krows) * 2 * dd;
     }
-    const int a_doubles = (unit == 0 ? 1 : 2) * geo.MT * 32;
+    // diagonal unit (transposed layout: only K slot 0 carries it)
+    double diag = 0.0;
+    if (live && !(geo.transposed && slot != 0))
+      for (int m = 0; m < d; ++m) diag += Bm[2 * (m * d + m)] * Cm[2 * (m * d + m)];
+    out[item] = diag;
+    // pair units
+    int m = 0, n = 1;  // level pair of unit 1 in the regular layout
+    for (int u = 1; u <= geo.n_pairs; ++u) {
+      const int pair = geo.transposed ? (u - 1) * 4 + slot : u - 1;
+      double re = 0.0, im = 0.0;
+      if (live && pair < geo.real_pairs) {
+        if (geo.transposed) pair_from_index(pair, d, m, n);
+        const cplx bv = {Bm[2 * (m * d + n)], Bm[2 * (m * d + n) + 1]};
+        const cplx cv = {Cm[2 * (n * d + m)], Cm[2 * (n * d + m) + 1]};
+        const cplx prod = cmul(bv, cv);
+        re = prod.re;
+        im = prod.im;
+      }
+      double* unit = out + geo.diag_unit + (size_t)(u - 1) * geo.pair_unit;
+      unit[item] = re;
+      unit[col + item] = im;
+      if (!geo.transposed && ++n == d) {  // next pair (m, n) in row-major order of the upper triangle
+        ++m;
+        n = m + 1;
+      }
+    }
+  }
+
+  // ---- constants: t[4], dt[4] behind the diagonal column; Omega[4], cos[4], sin[4] behind a pair's columns
+  for (int e = threadIdx.x; e < 8 + 12 * geo.n_pairs; e += blockDim.x) {
     double val = 0.0;
-    if (off < a_doubles) {
-      const int col = off / (geo.MT * 32);  // 0: diag or Re, 1: Im
-      const int mt = (off / 32) % geo.MT;
-      const int l = off % 32;
-      const int row = (rb * geo.MT + mt) * 8 + (l >> 2);
-      const int slot = l & 3;
-      const int g = geo.transposed ? pass : pass * 4 + slot;
-      // level pair of this K slot (-1: the diagonal term; -2: padding)
-      int pair;
-      if (unit == 0) pair = (geo.transposed && slot != 0) ? -2 : -1;
-      else pair = geo.transposed ? (unit - 1) * 4 + slot : unit - 1;
-      if (pair >= geo.real_pairs) pair = -2;
-      if (row < rows && g < G && pair != -2) {
-        const int jr = row / n_krows, kr = row % n_krows;
-        const double* Bm = Bbar + ((size_t)g * n_jrows + jr) * 2 * dd;
-        const double* Cm = Cbar + ((size_t)g * n_krows + kr) * 2 * dd;
-        if (pair == -1) {
-          double acc = 0.0;
-          for (int m = 0; m < d; ++m) acc += Bm[2 * (m * d + m)] * Cm[2 * (m * d + m)];
-          val = acc;
-        } else {
-          int m, n;
-          pair_from_index(pair, d, m, n);
-          const cplx b = {Bm[2 * (m * d + n)], Bm[2 * (m * d + n) + 1]};
-          const cplx c = {Cm[2 * (n * d + m)], Cm[2 * (n * d + m) + 1]};
-          const cplx prod = cmul(b, c);
-          val = col == 0 ? prod.re : prod.im;
-        }
-      }
+    if (e < 8) {
+      const int which = e >> 2, slot = e & 3;
+      const int g = geo.transposed ? pass : g0 + slot;
+      if (g < G) val = which == 0 ? t[g] : dt[g];
+      out[col + e] = val;
     } else {
-      const int c = off - a_doubles;  // constants
-      const int which = c / 4;
-      const int slot = c & 3;
-      const int g = geo.transposed ? pass : pass * 4 + slot;
-      if (unit == 0) {
-        if (g < G) val = which == 0 ? t[g] : dt[g];
-      } else {
-        // padding slots (A coefficients 0) repeat the constants of the last real pair, so that they
-        // take the removable-singularity fix-up only where that pair takes it anyway
-        const int pair = min(geo.transposed ? (unit - 1) * 4 + slot : unit - 1, geo.real_pairs - 1);
-        double Om = 0.0, dtg = 0.0;
-        if (g < G) {
-          int m, n;
-          pair_from_index(pair, d, m, n);
-          Om = eigvals[(size_t)g * d + m] - eigvals[(size_t)g * d + n];
-          dtg = dt[g];
-        }
-        if (which == 0) {
-          val = Om;
-        } else {
-          double sn, cs;
-          sincos(0.5 * (Om * dtg), &sn, &cs);  // e^{i Omega dt / 2}
-          val = which == 1 ? cs : sn;
-        }
+      const int u = 1 + (e - 8) / 12, c = (e - 8) % 12;
+      const int which = c >> 2, slot = c & 3;
+      const int g = geo.transposed ? pass : g0 + slot;
+      // padding slots (A coefficients 0) repeat the constants of the last real pair, so that they
+      // take the removable-singularity fix-up only where that pair takes it anyway
+      const int pair = min(geo.transposed ? (u - 1) * 4 + slot : u - 1, geo.real_pairs - 1);
+      double Om = 0.0, dtg = 0.0;
+      if (g < G) {
+        int m, n;
+        pair_from_index(pair, d, m, n);
+        Om = eigvals[(size_t)g * d + m] - eigvals[(size_t)g * d + n];
+        dtg = dt[g];
       }
+      if (which == 0) {
+        val = Om;
+      } else {
+        double sn, cs;
+        sincos(0.5 * (Om * dtg), &sn, &cs);  // e^{i Omega dt / 2}
+        val = which == 1 ? cs : sn;
+      }
+      out[geo.diag_unit + (size_t)(u - 1) * geo.pair_unit + 2 * col + c] = val;
     }
-    out[e] = val;
   }
 }
 
@@ -1624,11 +1649,19 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
                                                           eigvals, dt, t, stream.as<double>());
     FFB_LAUNCHED(ctx);
   } else {
-    const dim3 blocks((unsigned)(geo.n_rb * geo.n_pass),
-                      (unsigned)std::min<size_t>(ceil_div_sz(geo.pass_doubles, 256), 1024));
-    assemble_kernel<<<blocks, 256, 0, ctx->stream>>>(geo, G, d, rows, n_jrows, n_krows,
-                                                     Bbar.as<double>(), Cbar.as<double>(), eigvals,
-                                                     dt, t, stream.as<double>());
+    // operators of a pass's segments in shared memory when they fit
+    const size_t stage_bytes = (size_t)(geo.transposed ? 1 : 4) * (n_jrows + n_krows) * 2 * dd * sizeof(double);
+    const unsigned blocks = (unsigned)(geo.n_rb * geo.n_pass);
+    if (stage_bytes <= 96 * 1024) {
+      FFB_TRY(ffb_func_smem(ctx, assemble_kernel<true>, stage_bytes));
+      assemble_kernel<true><<<blocks, 256, stage_bytes, ctx->stream>>>(
+          geo, G, d, rows, n_jrows, n_krows, Bbar.as<double>(), Cbar.as<double>(), eigvals, dt, t,
+          stream.as<double>());
+    } else {
+      assemble_kernel<false><<<blocks, 256, 0, ctx->stream>>>(
+          geo, G, d, rows, n_jrows, n_krows, Bbar.as<double>(), Cbar.as<double>(), eigvals, dt, t,
+          stream.as<double>());
+    }
     FFB_LAUNCHED(ctx);
   }
 
