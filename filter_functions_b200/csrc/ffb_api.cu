@@ -590,6 +590,11 @@ struct OutputBlock {
       for (size_t i = 1; i < order.size(); ++i)
         if (order[i]->host < order[i - 1]->host + order[i - 1]->bytes) mirrored = false;
     }
+    if (mirrored) {  // results scattered over a large block: mirroring would waste device memory
+      size_t sum = 0;
+      for (const Item& it : items) sum += it.bytes;
+      if ((size_t)(hi - lo) > 2 * sum + ((size_t)1 << 20)) mirrored = false;
+    }
     if (mirrored) {
       host_base = lo;
       total = ((size_t)(hi - lo) + ALIGN - 1) & ~(ALIGN - 1);
