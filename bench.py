@@ -31,6 +31,13 @@ if '--impl' in sys.argv and 'reference' in sys.argv:
     for _var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
         os.environ[_var] = str(os.cpu_count() or 1)
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to
+# stdout at init, nvcc output of a first build, ...): keep a private handle on the real stdout for the
+# result line and point file descriptor 1 at stderr for everything else, native code included.
+sys.stdout.flush()
+RESULT_OUT = os.fdopen(os.dup(1), 'w')
+os.dup2(2, 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -127,7 +134,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -390,7 +397,7 @@ def run_b200(args):
         'parity_device_vs_api': parity,
         'infidelity': np.asarray(infid_e2e).ravel().tolist()[:6],
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
