@@ -540,23 +540,20 @@ def _join_hamiltonians(pulses, kind: str):
     bookkeeping is one pass over dictionaries instead of ``np.unique`` + masks.
     """
     attr = 'c' if kind == 'control' else 'n'
-    # one entry per DISTINCT pulse object (a sequence of 100 Cliffords has at most 24)
-    entries, per_pulse = {}, []
-    for p in pulses:
-        entry = entries.get(id(p))
-        if entry is None:
-            entry = entries[id(p)] = (_oper_hashes(p, kind),
-                                      getattr(p, f'{attr}_oper_identifiers').tolist(),
-                                      getattr(p, f'{attr}_opers'), getattr(p, f'{attr}_coeffs'))
-        per_pulse.append(entry)
+    # one entry per DISTINCT pulse object (a sequence of 100 Cliffords has at most 24): the bookkeeping
+    # below runs over the distinct objects, positions only index into them
+    slot, entries, first_pos, order = {}, [], [], []
+    for pos, p in enumerate(pulses):
+        i = slot.get(id(p))
+        if i is None:
+            i = slot[id(p)] = len(entries)
+            entries.append((_oper_hashes(p, kind), getattr(p, f'{attr}_oper_identifiers').tolist(),
+                            getattr(p, f'{attr}_opers'), getattr(p, f'{attr}_coeffs')))
+            first_pos.append(pos)
+        order.append(i)
     first = {}              # hash -> (pulse position, index within that pulse) of first occurrence
     ids_of_oper, opers_of_id = {}, {}
-    seen = set()
-    for pos, entry in enumerate(per_pulse):
-        if id(entry) in seen:       # a pulse object that occurred before adds nothing new
-            continue
-        seen.add(id(entry))
-        hashes, idents = entry[0], entry[1]
+    for pos, (hashes, idents, _, _) in zip(first_pos, entries):   # in order of first occurrence
         for loc, (h, ident) in enumerate(zip(hashes, idents)):
             if h not in first:
                 first[h] = (pos, loc)
@@ -569,8 +566,9 @@ def _join_hamiltonians(pulses, kind: str):
                          + f'different identifiers. Please choose unique {kind} identifiers!')
 
     row_of = {h: i for i, h in enumerate(first)}
-    new_ids = [per_pulse[pos][1][loc] for pos, loc in first.values()]
-    mapping = {pos: dict(zip(idents, idents)) for pos, (_, idents, _, _) in enumerate(per_pulse)}
+    new_ids = [entries[order[pos]][1][loc] for pos, loc in first.values()]
+    identity_maps = [dict(zip(entry[1], entry[1])) for entry in entries]
+    mapping = {pos: dict(identity_maps[i]) for pos, i in enumerate(order)}
     for ident, hashes in opers_of_id.items():
         if len(hashes) > 1:
             for h in hashes:
@@ -578,19 +576,19 @@ def _join_hamiltonians(pulses, kind: str):
                 new_ids[row_of[h]] = f'{ident}_{pulse_pos}'
                 mapping[pulse_pos][ident] = new_ids[row_of[h]]
 
-    hashes0 = per_pulse[0][0]
-    if all(entry[0] == hashes0 for entry in entries.values()):
+    hashes0 = entries[0][0]
+    if all(entry[0] == hashes0 for entry in entries):
         # every pulse carries the same operators in the same order: rows are those of the first pulse
-        joined = np.concatenate([entry[3] for entry in per_pulse], axis=1).astype(float, copy=False)
+        joined = np.concatenate([entries[i][3] for i in order], axis=1).astype(float, copy=False)
     else:
         # per distinct pulse its block of the joined array (NaN rows for operators it does not carry),
         # then ONE concatenation along the time axis instead of a slice assignment per pulse and row
-        expanded = {}
-        for entry in entries.values():
+        expanded = []
+        for entry in entries:
             block = np.full((len(new_ids), entry[3].shape[1]), np.nan)
             block[[row_of[h] for h in entry[0]]] = entry[3]
-            expanded[id(entry)] = block
-        joined = np.concatenate([expanded[id(entry)] for entry in per_pulse], axis=1)
+            expanded.append(block)
+        joined = np.concatenate([expanded[i] for i in order], axis=1)
 
     missing = np.isnan(joined)
     if missing.any():
@@ -605,9 +603,9 @@ def _join_hamiltonians(pulses, kind: str):
         else:
             joined[missing] = 0
 
-    order = np.argsort(new_ids)
-    opers = np.array([per_pulse[pos][2][loc] for pos, loc in first.values()])
-    return opers[order], np.array([new_ids[i] for i in order]), joined[order], mapping
+    by_id = np.argsort(new_ids)
+    opers = np.array([entries[order[pos]][2][loc] for pos, loc in first.values()])
+    return opers[by_id], np.array([new_ids[i] for i in by_id]), joined[by_id], mapping
 
 
 def _unique_by_identity(items):

@@ -262,3 +262,45 @@ def test_frequency_shard_partition(n_omega, world):
     assert (owned == 1).all()
     with pytest.raises(ValueError):
         ffd.frequency_shard(10, 3, 3)
+
+
+def test_concatenate_hamiltonians_randomized():
+    """Long random sequences of recurring pulse objects (the randomized-benchmarking pattern the join
+    is written for): every pulse's coefficients must sit in its time slice of the row its (possibly
+    renamed) identifier maps to, missing control operators are zero there, missing noise operators
+    carry the inferred constant."""
+    rng = np.random.default_rng(42)
+
+    def mk(c_ops, n_ops, G):
+        return ff.PulseSequence([[o, rng.standard_normal(G), i] for o, i in c_ops],
+                                [[o, np.full(G, c), i] for o, i, c in n_ops], np.full(G, 0.3))
+    lib = [mk([(X/2, 'X')], [(Z/2, 'Z', 1.0)], 1), mk([(Y/2, 'Y')], [(Z/2, 'Z', 1.0)], 2),
+           mk([(X/2, 'X'), (Y/2, 'Y')], [(Z/2, 'Z', 1.0), (X/2, 'Xn', 2.0)], 3),
+           mk([(Z/2, 'X')], [(Z/2, 'Z', 1.0)], 1),      # 'X' names another operator here
+           mk([(Y/2, 'Y'), (X/2, 'X')], [(X/2, 'Xn', 2.0), (Z/2, 'Z', 1.0)], 2)]
+    for _ in range(60):
+        seq = [lib[i] for i in rng.integers(0, len(lib), rng.integers(1, 40))]
+        new, cmap, nmap = concatenate_without_filter_function(seq, return_identifier_mappings=True)
+        edges = np.concatenate(([0], np.cumsum([len(p.dt) for p in seq])))
+        assert len(new.dt) == edges[-1]
+        for kind, ids, coeffs, maps in (('c', new.c_oper_identifiers, new.c_coeffs, cmap),
+                                        ('n', new.n_oper_identifiers, new.n_coeffs, nmap)):
+            ids = list(ids)
+            assert ids == sorted(ids) and len(set(ids)) == len(ids)
+            new_opers = getattr(new, f'{kind}_opers')
+            for pos, p in enumerate(seq):
+                lo, hi = edges[pos], edges[pos + 1]
+                carried = set()
+                for ident, op, c in zip(getattr(p, f'{kind}_oper_identifiers'),
+                                        getattr(p, f'{kind}_opers'), getattr(p, f'{kind}_coeffs')):
+                    # (rows are found by operator: like the reference, the identifier mapping is only
+                    # rewritten for the pulse in which a clashing identifier occurs first)
+                    row = [k for k in range(len(ids)) if np.array_equal(new_opers[k], op)]
+                    assert len(row) == 1
+                    carried.add(row[0])
+                    np.testing.assert_array_equal(coeffs[row[0], lo:hi], c)
+                    assert ids[row[0]] == ident or ids[row[0]].startswith(f'{ident}_')
+                    assert maps[pos][ident] in (ident, ids[row[0]])
+                for row in set(range(len(ids))) - carried:
+                    want = 0.0 if kind == 'c' else coeffs[row][0]
+                    assert (coeffs[row, lo:hi] == want).all()
