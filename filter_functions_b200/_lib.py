@@ -75,7 +75,19 @@ EXPORTED_SYMBOLS = {
     'ffb_host_free': (c_int, [c_void_p, c_void_p]),
     'ffb_kernel_timing_enable': (c_int, [c_void_p, c_int]),
     'ffb_kernel_timing_read': (c_int, [c_void_p, _dp, POINTER(c_int64), c_int]),
+    'ffb_comm_create': (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    'ffb_comm_connect': (c_int, [c_void_p, c_void_p]),
+    'ffb_comm_destroy': (c_int, [c_void_p]),
+    'ffb_comm_info': (c_int, [c_void_p, _ip, _ip, POINTER(c_size_t)]),
+    'ffb_comm_reduce_infidelity': (c_int, [c_void_p, c_int]),
+    'ffb_allreduce_sum': (c_int, [c_void_p, c_void_p, c_int]),
+    'ffb_dev_allreduce_sum': (c_int, [c_void_p, c_void_p, c_int]),
+    'ffb_comm_data_window': (c_int, [c_void_p, c_size_t, c_void_p]),
+    'ffb_comm_data_connect': (c_int, [c_void_p, c_void_p]),
+    'ffb_allgather_columns': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }
+
+COMM_HANDLE_BYTES = 64
 
 
 class FFBError(RuntimeError):
@@ -85,6 +97,31 @@ class FFBError(RuntimeError):
 _lib = None
 _lib_lock = threading.Lock()
 _contexts = {}
+#: A context (device pools, staging block, ticket counters) must be used by one thread at a time
+#: (include/ffb200.h) and ctypes drops the GIL during a call, so every entry into the library --
+#: including the ``ffb_host_free`` a garbage-collected result array triggers from whatever thread
+#: the collector happens to run on -- takes this re-entrant lock.
+_call_lock = threading.RLock()
+
+
+class _SerialisedLibrary:
+    """The loaded library with every exported function wrapped to hold ``_call_lock``."""
+
+    def __init__(self, handle):
+        self._handle = handle
+        for name, (restype, argtypes) in EXPORTED_SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+            setattr(self, name, self._serialised(fn))
+
+    @staticmethod
+    def _serialised(fn):
+        def call(*args):
+            with _call_lock:
+                return fn(*args)
+        call.__name__ = fn.__name__
+        return call
 
 
 def lib():
@@ -98,12 +135,7 @@ def lib():
                         f'{library_path} not found. Build it with '
                         '`python -c "import __graft_entry__ as g; g.build()"` from the repository '
                         'root (needs nvcc). filter_functions_b200 has no CPU fallback.')
-                handle = ctypes.CDLL(library_path)
-                for name, (restype, argtypes) in EXPORTED_SYMBOLS.items():
-                    fn = getattr(handle, name)
-                    fn.restype = restype
-                    fn.argtypes = argtypes
-                _lib = handle
+                _lib = _SerialisedLibrary(ctypes.CDLL(library_path))
     return _lib
 
 

@@ -192,6 +192,7 @@ void ffb_destroy(ffb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  ffbi_comm_release(ctx);
   for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
   for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
   for (auto& ev : ctx->event_pool) {
@@ -230,7 +231,9 @@ int ffb_set_stream(ffb_ctx* ctx, void* cuda_stream, int external) {
 int ffb_sync(ffb_ctx* ctx) {
   if (!ctx) return FFB_EINVAL;
   FFB_TRY(ffb_conv_fetch(ctx));  // device-resident callers learn about a non-converged eigensolver here
+  FFB_TRY(ffbi_comm_fetch_error(ctx));  // ... and about a peer that never arrived
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  FFB_TRY(ffbi_comm_check_error(ctx));
   return ffb_conv_check(ctx);
 }
 
@@ -882,8 +885,9 @@ int ffb_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* i
   FFB_TRY(ffbi_infidelity(ctx, n_lead, n_nops, n_sel, Id.buf.as<int>(), n_omega, Fd.d(), Sd.d(),
                           spectrum_ndim, spectrum_is_complex, Od.d(), d, res.as<double>()));
   FFB_TRY(ffb_d2h(ctx, out, res.p, n_out * 8));
+  FFB_TRY(ffbi_comm_fetch_error(ctx));
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return FFB_OK;
+  return ffbi_comm_check_error(ctx);
 }
 
 int ffb_decay_amplitudes(ffb_ctx* ctx, int P, int n_nops, int n_sel, const int* idx, int n_basis,
@@ -1349,11 +1353,13 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
     FFB_TRY(out.download(ctx, {o_ev, o_V, o_Q, o_ph, o_li, o_B, o_F, o_I}, ctx->stream));
   }
   FFB_TRY(ffb_conv_fetch(ctx));
+  if (infidelity) FFB_TRY(ffbi_comm_fetch_error(ctx));
   us_enqueued = since();
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   us_main = since();
   if (overlap || fb.n_blocks > 1) FFB_CUDA(ctx, cudaStreamSynchronize(cs));  // anything on the copy stream?
   FFB_TRY(ffb_conv_check(ctx));
+  FFB_TRY(ffbi_comm_check_error(ctx));
   if (trace)
     fprintf(stderr, "[ffb trace] pulse pipeline: inputs packed+upload enqueued %.0f us, all work enqueued "
             "%.0f us, main stream done %.0f us, copy stream done %.0f us;%s\n", us_packed, us_enqueued,

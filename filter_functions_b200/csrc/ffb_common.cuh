@@ -14,9 +14,41 @@
 #include "../../include/ffb200.h"
 
 // ------------------------------------------------------------------------------------------------
+// peer group: the GPUs of one node, one process each, exchanging through NVLink peer memory
+// ------------------------------------------------------------------------------------------------
+constexpr int FFB_MAX_PEERS = 16;
+constexpr int FFB_PEER_SLOTS = 1024;  // doubles one all-reduce can carry
+
+// Kernel-side view of the group (passed by value).  world <= 1: no exchange.
+struct PeerReduce {
+  unsigned long long window[FFB_MAX_PEERS];  // every rank's exchange window as mapped in THIS process
+  int rank = 0, world = 1;
+  unsigned seq = 0;          // flag value of this collective (never 0, same on all ranks)
+  unsigned timeout_ms = 0;
+  int* error = nullptr;      // device flag, set when a peer did not arrive in time
+};
+
+struct ffb_comm {
+  int rank = 0, world = 1;
+  bool connected = false;
+  void* window = nullptr;                 // mine (cudaMalloc, exported through CUDA IPC)
+  void* peer[FFB_MAX_PEERS] = {};         // peers' windows (peer[rank] == window)
+  unsigned seq = 0;                       // collectives issued so far
+  bool reduce_infidelity = false;         // all-reduce every infidelity integral before it is returned
+  unsigned timeout_ms = 20000;
+  int* err_dev = nullptr;
+  int* err_host = nullptr;
+  // symmetric data window for the all-gather of frequency blocks (grow-only, re-exported on growth)
+  void* data = nullptr;
+  size_t data_bytes = 0;
+  void* peer_data[FFB_MAX_PEERS] = {};
+};
+
+// ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
 struct ffb_ctx {
+  ffb_comm comm;
   int device = 0;
   int sm_count = 148;
   int cc_major = 0, cc_minor = 0;
@@ -201,6 +233,13 @@ int ffbi_liouville(ffb_ctx* ctx, int n, int d, int n_basis, const double* U, con
                    double* out);
 int ffbi_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out);
 int ffbi_fp64_peak(ffb_ctx* ctx, double* dfma, double* dmma);
+// peer group (ffb_comm.cu): the kernel-side descriptor of the NEXT collective (advances the sequence
+// number); in-place all-reduce of n doubles in device memory; release of everything the group holds
+PeerReduce ffbi_peer_next(ffb_ctx* ctx);
+int ffbi_allreduce_sum(ffb_ctx* ctx, double* data_dev, int n);
+void ffbi_comm_release(ffb_ctx* ctx);
+int ffbi_comm_fetch_error(ffb_ctx* ctx);   // enqueue the download of the time-out flag
+int ffbi_comm_check_error(ffb_ctx* ctx);   // after a stream synchronisation
 
 // ------------------------------------------------------------------------------------------------
 // device helpers

@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 #include "ffb_common.cuh"
+#include "ffb_peer.cuh"
 
 namespace {
 
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(1024)
 infidelity_kernel(int n_nops, int n_sel, const int* __restrict__ idx, int n_omega,
                   const double2* __restrict__ F, const double* __restrict__ spectrum,
                   int spectrum_ndim, int spectrum_is_complex, const double* __restrict__ omega,
-                  double norm, double* __restrict__ out) {
+                  double norm, double* __restrict__ out, PeerReduce peers) {
   __shared__ double warp_sums[32];
   const int o = blockIdx.x;  // output index
   int lead, a, b;
@@ -114,7 +115,9 @@ infidelity_kernel(int n_nops, int n_sel, const int* __restrict__ idx, int n_omeg
   if (threadIdx.x == 0) {
     double total = 0.0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) total += warp_sums[i];
-    out[o] = total / 2.0 / norm;
+    // frequency-sharded run: the partial integral of this rank's block is exchanged with the peers
+    // over NVLink right here (peers.world == 1 otherwise)
+    out[o] = peer_allreduce_slot(peers, o, total / 2.0 / norm);
   }
 }
 
@@ -132,7 +135,7 @@ infidelity_chunked_kernel(int n_nops, int n_sel, const int* __restrict__ idx, in
                           int spectrum_ndim, int spectrum_is_complex,
                           const double* __restrict__ omega, double norm, int n_chunks,
                           double* __restrict__ partial, unsigned* __restrict__ tickets,
-                          double* __restrict__ out) {
+                          double* __restrict__ out, PeerReduce peers) {
   __shared__ double warp_sums[8];
   __shared__ bool last;
   const int o = blockIdx.x, chunk = blockIdx.y;
@@ -177,8 +180,8 @@ infidelity_chunked_kernel(int n_nops, int n_sel, const int* __restrict__ idx, in
       double all = 0.0;
       for (int c = 0; c < n_chunks; ++c)
         all += reinterpret_cast<volatile double*>(partial)[(size_t)o * n_chunks + c];
-      out[o] = all / 2.0 / norm;
       tickets[o] = 0;  // ready for the next launch (launches on one stream are ordered)
+      out[o] = peer_allreduce_slot(peers, o, all / 2.0 / norm);  // sum over the frequency shards
     }
   }
 }
@@ -236,6 +239,10 @@ int ffbi_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* 
               n_omega, d);
   const int n_out = n_lead * (spectrum_ndim == 3 ? n_sel * n_sel : n_sel);
   const double norm = 2.0 * 3.141592653589793238462643383279502884 * d;
+  // frequency-sharded run (ffb_comm_reduce_infidelity): the exchange is the epilogue of the kernel when
+  // the outputs fit one exchange window, a stand-alone all-reduce behind it otherwise
+  const bool reduce = ctx->comm.reduce_infidelity && ctx->comm.connected && ctx->comm.world > 1;
+  const bool fused = reduce && n_out <= FFB_PEER_SLOTS;
   static const bool chunked_ok = !(getenv("FFB_INFIDELITY_CHUNKED") && atoi(getenv("FFB_INFIDELITY_CHUNKED")) == 0);
   if (chunked_ok && n_out <= INFID_MAX_OUT && n_omega - 1 >= 2 * INFID_CHUNK) {
     const int n_chunks = std::min(INFID_MAX_CHUNKS, ceil_div(n_omega - 1, INFID_CHUNK));
@@ -250,14 +257,16 @@ int ffbi_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* 
     unsigned* tickets = reinterpret_cast<unsigned*>(partial + (size_t)INFID_MAX_OUT * INFID_MAX_CHUNKS);
     infidelity_chunked_kernel<<<dim3(n_out, n_chunks), 256, 0, ctx->stream>>>(
         n_nops, n_sel, idx_dev, n_omega, reinterpret_cast<const double2*>(F), spectrum, spectrum_ndim,
-        spectrum_is_complex, omega, norm, n_chunks, partial, tickets, out);
+        spectrum_is_complex, omega, norm, n_chunks, partial, tickets, out,
+        fused ? ffbi_peer_next(ctx) : PeerReduce());
     FFB_LAUNCHED(ctx);
     return FFB_OK;
   }
   const int threads = n_omega > 4096 ? 1024 : 256;
   infidelity_kernel<<<n_out, threads, 0, ctx->stream>>>(
       n_nops, n_sel, idx_dev, n_omega, reinterpret_cast<const double2*>(F), spectrum,
-      spectrum_ndim, spectrum_is_complex, omega, norm, out);
+      spectrum_ndim, spectrum_is_complex, omega, norm, out, fused ? ffbi_peer_next(ctx) : PeerReduce());
   FFB_LAUNCHED(ctx);
+  if (reduce && !fused) FFB_TRY(ffbi_allreduce_sum(ctx, out, n_out));
   return FFB_OK;
 }

@@ -1,24 +1,38 @@
-"""Frequency-sharded multi-GPU execution: one process per GPU, ``torch.distributed`` for plumbing.
+"""Frequency-sharded multi-GPU execution: one process per GPU.
 
 Every quantity on the path depends on a single frequency: control matrix,
 filter function and the concatenation have no cross-omega term, and the infidelity is a sum over
 frequency intervals.  So the omega axis is partitioned into contiguous blocks of trapezoid intervals,
 the tiny per-segment operands are replicated (each rank uploads them itself, no collective), and the
-only exchange on the path is ONE all-reduce of the per-noise-operator partial integrals (<= n_nops^2
-doubles) -- or an all-gather of F(omega) slices when the caller wants the whole filter function.
+only exchange on the path is ONE sum of the per-noise-operator partial integrals (<= n_nops^2
+doubles) -- or a gather of F(omega) column blocks when the caller wants the whole filter function.
 The segment axis is a reduction axis and is deliberately not sharded.
 
+Both exchanges run inside the library's own kernels over NVLink peer memory
+(``csrc/ffb_peer.cuh``, ``csrc/ffb_comm.cu``): the sum is the epilogue of the infidelity kernel -- the
+thread that finishes a partial integral stores it into every peer's exchange window and adds up what
+the peers stored -- so a sharded ``infidelity`` is the single-GPU call on a frequency block, with no
+host round trip and no extra launch; the gather stores each rank's block into all peers' windows.
+``torch.distributed`` is the plumbing: it carries the 64-byte CUDA-IPC handles at set-up and provides
+the barrier.  Where peer memory is not available (no P2P path, IPC not permitted, or the CPU-only
+``gloo`` backend used by the host-logic tests) the same functions fall back to ``all_reduce`` /
+``all_gather`` of ``torch.distributed`` on the partial results.
+
 Launch with ``torchrun`` (``RANK`` / ``LOCAL_RANK`` / ``WORLD_SIZE`` from the environment); rank r uses
-GPU ``LOCAL_RANK``.  With the ``gloo`` backend the collectives run on CPU tensors, which is how the
-host-side logic is tested without GPUs.
+GPU ``LOCAL_RANK``.
 """
+import contextlib
+import ctypes
 import os
-from typing import Callable, Optional, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 
-__all__ = ['frequency_shard', 'init_process_group', 'allreduce_sum', 'allgather_frequency_axis',
-           'infidelity', 'filter_function', 'concatenate']
+from . import _lib, numeric, pulse_sequence
+
+__all__ = ['frequency_shard', 'owned_frequencies', 'init_process_group', 'peer_group',
+           'allreduce_sum', 'allgather_frequency_axis', 'infidelity', 'filter_function',
+           'concatenate']
 
 
 def frequency_shard(n_omega: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -63,11 +77,14 @@ def init_process_group(backend: Optional[str] = None):
         return dist.group.WORLD
     if backend is None:
         backend = 'nccl' if torch.cuda.is_available() else 'gloo'
-    if backend == 'nccl':
-        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     os.environ.setdefault('MASTER_PORT', '29511')
-    dist.init_process_group(backend=backend)
+    if backend == 'nccl':
+        local = int(os.environ.get('LOCAL_RANK', 0))
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, device_id=torch.device('cuda', local))
+    else:
+        dist.init_process_group(backend=backend)
     return dist.group.WORLD
 
 
@@ -78,21 +95,124 @@ def _world(group):
     return dist.get_rank(group), dist.get_world_size(group)
 
 
+# ------------------------------------------------------------------------------------------------
+# peer group over NVLink
+# ------------------------------------------------------------------------------------------------
+class PeerGroup:
+    """The ranks of a ``torch.distributed`` group connected through the library's exchange windows
+    (``ffb_comm_*`` of include/ffb200.h).  Created collectively by :func:`peer_group`."""
+
+    def __init__(self, ctx, rank, world, group):
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.data_bytes = 0
+
+    def _exchange(self, mine: bytes):
+        import torch.distributed as dist
+        handles = [None]*self.world
+        dist.all_gather_object(handles, mine, group=self.group)
+        return b''.join(handles)
+
+    @contextlib.contextmanager
+    def reducing(self):
+        """Inside this block every infidelity integral the library computes on this rank is summed
+        over the ranks (in the epilogue of the kernel) before it is returned."""
+        L = _lib.lib()
+        _lib.check(self.ctx, L.ffb_comm_reduce_infidelity(self.ctx, 1))
+        try:
+            yield self
+        finally:
+            L.ffb_comm_reduce_infidelity(self.ctx, 0)
+
+    def allreduce_sum(self, arr: np.ndarray) -> np.ndarray:
+        out = np.array(arr, dtype=np.float64, order='C', copy=True)
+        _lib.check(self.ctx, _lib.lib().ffb_allreduce_sum(self.ctx, _lib.ptr(out), out.size))
+        return out
+
+    def ensure_data_window(self, nbytes: int) -> None:
+        """Collective: make every rank's symmetric data window at least ``nbytes`` large (the argument
+        is the same on all ranks, so all of them take the same branch)."""
+        import torch.distributed as dist
+        if nbytes <= self.data_bytes:
+            return
+        nbytes = max(int(nbytes*1.25), 64 << 20)
+        dist.barrier(group=self.group)      # nobody is still using the old windows
+        mine = ctypes.create_string_buffer(_lib.COMM_HANDLE_BYTES)
+        _lib.check(self.ctx, _lib.lib().ffb_comm_data_window(self.ctx, nbytes, mine))
+        handles = self._exchange(mine.raw)
+        _lib.check(self.ctx, _lib.lib().ffb_comm_data_connect(self.ctx, handles))
+        dist.barrier(group=self.group)
+        self.data_bytes = nbytes
+
+    def allgather_columns(self, local: np.ndarray, counts) -> np.ndarray:
+        """``local`` (rows, counts[rank]) complex128 -> (rows, sum(counts)) on every rank."""
+        rows = int(local.shape[0])
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        total = int(counts.sum())
+        self.ensure_data_window(rows*total*16)
+        local = _lib.as_c128(local)
+        out = _lib.empty((rows, total))
+        if out.size:
+            _lib.check(self.ctx, _lib.lib().ffb_allgather_columns(
+                self.ctx, rows, _lib.ptr(counts), _lib.ptr(local), _lib.ptr(out)))
+        return out
+
+
+_PEER_GROUPS = {}
+
+
+def peer_group(group=None) -> Optional[PeerGroup]:
+    """The NVLink peer group of ``group`` (created on first use, collectively), or ``None`` when the
+    ranks cannot map each other's memory -- CPU-only backend, one rank, ``FFB_PEER=0``, or CUDA IPC
+    failing on ANY rank (all ranks agree on the outcome)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = _world(group)
+    if world == 1:
+        return None
+    key = id(group) if group is not None else 0
+    if key in _PEER_GROUPS:
+        return _PEER_GROUPS[key]
+    usable = (dist.get_backend(group) == 'nccl' and torch.cuda.is_available()
+              and os.environ.get('FFB_PEER', '1') != '0' and world <= 16)
+    peers = None
+    if usable:
+        ctx = _lib.context(torch.cuda.current_device())
+        L = _lib.lib()
+        mine = ctypes.create_string_buffer(_lib.COMM_HANDLE_BYTES)
+        ok = L.ffb_comm_create(ctx, rank, world, mine) == _lib.FFB_OK
+        peers = PeerGroup(ctx, rank, world, group)
+        handles = peers._exchange(mine.raw if ok else b'\0'*_lib.COMM_HANDLE_BYTES)
+        ok = ok and L.ffb_comm_connect(ctx, handles) == _lib.FFB_OK
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            if not ok and rank == 0:
+                import warnings
+                warnings.warn('filter_functions_b200: no peer-memory path between the GPUs ('
+                              + L.ffb_last_error(ctx).decode() + '); using NCCL collectives')
+            L.ffb_comm_destroy(ctx)
+            peers = None
+    _PEER_GROUPS[key] = peers
+    return peers
+
+
+# ------------------------------------------------------------------------------------------------
+# collectives on host arrays (peer memory when available, torch.distributed otherwise)
+# ------------------------------------------------------------------------------------------------
 _REDUCE_BUFFERS = {}
 
 
 def allreduce_sum(arr: np.ndarray, group=None) -> np.ndarray:
-    """Sum a small host array over all ranks (NCCL on the rank's GPU, or gloo on the CPU).
-
-    NCCL: the page-locked host buffer and its device twin are allocated once per size and reused
-    (the exchange is latency-bound: <= n_nops^2 doubles; a fresh pinned allocation per call would
-    cost more than the all-reduce itself)."""
+    """Sum a small host array over all ranks; identical bits on every rank."""
     import torch
     import torch.distributed as dist
     rank, world = _world(group)
     if world == 1:
         return np.array(arr, copy=True)
     arr = np.ascontiguousarray(arr, dtype=np.float64)
+    peers = peer_group(group)
+    if peers is not None:
+        return peers.allreduce_sum(arr).reshape(arr.shape)
     if dist.get_backend(group) != 'nccl':
         t = torch.from_numpy(arr.copy())
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
@@ -112,12 +232,9 @@ def allreduce_sum(arr: np.ndarray, group=None) -> np.ndarray:
 
 
 def allgather_frequency_axis(local: np.ndarray, n_omega: int, group=None) -> np.ndarray:
-    """Assemble an array whose last axis is the (sharded) frequency axis on every rank.
-
-    NCCL: the rank's block goes to its GPU once, ONE ``all_gather_into_tensor`` moves the blocks over
-    NVLink, the blocks are stitched along the frequency axis on the device and the result comes back
-    in a single copy into page-locked memory (the 51.8 MB filter function of config 5: 5 ms instead of
-    the 54 ms a per-rank host assembly took).  gloo: the same exchange on CPU tensors."""
+    """Assemble an array whose last axis is the (sharded) frequency axis on every rank.  ``local`` is
+    this rank's block INCLUDING its halo point (the layout :func:`frequency_shard` describes); the
+    halo columns are dropped, every frequency is taken from the rank that owns it."""
     import torch
     import torch.distributed as dist
     rank, world = _world(group)
@@ -125,11 +242,17 @@ def allgather_frequency_axis(local: np.ndarray, n_omega: int, group=None) -> np.
         return local
     start, _ = frequency_shard(n_omega, rank, world)
     o0, o1 = owned_frequencies(n_omega, rank, world)
-    mine = np.ascontiguousarray(local[..., o0 - start:o1 - start])
     counts = [int(np.subtract(*owned_frequencies(n_omega, r, world)[::-1])) for r in range(world)]
+    lead = local.shape[:-1]
+    is_complex = np.iscomplexobj(local)
+    peers = peer_group(group)
+    if peers is not None:
+        mine = np.ascontiguousarray(local[..., o0 - start:o1 - start], dtype=np.complex128)
+        rows = int(np.prod(lead)) if lead else 1
+        out = peers.allgather_columns(mine.reshape(rows, o1 - o0), counts).reshape(lead + (n_omega,))
+        return out if is_complex else np.ascontiguousarray(out.real)
+    mine = np.ascontiguousarray(local[..., o0 - start:o1 - start])
     width = max(counts)
-    lead = mine.shape[:-1]
-    is_complex = np.iscomplexobj(mine)
     comps = 2 if is_complex else 1
     mine_t = torch.from_numpy(mine.view(np.float64) if is_complex else
                               np.ascontiguousarray(mine, dtype=np.float64))
@@ -155,47 +278,54 @@ def allgather_frequency_axis(local: np.ndarray, n_omega: int, group=None) -> np.
     return out if out.dtype == mine.dtype else out.astype(mine.dtype)
 
 
-def infidelity(pulse, spectrum, omega, n_oper_identifiers=None, group=None,
-               _local: Optional[Callable] = None) -> np.ndarray:
+# ------------------------------------------------------------------------------------------------
+# the sharded path
+# ------------------------------------------------------------------------------------------------
+def infidelity(pulse, spectrum, omega, n_oper_identifiers=None, group=None) -> np.ndarray:
     """Frequency-sharded ``ff.infidelity(pulse, spectrum, omega)``: every rank integrates its block
-    of intervals on its own GPU; one all-reduce combines the partial integrals.  The result is
+    of intervals on its own GPU and the partial integrals are summed over the ranks -- inside the
+    infidelity kernel when the ranks share a peer group, by one all-reduce otherwise.  The result is
     identical on all ranks and equals the single-GPU result up to summation order."""
-    from . import numeric
-    local_fn = numeric.infidelity if _local is None else _local
     omega = np.asarray(omega, dtype=float)
     spectrum = np.asarray(spectrum)
     rank, world = _world(group)
     start, stop = frequency_shard(len(omega), rank, world)
-    if stop - start >= 2 or (len(omega) == 1 and rank == 0):
-        part = np.asarray(local_fn(pulse, spectrum[..., start:stop], omega[start:stop],
-                                   n_oper_identifiers=n_oper_identifiers))
-    else:
-        part = None
+    has_work = stop - start >= 2 or (len(omega) == 1 and rank == 0)
     if world == 1:
-        return part
-    if part is None:
-        # ranks without intervals contribute zeros of the right shape
-        n_sel = len(pulse.n_oper_identifiers if n_oper_identifiers is None else n_oper_identifiers)
-        part = np.zeros((n_sel, n_sel) if spectrum.ndim == 3 else (n_sel,))
+        return np.asarray(numeric.infidelity(pulse, spectrum, omega,
+                                             n_oper_identifiers=n_oper_identifiers))
+    n_sel = len(pulse.n_oper_identifiers if n_oper_identifiers is None else n_oper_identifiers)
+    shape = (n_sel, n_sel) if spectrum.ndim == 3 else (n_sel,)
+    peers = peer_group(group)
+    if peers is not None:
+        if not has_work:        # no intervals: contribute zeros to the same collective
+            return peers.allreduce_sum(np.zeros(shape))
+        with peers.reducing():
+            return np.asarray(numeric.infidelity(pulse, spectrum[..., start:stop],
+                                                 omega[start:stop],
+                                                 n_oper_identifiers=n_oper_identifiers))
+    if has_work:
+        part = np.asarray(numeric.infidelity(pulse, spectrum[..., start:stop], omega[start:stop],
+                                             n_oper_identifiers=n_oper_identifiers))
+    else:
+        part = np.zeros(shape)
     return allreduce_sum(part, group).reshape(part.shape)
 
 
-def filter_function(pulse, omega, group=None, _local: Optional[Callable] = None) -> np.ndarray:
+def filter_function(pulse, omega, group=None) -> np.ndarray:
     """Frequency-sharded ``pulse.get_filter_function(omega)`` gathered on every rank."""
     omega = np.asarray(omega, dtype=float)
     rank, world = _world(group)
     start, stop = frequency_shard(len(omega), rank, world)
-    local_fn = (lambda p, w: p.get_filter_function(w)) if _local is None else _local
     if stop - start > 0:
-        local = np.asarray(local_fn(pulse, omega[start:stop]))
+        local = np.asarray(pulse.get_filter_function(omega[start:stop]))
     else:
         n = len(pulse.n_opers)
         local = np.zeros((n, n, 0), dtype=complex)
     return allgather_frequency_axis(local, len(omega), group)
 
 
-def concatenate(pulses, omega, group=None, gather: bool = True,
-                _local: Optional[Callable] = None):
+def concatenate(pulses, omega, group=None, gather: bool = True):
     """Frequency-sharded ``ff.concatenate(pulses, omega=omega)`` (BASELINE config 5: the QFT assembled
     from gate pulses with omega split over the GPUs of one node).
 
@@ -204,40 +334,35 @@ def concatenate(pulses, omega, group=None, gather: bool = True,
     rank's GPU otherwise, then concatenated there; nothing frequency-dependent is replicated and the
     concatenation needs no exchange at all.  Returns ``(pulse, filter_function)``: the concatenated
     ``PulseSequence`` with THIS RANK's frequency block cached, and -- if ``gather`` -- the fidelity
-    filter function on the whole grid, all-gathered on every rank (``None`` otherwise).  The caller's
+    filter function on the whole grid, gathered on every rank (``None`` otherwise).  The caller's
     pulses are not modified.
     """
     import copy
-
-    from . import pulse_sequence
     omega = np.asarray(omega, dtype=float)
     rank, world = _world(group)
     start, stop = frequency_shard(len(omega), rank, world)
     o0, o1 = owned_frequencies(len(omega), rank, world)   # no halo needed: nothing is integrated here
     local_omega = omega[o0:o1]
-    if _local is not None:      # test hook: (pulses, local_omega) -> (pulse or None, F_local)
-        new, F_local = _local(pulses, local_omega)
+    local_pulses, seen = [], {}
+    for pls in pulses:
+        if id(pls) not in seen:
+            mine = copy.copy(pls)
+            mine.cleanup('frequency dependent')
+            cached = pls._frequency_data.get('omega')
+            if (o1 > o0 and cached is not None and 'control_matrix' in pls._frequency_data
+                    and np.array_equal(cached, omega)):
+                mine.cache_control_matrix(
+                    local_omega,
+                    np.ascontiguousarray(pls._frequency_data['control_matrix'][..., o0:o1]))
+            seen[id(pls)] = mine
+        local_pulses.append(seen[id(pls)])
+    if o1 > o0:
+        new = pulse_sequence.concatenate(local_pulses, omega=local_omega)
+        F_local = new.get_filter_function(local_omega)
     else:
-        local_pulses, seen = [], {}
-        for pls in pulses:
-            if id(pls) not in seen:
-                mine = copy.copy(pls)
-                mine.cleanup('frequency dependent')
-                cached = pls._frequency_data.get('omega')
-                if (o1 > o0 and cached is not None and 'control_matrix' in pls._frequency_data
-                        and np.array_equal(cached, omega)):
-                    mine.cache_control_matrix(
-                        local_omega,
-                        np.ascontiguousarray(pls._frequency_data['control_matrix'][..., o0:o1]))
-                seen[id(pls)] = mine
-            local_pulses.append(seen[id(pls)])
-        if o1 > o0:
-            new = pulse_sequence.concatenate(local_pulses, omega=local_omega)
-            F_local = new.get_filter_function(local_omega)
-        else:
-            new = pulse_sequence.concatenate(local_pulses, calc_filter_function=False)
-            n = len(new.n_opers)
-            F_local = np.zeros((n, n, 0), dtype=complex)
+        new = pulse_sequence.concatenate(local_pulses, calc_filter_function=False)
+        n = len(new.n_opers)
+        F_local = np.zeros((n, n, 0), dtype=complex)
     if not gather:
         return new, None
     if world == 1:

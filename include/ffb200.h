@@ -268,6 +268,40 @@ int ffb_dev_decay_amplitudes(ffb_ctx* ctx, int P, int n_nops, int n_sel, const i
 #define FFB_HERM_BASIS 2
 #define FFB_BASIS_IDENTITY0 4
 
+/* ---- e: peer group of the GPUs of one node (nothing in the reference) ---------------
+ * One process per GPU.  The frequency axis is sharded by the caller (every output element depends on
+ * one frequency only); the exchanges of the path run over NVLink peer memory inside this library's own
+ * kernels: the sum of the per-noise-operator partial integrals is the EPILOGUE of the infidelity
+ * kernels (the thread that holds a finished partial integral stores it into all peers' windows and
+ * adds up what the peers stored, in rank order -- identical bits on every rank), and the gather of
+ * F(omega) column blocks stores every block straight into all peers' windows.
+ * Set-up: every rank calls ffb_comm_create (allocates its exchange window, returns a 64-byte CUDA IPC
+ * handle), the host program all-gathers the handles by any means (distributed.py: torch.distributed)
+ * and passes the concatenation (world x 64 bytes, rank order) to ffb_comm_connect.  All ranks must
+ * issue the same sequence of collectives.  A peer that does not arrive within FFB_PEER_TIMEOUT_MS
+ * (default 20000) makes the call fail with FFB_ECUDA instead of hanging the GPU. */
+#define FFB_COMM_HANDLE_BYTES 64
+int ffb_comm_create(ffb_ctx* ctx, int rank, int world, void* handle_out);
+int ffb_comm_connect(ffb_ctx* ctx, const void* handles);
+int ffb_comm_destroy(ffb_ctx* ctx);
+int ffb_comm_info(const ffb_ctx* ctx, int* rank, int* world, size_t* data_window_bytes);
+/* enable != 0: every infidelity integral this context computes (ffb_infidelity, ffb_dev_infidelity,
+ * ffb_pulse_filter_function) is summed over the ranks before it is stored: numeric.infidelity
+ * (numeric.py:2318-2320) on a frequency shard then returns the integral over the whole grid. */
+int ffb_comm_reduce_infidelity(ffb_ctx* ctx, int enable);
+/* In-place sum over the ranks of n doubles (host / device pointer). */
+int ffb_allreduce_sum(ffb_ctx* ctx, double* data, int n);
+int ffb_dev_allreduce_sum(ffb_ctx* ctx, double* data, int n);
+/* Symmetric data window for ffb_allgather_columns: (re)allocate `bytes` on this rank and return its
+ * handle; the ranks must be synchronised by the caller around the call (nobody may still use the old
+ * window), then exchange the handles and call ffb_comm_data_connect. */
+int ffb_comm_data_window(ffb_ctx* ctx, size_t bytes, void* handle_out);
+int ffb_comm_data_connect(ffb_ctx* ctx, const void* handles);
+/* All-gather along the last (frequency) axis: this rank holds `local` (rows, counts[rank]) c128, on
+ * return `out` (rows, sum(counts)) c128 holds the blocks of all ranks side by side, on every rank. */
+int ffb_allgather_columns(ffb_ctx* ctx, int rows, const int* counts, const double* local,
+                          double* out);
+
 /* Raw device memory for the callers of ffb_dev_* that do not bring their own (e.g. torch). */
 int ffb_dev_alloc(ffb_ctx* ctx, size_t bytes, void** ptr);
 int ffb_dev_free(ffb_ctx* ctx, void* ptr);

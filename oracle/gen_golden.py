@@ -158,6 +158,68 @@ def workloads_small():
     np.savez_compressed(os.path.join(OUT, 'workloads_small.npz'), **out)
 
 
+def resonance_frequency_picks(wl, n_pick=1024, seed=5):
+    """Indices into ``wl.omega`` for the full-size parity fixtures: both ends of the grid, the
+    neighbourhoods of the level splittings |E_m - E_n| of a sample of segments (where the first-order
+    integral goes through its removable singularity and the kernels switch to their fix-up branch),
+    and a uniform random remainder.  Deterministic given the workload."""
+    rng = np.random.default_rng(seed)
+    n = len(wl.omega)
+    H = np.einsum('ijk,il->ljk', wl.c_opers, wl.c_coeffs[:, ::max(1, wl.G//64)])
+    ev = np.linalg.eigvalsh(H)
+    gaps = np.abs(ev[:, :, None] - ev[:, None, :])
+    gaps = np.unique(gaps[gaps > 0])
+    near = np.searchsorted(wl.omega, gaps).clip(1, n - 2)
+    picks = [np.arange(48), np.arange(n - 48, n)]
+    picks += [near + k for k in (-1, 0, 1)]
+    have = np.unique(np.concatenate(picks).clip(0, n - 1))
+    if len(have) > n_pick - 64:
+        have = np.sort(rng.choice(have, n_pick - 64, replace=False))
+    rest = np.setdiff1d(np.arange(n), have)
+    extra = rng.choice(rest, n_pick - len(have), replace=False)
+    return np.sort(np.concatenate([have, extra]))
+
+
+def workloads_full():
+    """The bench workloads at BASELINE.json's FULL sizes, computed once by the unmodified reference
+    (config 2: ~70 s, config 3 and the north_star d = 4 shape: a few minutes each on 8 cores).  Config 2
+    keeps its whole control matrix (1.9 MB); the d = 4 shapes keep the control matrix on 1024 selected
+    frequencies (both grid ends, resonance neighbourhoods, random rest) and the infidelities of the
+    whole grid.  The inputs come from workloads.py (seeded); a checksum of them is stored."""
+    import hashlib
+    import time
+    sys.path.insert(0, ROOT)
+    import workloads
+    names = sys.argv[2:] or ['c2', 'c3', 'd4']
+    for name in names:
+        wl = workloads.get(name)
+        pulse = ff.PulseSequence(
+            [[op, c, i] for op, c, i in zip(wl.c_opers, wl.c_coeffs, wl.c_ids)],
+            [[op, c, i] for op, c, i in zip(wl.n_opers, wl.n_coeffs, wl.n_ids)],
+            wl.dt, ff.Basis.pauli(int(np.log2(wl.d))))
+        t0 = time.perf_counter()
+        B = pulse.get_control_matrix(wl.omega)
+        seconds = time.perf_counter() - t0
+        digest = hashlib.sha256(np.ascontiguousarray(wl.c_coeffs).tobytes()
+                                + np.ascontiguousarray(wl.n_coeffs).tobytes()
+                                + np.ascontiguousarray(wl.omega).tobytes()).hexdigest()
+        out = dict(n_ids=np.asarray(pulse.n_oper_identifiers, dtype='U8'),
+                   infidelity=ff.infidelity(pulse, wl.spectrum, wl.omega),
+                   scale=np.abs(B).max(axis=(1, 2)), input_sha256=np.asarray(digest),
+                   reference_seconds=seconds, total_propagator=pulse.total_propagator)
+        if name == 'c2':
+            out['pick'] = np.arange(len(wl.omega))
+            out['control_matrix'] = B
+        else:
+            pick = resonance_frequency_picks(wl)
+            out['pick'] = pick
+            out['control_matrix'] = np.ascontiguousarray(B[..., pick])
+        F = pulse.get_filter_function(wl.omega)
+        out['filter_function'] = np.ascontiguousarray(F[..., out['pick']])
+        np.savez_compressed(os.path.join(OUT, f'workload_full_{name}.npz'), **out)
+        print(name, f'{seconds:.1f} s reference control matrix', flush=True)
+
+
 def decay_amplitudes():
     """Decay amplitudes, cumulant function and error transfer matrix (numeric.py:957-1337, :1938-2059;
     cf. tests/test_precision.py:631-727) for the three spectrum shapes, plus the pulse-correlation

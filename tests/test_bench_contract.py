@@ -21,8 +21,13 @@ def test_reference_arm_prints_one_json_line():
                 'e2e'):
         assert key in line, key
     assert line['impl'] == 'reference' and line['value'] > 0 and line['unit'] == 'seg*omega/s'
-    assert line['config']['workload'].startswith('c2')
-    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    # the headline workload is the north_star target shape; the arm runs the unmodified reference when it
+    # is staged under baseline/_ref (always the case where /root/reference exists), else the oracle port
+    assert line['config']['workload'].startswith('d4') and line['scaling'] == 'strong'
+    staged = os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'filter_functions'))
+    assert line['cpu_baseline']['kind'] == ('reference' if staged else 'port')
+    assert line['cpu_baseline']['cores'] >= 1
+    assert line['extrapolated'] is True and 'EXTRAPOLATED' in line['ms_per_step_note']
     assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0,
                            'd2h_bytes_per_step': 0}
     assert line['vs_baseline'] is None and line['dtype'] == 'f64' and line['data'] == 'synthetic'

@@ -1,0 +1,46 @@
+"""Multi-rank parity of the frequency-sharded CUDA path (one process per GPU, NCCL plumbing, exchanges
+over NVLink peer memory) against the oracle and the reference's fixtures; skipped on a one-GPU box."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def run_world(world, env_extra=None):
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}',
+           '--master-addr', '127.0.0.1', '--master-port', str(free_port()),
+           os.path.join(HERE, '_dist_gpu_worker.py')]
+    env = dict(os.environ, OMP_NUM_THREADS='4', FFB_PEER_TIMEOUT_MS='60000', **(env_extra or {}))
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert f'DIST_GPU_OK world={world}' in out.stdout
+    return out.stdout
+
+
+@pytest.mark.parametrize('world', [2, 3, 8])
+def test_sharded_path_over_nvlink(engine, world):
+    if device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
+    assert 'peers=nvlink' in run_world(world)
+
+
+def test_sharded_path_over_nccl(engine):
+    if device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    assert 'peers=nccl' in run_world(2, {'FFB_PEER': '0'})
