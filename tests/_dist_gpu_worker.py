@@ -47,7 +47,7 @@ def main():
     failures = []
 
     def check(name, got, want, tol=TOL):
-        got, want = np.asarray(got), np.asarray(want)
+        got, want = np.ascontiguousarray(got), np.ascontiguousarray(want)
         if got.shape != want.shape or not np.isfinite(got.view(float)).all() or nerr(got, want) > tol:
             failures.append((name, got.shape, want.shape,
                              nerr(got, want) if got.shape == want.shape else None))

@@ -28,6 +28,11 @@ def run_world(world, env_extra=None):
            os.path.join(HERE, '_dist_gpu_worker.py')]
     env = dict(os.environ, OMP_NUM_THREADS='4', FFB_PEER_TIMEOUT_MS='60000', **(env_extra or {}))
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    log_dir = os.path.join(os.path.dirname(HERE), 'gpurun_out')
+    if os.path.isdir(log_dir):      # keep the ranks' output where a GPU-box run brings it back
+        tag = 'nccl' if env_extra else 'nvlink'
+        with open(os.path.join(log_dir, f'dist_worker_{world}_{tag}.log'), 'w') as fh:
+            fh.write(out.stdout + '\n---- stderr ----\n' + out.stderr)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert f'DIST_GPU_OK world={world}' in out.stdout
     return out.stdout

@@ -36,7 +36,11 @@ def test_reduced_workloads_against_reference(engine, name, kwargs):
 
 @pytest.mark.parametrize('name', ['c2', 'c3', 'd4'])
 def test_full_size_workloads(engine, name):
-    """Full bench size: oracle spot check on 12 frequencies, device-resident path == API path,
+    """Full bench size: EVERY frequency the reference fixture holds (tests/golden/workload_full_*.npz,
+    computed once by the unmodified reference: the whole grid for config 2; 1024 frequencies -- both
+    grid ends, the neighbourhoods of the level splittings where the kernels take their fix-up branch,
+    a random rest -- plus the infidelities of the whole grid for the d = 4 shapes), an oracle spot
+    check on 12 more frequencies, device-resident path == API path,
     filter function Hermitian and positive on the diagonal, infidelity additive over frequency
     blocks (the property the omega-sharded multi-GPU path relies on)."""
     ff = engine
@@ -59,6 +63,16 @@ def test_full_size_workloads(engine, name):
     for j in range(n_nops):
         assert np.abs(B[j][:, pick] - B_o[j]).max() < TOL*scale[j]
     assert nerr(F[..., pick], oracle.filter_function(B_o)) < TOL
+    # the reference's own results at full size
+    g = np.load(os.path.join(GOLDEN, f'workload_full_{name}.npz'))
+    assert list(pulse.n_oper_identifiers) == list(g['n_ids'])
+    gp = g['pick']
+    assert len(gp) == (len(wl.omega) if name == 'c2' else 1024)
+    for j in range(n_nops):     # normalised per noise operator, scale = max over the WHOLE grid
+        assert np.abs(B[j][:, gp] - g['control_matrix'][j]).max() < TOL*g['scale'][j]
+        assert abs(scale[j] - g['scale'][j]) < TOL*g['scale'][j]
+    assert nerr(F[..., gp], g['filter_function']) < TOL
+    assert nerr(pulse.total_propagator, g['total_propagator']) < TOL
     # structure
     assert nerr(F, F.conj().transpose(1, 0, 2)) < 1e-14
     assert (F[range(n_nops), range(n_nops)].real >= 0).all()
@@ -70,6 +84,7 @@ def test_full_size_workloads(engine, name):
         part = make_pulse(ff, wl)
         halves = halves + ff.infidelity(part, wl.spectrum[sl], wl.omega[sl])
     np.testing.assert_allclose(halves, full, rtol=1e-10)
+    np.testing.assert_allclose(full, g['infidelity'], rtol=TOL)
     want = oracle.infidelity_from_filter_function(F, wl.spectrum, wl.omega, wl.d)
     np.testing.assert_allclose(full, want, rtol=1e-12)
     # device-resident path (what bench.py times) gives the same numbers
