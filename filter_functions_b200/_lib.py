@@ -57,6 +57,7 @@ EXPORTED_SYMBOLS = {
     'ffb_liouville_representation': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                              c_void_p]),
     'ffb_cexp': (c_int, [c_void_p, c_int, c_void_p, c_double, c_void_p]),
+    'ffb_cexpm1': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     'ffb_pulse_filter_function': (c_int, [c_void_p] + [c_int]*6 + [c_void_p]*9 + [c_int, c_int]
                                   + [c_void_p]*8),
     'ffb_dev_diagonalize': (c_int, [c_void_p, c_int, c_int, c_int] + [c_void_p]*6),
@@ -75,6 +76,10 @@ EXPORTED_SYMBOLS = {
     'ffb_host_free': (c_int, [c_void_p, c_void_p]),
     'ffb_kernel_timing_enable': (c_int, [c_void_p, c_int]),
     'ffb_kernel_timing_read': (c_int, [c_void_p, _dp, POINTER(c_int64), c_int]),
+    'ffb_shadow_enable_next': (c_int, [c_void_p, c_int]),
+    'ffb_shadow_query': (c_int, [c_void_p, c_void_p, c_size_t]),
+    'ffb_shadow_drop': (c_int, [c_void_p, c_void_p, c_size_t]),
+    'ffb_shadow_stats': (c_int, [c_void_p, _ip, POINTER(c_size_t), POINTER(c_int64), POINTER(c_size_t)]),
     'ffb_comm_create': (c_int, [c_void_p, c_int, c_int, c_void_p]),
     'ffb_comm_connect': (c_int, [c_void_p, c_void_p]),
     'ffb_comm_destroy': (c_int, [c_void_p]),
@@ -225,6 +230,29 @@ def empty_many(specs, ctx=None):
     weakref.finalize(buf, _host_free, ctx, address.value)
     return [np.frombuffer(buf, dtype=dt, count=n//dt.itemsize, offset=off).reshape(sh)
             for sh, dt, n, off in zip(shapes, dtypes, sizes, offsets)]
+
+
+def keep_on_device(ctx):
+    """The results of the NEXT library call stay mirrored in device memory (``ffb_shadow_*`` of
+    include/ffb200.h), so that later calls that are handed those arrays skip the upload."""
+    lib().ffb_shadow_enable_next(ctx, 1)
+
+
+def freeze_shadowed(ctx, *arrays):
+    """Arrays that have a device mirror become read-only: the mirror is what later library calls read,
+    so an in-place edit of the host copy would silently not be seen (copy the array to modify it)."""
+    query = lib().ffb_shadow_query
+    for arr in arrays:
+        if arr is not None and arr.nbytes >= (64 << 10) and query(ctx, arr.ctypes.data, arr.nbytes):
+            arr.flags.writeable = False
+
+
+def shadow_stats(ctx=None):
+    """(number of shadows, bytes held, uploads avoided, bytes not uploaded) of a context."""
+    ctx = context() if ctx is None else ctx
+    n, nbytes, hits, hit_bytes = c_int(), c_size_t(), c_int64(), c_size_t()
+    lib().ffb_shadow_stats(ctx, byref(n), byref(nbytes), byref(hits), byref(hit_bytes))
+    return n.value, nbytes.value, hits.value, hit_bytes.value
 
 
 def ptr(arr):

@@ -29,34 +29,46 @@ class Basis(np.ndarray):
         if not util.is_sequence_like(basis_array):
             raise TypeError('Invalid data type. Must be array_like')
         if isinstance(basis_array, cls):
-            basis = basis_array
+            elements = basis_array
         else:
-            if hasattr(basis_array, 'shape') and len(basis_array.shape) == 2:
-                basis_array = [basis_array]
-            basis = util.parse_operators(basis_array, 'basis_array')
-            if basis.shape[0] > np.prod(basis.shape[1:]):
+            if np.ndim(basis_array) == 2 and hasattr(basis_array, 'shape'):
+                basis_array = [basis_array]                  # a single d x d element
+            elements = util.parse_operators(basis_array, 'basis_array')
+            n, d = elements.shape[0], elements.shape[-1]
+            if n > d*d:
                 raise ValueError('Given overcomplete set of basis matrices. '
                                  'Not linearly independent.')
-        basis = basis.view(cls)
-        basis.btype = btype or 'Custom'
-        basis.d = basis.shape[-1]
-        if labels is not None:
-            if len(labels) != len(basis):
-                raise ValueError(f'Got {len(labels)} basis labels but expected {len(basis)}')
-            basis.labels = labels
-        else:
-            basis.labels = [f'$C_{{{i}}}$' for i in range(len(basis))]
-        return basis
+        if labels is not None and len(labels) != len(elements):
+            raise ValueError(f'Got {len(labels)} basis labels but expected {len(elements)}')
+        new = elements.view(cls)
+        new._describe(btype or 'Custom', labels)
+        return new
 
-    def __array_finalize__(self, basis) -> None:
-        if basis is None:
-            return
-        self.btype = getattr(basis, 'btype', 'Custom')
-        self.labels = getattr(basis, 'labels', [f'$C_{{{i}}}$' for i in range(len(basis))])
-        self.d = getattr(basis, 'd', basis.shape[-1])
+    @staticmethod
+    def _default_labels(n: int):
+        return [f'$C_{{{i}}}$' for i in range(n)]
+
+    def _describe(self, btype, labels) -> None:
+        """Metadata of the reference's Basis (``basis.py:162-201``): type, element labels, dimension
+        and the tolerances its comparisons use (eps d^3 absolute, no relative part)."""
+        self.btype = btype
+        self.labels = labels if labels is not None else self._default_labels(len(self))
+        self.d = self.shape[-1]
         self._eps = np.finfo(complex).eps
-        self._atol = self._eps*self.d**3
-        self._rtol = 0
+        self._atol, self._rtol = self._eps*self.d**3, 0
+
+    def __array_finalize__(self, parent) -> None:
+        # views and slices inherit the parent's description (ndarray subclassing protocol)
+        if parent is None:
+            return
+        shape = getattr(parent, 'shape', ())
+        self.btype = getattr(parent, 'btype', 'Custom')
+        self.labels = getattr(parent, 'labels', None)
+        if self.labels is None:
+            self.labels = self._default_labels(shape[0] if shape else 0)
+        self.d = getattr(parent, 'd', shape[-1] if shape else 0)
+        self._eps = np.finfo(complex).eps
+        self._atol, self._rtol = self._eps*self.d**3, 0
 
     def __eq__(self, other) -> bool:
         try:
@@ -135,10 +147,17 @@ class Basis(np.ndarray):
         pair = np.einsum('iab,jbc->ijac', arr, arr)
         return np.einsum('ijac,klca->ijkl', pair, pair)
 
+    def _invalidate_cached_properties(self) -> None:
+        """Forget the predicates computed for the previous contents (in-place changes)."""
+        for name in ('isherm', 'isnorm', 'isorthogonal', 'isorthonorm', 'istraceless', 'iscomplete',
+                     'four_element_traces'):
+            self.__dict__.pop(name, None)
+
     def normalize(self, copy: bool = False):
         if copy:
             return normalize(self)
         self /= _norm(self)
+        self._invalidate_cached_properties()
         return None
 
     def expand(self, M, hermitian: bool = False, traceless: bool = False, tidyup: bool = False):

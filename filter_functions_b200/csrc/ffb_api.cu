@@ -70,8 +70,80 @@ int ffb_h2d(ffb_ctx* ctx, void* dst, const void* src, size_t bytes) {
 
 int ffb_d2h(ffb_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (bytes == 0) return FFB_OK;
+  ffb_shadow_drop_range(ctx, dst, bytes);  // whatever mirrored these host bytes is stale now
   FFB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return FFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device shadows of result arrays
+// ------------------------------------------------------------------------------------------------
+static constexpr size_t SHADOW_MIN_BYTES = (size_t)64 << 10;  // below this an upload costs nothing
+
+static void shadow_erase(ffb_ctx* ctx, std::map<char*, ffb_ctx::Shadow>::iterator it) {
+  ffb_pool_release(ctx, it->second.dev);
+  ctx->shadow_bytes -= it->second.bytes;
+  ctx->shadows.erase(it);
+}
+
+const void* ffb_shadow_lookup(ffb_ctx* ctx, const void* host, size_t bytes) {
+  if (ctx->shadows.empty() || !host || !bytes) return nullptr;
+  char* h = static_cast<char*>(const_cast<void*>(host));
+  auto it = ctx->shadows.upper_bound(h);
+  if (it == ctx->shadows.begin()) return nullptr;
+  --it;
+  if (h + bytes > it->first + it->second.bytes) return nullptr;
+  const size_t off = (size_t)(h - it->first);
+  for (const auto& v : it->second.valid) {
+    if (off >= v.first && off + bytes <= v.first + v.second) {
+      it->second.stamp = ++ctx->shadow_clock;
+      ctx->shadow_hits++;
+      ctx->shadow_hit_bytes += bytes;
+      return static_cast<char*>(it->second.dev) + off;
+    }
+  }
+  return nullptr;
+}
+
+void ffb_shadow_drop_range(ffb_ctx* ctx, const void* host, size_t bytes) {
+  if (ctx->shadows.empty() || !host) return;
+  char* lo = static_cast<char*>(const_cast<void*>(host));
+  char* hi = lo + bytes;
+  auto it = ctx->shadows.upper_bound(lo);
+  if (it != ctx->shadows.begin()) --it;
+  while (it != ctx->shadows.end() && it->first < hi) {
+    auto next = std::next(it);
+    if (it->first + it->second.bytes > lo) shadow_erase(ctx, it);
+    it = next;
+  }
+}
+
+bool ffb_shadow_retain(ffb_ctx* ctx, DevBuf& buf, void* host_lo, size_t bytes,
+                       const std::vector<std::pair<size_t, size_t>>& valid) {
+  if (!buf.p || !host_lo || bytes < SHADOW_MIN_BYTES || bytes > ctx->shadow_limit || valid.empty())
+    return false;
+  // only arrays that live in this context's page-locked pool: their release (ffb_host_free) is the
+  // event that ends the shadow's life
+  char* h = static_cast<char*>(host_lo);
+  auto ub = ctx->host_live_blocks.upper_bound(h);
+  if (ub == ctx->host_live_blocks.begin()) return false;
+  --ub;
+  if (h + bytes > static_cast<char*>(ub->first) + ub->second) return false;
+  ffb_shadow_drop_range(ctx, host_lo, bytes);
+  while (ctx->shadow_bytes + bytes > ctx->shadow_limit && !ctx->shadows.empty()) {  // oldest first
+    auto oldest = ctx->shadows.begin();
+    for (auto it = ctx->shadows.begin(); it != ctx->shadows.end(); ++it)
+      if (it->second.stamp < oldest->second.stamp) oldest = it;
+    shadow_erase(ctx, oldest);
+  }
+  ffb_ctx::Shadow sh;
+  sh.dev = buf.detach();
+  sh.bytes = bytes;
+  sh.valid = valid;
+  sh.stamp = ++ctx->shadow_clock;
+  ctx->shadows[h] = sh;
+  ctx->shadow_bytes += bytes;
+  return true;
 }
 
 int ffb_func_smem_impl(ffb_ctx* ctx, const void* func, size_t smem) {
@@ -184,6 +256,8 @@ int ffb_init(ffb_ctx** out, int device) {
     return ffb_fail(nullptr, FFB_ECUDA, "%s", cudaGetErrorString(e));
   }
   ctx->stream = ctx->own_stream;
+  ctx->shadow_limit = prop.totalGlobalMem / 4;
+  if (const char* e = getenv("FFB_SHADOW_BYTES")) ctx->shadow_limit = (size_t)strtoull(e, nullptr, 10);
   *out = ctx;
   return FFB_OK;
 }
@@ -193,6 +267,7 @@ void ffb_destroy(ffb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ffbi_comm_release(ctx);
+  while (!ctx->shadows.empty()) shadow_erase(ctx, ctx->shadows.begin());
   for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
   for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
   for (auto& ev : ctx->event_pool) {
@@ -329,8 +404,41 @@ int ffb_host_free(ffb_ctx* ctx, void* ptr) {
   if (!ctx) return FFB_EINVAL;
   auto it = ctx->host_live_blocks.find(ptr);
   if (it == ctx->host_live_blocks.end()) return FFB_OK;
+  ffb_shadow_drop_range(ctx, ptr, it->second);  // the arrays in this block are gone: so are their mirrors
   ctx->host_free_blocks.emplace(it->second, ptr);
   ctx->host_live_blocks.erase(it);
+  return FFB_OK;
+}
+
+int ffb_shadow_enable_next(ffb_ctx* ctx, int enable) {
+  if (!ctx) return FFB_EINVAL;
+  static const bool allowed = !(getenv("FFB_SHADOWS") && atoi(getenv("FFB_SHADOWS")) == 0);
+  ctx->shadow_next = allowed && enable != 0;
+  return FFB_OK;
+}
+
+int ffb_shadow_query(ffb_ctx* ctx, const void* host, size_t bytes) {
+  if (!ctx) return 0;
+  const int64_t hits = ctx->shadow_hits;
+  const size_t hit_bytes = ctx->shadow_hit_bytes;
+  const bool found = ffb_shadow_lookup(ctx, host, bytes) != nullptr;
+  ctx->shadow_hits = hits;  // a query is not a use
+  ctx->shadow_hit_bytes = hit_bytes;
+  return found ? 1 : 0;
+}
+
+int ffb_shadow_drop(ffb_ctx* ctx, const void* host, size_t bytes) {
+  if (!ctx) return FFB_EINVAL;
+  ffb_shadow_drop_range(ctx, host, bytes);
+  return FFB_OK;
+}
+
+int ffb_shadow_stats(ffb_ctx* ctx, int* count, size_t* bytes, int64_t* hits, size_t* hit_bytes) {
+  if (!ctx) return FFB_EINVAL;
+  if (count) *count = (int)ctx->shadows.size();
+  if (bytes) *bytes = ctx->shadow_bytes;
+  if (hits) *hits = ctx->shadow_hits;
+  if (hit_bytes) *hit_bytes = ctx->shadow_hit_bytes;
   return FFB_OK;
 }
 
@@ -440,11 +548,14 @@ int basis_flags(const double* basis, int n_basis, int d) {
 
 struct Upload {
   DevBuf buf;
+  const void* shadow = nullptr;  // the host bytes are mirrored on the device already
   int put(ffb_ctx* ctx, const void* host, size_t bytes) {
+    shadow = ffb_shadow_lookup(ctx, host, bytes);
+    if (shadow) return FFB_OK;
     FFB_TRY(buf.alloc(ctx, bytes));
     return ffb_h2d(ctx, buf.p, host, bytes);
   }
-  const double* d() const { return buf.as<double>(); }
+  const double* d() const { return shadow ? static_cast<const double*>(shadow) : buf.as<double>(); }
 };
 
 int enter(ffb_ctx* ctx) {
@@ -461,15 +572,20 @@ struct PackedUpload {
   static constexpr size_t ALIGN = 256;
   static constexpr size_t PACK_LIMIT = (size_t)512 << 10;  // larger parts are copied from where they lie
   static constexpr size_t RUN_BYTES = (size_t)128 << 10;   // a run of packed parts is sent at this size
-  std::vector<const void*> src;
+  std::vector<const void*> src, mirror;
   std::vector<size_t> bytes, offset;
   size_t total = 0;
   DevBuf dev;
+  ffb_ctx* owner = nullptr;
+  explicit PackedUpload(ffb_ctx* ctx = nullptr) : owner(ctx) {}
   int add(const void* host, size_t n) {
+    // a part that is mirrored on the device already (a cached result array) is not sent again
+    const void* m = owner ? ffb_shadow_lookup(owner, host, n) : nullptr;
     src.push_back(host);
-    bytes.push_back(n);
+    mirror.push_back(m);
+    bytes.push_back(m ? 0 : n);
     offset.push_back(total);
-    total += (n + ALIGN - 1) & ~(ALIGN - 1);
+    if (!m) total += (n + ALIGN - 1) & ~(ALIGN - 1);
     return (int)src.size() - 1;
   }
   int upload(ffb_ctx* ctx) {
@@ -483,7 +599,7 @@ struct PackedUpload {
     }
     char* stage = static_cast<char*>(ctx->stage_host);
     char* d0 = nullptr;
-    FFB_TRY(dev.alloc(ctx, total));
+    FFB_TRY(dev.alloc(ctx, total ? total : 8));
     d0 = static_cast<char*>(dev.p);
     // the device block mirrors the staging layout: runs of consecutive small parts travel in one copy
     // out of the staging block, a large part in its own copy straight from the caller's array (which
@@ -512,6 +628,7 @@ struct PackedUpload {
     return flush();
   }
   const double* d(int i) const {
+    if (mirror[i]) return static_cast<const double*>(mirror[i]);
     return reinterpret_cast<const double*>(static_cast<const char*>(dev.p) + offset[i]);
   }
 };
@@ -562,7 +679,21 @@ struct OutputBlock {
     items.push_back({static_cast<char*>(host), bytes, 0});
     return (int)items.size() - 1;
   }
+  // keep the device block as the shadow of the listed results (they must have been downloaded)
+  bool retain(ffb_ctx* ctx, std::initializer_list<int> which) {
+    if (!mirrored) return false;
+    std::vector<std::pair<size_t, size_t>> valid;
+    size_t hi = 0;
+    for (int i : which)
+      if (i >= 0 && items[i].host && items[i].bytes) {
+        valid.emplace_back(items[i].off, items[i].bytes);
+        hi = std::max(hi, items[i].off + items[i].bytes);
+      }
+    return ffb_shadow_retain(ctx, dev, host_base, hi, valid);
+  }
   int alloc(ffb_ctx* ctx) {
+    for (const Item& it : items)
+      if (it.host && it.bytes) ffb_shadow_drop_range(ctx, it.host, it.bytes);
     // one pool block that contains every requested result?
     char* lo = nullptr;
     char* hi = nullptr;
@@ -656,6 +787,7 @@ int ffb_diagonalize(ffb_ctx* ctx, int G, int d, int n_cops, const double* c_oper
                     double* propagators) {
   FFB_TRY(enter(ctx));
   FFB_REQUIRE(ctx, c_opers && dt && eigvals && eigvecs && propagators, "diagonalize: null pointer");
+  FFB_CHECK_DIM(ctx, d);
   FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32, "diagonalize: G=%d, d=%d unsupported", G, d);
   const size_t dd = (size_t)d * d;
   Upload ops, coeffs, dts;
@@ -686,18 +818,22 @@ int ffb_control_matrix_from_scratch(ffb_ctx* ctx, int G, int d, int n_nops, int 
   FFB_TRY(enter(ctx));
   FFB_REQUIRE(ctx, eigvals && eigvecs && propagators && omega && basis && n_opers && n_coeffs &&
                        dt && t && out, "control matrix: null pointer");
+  FFB_CHECK_DIM(ctx, d);
   FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
               "control matrix: bad shape");
+  const bool keep = ctx->shadow_next;
+  ctx->shadow_next = false;
   const size_t dd = (size_t)d * d;
   const int herm = (all_hermitian(n_opers, n_nops, d) ? FFB_HERM_NOPERS : 0) |
                    basis_flags(basis, n_basis, d);
   FFB_TRY(ensure_copy_stream(ctx));
+  ffb_shadow_drop_range(ctx, out, (size_t)n_nops * n_basis * n_omega * 16);
   static const bool trace = getenv("FFB_TRACE") && atoi(getenv("FFB_TRACE")) != 0;
   const auto t_enter = std::chrono::steady_clock::now();
   auto since = [&]() {
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_enter).count();
   };
-  PackedUpload in;
+  PackedUpload in(ctx);
   DevBuf B;
   CopyStreamDrain drain{ctx};
   const int i_ev = in.add(eigvals, (size_t)G * d * 8);
@@ -736,6 +872,7 @@ int ffb_control_matrix_from_scratch(ffb_ctx* ctx, int G, int d, int n_nops, int 
   if (trace)
     fprintf(stderr, "[ffb trace] control matrix: all work enqueued %.0f us, main stream done %.0f us, "
             "copy stream done %.0f us (%d blocks)\n", us_enqueued, us_main, since(), fb.n_blocks);
+  if (keep) ffb_shadow_retain(ctx, B, out, out_bytes, {{0, out_bytes}});
   return FFB_OK;
 }
 
@@ -755,6 +892,7 @@ int ffb_control_matrix_intermediates(ffb_ctx* ctx, int G, int d, int n_nops, int
                        basis_transformed && phase_factors && first_order_integral &&
                        control_matrix_step && (G == 1 || control_matrix_step_cumulative),
               "control matrix intermediates: null pointer");
+  FFB_CHECK_DIM(ctx, d);
   FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
               "control matrix intermediates: bad shape");
   const size_t dd = (size_t)d * d;
@@ -939,13 +1077,15 @@ int ffb_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int n_lib, int d, int n
               "concatenate_many: infidelity requested without spectrum and omega");
   FFB_REQUIRE(ctx, !total_propagator_liouville || basis,
               "concatenate_many: Liouville representation requested without basis");
+  const bool keep = ctx->shadow_next;
+  ctx->shadow_next = false;
   for (size_t i = 0; i < (size_t)n_seq * L; ++i)
     FFB_REQUIRE(ctx, indices[i] < n_lib, "concatenate_many: index %d at position %zu out of range "
                 "[0, %d)", indices[i], i, n_lib);
   const size_t dd = (size_t)d * d, nn = (size_t)n_basis * n_basis;
   // inputs in one packed upload, results in one (mirrored) device block: a single-sequence call -- the
   // tail of every ff.concatenate -- is bound by driver calls and blocking copies, not by bytes
-  PackedUpload in;
+  PackedUpload in(ctx);
   const int i_om = omega ? in.add(omega, (size_t)n_omega * 8) : -1;
   const int i_ix = in.add(indices, (size_t)n_seq * L * sizeof(int));
   const int i_lb = in.add(lib_control_matrix, (size_t)n_lib * n_nops * n_basis * n_omega * 16);
@@ -989,6 +1129,7 @@ int ffb_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int n_lib, int d, int n
       FFB_TRY(ffbi_cexp(ctx, n_omega, in.d(i_om), tau[s], out.d(o_ph) + (size_t)s * n_omega * 2));
   FFB_TRY(out.download(ctx, {o_U, o_L, o_ph, o_B, o_F, o_I}, ctx->stream));
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (keep) out.retain(ctx, {o_U, o_ph, o_B, filter_function ? o_F : -1});
   return FFB_OK;
 }
 
@@ -1005,15 +1146,20 @@ int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, 
   FFB_REQUIRE(ctx, row_of && cached && G && eigvals && eigvecs && propagators && dt && t &&
                        n_coeffs && n_opers && basis && omega && (P == 1 || (phases && liouville)),
               "concatenate_pulses: null input pointer");
+  FFB_CHECK_DIM(ctx, d);
   FFB_REQUIRE(ctx, P >= 1 && d >= 1 && d <= 32 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
               "concatenate_pulses: bad shape");
   FFB_REQUIRE(ctx, filter_function_kind >= 0 && filter_function_kind <= 2 &&
                        (filter_function_kind == 0 || filter_function),
               "concatenate_pulses: filter_function_kind=%d", filter_function_kind);
+  const bool keep_shadow = ctx->shadow_next;
+  ctx->shadow_next = false;
+  double* const control_matrix_host = control_matrix;
   const size_t dd = (size_t)d * d;
   const size_t row_bytes = (size_t)n_basis * n_omega * 16;
   const size_t pulse_bytes = (size_t)n_nops * row_bytes;
   const bool basis_herm = all_hermitian(basis, n_basis, d);
+  if (control_matrix) ffb_shadow_drop_range(ctx, control_matrix, (size_t)(correlations ? P : 1) * pulse_bytes);
   for (int p = 0; p < P; ++p)
     for (int j = 0; j < n_nops; ++j)
       FFB_REQUIRE(ctx, row_of[(size_t)p * n_nops + j] < 0 || cached[p],
@@ -1054,9 +1200,14 @@ int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, 
       // consecutive rows of the cached array that map to consecutive merged rows go in one copy
       int run = 1;
       while (j + run < n_nops && rows[j + run] == rows[j] + run) ++run;
-      FFB_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)j * row_bytes,
-                                    reinterpret_cast<const char*>(cached[p]) + (size_t)rows[j] * row_bytes,
-                                    (size_t)run * row_bytes, cudaMemcpyHostToDevice, up_stream));
+      // rows that are still mirrored on the device (the pulse's control matrix was computed by this
+      // context and its array is alive) are copied device-to-device: no PCIe traffic
+      const char* src_host = reinterpret_cast<const char*>(cached[p]) + (size_t)rows[j] * row_bytes;
+      const void* mirror = ffb_shadow_lookup(ctx, src_host, (size_t)run * row_bytes);
+      FFB_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)j * row_bytes, mirror ? mirror : src_host,
+                                    (size_t)run * row_bytes,
+                                    mirror ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                    up_stream));
       j += run - 1;
     }
     return FFB_OK;
@@ -1173,6 +1324,12 @@ int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, 
   }
   if (full_stack) FFB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (keep_shadow) {
+    if (full_stack && control_matrix_host)
+      ffb_shadow_retain(ctx, result, control_matrix_host, (size_t)lead * pulse_bytes,
+                        {{0, (size_t)lead * pulse_bytes}});
+    if (filter_function_kind) ffb_shadow_retain(ctx, F, filter_function, f_bytes, {{0, f_bytes}});
+  }
   return FFB_OK;
 }
 
@@ -1207,6 +1364,19 @@ int ffb_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out) {
   return FFB_OK;
 }
 
+int ffb_cexpm1(ffb_ctx* ctx, int n, const double* x, double* out) {
+  FFB_TRY(enter(ctx));
+  FFB_REQUIRE(ctx, x && out && n >= 1, "cexpm1: bad arguments");
+  Upload xd;
+  DevBuf O;
+  FFB_TRY(xd.put(ctx, x, (size_t)n * 8));
+  FFB_TRY(O.alloc(ctx, (size_t)n * 16));
+  FFB_TRY(ffbi_cexpm1(ctx, n, xd.d(), O.as<double>()));
+  FFB_TRY(ffb_d2h(ctx, out, O.p, (size_t)n * 16));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FFB_OK;
+}
+
 int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops, int n_basis,
                               int n_omega, const double* c_opers, const double* c_coeffs,
                               const double* n_opers, const double* n_coeffs, const double* dt,
@@ -1219,9 +1389,12 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
   FFB_TRY(enter(ctx));
   FFB_REQUIRE(ctx, c_opers && c_coeffs && n_opers && n_coeffs && dt && basis && omega,
               "pulse pipeline: null input pointer");
+  FFB_CHECK_DIM(ctx, d);
   FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32 && n_cops >= 1 && n_nops >= 1 && n_basis >= 1 &&
                        n_omega >= 1, "pulse pipeline: bad shape");
   FFB_REQUIRE(ctx, !infidelity || spectrum, "pulse pipeline: infidelity requested without spectrum");
+  const bool keep = ctx->shadow_next;
+  ctx->shadow_next = false;
   const size_t dd = (size_t)d * d;
   const int herm = (all_hermitian(n_opers, n_nops, d) ? FFB_HERM_NOPERS : 0) |
                    basis_flags(basis, n_basis, d);
@@ -1240,7 +1413,7 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
     snprintf(buf, sizeof(buf), " %s@%.0f", what, since());
     marks += buf;
   };
-  PackedUpload in;
+  PackedUpload in(ctx);
   const int i_co = in.add(c_opers, (size_t)n_cops * dd * 16);
   const int i_cc = in.add(c_coeffs, (size_t)n_cops * G * 8);
   const int i_dt = in.add(dt, (size_t)G * 8);
@@ -1364,6 +1537,9 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
     fprintf(stderr, "[ffb trace] pulse pipeline: inputs packed+upload enqueued %.0f us, all work enqueued "
             "%.0f us, main stream done %.0f us, copy stream done %.0f us;%s\n", us_packed, us_enqueued,
             us_main, since(), marks.c_str());
+  // the eigensystem, control matrix and filter function stay mirrored on the device for the consumers
+  // of the pulse's cache (the infidelity and the Liouville matrix are post-processed on the host)
+  if (keep) out.retain(ctx, {o_ev, o_V, o_Q, o_ph, control_matrix ? o_B : -1, filter_function ? o_F : -1});
   return FFB_OK;
 }
 

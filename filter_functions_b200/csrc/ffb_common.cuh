@@ -88,6 +88,26 @@ struct ffb_ctx {
   std::map<void*, size_t> host_live_blocks;
   size_t host_pool_bytes = 0;
 
+  // device-resident shadows of result arrays (SURVEY.md 8b "dev_handle"): when a host-pointer entry
+  // point has written results into page-locked blocks of this context's own pool, the device copy they
+  // were downloaded from can be kept, keyed by the host address range it mirrors.  A later call that
+  // is handed a host pointer inside such a range reads the device copy instead of uploading the
+  // bytes again (ff.infidelity with another spectrum, decay amplitudes, concatenation of cached gates).
+  // Dropped when the host block goes back to the pool (the NumPy array was garbage collected), when a
+  // call writes into the range, or -- oldest first -- when the shadows exceed `shadow_limit` bytes.
+  struct Shadow {
+    void* dev = nullptr;
+    size_t bytes = 0;                                  // mirrors host [key, key + bytes)
+    std::vector<std::pair<size_t, size_t>> valid;      // (offset, length) of the results inside
+    uint64_t stamp = 0;
+  };
+  std::map<char*, Shadow> shadows;
+  size_t shadow_bytes = 0, shadow_limit = 0;
+  uint64_t shadow_clock = 0;
+  bool shadow_next = false;  // keep the results of the next host-pointer call (one-shot)
+  int64_t shadow_hits = 0;
+  size_t shadow_hit_bytes = 0;
+
   // timing of the dominant kernel
   bool timing = false;
   double timed_ms = 0.0;
@@ -117,6 +137,12 @@ int ffb_fail(ffb_ctx* ctx, int code, const char* fmt, ...);
     if (!(cond)) return ffb_fail((ctx), FFB_EINVAL, __VA_ARGS__); \
   } while (0)
 
+// the kernels hold a d x d matrix per warp / thread in shared memory and registers: d <= 32
+#define FFB_MAX_DIM 32
+#define FFB_CHECK_DIM(ctx, d)                                                                        \
+  FFB_REQUIRE((ctx), (d) <= FFB_MAX_DIM, "Hilbert-space dimension d = %d exceeds the supported maximum " \
+              "of %d of filter_functions_b200 (README: limits)", (d), FFB_MAX_DIM)
+
 // counts the launch and checks the launch error
 #define FFB_LAUNCHED(ctx)         \
   do {                            \
@@ -145,6 +171,11 @@ struct DevBuf {
     if (p) ffb_pool_release(ctx, p);
     p = nullptr;
   }
+  void* detach() {  // ownership moves to the caller (a shadow)
+    void* q = p;
+    p = nullptr;
+    return q;
+  }
   template <typename T>
   T* as() const { return static_cast<T*>(p); }
 };
@@ -162,6 +193,13 @@ int ffb_occupancy(ffb_ctx* ctx, K kern, int block_threads, size_t smem, int* blo
   return ffb_occupancy_impl(ctx, reinterpret_cast<const void*>(kern), block_threads, smem, blocks);
 }
 int ffb_h2d(ffb_ctx* ctx, void* dst, const void* src, size_t bytes);
+// device shadows of result arrays (ffb_api.cu)
+const void* ffb_shadow_lookup(ffb_ctx* ctx, const void* host, size_t bytes);
+void ffb_shadow_drop_range(ffb_ctx* ctx, const void* host, size_t bytes);
+// `buf` mirrors host [host_lo, host_lo + bytes); `valid` lists the results inside.  Takes the buffer out
+// of `buf` if the shadow is kept (host range inside one live block of the host pool, size limits).
+bool ffb_shadow_retain(ffb_ctx* ctx, DevBuf& buf, void* host_lo, size_t bytes,
+                       const std::vector<std::pair<size_t, size_t>>& valid);
 // convergence counter of the eigensolver: device pointer (created on first use); enqueue its download;
 // after a stream synchronisation: FFB_ENOTCONV (and reset) if any matrix failed to converge
 int ffb_conv_counter(ffb_ctx* ctx, int** dev);
@@ -232,6 +270,7 @@ int ffbi_control_matrix_periodic(ffb_ctx* ctx, int n_nops, int n_basis, int n_om
 int ffbi_liouville(ffb_ctx* ctx, int n, int d, int n_basis, const double* U, const double* basis,
                    double* out);
 int ffbi_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out);
+int ffbi_cexpm1(ffb_ctx* ctx, int n, const double* x, double* out);
 int ffbi_fp64_peak(ffb_ctx* ctx, double* dfma, double* dmma);
 // peer group (ffb_comm.cu): the kernel-side descriptor of the NEXT collective (advances the sequence
 // number); in-place all-reduce of n doubles in device memory; release of everything the group holds

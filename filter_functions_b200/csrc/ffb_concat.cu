@@ -158,6 +158,14 @@ __global__ void cexp_kernel(int n, const double* __restrict__ x, double scale,
   out[i] = make_double2(cs, sn);
 }
 
+// exp(i x) - 1 = -2 sin^2(x/2) + i sin(x) (util.cexpm1, util.py:165-182: no cancellation for small x)
+__global__ void cexpm1_kernel(int n, const double* __restrict__ x, double2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double s = sin(x[i] / 2);
+  out[i] = make_double2(-2.0 * (s * s), sin(x[i]));
+}
+
 // ------------------------------------------------------------------------------------------------
 // Batched concatenation: n_seq gate sequences drawn from a library of n_lib
 // pulses with cached control matrices (randomized benchmarking, examples/randomized_benchmarking.py:
@@ -470,6 +478,13 @@ int ffbi_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out) {
   FFB_REQUIRE(ctx, n >= 1, "cexp: n=%d", n);
   cexp_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, x, scale,
                                                          reinterpret_cast<double2*>(out));
+  FFB_LAUNCHED(ctx);
+  return FFB_OK;
+}
+
+int ffbi_cexpm1(ffb_ctx* ctx, int n, const double* x, double* out) {
+  FFB_REQUIRE(ctx, n >= 1, "cexpm1: n=%d", n);
+  cexpm1_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, x, reinterpret_cast<double2*>(out));
   FFB_LAUNCHED(ctx);
   return FFB_OK;
 }

@@ -1565,6 +1565,7 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
                         double* out_all, const FreqBlocks* blocks) {
   const double* const omega_all = omega;
   const int n_omega_all = n_omega;
+  FFB_CHECK_DIM(ctx, d);
   FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32, "control matrix: G=%d, d=%d unsupported", G, d);
   FFB_REQUIRE(ctx, n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
               "control matrix: n_nops=%d n_basis=%d n_omega=%d must all be positive", n_nops,

@@ -179,6 +179,7 @@ int ffbi_control_matrix_intermediates(ffb_ctx* ctx, int G, int d, int n_nops, in
                                       double* eigvecs_propagated, double* basis_transformed,
                                       double* phase_factors, double* first_order_integral,
                                       double* step, double* cumulative) {
+  FFB_CHECK_DIM(ctx, d);
   FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
               "control matrix intermediates: bad shape");
   FFB_REQUIRE(ctx, G <= 65535 && (long long)n_nops * n_basis <= 65535,

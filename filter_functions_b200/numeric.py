@@ -71,6 +71,16 @@ def calculate_control_matrix_from_scratch(eigvals, eigvecs, propagators, omega, 
                                           out: Optional[ndarray] = None):
     r"""Control matrix :math:`\tilde{\mathcal{B}}_{\alpha k}(\omega)` of shape
     (n_nops, n_basis, n_omega) without knowledge of more atomic pulses."""
+    return _control_matrix_from_scratch(eigvals, eigvecs, propagators, omega, basis, n_opers,
+                                        n_coeffs, dt, t, cache_intermediates, out, keep=False)
+
+
+def _control_matrix_from_scratch(eigvals, eigvecs, propagators, omega, basis, n_opers, n_coeffs, dt,
+                                 t=None, cache_intermediates: bool = False,
+                                 out: Optional[ndarray] = None, keep: bool = False):
+    """Body of :func:`calculate_control_matrix_from_scratch`.  ``keep``: the result stays mirrored on the
+    device (and becomes read-only on the host) -- used by ``PulseSequence``, whose cache hands the array
+    to later device computations."""
     eigvals = _lib.as_f64(eigvals)
     eigvecs = _lib.as_c128(eigvecs)
     propagators = _lib.as_c128(propagators)
@@ -119,10 +129,14 @@ def calculate_control_matrix_from_scratch(eigvals, eigvecs, propagators, omega, 
             result = out
         return result, inter
     if n_omega:
+        if keep and out is None:
+            _lib.keep_on_device(ctx)
         _lib.check(ctx, _lib.lib().ffb_control_matrix_from_scratch(
             ctx, G, d, n_nops, n_basis, n_omega, _lib.ptr(eigvals), _lib.ptr(eigvecs),
             _lib.ptr(propagators), _lib.ptr(omega), _lib.ptr(basis_arr), _lib.ptr(n_opers),
             _lib.ptr(n_coeffs), _lib.ptr(dt), _lib.ptr(t), _lib.ptr(result)))
+        if keep and out is None:
+            _lib.freeze_shadowed(ctx, result)
     if out is not None and not direct:
         out[:] = result
         return out
@@ -250,6 +264,46 @@ def _integrate_against_spectrum(filter_function, spectrum, omega, idx, d):
     return out
 
 
+def _infidelity_convergence(pulse, spectrum, omega, n_oper_identifiers, n_sel, show_progressbar):
+    """``test_convergence=True`` (behaviour of reference ``numeric.py:2254-2292``): ``spectrum`` is a
+    function of frequency, ``omega`` a dict of grid parameters; the infidelity is evaluated on
+    ``n_points`` grids of growing size between ``omega_IR`` and ``omega_UV``.  Returns
+    ``(n_samples, infidelities[len(n_samples), n_sel])``."""
+    if not callable(spectrum):
+        raise TypeError('Spectrum should be callable when test_convergence == True.')
+    if not hasattr(omega, 'get'):
+        raise TypeError('omega should be dictionary with parameters when test_convergence == True.')
+    base = 2*np.pi/pulse.tau
+    settings = {'omega_IR': base*1e-2, 'omega_UV': base*1e+2, 'spacing': 'linear', 'n_min': 100,
+                'n_max': 500, 'n_points': 10}
+    settings.update({key: omega[key] for key in settings if omega.get(key) is not None})
+    grids = {'linear': np.linspace, 'log': np.geomspace}
+    if settings['spacing'] not in grids:
+        raise ValueError("spacing should be either 'linear' or 'log'.")
+    make_grid = grids[settings['spacing']]
+    step = (settings['n_max'] - settings['n_min'])//(settings['n_points'] - 1)
+    n_samples = np.arange(settings['n_min'], settings['n_max'] + step, step)
+    results = np.empty((len(n_samples), n_sel))
+    for row, n in zip(results, n_samples):
+        grid = make_grid(settings['omega_IR'], settings['omega_UV'], n)
+        row[:] = infidelity(pulse, spectrum(grid), grid, n_oper_identifiers=n_oper_identifiers,
+                            show_progressbar=show_progressbar)
+    return n_samples, results
+
+
+def _smallness_parameter(pulse, spectrum, omega, idx):
+    r"""The parameter :math:`\xi` that bounds the validity of the perturbative expansion (reference
+    ``numeric.py:2322-2332``): :math:`\xi^2=\sum_\alpha\big[\int\frac{d\omega}{2\pi}S_\alpha(\omega)\big]
+    \big[\sum_g s_\alpha^{(g)}\Delta t_g\big]^2\lVert B_\alpha\rVert^2`."""
+    if spectrum.ndim > 2:
+        raise NotImplementedError('Smallness parameter only implemented for uncorrelated noise '
+                                  'sources')
+    noise_power = util.integrate(spectrum, np.asarray(omega))/(2*np.pi)
+    sensitivity = np.sum(pulse.dt*pulse.n_coeffs[idx], axis=-1)
+    operator_norm = util.abs2(pulse.n_opers[idx]).sum(axis=(1, 2))
+    return np.sqrt(np.sum(noise_power*sensitivity**2*operator_norm))
+
+
 @util.parse_optional_parameters(which=('total', 'correlations'))
 def infidelity(pulse, spectrum, omega, n_oper_identifiers=None, which: str = 'total',
                show_progressbar: bool = False, cache_intermediates: bool = False,
@@ -261,35 +315,8 @@ def infidelity(pulse, spectrum, omega, n_oper_identifiers=None, which: str = 'to
     idx = util.get_indices_from_identifiers(pulse.n_oper_identifiers, n_oper_identifiers)
 
     if test_convergence:
-        if not callable(spectrum):
-            raise TypeError('Spectrum should be callable when test_convergence == True.')
-        try:
-            omega_IR = omega.get('omega_IR', 2*np.pi/pulse.tau*1e-2)
-        except AttributeError:
-            raise TypeError('omega should be dictionary with parameters '
-                            + 'when test_convergence == True.')
-        omega_UV = omega.get('omega_UV', 2*np.pi/pulse.tau*1e+2)
-        spacing = omega.get('spacing', 'linear')
-        n_min = omega.get('n_min', 100)
-        n_max = omega.get('n_max', 500)
-        n_points = omega.get('n_points', 10)
-        if spacing == 'linear':
-            xspace = np.linspace
-        elif spacing == 'log':
-            xspace = np.geomspace
-        else:
-            raise ValueError("spacing should be either 'linear' or 'log'.")
-        delta_n = (n_max - n_min)//(n_points - 1)
-        n_samples = np.arange(n_min, n_max + delta_n, delta_n)
-        convergence_infids = np.empty((len(n_samples), len(idx)))
-        for i, n in enumerate(n_samples):
-            freqs = xspace(omega_IR, omega_UV, n)
-            convergence_infids[i] = infidelity(pulse, spectrum(freqs), freqs,
-                                               n_oper_identifiers=n_oper_identifiers,
-                                               which='total', show_progressbar=show_progressbar,
-                                               cache_intermediates=False, return_smallness=False,
-                                               test_convergence=False)
-        return n_samples, convergence_infids
+        return _infidelity_convergence(pulse, spectrum, omega, n_oper_identifiers, len(idx),
+                                       show_progressbar)
 
     spectrum = np.asarray(spectrum)
     if (which == 'total' and n_oper_identifiers is None and not cache_intermediates
@@ -326,14 +353,7 @@ def infidelity(pulse, spectrum, omega, n_oper_identifiers=None, which: str = 'to
     infid = _integrate_against_spectrum(filter_function, spectrum, omega, idx, pulse.d)
 
     if return_smallness:
-        if spectrum.ndim > 2:
-            raise NotImplementedError('Smallness parameter only implemented '
-                                      + 'for uncorrelated noise sources')
-        T1 = util.integrate(spectrum, np.asarray(omega))/(2*np.pi)
-        T2 = (pulse.dt*pulse.n_coeffs[idx]).sum(axis=-1)**2
-        T3 = util.abs2(pulse.n_opers[idx]).sum(axis=(1, 2))
-        xi = np.sqrt((T1*T2*T3).sum())
-        return infid, xi
+        return infid, _smallness_parameter(pulse, spectrum, omega, idx)
 
     return infid
 
@@ -477,16 +497,19 @@ def error_transfer_matrix(pulse=None, spectrum=None, omega=None, n_oper_identifi
     shape (n_basis, n_basis), summed over all noise operators (reference ``numeric.py:1938-2059``)."""
     from scipy import linalg as sla
     if cumulant_function is None:
-        if pulse is None or spectrum is None or omega is None:
+        if any(arg is None for arg in (pulse, spectrum, omega)):
             raise ValueError('Require either precomputed cumulant function '
                              + 'or pulse, spectrum, and omega as arguments.')
         cumulant_function = calculate_cumulant_function(
             pulse, spectrum, omega, n_oper_identifiers, 'total', second_order,
             show_progressbar=show_progressbar, memory_parsimonious=memory_parsimonious,
             cache_intermediates=cache_intermediates)
-    try:
-        return sla.expm(cumulant_function.sum(axis=tuple(range(cumulant_function.ndim - 2))))
-    except AttributeError as aerr:
-        raise TypeError(f'cumulant_function invalid type: {type(cumulant_function)}') from aerr
-    except ValueError as verr:
-        raise ValueError(f'cumulant_function invalid shape: {cumulant_function.shape}') from verr
+    if not hasattr(cumulant_function, 'sum'):
+        raise TypeError(f'cumulant_function invalid type: {type(cumulant_function)}')
+    if np.ndim(cumulant_function) < 2:
+        raise ValueError(f'cumulant_function invalid shape: {np.shape(cumulant_function)}')
+    # all leading axes enumerate noise operators (pairs): their cumulants add up in the exponent
+    summed = cumulant_function.reshape(-1, *cumulant_function.shape[-2:]).sum(axis=0)
+    if summed.shape[0] != summed.shape[1]:
+        raise ValueError(f'cumulant_function invalid shape: {cumulant_function.shape}')
+    return sla.expm(summed)

@@ -18,7 +18,7 @@ from numpy import ndarray
 
 from . import _lib, numeric, util
 from .basis import Basis
-from .superoperator import liouville_representation
+from .superoperator import liouville_representation, normalize_liouville_columns
 
 __all__ = ['PulseSequence', 'SequenceBatch', 'concatenate', 'concatenate_many',
            'concatenate_periodic', 'concatenate_without_filter_function']
@@ -346,10 +346,9 @@ class PulseSequence:
                 self._frequency_data['control_matrix_pc'], axis=0)
             return self._frequency_data['control_matrix']
         self.diagonalize()
-        control_matrix = numeric.calculate_control_matrix_from_scratch(
+        control_matrix = numeric._control_matrix_from_scratch(
             self.eigvals, self.eigvecs, self.propagators, self.omega, self.basis, self.n_opers,
-            self.n_coeffs, self.dt, self.t, show_progressbar=show_progressbar,
-            cache_intermediates=cache_intermediates)
+            self.n_coeffs, self.dt, self.t, cache_intermediates=cache_intermediates, keep=True)
         if cache_intermediates:
             control_matrix, intermediates = control_matrix
             self._intermediates.update(intermediates)
@@ -418,14 +417,18 @@ class PulseSequence:
             infid = arrays[7]
         ctx = _lib.context()
         p = _lib.ptr
+        # the cached arrays stay mirrored on the device: a second spectrum, decay amplitudes or a
+        # concatenation that is handed them later does not upload them again
+        _lib.keep_on_device(ctx)
         _lib.check(ctx, _lib.lib().ffb_pulse_filter_function(
             ctx, G, d, n_cops, n_nops, n_basis, n_omega, p(c_opers), p(c_coeffs), p(n_opers),
             p(n_coeffs), p(dt), p(t), p(basis), p(omega_arr), p(S), s_ndim, s_complex, p(eigvals),
             p(eigvecs), p(propagators), p(B), p(F), p(infid), p(phases), p(liouville)))
+        _lib.freeze_shadowed(ctx, eigvals, eigvecs, propagators, phases, B, F)
         self._data.update(eigvals=eigvals, eigvecs=eigvecs, propagators=propagators,
                           total_propagator=propagators[-1])
-        self._data['total_propagator_liouville'] = (
-            np.ascontiguousarray(liouville.real) if self.basis.isherm else liouville)
+        self._data['total_propagator_liouville'] = normalize_liouville_columns(
+            np.ascontiguousarray(liouville.real) if self.basis.isherm else liouville, self.basis)
         self._frequency_data.update(control_matrix=B, total_phases=phases, filter_function=F)
         if infid is not None and self.d != d:
             infid *= d/self.d
@@ -696,8 +699,9 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
     equal_n_opers = (n_opers_present.sum(axis=0) > 1).any()
     distinct = _unique_by_identity(pulses)
     if omega is None:
-        with_ctrl = [pls for pls in distinct if 'control_matrix' in pls._frequency_data
-                     or 'control_matrix_pc' in pls._frequency_data]
+        # the reference's predicate is is_cached('control_matrix') -- a pulse that only holds a
+        # pulse-correlation control matrix does not count (pulse_sequence.py:1783)
+        with_ctrl = [pls for pls in distinct if 'control_matrix' in pls._frequency_data]
         with_omega = with_ctrl or [pls for pls in distinct if 'omega' in pls._frequency_data]
         grids = _unique_by_identity(pls.omega for pls in with_omega)
         equal_omega = bool(grids) and (len(grids) == 1 or util.all_array_equal(grids))
@@ -750,15 +754,18 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         tau = np.array([newpulse.tau], dtype=np.float64)
         ctx = _lib.context()
         p = _lib.ptr
+        _lib.keep_on_device(ctx)
         _lib.check(ctx, _lib.lib().ffb_concatenate_many(
             ctx, 1, len(index), len(distinct), d, n_nops, n_basis, n_omega, p(index), p(lib_B),
             p(lib_ph), p(lib_L), p(lib_U), p(basis), None, 0, 0, p(omega_arr), p(U), p(liouville),
             p(B), p(F), None, p(tau), p(total_phases)))
+        _lib.freeze_shadowed(ctx, total_phases, B, F)
         if 'total_propagator' not in newpulse._data:
             newpulse.total_propagator = U[0]
         newpulse._frequency_data['omega'] = np.array(omega, copy=True)
         newpulse._frequency_data['total_phases'] = total_phases[0]
-        newpulse.total_propagator_liouville = np.ascontiguousarray(liouville[0].real)
+        newpulse.total_propagator_liouville = normalize_liouville_columns(
+            np.ascontiguousarray(liouville[0].real), newpulse.basis)
         newpulse._frequency_data['control_matrix'] = B[0]
         newpulse._frequency_data['filter_function'] = F[0]
         return newpulse
@@ -859,10 +866,12 @@ def _concatenate_on_device(pulses, newpulse, n_opers_present, ctrl, omega, phase
     F = _lib.empty(lead*2 + (n_nops, n_nops) + ((n_basis, n_basis) if gen else ()) + (n_omega,))
     ctx = _lib.context()
     p = _lib.ptr
+    _lib.keep_on_device(ctx)
     _lib.check(ctx, _lib.lib().ffb_concatenate_pulses(
         ctx, P, d, n_nops, n_basis, n_omega, p(row_of), cached, p(G), eigvals, eigvecs, props, dts,
         ts, coeffs, p(n_opers), p(basis), p(omega_arr), p(phases), p(liouville), int(correlations),
         2 if gen else 1, p(B), p(F)))
+    _lib.freeze_shadowed(ctx, B, F)
     return B, F
 
 
@@ -1032,7 +1041,8 @@ def concatenate_many(pulses, indices, spectrum=None, omega=None, calc_control_ma
             p(lib_phase), p(lib_liouville), p(lib_U), p(basis), p(S), s_ndim, s_complex, p(omega),
             sub(batch.total_propagator), sub(liouville), sub(batch.control_matrix),
             sub(batch.filter_function), sub(batch.infidelities), None, None))
-    batch.total_propagator_liouville = np.ascontiguousarray(liouville.real)
+    batch.total_propagator_liouville = normalize_liouville_columns(
+        np.ascontiguousarray(liouville.real), first.basis)
     if batch.infidelities is not None and first.d != d:
         batch.infidelities *= d/first.d
     return batch

@@ -6,8 +6,25 @@ Mirror of the one function of the reference's ``superoperator.py`` that the hot 
 import numpy as np
 
 from . import _lib
+from . import basis as _basis
 
 __all__ = ['liouville_representation']
+
+
+def normalize_liouville_columns(liouville, basis):
+    """Turn raw traces tr(C_i U C_j U^dagger) into expansion coefficients: column j is divided by
+    tr(C_j C_j) when the basis elements are not normalised -- what ``basis.expand(...)`` of the
+    reference does for ``basis.isnorm == False`` (``basis.py:650-698``); a no-op for the orthonormal
+    Pauli / GGM bases."""
+    if getattr(basis, 'isnorm', None) is None:
+        basis = np.asarray(basis).view(_basis.Basis)
+    if basis.isnorm:
+        return liouville
+    arr = np.asarray(basis)
+    norms = np.einsum('bij,bji->b', arr, arr)
+    if not np.iscomplexobj(liouville):
+        norms = norms.real
+    return liouville/norms
 
 
 def liouville_representation(U, basis) -> np.ndarray:
@@ -28,4 +45,4 @@ def liouville_representation(U, basis) -> np.ndarray:
     herm = getattr(basis, 'isherm', None)
     if herm is None:
         herm = np.allclose(Bc, Bc.conj().swapaxes(-1, -2), atol=1e-14, rtol=0)
-    return np.ascontiguousarray(out.real) if herm else out
+    return normalize_liouville_columns(np.ascontiguousarray(out.real) if herm else out, basis)

@@ -13,7 +13,7 @@ from numpy import ndarray
 
 from . import _lib
 
-__all__ = ['paulis', 'abs2', 'cexp', 'get_sample_frequencies', 'mdot', 'adot', 'integrate',
+__all__ = ['paulis', 'abs2', 'cexp', 'cexpm1', 'get_sample_frequencies', 'mdot', 'adot', 'integrate',
            'parse_optional_parameters', 'parse_spectrum', 'parse_operators',
            'get_indices_from_identifiers', 'is_sequence_like', 'hash_array_along_axis',
            'all_array_equal', 'CalculationError', 'dot_HS', 'oper_equiv']
@@ -33,21 +33,35 @@ def abs2(x):
     return x.real**2 + x.imag**2
 
 
-def cexp(x, out=None, where=True):
-    """exp(i x) on the GPU (reference ``util.py:136-162``)."""
+def _elementwise_on_device(x, out, where, kernel):
+    """Shared shell of :func:`cexp` / :func:`cexpm1`: evaluate on the GPU, then honour ``out`` and the
+    ufunc-style ``where`` mask (entries where the mask is False keep what ``out`` held)."""
     x = np.asarray(x, dtype=float)
-    if where is not True:
-        raise NotImplementedError('cexp: the `where` mask of the reference is not supported')
     flat = _lib.as_f64(x.ravel())
     res = np.empty(flat.shape, dtype=np.complex128)
     if flat.size:
         ctx = _lib.context()
-        _lib.check(ctx, _lib.lib().ffb_cexp(ctx, flat.size, _lib.ptr(flat), 1.0, _lib.ptr(res)))
+        _lib.check(ctx, kernel(ctx, flat, res))
     res = res.reshape(x.shape)
-    if out is not None:
-        out[...] = res
-        return out
-    return res
+    if where is True and out is None:
+        return res
+    if out is None:
+        out = np.empty(x.shape, dtype=np.complex128)
+    np.copyto(out, res, where=np.broadcast_to(where, x.shape) if where is not True else True)
+    return out
+
+
+def cexp(x, out=None, where=True):
+    """exp(i x) on the GPU (reference ``util.py:136-162``)."""
+    return _elementwise_on_device(x, out, where, lambda ctx, flat, res: _lib.lib().ffb_cexp(
+        ctx, flat.size, _lib.ptr(flat), 1.0, _lib.ptr(res)))
+
+
+def cexpm1(x, out=None, where=True):
+    r"""exp(i x) - 1 = -2 sin^2(x/2) + i sin(x) on the GPU, without the cancellation of
+    ``cexp(x) - 1`` at small x (reference ``util.py:165-182``)."""
+    return _elementwise_on_device(x, out, where, lambda ctx, flat, res: _lib.lib().ffb_cexpm1(
+        ctx, flat.size, _lib.ptr(flat), _lib.ptr(res)))
 
 
 def integrate(f, x=None, dx=1.0):

@@ -213,6 +213,8 @@ int ffb_liouville_representation(ffb_ctx* ctx, int n, int d, int n_basis, const 
 
 /* exp(i * x * scale) element-wise (util.cexp, util.py:136-162); x (n) f64 -> out (n) c128. */
 int ffb_cexp(ffb_ctx* ctx, int n, const double* x, double scale, double* out);
+/* exp(i x) - 1 = -2 sin^2(x/2) + i sin(x) element-wise (util.cexpm1, util.py:165-182). */
+int ffb_cexpm1(ffb_ctx* ctx, int n, const double* x, double* out);
 
 /* ---- fused pulse pipeline ------------------------------------------------------------------------
  * What PulseSequence.get_filter_function (pulse_sequence.py:691-805) does on a cold cache, in one
@@ -314,6 +316,22 @@ int ffb_memcpy_d2h(ffb_ctx* ctx, void* dst_host, const void* src_dev, size_t byt
  * the pool. */
 int ffb_host_alloc(ffb_ctx* ctx, size_t bytes, void** ptr);
 int ffb_host_free(ffb_ctx* ctx, void* ptr);
+
+/* ---- device-resident shadows of cached arrays (the reference's cache is
+ * pulse_sequence.py:262-271, :1158-1245) ----------------------------------------------------------------
+ * ffb_shadow_enable_next(ctx, 1) before ffb_pulse_filter_function, ffb_control_matrix_from_scratch,
+ * ffb_concatenate_pulses or a single-sequence ffb_concatenate_many: the device copy of the results that
+ * land in page-locked blocks of ffb_host_alloc is kept after the call, keyed by the host address range it
+ * mirrors.  Any later host-pointer call that is handed a pointer into such a range (ffb_infidelity,
+ * ffb_decay_amplitudes, ffb_filter_function, ffb_concatenate_pulses, ...) reads the device copy instead
+ * of uploading the bytes.  A shadow ends when its host block is returned (ffb_host_free), when a call
+ * writes into the range, by ffb_shadow_drop, or -- oldest first -- when all shadows together exceed a
+ * quarter of the device memory (FFB_SHADOW_BYTES).  The caller must not modify a shadowed host array
+ * (ffb_shadow_query tells; the Python shell marks such arrays read-only). */
+int ffb_shadow_enable_next(ffb_ctx* ctx, int enable);
+int ffb_shadow_query(ffb_ctx* ctx, const void* host, size_t bytes);
+int ffb_shadow_drop(ffb_ctx* ctx, const void* host, size_t bytes);
+int ffb_shadow_stats(ffb_ctx* ctx, int* count, size_t* bytes, int64_t* hits, size_t* hit_bytes);
 
 /* Kernel-level timing of the control-matrix main kernel: average duration (ms) of the launches of
  * the dominant kernel recorded with CUDA events on the launching stream since the last reset. */

@@ -92,6 +92,12 @@ def main():
         L_r = ref_super.liouville_representation(Q_r[1:4], basis)
         record('liouville', nerr(oracle.liouville_representation(Q_r[1:4], my_basis), L_r))
 
+        # un-normalised (rescaled) basis: the expansion divides by tr(C_j C_j)
+        scaled = ff.Basis(np.asarray(basis)*np.linspace(0.5, 2.0, len(basis))[:, None, None])
+        record('liouville_unnormalised',
+               nerr(oracle.liouville_representation(Q_r[1:4], np.asarray(scaled)),
+                    ref_super.liouville_representation(Q_r[1:4], scaled)))
+
         # concatenation of three "pulses" whose control matrices are random
         P = 4
         atomic = (rng.standard_normal((P, n_nops, len(my_basis), len(omega)))

@@ -22,7 +22,7 @@ def _setup(rng, d, G, n_nops, n_cops=3):
 
 
 @pytest.mark.parametrize('d,G', [(2, 1), (2, 33), (3, 10), (4, 64), (5, 7), (8, 19), (16, 5),
-                                 (2, 1000)])
+                                 (2, 1000), (17, 3), (24, 4), (32, 3)])
 def test_diagonalize(engine, d, G):
     rng = np.random.default_rng(100 + d*1000 + G)
     *_, dt, H = _setup(rng, d, G, 2)
@@ -88,6 +88,7 @@ def test_diagonalize_reports_non_convergence(engine, d):
     (2, 1, 1, 'pauli', 1), (2, 2, 1, 'pauli', 300), (2, 37, 3, 'pauli', 257), (2, 50, 2, 'ggm', 64),
     (3, 21, 2, 'ggm', 100), (4, 40, 6, 'pauli', 203), (4, 9, 3, 'ggm', 77), (5, 6, 2, 'ggm', 50),
     (6, 5, 2, 'ggm', 40), (8, 7, 2, 'pauli', 33), (16, 3, 2, 'ggm', 24), (2, 1003, 3, 'pauli', 129),
+    (17, 2, 1, 'ggm', 20), (24, 2, 1, 'ggm', 16), (32, 2, 1, 'pauli', 12),   # up to the documented d <= 32
 ])
 def test_control_matrix_from_scratch(engine, d, G, n_nops, btype, n_omega):
     rng = np.random.default_rng(7 + 31*d + G)

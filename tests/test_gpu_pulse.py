@@ -458,3 +458,76 @@ def test_pulse_caches_intermediates(engine):
     assert set(fresh.intermediates) == keys
     fresh.cleanup('greedy')
     assert not fresh.intermediates
+
+
+def test_unnormalised_basis_liouville_and_concatenation(engine):
+    """A custom basis whose elements are not normalised (``ff.Basis(util.paulis)``; the constructor does
+    not normalise): the Liouville representation carries the 1/tr(C_j C_j) of ``Basis.expand``
+    (reference ``superoperator.py:82-84``, ``basis.py:650-698``), so that concatenation from cached
+    control matrices still equals the control matrix from scratch."""
+    ff = engine
+    rng = np.random.default_rng(515)
+    scaled = np.asarray(ff.Basis.pauli(1))*np.array([1.0, 2.0, 0.5, 3.0])[:, None, None]
+    for basis in (ff.Basis(ff.util.paulis), ff.Basis(scaled)):
+        assert not basis.isnorm and basis.isherm
+        G = 11
+        X, Y, Z = ff.util.paulis[1:]
+        H_c = [[X/2, rng.standard_normal(G), 'X'], [Y/2, rng.standard_normal(G), 'Y']]
+        H_n = [[Z/2, rng.random(G) + 0.5, 'Z'], [X/2, np.ones(G), 'Xn']]
+        pulse = ff.PulseSequence(H_c, H_n, 1 - rng.random(G)*0.5, basis)
+        omega = np.geomspace(1e-2, 30, 80)
+        U = pulse.propagators[1:5]
+        assert nerr(ff.liouville_representation(U, basis),
+                    oracle.liouville_representation(U, np.asarray(basis))) < 1e-13
+        B_scratch = pulse.get_control_matrix(omega)
+        assert nerr(pulse.total_propagator_liouville,
+                    oracle.liouville_representation(pulse.total_propagator, np.asarray(basis))) < 1e-13
+        H = oracle.hamiltonian_from_coeffs(pulse.c_opers, pulse.c_coeffs)
+        ev, V, Q = oracle.diagonalize(H, pulse.dt)
+        B_o = oracle.control_matrix_from_scratch(ev, V, Q, omega, np.asarray(basis), pulse.n_opers,
+                                                 pulse.n_coeffs, pulse.dt)
+        assert nerr(B_scratch, B_o) < TOL
+        pieces = [pulse[0:4], pulse[4:5], pulse[5:G]]
+        for piece in pieces:
+            piece.cache_control_matrix(omega)
+            assert nerr(piece.total_propagator_liouville, oracle.liouville_representation(
+                piece.total_propagator, np.asarray(basis))) < 1e-13
+        joined = ff.concatenate(pieces)                          # single-call fast path
+        assert nerr(joined.get_control_matrix(omega), B_o) < TOL
+        assert nerr(joined.total_propagator_liouville, pulse.total_propagator_liouville) < 1e-12
+        joined_pc = ff.concatenate(pieces, calc_pulse_correlation_FF=True)   # general path
+        assert nerr(joined_pc.get_control_matrix(omega), B_o) < TOL
+        repeated = ff.concatenate_periodic(pieces[0], 3)
+        whole = ff.concatenate([pieces[0]]*3, calc_filter_function=False)
+        assert nerr(repeated.get_control_matrix(omega), whole.get_control_matrix(omega)) < 1e-9
+    # in-place normalisation forgets the cached predicates (reference basis.py:373-379)
+    b = ff.Basis(ff.util.paulis)
+    assert not b.isnorm
+    b.normalize()
+    assert b.isnorm and b == ff.Basis.pauli(1)
+
+
+def test_cexp_and_cexpm1(engine):
+    """util.cexp / util.cexpm1 incl. the ufunc-style ``out`` and ``where`` arguments (reference
+    ``util.py:136-182``, tests/test_util.py:41-66)."""
+    ff = engine
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((7, 50))*20
+    x[0, :5] = [0.0, 1e-18, -1e-9, 1e-5, 3e-3]
+    np.testing.assert_allclose(ff.util.cexp(x), np.exp(1j*x), rtol=0, atol=4e-16)
+    ref = oracle.cexpm1(x)
+    got = ff.util.cexpm1(x)
+    assert np.abs(got - ref).max() <= 4e-16
+    # no cancellation for tiny arguments: relative accuracy of the real part
+    tiny = np.array([1e-9, -3e-7, 1e-5])
+    np.testing.assert_allclose(ff.util.cexpm1(tiny).real, -2*np.sin(tiny/2)**2, rtol=1e-14)
+    mask = rng.random(x.shape) < 0.5
+    for fn, want in ((ff.util.cexp, np.exp(1j*x)), (ff.util.cexpm1, ref)):
+        out = np.full(x.shape, 7 + 7j)
+        res = fn(x, out=out, where=mask)
+        assert res is out
+        np.testing.assert_allclose(out[mask], want[mask], rtol=0, atol=4e-16)
+        assert (out[~mask] == 7 + 7j).all()
+        out2 = np.empty(x.shape, dtype=complex)
+        assert fn(x, out=out2) is out2
+        np.testing.assert_allclose(out2, want, rtol=0, atol=4e-16)
