@@ -77,6 +77,7 @@ EXPORTED_SYMBOLS = {
     'ffb_kernel_timing_enable': (c_int, [c_void_p, c_int]),
     'ffb_kernel_timing_read': (c_int, [c_void_p, _dp, POINTER(c_int64), c_int]),
     'ffb_shadow_enable_next': (c_int, [c_void_p, c_int]),
+    'ffb_shadow_upload': (c_int, [c_void_p, c_void_p, c_size_t]),
     'ffb_shadow_query': (c_int, [c_void_p, c_void_p, c_size_t]),
     'ffb_shadow_drop': (c_int, [c_void_p, c_void_p, c_size_t]),
     'ffb_shadow_stats': (c_int, [c_void_p, _ip, POINTER(c_size_t), POINTER(c_int64), POINTER(c_size_t)]),
@@ -245,6 +246,13 @@ def freeze_shadowed(ctx, *arrays):
     for arr in arrays:
         if arr is not None and arr.nbytes >= (64 << 10) and query(ctx, arr.ctypes.data, arr.nbytes):
             arr.flags.writeable = False
+
+
+def mirror_input(ctx, arr):
+    """Upload ``arr`` (allocated by :func:`empty`) once and keep the device copy for later calls that are
+    handed the same array; the array becomes read-only if the mirror was kept."""
+    lib().ffb_shadow_upload(ctx, arr.ctypes.data, arr.nbytes)
+    freeze_shadowed(ctx, arr)
 
 
 def shadow_stats(ctx=None):

@@ -417,6 +417,19 @@ int ffb_shadow_enable_next(ffb_ctx* ctx, int enable) {
   return FFB_OK;
 }
 
+int ffb_shadow_upload(ffb_ctx* ctx, const void* host, size_t bytes) {
+  if (!ctx || !host || !bytes) return FFB_EINVAL;
+  FFB_CUDA(ctx, cudaSetDevice(ctx->device));
+  static const bool allowed = !(getenv("FFB_SHADOWS") && atoi(getenv("FFB_SHADOWS")) == 0);
+  if (!allowed) return FFB_OK;
+  DevBuf buf;
+  FFB_TRY(buf.alloc(ctx, bytes));
+  FFB_TRY(ffb_h2d(ctx, buf.p, host, bytes));
+  FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ffb_shadow_retain(ctx, buf, const_cast<void*>(host), bytes, {{0, bytes}});  // may decline (size, pool)
+  return FFB_OK;
+}
+
 int ffb_shadow_query(ffb_ctx* ctx, const void* host, size_t bytes) {
   if (!ctx) return 0;
   const int64_t hits = ctx->shadow_hits;
@@ -1152,6 +1165,12 @@ int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, 
   FFB_REQUIRE(ctx, filter_function_kind >= 0 && filter_function_kind <= 2 &&
                        (filter_function_kind == 0 || filter_function),
               "concatenate_pulses: filter_function_kind=%d", filter_function_kind);
+  static const bool trace = getenv("FFB_TRACE") && atoi(getenv("FFB_TRACE")) != 0;
+  const auto t_enter = std::chrono::steady_clock::now();
+  auto since = [&]() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_enter).count();
+  };
+  const int64_t hits0 = ctx->shadow_hits;
   const bool keep_shadow = ctx->shadow_next;
   ctx->shadow_next = false;
   double* const control_matrix_host = control_matrix;
@@ -1272,6 +1291,7 @@ int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, 
                                stack.as<double>()));
     }
   }
+  const double us_fills = since();
   const double* B_dev = stack.as<double>();
   if (full_stack) {
     // cached rows: issued after the fills were enqueued, so that even a pageable source (staged by the
@@ -1322,8 +1342,15 @@ int ffb_concatenate_pulses(ffb_ctx* ctx, int P, int d, int n_nops, int n_basis, 
                                  filter_function_kind == 2, F.as<double>()));
     FFB_TRY(ffb_d2h(ctx, filter_function, F.p, f_bytes));
   }
+  const double us_enqueued = since();
   if (full_stack) FFB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  const double us_copy = since();
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (trace)
+    fprintf(stderr, "[ffb trace] concatenate_pulses: P=%d, fills enqueued %.0f us, all enqueued %.0f us, "
+            "copy stream done %.0f us, main stream done %.0f us; %lld cached row runs read from device "
+            "shadows; %s stack\n", P, us_fills, us_enqueued, us_copy, since(),
+            (long long)(ctx->shadow_hits - hits0), full_stack ? "full" : "two-slot");
   if (keep_shadow) {
     if (full_stack && control_matrix_host)
       ffb_shadow_retain(ctx, result, control_matrix_host, (size_t)lead * pulse_bytes,

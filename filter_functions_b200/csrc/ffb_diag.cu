@@ -154,7 +154,11 @@ diag_kernel(int G, int d, int n_cops, const double* __restrict__ c_opers,
     int rank = 0;
     for (int j = 0; j < d; ++j) {
       const double other = ev[j];
-      rank += (other < mine) || (other == mine && j < lane);
+      // total order (NaN last, ties by index): the ranks are a permutation for ANY input, so no two
+      // lanes ever write the same entry (compute-sanitizer racecheck, NaN Hamiltonians)
+      const bool mine_nan = mine != mine, other_nan = other != other;
+      rank += mine_nan ? (!other_nan || j < lane)
+                       : (!other_nan && ((other < mine) || (other == mine && j < lane)));
     }
     perm[rank] = lane;
   }

@@ -532,28 +532,66 @@ def _oper_hashes(pulse, kind: str):
     return entry[1]
 
 
-def _join_hamiltonians(pulses, kind: str):
+class _JoinPlan:
+    """Everything about the joined Hamiltonian of a SET of distinct pulse objects that does not depend
+    on the order in which they appear in a sequence (valid when no identifier clash occurs): the merged
+    operators and identifiers, and per pulse object its block of the joined coefficient array (rows in
+    final order, rows of operators the pulse does not carry already filled in)."""
+    __slots__ = ('refs', 'arrays', 'opers', 'identifiers', 'blocks', 'maps')
+
+
+#: plans of recently joined pulse sets, keyed by (kind, sorted ids of the distinct pulse objects); an entry
+#: is only used when its weak references still point at the very objects of the call and those objects
+#: still carry the very operator / coefficient arrays the plan was made from (the arrays of a
+#: PulseSequence are treated as immutable, as for the operator hashes above)
+_JOIN_PLANS = {}
+_JOIN_PLAN_LIMIT = 32
+_JOIN_PLAN_MAX_BYTES = 1 << 20
+
+
+def _plan_lookup(kind, distinct):
+    key = (kind, tuple(sorted(id(p) for p in distinct)))
+    plan = _JOIN_PLANS.get(key)
+    if plan is None:
+        return key, None
+    attr = 'c' if kind == 'control' else 'n'
+    for p in distinct:
+        ref = plan.refs.get(id(p))
+        opers, coeffs = plan.arrays.get(id(p), (None, None))
+        if (ref is None or ref() is not p or getattr(p, f'{attr}_opers') is not opers
+                or getattr(p, f'{attr}_coeffs') is not coeffs):
+            del _JOIN_PLANS[key]
+            return key, None
+    return key, plan
+
+
+def _join_hamiltonians(pulses, kind: str, distinct=None, order=None):
     """Merge the operator lists of several pulses into one Hamiltonian.
 
     Equal operators (byte-wise) are merged; an identifier used for two different operators gets the
     pulse position appended; operators missing on some pulse get zero (control) or, if constant
     elsewhere, that constant (noise) coefficients.  Behaviour of the reference's
     ``_concatenate_hamiltonian`` (``:1340-1483``), including its error messages.  Written for long
-    sequences of recurring gates (randomized benchmarking): hashes are cached per pulse and the
-    bookkeeping is one pass over dictionaries instead of ``np.unique`` + masks.
+    sequences of recurring gates (randomized benchmarking): all bookkeeping runs over the DISTINCT
+    pulse objects (a sequence of 100 Cliffords has at most 24), its outcome is remembered per set of
+    objects, and a call then costs one concatenation of prepared coefficient blocks.
     """
+    import weakref
     attr = 'c' if kind == 'control' else 'n'
-    # one entry per DISTINCT pulse object (a sequence of 100 Cliffords has at most 24): the bookkeeping
-    # below runs over the distinct objects, positions only index into them
-    slot, entries, first_pos, order = {}, [], [], []
-    for pos, p in enumerate(pulses):
-        i = slot.get(id(p))
-        if i is None:
-            i = slot[id(p)] = len(entries)
-            entries.append((_oper_hashes(p, kind), getattr(p, f'{attr}_oper_identifiers').tolist(),
-                            getattr(p, f'{attr}_opers'), getattr(p, f'{attr}_coeffs')))
-            first_pos.append(pos)
-        order.append(i)
+    if distinct is None:
+        distinct, order = _distinct_pulses(pulses)
+    key, plan = _plan_lookup(kind, distinct)
+    if plan is not None:
+        joined = np.concatenate([plan.blocks[id(distinct[i])] for i in order], axis=1)
+        mapping = {pos: plan.maps[id(distinct[i])] for pos, i in enumerate(order)}
+        return plan.opers, plan.identifiers, joined, mapping
+
+    entries = [(_oper_hashes(p, kind), getattr(p, f'{attr}_oper_identifiers').tolist(),
+                getattr(p, f'{attr}_opers'), getattr(p, f'{attr}_coeffs')) for p in distinct]
+    first_pos = [None]*len(distinct)
+    for pos, i in enumerate(order):
+        if first_pos[i] is None:
+            first_pos[i] = pos
     first = {}              # hash -> (pulse position, index within that pulse) of first occurrence
     ids_of_oper, opers_of_id = {}, {}
     for pos, (hashes, idents, _, _) in zip(first_pos, entries):   # in order of first occurrence
@@ -570,45 +608,80 @@ def _join_hamiltonians(pulses, kind: str):
 
     row_of = {h: i for i, h in enumerate(first)}
     new_ids = [entries[order[pos]][1][loc] for pos, loc in first.values()]
-    identity_maps = [dict(zip(entry[1], entry[1])) for entry in entries]
-    mapping = {pos: dict(identity_maps[i]) for pos, i in enumerate(order)}
+    maps = [dict(zip(entry[1], entry[1])) for entry in entries]
+    mapping = {pos: maps[i] for pos, i in enumerate(order)}
+    clash = False
     for ident, hashes in opers_of_id.items():
         if len(hashes) > 1:
+            clash = True
             for h in hashes:
                 pulse_pos = first[h][0]
                 new_ids[row_of[h]] = f'{ident}_{pulse_pos}'
+                mapping[pulse_pos] = dict(mapping[pulse_pos])      # this position only
                 mapping[pulse_pos][ident] = new_ids[row_of[h]]
 
-    hashes0 = entries[0][0]
-    if all(entry[0] == hashes0 for entry in entries):
-        # every pulse carries the same operators in the same order: rows are those of the first pulse
-        joined = np.concatenate([entries[i][3] for i in order], axis=1).astype(float, copy=False)
-    else:
-        # per distinct pulse its block of the joined array (NaN rows for operators it does not carry),
-        # then ONE concatenation along the time axis instead of a slice assignment per pulse and row
-        expanded = []
-        for entry in entries:
-            block = np.full((len(new_ids), entry[3].shape[1]), np.nan)
-            block[[row_of[h] for h in entry[0]]] = entry[3]
-            expanded.append(block)
-        joined = np.concatenate([expanded[i] for i in order], axis=1)
-
-    missing = np.isnan(joined)
-    if missing.any():
-        if kind == 'noise':
-            for row in missing.any(axis=1).nonzero()[0]:
-                present = joined[row][~missing[row]]
-                if (present == present[0]).all():
-                    joined[row, missing[row]] = present[0]
-                else:
+    by_id = np.argsort(new_ids)
+    final_row = np.empty(len(by_id), dtype=int)
+    final_row[by_id] = np.arange(len(by_id))            # unsorted row -> row after sorting by identifier
+    n_rows = len(new_ids)
+    # per distinct pulse its block of the joined array in FINAL row order, NaN where it lacks an operator
+    blocks, lacking = [], np.zeros(n_rows, dtype=bool)
+    for entry in entries:
+        rows = final_row[[row_of[h] for h in entry[0]]]
+        if len(rows) == n_rows and (rows == np.arange(n_rows)).all():
+            block = np.asarray(entry[3], dtype=float)
+        else:
+            block = np.full((n_rows, entry[3].shape[1]), np.nan)
+            block[rows] = entry[3]
+            present = np.zeros(n_rows, dtype=bool)
+            present[rows] = True
+            lacking |= ~present
+        blocks.append(block)
+    if lacking.any():
+        # every pulse of the call appears in `distinct`, so what is inferred from the distinct blocks is
+        # what the reference infers from the whole joined array
+        for row in lacking.nonzero()[0]:
+            if kind == 'noise':
+                present = np.concatenate([blk[row][~np.isnan(blk[row])] for blk in blocks])
+                if not (present == present[0]).all():
                     raise ValueError('Not all pulses have the same noise operators and '
                                      + 'non-trivial noise sensitivities so I cannot infer them.')
-        else:
-            joined[missing] = 0
+                fill = present[0]
+            else:
+                fill = 0.0
+            for i, blk in enumerate(blocks):
+                if np.isnan(blk[row]).any():
+                    if blk is entries[i][3]:
+                        blk = blocks[i] = blk.copy()
+                    blk[row, np.isnan(blk[row])] = fill
+    joined = np.concatenate([blocks[i] for i in order], axis=1)
+    opers = np.array([entries[order[pos]][2][loc] for pos, loc in first.values()])[by_id]
+    identifiers = np.array([new_ids[i] for i in by_id])
 
-    by_id = np.argsort(new_ids)
-    opers = np.array([entries[order[pos]][2][loc] for pos, loc in first.values()])
-    return opers[by_id], np.array([new_ids[i] for i in by_id]), joined[by_id], mapping
+    if not clash and sum(blk.nbytes for blk in blocks) <= _JOIN_PLAN_MAX_BYTES:
+        plan = _JoinPlan()
+        plan.refs = {id(p): weakref.ref(p) for p in distinct}
+        plan.arrays = {id(p): (entry[2], entry[3]) for p, entry in zip(distinct, entries)}
+        plan.opers, plan.identifiers = opers, identifiers
+        plan.blocks = {id(p): blk for p, blk in zip(distinct, blocks)}
+        plan.maps = {id(p): m for p, m in zip(distinct, maps)}
+        while len(_JOIN_PLANS) >= _JOIN_PLAN_LIMIT:
+            _JOIN_PLANS.pop(next(iter(_JOIN_PLANS)))
+        _JOIN_PLANS[key] = plan
+    return opers, identifiers, joined, mapping
+
+
+def _distinct_pulses(pulses):
+    """Distinct pulse objects of a sequence in order of first occurrence, and for every position the
+    index of its object in that list."""
+    slot, distinct, order = {}, [], []
+    for p in pulses:
+        i = slot.get(id(p))
+        if i is None:
+            i = slot[id(p)] = len(distinct)
+            distinct.append(p)
+        order.append(i)
+    return distinct, order
 
 
 def _unique_by_identity(items):
@@ -620,29 +693,131 @@ def _unique_by_identity(items):
     return out
 
 
-def concatenate_without_filter_function(pulses: Iterable[PulseSequence],
-                                        return_identifier_mappings: bool = False) -> Any:
-    """Concatenate the Hamiltonians only (reference ``:1599-1665``)."""
+def _join_pulses(pulses):
+    """Host part of a concatenation: validation, joined Hamiltonians, new PulseSequence.  Returns
+    ``(newpulse, control mapping, noise mapping, distinct pulse objects, position -> distinct index)``."""
     try:
         pulses = tuple(pulses)
     except TypeError:
         raise TypeError(f'Expected pulses to be iterable, not {type(pulses)}')
     if not all(isinstance(pulse, PulseSequence) for pulse in pulses):
         raise TypeError('Can only concatenate PulseSequences!')
-    if len(set(pulse.d for pulse in pulses)) != 1:
+    distinct, order = _distinct_pulses(pulses)
+    if len(set(pulse.d for pulse in distinct)) != 1:
         raise ValueError('Trying to concatenate PulseSequence instances with different dimension!')
-    bases = _unique_by_identity(pulse.basis for pulse in pulses)
+    bases = _unique_by_identity(pulse.basis for pulse in distinct)
     if len(bases) > 1 and not util.all_array_equal(bases):
         raise ValueError('Trying to concatenate PulseSequence instances with different bases!')
 
-    *control, c_map = _join_hamiltonians(pulses, 'control')
-    *noise, n_map = _join_hamiltonians(pulses, 'noise')
-    dt = np.concatenate(tuple(pulse.dt for pulse in pulses))
+    *control, c_map = _join_hamiltonians(pulses, 'control', distinct, order)
+    *noise, n_map = _join_hamiltonians(pulses, 'noise', distinct, order)
+    dts = [pulse.dt for pulse in distinct]
+    dt = np.concatenate([dts[i] for i in order])
     newpulse = PulseSequence.from_arrays(*control, *noise, dt, pulses[0].basis)
-    newpulse.tau = sum(pulse.tau for pulse in pulses)
+    taus = [pulse.tau for pulse in distinct]
+    newpulse.tau = sum(taus[i] for i in order)      # same left-to-right sum as over the pulses
+    return newpulse, c_map, n_map, distinct, order
+
+
+def concatenate_without_filter_function(pulses: Iterable[PulseSequence],
+                                        return_identifier_mappings: bool = False) -> Any:
+    """Concatenate the Hamiltonians only (reference ``:1599-1665``)."""
+    newpulse, c_map, n_map, _, _ = _join_pulses(pulses)
     if return_identifier_mappings:
         return newpulse, c_map, n_map
     return newpulse
+
+
+class _GateLibrary:
+    """Stacked arrays of a set of gate pulses (control matrices, total phases, Liouville and Hilbert
+    propagators) in the layout ``ffb_concatenate_many`` takes, mirrored on the device."""
+    __slots__ = ('refs', 'stacks', 'rank')
+
+
+_GATE_LIBRARIES = {}
+_GATE_LIBRARY_LIMIT = 8
+_GATE_LIBRARY_MAX_BYTES = 16 << 20
+
+
+def _gate_library(ctx, distinct, ctrl, phases, liouville, basis):
+    """Stacks for the fused concatenation call.  Sequences drawn from the same set of cached gate objects
+    (randomized benchmarking: 1000 sequences over 24 Cliffords) reuse ONE set of stacks that stays
+    mirrored in device memory: no per-call stacking, no per-call upload.  An entry is valid only while
+    every pulse still holds the very arrays it was built from (identity, not value)."""
+    import weakref
+    props = [pls.total_propagator for pls in distinct]
+    parts = list(zip(ctrl, phases, liouville, props))
+    ids = sorted(range(len(distinct)), key=lambda i: id(distinct[i]))
+    rank = [0]*len(distinct)
+    for r, i in enumerate(ids):
+        rank[i] = r
+    key = tuple(id(distinct[i]) for i in ids) + (id(basis),)
+    entry = _GATE_LIBRARIES.get(key)
+    if entry is not None:
+        for i in ids:
+            refs = entry.refs[rank[i]]
+            if refs[0]() is not distinct[i] or any(r() is not a for r, a in zip(refs[1:], parts[i])):
+                del _GATE_LIBRARIES[key]
+                entry = None
+                break
+        else:
+            if entry.refs[-1]() is not basis:
+                del _GATE_LIBRARIES[key]
+                entry = None
+    if entry is not None:
+        return (*entry.stacks, rank)
+    n = len(distinct)
+    shapes = [((n,) + np.shape(ctrl[0]), np.complex128), ((n,) + np.shape(phases[0]), np.complex128),
+              ((n,) + np.shape(liouville[0]), np.float64), ((n,) + np.shape(props[0]), np.complex128),
+              (np.shape(basis), np.complex128)]
+    total = sum(int(np.prod(sh))*np.dtype(dt).itemsize for sh, dt in shapes)
+    cacheable = total <= _GATE_LIBRARY_MAX_BYTES
+    if cacheable:
+        stacks = _lib.empty_many(shapes, ctx)
+    else:
+        stacks = [np.empty(sh, dtype=dt) for sh, dt in shapes]
+    for i in ids:
+        for stack, part in zip(stacks[:4], parts[i]):
+            stack[rank[i]] = part
+    stacks[4][...] = np.asarray(basis)
+    if cacheable:
+        try:
+            refs = [tuple(weakref.ref(x) for x in (distinct[i],) + parts[i]) for i in ids]
+            refs.append(weakref.ref(basis))
+        except TypeError:       # something not weak-referenceable (a view created on the fly)
+            return (*stacks, rank)
+        for stack in stacks:
+            _lib.mirror_input(ctx, stack)
+        entry = _GateLibrary()
+        entry.refs, entry.stacks, entry.rank = refs, tuple(stacks), None
+        while len(_GATE_LIBRARIES) >= _GATE_LIBRARY_LIMIT:
+            _GATE_LIBRARIES.pop(next(iter(_GATE_LIBRARIES)))
+        _GATE_LIBRARIES[key] = entry
+    return (*stacks, rank)
+
+
+_SAME_GRID = {}
+
+
+def _same_grid(cached, omega) -> bool:
+    """``np.array_equal(cached, omega)``, remembered per pair of array OBJECTS: a sequence of gates whose
+    pulses each hold their own copy of the same frequency grid would otherwise compare the grids once
+    per gate and call."""
+    if cached is omega:
+        return True
+    key = (id(cached), id(omega))
+    memo = _SAME_GRID.get(key)
+    if memo is not None and memo[0]() is cached and memo[1]() is omega:
+        return memo[2]
+    equal = bool(np.shape(cached) == np.shape(omega) and np.array_equal(cached, omega))
+    try:
+        import weakref
+        if len(_SAME_GRID) > 4096:
+            _SAME_GRID.clear()
+        _SAME_GRID[key] = (weakref.ref(cached), weakref.ref(omega), equal)
+    except TypeError:
+        pass
+    return equal
 
 
 def _frequency_entries(pls, keys, omega):
@@ -650,8 +825,7 @@ def _frequency_entries(pls, keys, omega):
     (one comparison for all of them, and without the copy + comparison the ``omega`` setter makes on
     every access); ``None`` for what is not cached or belongs to another grid."""
     cached = pls._frequency_data.get('omega')
-    if cached is None or not (cached is omega or (cached.shape == np.shape(omega)
-                                                  and np.array_equal(cached, omega))):
+    if cached is None or not _same_grid(cached, omega):
         return (None,)*len(keys)
     return tuple(pls._frequency_data.get(key) for key in keys)
 
@@ -674,30 +848,37 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
     if len(pulses) == 1:
         return copy.deepcopy(pulses[0])
 
-    newpulse, _, n_oper_mapping = concatenate_without_filter_function(
-        pulses, return_identifier_mappings=True)
+    newpulse, _, n_oper_mapping, distinct, inverse = _join_pulses(pulses)
+    have_propagators = all('total_propagator' in pls._data for pls in distinct)
 
-    if all('total_propagator' in pls._data for pls in pulses):
-        newpulse.total_propagator = util.mdot([pls.total_propagator for pls in pulses][::-1])
+    def host_total_propagator():
+        if have_propagators and 'total_propagator' not in newpulse._data:
+            props = [pls.total_propagator for pls in distinct]
+            newpulse.total_propagator = util.mdot([props[i] for i in inverse][::-1])
 
     if calc_pulse_correlation_FF:
         calc_filter_function = True
     if calc_filter_function is False:
+        host_total_propagator()
         return newpulse
 
-    # which (renamed) noise operators does each pulse carry?
+    # which (renamed) noise operators does each pulse carry?  One row per distinct object and mapping
+    # (positions share their object's mapping unless an identifier clash renamed something there)
     new_ids = newpulse.n_oper_identifiers.tolist()
     column = {ident: i for i, ident in enumerate(new_ids)}
-    present_rows = []
+    rows_by_mapping, present_rows = {}, []
     for pos in range(len(pulses)):
-        row = [False]*len(new_ids)
-        for ident in n_oper_mapping[pos].values():
-            row[column[ident]] = True
+        mapping = n_oper_mapping[pos]
+        row = rows_by_mapping.get(id(mapping))
+        if row is None:
+            row = [False]*len(new_ids)
+            for ident in mapping.values():
+                row[column[ident]] = True
+            rows_by_mapping[id(mapping)] = row
         present_rows.append(row)
     n_opers_present = np.array(present_rows, dtype=bool)
 
     equal_n_opers = (n_opers_present.sum(axis=0) > 1).any()
-    distinct = _unique_by_identity(pulses)
     if omega is None:
         # the reference's predicate is is_cached('control_matrix') -- a pulse that only holds a
         # pulse-correlation control matrix does not count (pulse_sequence.py:1783)
@@ -706,6 +887,7 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         grids = _unique_by_identity(pls.omega for pls in with_omega)
         equal_omega = bool(grids) and (len(grids) == 1 or util.all_array_equal(grids))
         if not equal_omega:
+            host_total_propagator()
             if calc_filter_function:
                 raise ValueError("Calculation of filter function forced but not all pulses "
                                  + "have the same frequencies cached and none were supplied!")
@@ -714,16 +896,16 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
                                  + "have the frequencies at which to evaluate.")
             return newpulse
         if calc_filter_function is None and (not equal_n_opers or not with_ctrl):
+            host_total_propagator()
             return newpulse
         omega = with_omega[0].omega
 
     if not equal_n_opers:
+        host_total_propagator()
         newpulse.cache_filter_function(omega, which=which)
         return newpulse
 
     # per distinct pulse object: total phases, Liouville propagator, control matrix on this grid
-    slot = {id(pls): i for i, pls in enumerate(distinct)}
-    inverse = [slot[id(pls)] for pls in pulses]
     lib_phases, lib_liouville, lib_ctrl = [], [], []
     for pls in distinct:
         ph, B = _frequency_entries(pls, ('total_phases', 'control_matrix'), omega)
@@ -739,12 +921,10 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         # propagator / phase products, from_atomic, Liouville representation, filter function) is
         # ONE library call on the distinct pulses plus an index list, as in concatenate_many
         d = newpulse.c_opers.shape[-1]
-        lib_B = _lib.as_c128(np.array(lib_ctrl))
-        lib_ph = _lib.as_c128(np.array(lib_phases))
-        lib_L = _lib.as_f64(np.array(lib_liouville))
-        lib_U = _lib.as_c128(np.array([pls.total_propagator for pls in distinct]))
-        basis = _lib.as_c128(np.asarray(newpulse.basis))
-        index = np.array(inverse, dtype=np.int32)
+        ctx = _lib.context()
+        lib_B, lib_ph, lib_L, lib_U, basis, rank = _gate_library(
+            ctx, distinct, lib_ctrl, lib_phases, lib_liouville, newpulse.basis)
+        index = np.array([rank[i] for i in inverse], dtype=np.int32)
         n_nops = lib_B.shape[1]
         U, liouville, total_phases, B, F = _lib.empty_many([   # one block, one download
             ((1, d, d), np.complex128), ((1, n_basis, n_basis), np.complex128),
@@ -752,7 +932,6 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
             ((1, n_nops, n_nops, n_omega), np.complex128)])
         omega_arr = _lib.as_f64(omega)
         tau = np.array([newpulse.tau], dtype=np.float64)
-        ctx = _lib.context()
         p = _lib.ptr
         _lib.keep_on_device(ctx)
         _lib.check(ctx, _lib.lib().ffb_concatenate_many(
@@ -774,7 +953,8 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
     propagators_liouville = util.adot([lib_liouville[i] for i in inverse[:-1]])
 
     if 'total_propagator' not in newpulse._data:
-        newpulse.total_propagator = util.mdot([pls.total_propagator for pls in pulses][::-1])
+        props = [pls.total_propagator for pls in distinct]
+        newpulse.total_propagator = util.mdot([props[i] for i in inverse][::-1])
 
     if n_omega and np.isrealobj(propagators_liouville):
         # general case on the device: the atomic stack (cached rows + from-scratch rows of the noise

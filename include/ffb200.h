@@ -329,6 +329,10 @@ int ffb_host_free(ffb_ctx* ctx, void* ptr);
  * quarter of the device memory (FFB_SHADOW_BYTES).  The caller must not modify a shadowed host array
  * (ffb_shadow_query tells; the Python shell marks such arrays read-only). */
 int ffb_shadow_enable_next(ffb_ctx* ctx, int enable);
+/* Mirror an INPUT array the caller will pass again and again (the stacked control matrices of a gate
+ * library): uploaded once, then found by address like a result shadow.  The array must lie in a block of
+ * ffb_host_alloc and be at least 64 KiB, otherwise nothing is kept (and nothing breaks). */
+int ffb_shadow_upload(ffb_ctx* ctx, const void* host, size_t bytes);
 int ffb_shadow_query(ffb_ctx* ctx, const void* host, size_t bytes);
 int ffb_shadow_drop(ffb_ctx* ctx, const void* host, size_t bytes);
 int ffb_shadow_stats(ffb_ctx* ctx, int* count, size_t* bytes, int64_t* hits, size_t* hit_bytes);
