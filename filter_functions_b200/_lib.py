@@ -179,6 +179,8 @@ def check(ctx, rc):
 #: result arrays at least this large are allocated in page-locked memory (download at PCIe speed)
 PINNED_THRESHOLD = 256 << 10
 PINNED_LIMIT = 1 << 30
+#: results of one call that are smaller than this in total are not page-locked (nor mirrored on the device)
+SMALL_RESULT_BYTES = 64 << 10
 
 
 def _host_free(ctx, address):
@@ -218,11 +220,14 @@ def empty_many(specs, ctx=None):
     for n in sizes:
         offsets.append(total)
         total += (n + 255) & ~255
-    # (no lower limit here: with the results of a call in ONE pool block the library downloads
-    # neighbours in one asynchronous copy; pageable arrays cost one blocking copy each, which is what
-    # bounds a small pulse -- 8 copies x ~10 us for the README example)
     if total > PINNED_LIMIT:
         return [empty(sh, dt, ctx) for sh, dt in zip(shapes, dtypes)]
+    if total < SMALL_RESULT_BYTES:
+        # small results live in ordinary memory (thousands of small pulses must not pin host memory);
+        # the library downloads them in one copy through its own staging block and memcpy's them here
+        buf = np.empty(total, dtype=np.uint8)
+        return [np.frombuffer(buf, dtype=dt, count=n//dt.itemsize, offset=off).reshape(sh)
+                for sh, dt, n, off in zip(shapes, dtypes, sizes, offsets)]
     ctx = context() if ctx is None else ctx
     address = c_void_p()
     if lib().ffb_host_alloc(ctx, total, byref(address)) != FFB_OK:

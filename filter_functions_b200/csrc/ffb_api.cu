@@ -282,6 +282,7 @@ void ffb_destroy(ffb_ctx* ctx) {
   for (auto& kv : ctx->host_live_blocks) cudaFreeHost(kv.first);
   if (ctx->trig_table) cudaFree(ctx->trig_table);
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+  if (ctx->stage_out) cudaFreeHost(ctx->stage_out);
   if (ctx->conv_dev) cudaFree(ctx->conv_dev);
   if (ctx->infid_scratch) cudaFree(ctx->infid_scratch);
   if (ctx->conv_host) cudaFreeHost(ctx->conv_host);
@@ -684,9 +685,13 @@ struct OutputBlock {
     char* host;
     size_t bytes, off;
   };
+  static constexpr size_t STAGED_LIMIT = (size_t)256 << 10;
   std::vector<Item> items;
+  std::vector<const Item*> staged_items;  // downloaded into the context's staging block, not yet delivered
   DevBuf dev;
   bool mirrored = false;
+  bool staged = false;  // small results to pageable memory: one copy into ctx->stage_out + memcpy
+  size_t total_bytes = 0;
   char* host_base = nullptr;
   int add(void* host, size_t bytes) {
     items.push_back({static_cast<char*>(host), bytes, 0});
@@ -753,7 +758,22 @@ struct OutputBlock {
       it.off = total;
       total += (it.bytes + ALIGN - 1) & ~(ALIGN - 1);
     }
+    total_bytes = total;
+    staged = !mirrored && total <= STAGED_LIMIT;
+    if (staged && ctx->stage_out_bytes < total) {
+      if (ctx->stage_out) FFB_CUDA(ctx, cudaFreeHost(ctx->stage_out));
+      ctx->stage_out = nullptr;
+      ctx->stage_out_bytes = 0;
+      FFB_CUDA(ctx, cudaHostAlloc(&ctx->stage_out, STAGED_LIMIT, cudaHostAllocDefault));
+      ctx->stage_out_bytes = STAGED_LIMIT;
+    }
     return dev.alloc(ctx, total);
+  }
+  // after the stream the downloads were enqueued on has been synchronised
+  void finish(ffb_ctx* ctx) {
+    for (const Item* it : staged_items)
+      std::memcpy(it->host, static_cast<const char*>(ctx->stage_out) + it->off, it->bytes);
+    staged_items.clear();
   }
   template <typename T = double>
   T* d(int i) const {
@@ -765,6 +785,17 @@ struct OutputBlock {
     for (int i : which)
       if (i >= 0 && items[i].host && items[i].bytes) order.push_back(&items[i]);
     if (order.empty()) return FFB_OK;
+    if (staged) {  // one copy of the span that holds the requested results
+      size_t lo = order[0]->off, hi = lo;
+      for (const Item* it : order) {
+        lo = std::min(lo, it->off);
+        hi = std::max(hi, it->off + it->bytes);
+        staged_items.push_back(it);
+      }
+      FFB_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(ctx->stage_out) + lo, static_cast<char*>(dev.p) + lo,
+                                    hi - lo, cudaMemcpyDeviceToHost, stream));
+      return FFB_OK;
+    }
     if (!mirrored) {
       for (const Item* it : order)
         FFB_CUDA(ctx, cudaMemcpyAsync(it->host, static_cast<char*>(dev.p) + it->off, it->bytes,
@@ -1023,18 +1054,22 @@ int ffb_infidelity(ffb_ctx* ctx, int n_lead, int n_nops, int n_sel, const int* i
               spectrum_ndim);
   for (int i = 0; i < n_sel; ++i)
     FFB_REQUIRE(ctx, idx[i] >= 0 && idx[i] < n_nops, "infidelity: idx[%d]=%d out of range", i, idx[i]);
-  Upload Fd, Sd, Od, Id;
   DevBuf res;
   const size_t s_elems = (spectrum_ndim == 1 ? 1 : spectrum_ndim == 2 ? (size_t)n_sel
                                                                        : (size_t)n_sel * n_sel) * n_omega;
-  FFB_TRY(Fd.put(ctx, F, (size_t)n_lead * n_nops * n_nops * n_omega * 16));
-  FFB_TRY(Sd.put(ctx, spectrum, s_elems * (spectrum_is_complex ? 16 : 8)));
-  FFB_TRY(Od.put(ctx, omega, (size_t)n_omega * 8));
-  FFB_TRY(Id.put(ctx, idx, (size_t)n_sel * sizeof(int)));
+  // one packed upload for the four inputs (a filter function that is still mirrored on the device --
+  // the pulse's cached array -- is not sent at all)
+  PackedUpload in(ctx);
+  const int i_F = in.add(F, (size_t)n_lead * n_nops * n_nops * n_omega * 16);
+  const int i_S = in.add(spectrum, s_elems * (spectrum_is_complex ? 16 : 8));
+  const int i_om = in.add(omega, (size_t)n_omega * 8);
+  const int i_ix = in.add(idx, (size_t)n_sel * sizeof(int));
+  FFB_TRY(in.upload(ctx));
   const size_t n_out = (size_t)n_lead * (spectrum_ndim == 3 ? (size_t)n_sel * n_sel : n_sel);
   FFB_TRY(res.alloc(ctx, n_out * 8));
-  FFB_TRY(ffbi_infidelity(ctx, n_lead, n_nops, n_sel, Id.buf.as<int>(), n_omega, Fd.d(), Sd.d(),
-                          spectrum_ndim, spectrum_is_complex, Od.d(), d, res.as<double>()));
+  FFB_TRY(ffbi_infidelity(ctx, n_lead, n_nops, n_sel, reinterpret_cast<const int*>(in.d(i_ix)), n_omega,
+                          in.d(i_F), in.d(i_S), spectrum_ndim, spectrum_is_complex, in.d(i_om), d,
+                          res.as<double>()));
   FFB_TRY(ffb_d2h(ctx, out, res.p, n_out * 8));
   FFB_TRY(ffbi_comm_fetch_error(ctx));
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1142,6 +1177,7 @@ int ffb_concatenate_many(ffb_ctx* ctx, int n_seq, int L, int n_lib, int d, int n
       FFB_TRY(ffbi_cexp(ctx, n_omega, in.d(i_om), tau[s], out.d(o_ph) + (size_t)s * n_omega * 2));
   FFB_TRY(out.download(ctx, {o_U, o_L, o_ph, o_B, o_F, o_I}, ctx->stream));
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  out.finish(ctx);
   if (keep) out.retain(ctx, {o_U, o_ph, o_B, filter_function ? o_F : -1});
   return FFB_OK;
 }
@@ -1558,6 +1594,7 @@ int ffb_pulse_filter_function(ffb_ctx* ctx, int G, int d, int n_cops, int n_nops
   FFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   us_main = since();
   if (overlap || fb.n_blocks > 1) FFB_CUDA(ctx, cudaStreamSynchronize(cs));  // anything on the copy stream?
+  out.finish(ctx);
   FFB_TRY(ffb_conv_check(ctx));
   FFB_TRY(ffbi_comm_check_error(ctx));
   if (trace)

@@ -66,6 +66,11 @@ struct ffb_ctx {
   // page-locked staging block: the small host inputs of a call are packed here and uploaded by ONE copy
   void* stage_host = nullptr;
   size_t stage_bytes = 0;
+  // ... and its twin for small RESULTS that go to ordinary (pageable) caller memory: one device-to-host
+  // copy into this block, then plain memcpy to the caller's arrays (a pageable destination costs one
+  // blocking driver copy per array otherwise)
+  void* stage_out = nullptr;
+  size_t stage_out_bytes = 0;
   // eigensolver convergence: a device counter the Jacobi kernels bump for every matrix that did not
   // converge (allocated and zeroed once), and its page-locked host mirror; the synchronous entry points
   // fetch it with their last copies and return FFB_ENOTCONV (numpy.linalg.eigh raises LinAlgError)

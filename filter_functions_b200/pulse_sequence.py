@@ -353,7 +353,19 @@ class PulseSequence:
             control_matrix, intermediates = control_matrix
             self._intermediates.update(intermediates)
         self.cache_control_matrix(self.omega, control_matrix)
+        self._mark_computed(control_matrix)
         return self._frequency_data['control_matrix']
+
+    def _mark_computed(self, control_matrix) -> None:
+        """Remember that the cached control matrix is what this package computes for this pulse (as
+        opposed to an array the user handed to ``cache_control_matrix``): ``concatenate`` may then pick
+        the cheaper of two equivalent routes."""
+        import weakref
+        self.__dict__['_computed_control_matrix'] = weakref.ref(control_matrix)
+
+    def _control_matrix_is_computed(self) -> bool:
+        ref = self.__dict__.get('_computed_control_matrix')
+        return ref is not None and ref() is self._frequency_data.get('control_matrix')
 
     def cache_control_matrix(self, omega, control_matrix: Optional[ndarray] = None,
                              show_progressbar: bool = False,
@@ -430,6 +442,7 @@ class PulseSequence:
         self._data['total_propagator_liouville'] = normalize_liouville_columns(
             np.ascontiguousarray(liouville.real) if self.basis.isherm else liouville, self.basis)
         self._frequency_data.update(control_matrix=B, total_phases=phases, filter_function=F)
+        self._mark_computed(B)
         if infid is not None and self.d != d:
             infid *= d/self.d
         return infid
@@ -905,6 +918,14 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         newpulse.cache_filter_function(omega, which=which)
         return newpulse
 
+    if (not calc_pulse_correlation_FF and len(omega) and not n_opers_present.all()
+            and _from_scratch_is_cheaper(pulses, distinct, inverse, n_opers_present, newpulse, omega)):
+        # Few of the (pulse, noise operator) rows are cached (config 5: 22 of 162): filling the atomic
+        # stack from scratch and contracting it costs more FP64 work than the control matrix of the
+        # joined pulse from scratch, which is the same quantity (reference tests/test_core.py:685-743)
+        newpulse.get_filter_function(omega, which=which, show_progressbar=show_progressbar)
+        return newpulse
+
     # per distinct pulse object: total phases, Liouville propagator, control matrix on this grid
     lib_phases, lib_liouville, lib_ctrl = [], [], []
     for pls in distinct:
@@ -1000,6 +1021,37 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         which='correlations' if calc_pulse_correlation_FF else 'total')
     newpulse.cache_filter_function(omega, control_matrix, which=which)
     return newpulse
+
+
+def _from_scratch_is_cheaper(pulses, distinct, inverse, n_opers_present, newpulse, omega) -> bool:
+    """Cost model (real FP64 multiply-adds per frequency) of the two equivalent routes to the control
+    matrix of a concatenated pulse.  Atomic route (reference ``pulse_sequence.py:1822-1866``): rows a
+    pulse has not cached are computed from scratch on its segments, then the stack is contracted with
+    the cumulative Liouville propagators (``2 n_nops n_basis^2`` per pulse).  Scratch route: all rows on
+    all segments.  The scratch route is only admissible if every cached control matrix is one this
+    package computed (a user-supplied matrix must enter the result), and is taken only with a clear
+    margin.  ``FFB_CONCAT_ROUTE=atomic|scratch`` forces a route (measurements)."""
+    import os
+    forced = os.environ.get('FFB_CONCAT_ROUTE')
+    cached = []
+    for pls in distinct:
+        B, = _frequency_entries(pls, ('control_matrix',), omega)
+        if B is not None and not pls._control_matrix_is_computed():
+            return False
+        cached.append(B is not None)
+    if forced in ('atomic', 'scratch'):
+        return forced == 'scratch'
+    d = newpulse.c_opers.shape[-1]
+    n_basis, n_nops = len(newpulse.basis), n_opers_present.shape[1]
+    per_row_segment = n_basis*(2 + 2*d*(d - 1))
+    segments = [len(pls.dt) for pls in distinct]
+    atomic = 0
+    for pos, i in enumerate(inverse):
+        to_compute = n_nops - (int(n_opers_present[pos].sum()) if cached[i] else 0)
+        atomic += segments[i]*to_compute*per_row_segment
+    atomic += (len(pulses) - 1)*n_nops*n_basis*n_basis*2
+    scratch = len(newpulse.dt)*n_nops*per_row_segment
+    return scratch < 0.8*atomic
 
 
 def _concatenate_on_device(pulses, newpulse, n_opers_present, ctrl, omega, phases, liouville,
