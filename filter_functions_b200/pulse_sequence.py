@@ -85,6 +85,51 @@ def _merge_equal_segments(pulse):
     return c_coeffs, n_coeffs, dt
 
 
+class _CacheDict(dict):
+    """A cache dictionary of a ``PulseSequence`` that counts its mutations in a counter it shares with
+    the pulse (``pulse._stamp``).  Whatever ``concatenate`` remembers about a set of gate pulses is valid
+    exactly as long as their stamps have not moved."""
+    __slots__ = ('_counter',)
+
+    def __init__(self, counter, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._counter = counter
+
+    def __setitem__(self, key, value):
+        self._counter[0] += 1
+        dict.__setitem__(self, key, value)
+
+    def __delitem__(self, key):
+        self._counter[0] += 1
+        dict.__delitem__(self, key)
+
+    def update(self, *args, **kwargs):
+        self._counter[0] += 1
+        dict.update(self, *args, **kwargs)
+
+    def pop(self, *args):
+        self._counter[0] += 1
+        return dict.pop(self, *args)
+
+    def popitem(self):
+        self._counter[0] += 1
+        return dict.popitem(self)
+
+    def clear(self):
+        self._counter[0] += 1
+        dict.clear(self)
+
+    def setdefault(self, key, default=None):
+        self._counter[0] += 1
+        return dict.setdefault(self, key, default)
+
+    def __reduce__(self):       # pickles as a plain dict; PulseSequence restores the shared counter
+        return (dict, (dict(self),))
+
+
+_CACHE_NAMES = ('_data', '_frequency_data', '_intermediates')
+
+
 class PulseSequence:
     r"""A piecewise-constant control pulse with its noise operators.
 
@@ -96,10 +141,33 @@ class PulseSequence:
 
     def __new__(cls, *args, **kwargs):
         new = super().__new__(cls)
-        new._data = dict()
-        new._frequency_data = dict()
-        new._intermediates = dict()
+        stamp = new.__dict__['_stamp'] = [0]     # bumped by every attribute / cache change
+        for name in _CACHE_NAMES:
+            new.__dict__[name] = _CacheDict(stamp)
         return new
+
+    def __setattr__(self, name, value):
+        if name in _CACHE_NAMES and not isinstance(value, _CacheDict):
+            value = _CacheDict(self.__dict__['_stamp'], value)
+        object.__setattr__(self, name, value)
+        self.__dict__['_stamp'][0] += 1
+
+    def __getstate__(self):
+        state = {k: v for k, v in self.__dict__.items()
+                 if k not in ('_stamp', '_computed_control_matrix', '_oper_hash_cache')}
+        state['_control_matrix_was_computed'] = self._control_matrix_is_computed()
+        for name in _CACHE_NAMES:
+            state[name] = dict(state[name])
+        return state
+
+    def __setstate__(self, state):
+        computed = state.pop('_control_matrix_was_computed', False)
+        stamp = self.__dict__['_stamp']
+        for name in _CACHE_NAMES:
+            self.__dict__[name] = _CacheDict(stamp, state.pop(name, {}))
+        self.__dict__.update(state)
+        if computed and 'control_matrix' in self._frequency_data:
+            self._mark_computed(self._frequency_data['control_matrix'])
 
     def __init__(self, H_c, H_n, dt, basis: Optional[Basis] = None):
         if not util.is_sequence_like(dt):
@@ -140,7 +208,10 @@ class PulseSequence:
         new.n_coeffs = np.asanyarray(n_coeffs)
         new.dt = np.asanyarray(dt)
         new.d = new.c_opers.shape[-1]
-        new.basis = np.asanyarray(basis).view(Basis) if basis is not None else Basis.ggm(new.d)
+        if basis is None:
+            new.basis = Basis.ggm(new.d)
+        else:       # the same Basis OBJECT is kept: its cached predicates are shared by all pulses built on it
+            new.basis = basis if isinstance(basis, Basis) else np.asanyarray(basis).view(Basis)
         if not len(new.c_opers) == len(new.c_oper_identifiers) == len(new.c_coeffs):
             raise ValueError('Control Hamiltonian not same length!')
         if not len(new.n_opers) == len(new.n_oper_identifiers) == len(new.n_coeffs):
@@ -198,10 +269,16 @@ class PulseSequence:
 
     def __copy__(self) -> 'PulseSequence':
         copied = self.__class__.__new__(self.__class__)
-        copied.__dict__.update(self.__dict__)
-        copied._data = copy.copy(self._data)
-        copied._frequency_data = copy.copy(self._frequency_data)
-        copied._intermediates = copy.copy(self._intermediates)
+        for key, value in self.__dict__.items():
+            if key in _CACHE_NAMES:
+                copied.__dict__[key].update(value)       # own dictionaries, same cached arrays
+            elif key != '_stamp':
+                copied.__dict__[key] = value
+        return copied
+
+    def __deepcopy__(self, memo) -> 'PulseSequence':
+        copied = self.__class__.__new__(self.__class__)
+        copied.__setstate__(copy.deepcopy(self.__getstate__(), memo))
         return copied
 
     def __matmul__(self, other: 'PulseSequence') -> 'PulseSequence':
@@ -545,60 +622,19 @@ def _oper_hashes(pulse, kind: str):
     return entry[1]
 
 
-class _JoinPlan:
-    """Everything about the joined Hamiltonian of a SET of distinct pulse objects that does not depend
-    on the order in which they appear in a sequence (valid when no identifier clash occurs): the merged
-    operators and identifiers, and per pulse object its block of the joined coefficient array (rows in
-    final order, rows of operators the pulse does not carry already filled in)."""
-    __slots__ = ('refs', 'arrays', 'opers', 'identifiers', 'blocks', 'maps')
-
-
-#: plans of recently joined pulse sets, keyed by (kind, sorted ids of the distinct pulse objects); an entry
-#: is only used when its weak references still point at the very objects of the call and those objects
-#: still carry the very operator / coefficient arrays the plan was made from (the arrays of a
-#: PulseSequence are treated as immutable, as for the operator hashes above)
-_JOIN_PLANS = {}
-_JOIN_PLAN_LIMIT = 32
-_JOIN_PLAN_MAX_BYTES = 1 << 20
-
-
-def _plan_lookup(kind, distinct):
-    key = (kind, tuple(sorted(id(p) for p in distinct)))
-    plan = _JOIN_PLANS.get(key)
-    if plan is None:
-        return key, None
-    attr = 'c' if kind == 'control' else 'n'
-    for p in distinct:
-        ref = plan.refs.get(id(p))
-        opers, coeffs = plan.arrays.get(id(p), (None, None))
-        if (ref is None or ref() is not p or getattr(p, f'{attr}_opers') is not opers
-                or getattr(p, f'{attr}_coeffs') is not coeffs):
-            del _JOIN_PLANS[key]
-            return key, None
-    return key, plan
-
-
-def _join_hamiltonians(pulses, kind: str, distinct=None, order=None):
-    """Merge the operator lists of several pulses into one Hamiltonian.
+def _join_hamiltonians_core(distinct, order, kind: str):
+    """Merge the operator lists of the pulses of a sequence into one Hamiltonian.
 
     Equal operators (byte-wise) are merged; an identifier used for two different operators gets the
     pulse position appended; operators missing on some pulse get zero (control) or, if constant
     elsewhere, that constant (noise) coefficients.  Behaviour of the reference's
-    ``_concatenate_hamiltonian`` (``:1340-1483``), including its error messages.  Written for long
-    sequences of recurring gates (randomized benchmarking): all bookkeeping runs over the DISTINCT
-    pulse objects (a sequence of 100 Cliffords has at most 24), its outcome is remembered per set of
-    objects, and a call then costs one concatenation of prepared coefficient blocks.
-    """
-    import weakref
+    ``_concatenate_hamiltonian`` (``:1340-1483``), including its error messages.  All bookkeeping runs
+    over the DISTINCT pulse objects (a sequence of 100 Cliffords has at most 24).  Returns the merged
+    operators and identifiers (sorted by identifier), per distinct pulse its block of the joined
+    coefficient array (rows in final order, rows of operators it does not carry filled in) and its
+    identifier mapping, the mapping per position, and whether an identifier clash had to be renamed
+    (then the outcome depends on the positions and cannot be remembered per set of objects)."""
     attr = 'c' if kind == 'control' else 'n'
-    if distinct is None:
-        distinct, order = _distinct_pulses(pulses)
-    key, plan = _plan_lookup(kind, distinct)
-    if plan is not None:
-        joined = np.concatenate([plan.blocks[id(distinct[i])] for i in order], axis=1)
-        mapping = {pos: plan.maps[id(distinct[i])] for pos, i in enumerate(order)}
-        return plan.opers, plan.identifiers, joined, mapping
-
     entries = [(_oper_hashes(p, kind), getattr(p, f'{attr}_oper_identifiers').tolist(),
                 getattr(p, f'{attr}_opers'), getattr(p, f'{attr}_coeffs')) for p in distinct]
     first_pos = [None]*len(distinct)
@@ -607,7 +643,7 @@ def _join_hamiltonians(pulses, kind: str, distinct=None, order=None):
             first_pos[i] = pos
     first = {}              # hash -> (pulse position, index within that pulse) of first occurrence
     ids_of_oper, opers_of_id = {}, {}
-    for pos, (hashes, idents, _, _) in zip(first_pos, entries):   # in order of first occurrence
+    for pos, (hashes, idents, _, _) in sorted(zip(first_pos, entries), key=lambda t: t[0]):
         for loc, (h, ident) in enumerate(zip(hashes, idents)):
             if h not in first:
                 first[h] = (pos, loc)
@@ -667,21 +703,9 @@ def _join_hamiltonians(pulses, kind: str, distinct=None, order=None):
                     if blk is entries[i][3]:
                         blk = blocks[i] = blk.copy()
                     blk[row, np.isnan(blk[row])] = fill
-    joined = np.concatenate([blocks[i] for i in order], axis=1)
     opers = np.array([entries[order[pos]][2][loc] for pos, loc in first.values()])[by_id]
     identifiers = np.array([new_ids[i] for i in by_id])
-
-    if not clash and sum(blk.nbytes for blk in blocks) <= _JOIN_PLAN_MAX_BYTES:
-        plan = _JoinPlan()
-        plan.refs = {id(p): weakref.ref(p) for p in distinct}
-        plan.arrays = {id(p): (entry[2], entry[3]) for p, entry in zip(distinct, entries)}
-        plan.opers, plan.identifiers = opers, identifiers
-        plan.blocks = {id(p): blk for p, blk in zip(distinct, blocks)}
-        plan.maps = {id(p): m for p, m in zip(distinct, maps)}
-        while len(_JOIN_PLANS) >= _JOIN_PLAN_LIMIT:
-            _JOIN_PLANS.pop(next(iter(_JOIN_PLANS)))
-        _JOIN_PLANS[key] = plan
-    return opers, identifiers, joined, mapping
+    return opers, identifiers, blocks, maps, mapping, clash
 
 
 def _distinct_pulses(pulses):
@@ -697,6 +721,33 @@ def _distinct_pulses(pulses):
     return distinct, order
 
 
+class _SequencePlan:
+    """Everything ``concatenate`` derives from a SET of gate objects and not from their order in a
+    sequence: joined operators and identifiers, per gate its block of the joined [control; noise; dt]
+    rows, identifier mappings, which joined noise operators each gate carries, durations -- and, once a
+    sequence has been evaluated, the gates' stacked control matrices / phases / propagators mirrored in
+    device memory (``library``).  Valid while the gates' stamps have not moved."""
+    __slots__ = ('refs', 'stamps', 'control', 'noise', 'blocks', 'maps', 'n_control', 'n_noise',
+                 'taus', 'present', 'basis', 'library')
+
+
+_SEQUENCE_PLANS = {}
+_SEQUENCE_PLAN_LIMIT = 16
+_SEQUENCE_PLAN_MAX_BYTES = 1 << 20
+
+
+def _plan_for(distinct):
+    key = tuple(sorted(id(p) for p in distinct))
+    plan = _SEQUENCE_PLANS.get(key)
+    if plan is not None:
+        for p in distinct:
+            i = id(p)
+            if plan.refs[i]() is not p or plan.stamps[i] != p._stamp[0]:
+                del _SEQUENCE_PLANS[key]
+                return key, None
+    return key, plan
+
+
 def _unique_by_identity(items):
     seen, out = set(), []
     for item in items:
@@ -708,7 +759,11 @@ def _unique_by_identity(items):
 
 def _join_pulses(pulses):
     """Host part of a concatenation: validation, joined Hamiltonians, new PulseSequence.  Returns
-    ``(newpulse, control mapping, noise mapping, distinct pulse objects, position -> distinct index)``."""
+    ``(newpulse, control mapping, noise mapping, distinct pulse objects, position -> distinct index,
+    plan or None)``.  Written for long sequences of recurring gates (randomized benchmarking): the outcome
+    of the bookkeeping is remembered per set of gate objects (:class:`_SequencePlan`), and a call then
+    costs ONE concatenation of prepared coefficient blocks."""
+    import weakref
     try:
         pulses = tuple(pulses)
     except TypeError:
@@ -716,97 +771,106 @@ def _join_pulses(pulses):
     if not all(isinstance(pulse, PulseSequence) for pulse in pulses):
         raise TypeError('Can only concatenate PulseSequences!')
     distinct, order = _distinct_pulses(pulses)
+    key, plan = _plan_for(distinct)
+    if plan is not None:
+        ids = [id(p) for p in distinct]                     # per distinct object, then plain indexing
+        blocks = [plan.blocks[i] for i in ids]
+        joined = np.concatenate([blocks[i] for i in order], axis=1)
+        n_c, n_n = plan.n_control, plan.n_noise
+        newpulse = PulseSequence.from_arrays(plan.control[0], plan.control[1], joined[:n_c],
+                                             plan.noise[0], plan.noise[1], joined[n_c:n_c + n_n],
+                                             joined[-1], pulses[0].basis)
+        taus = [plan.taus[i] for i in ids]
+        newpulse.tau = sum([taus[i] for i in order])
+        c_maps, n_maps = [plan.maps[0][i] for i in ids], [plan.maps[1][i] for i in ids]
+        c_map = {pos: c_maps[i] for pos, i in enumerate(order)}
+        n_map = {pos: n_maps[i] for pos, i in enumerate(order)}
+        return newpulse, c_map, n_map, distinct, order, plan
+
     if len(set(pulse.d for pulse in distinct)) != 1:
         raise ValueError('Trying to concatenate PulseSequence instances with different dimension!')
     bases = _unique_by_identity(pulse.basis for pulse in distinct)
     if len(bases) > 1 and not util.all_array_equal(bases):
         raise ValueError('Trying to concatenate PulseSequence instances with different bases!')
 
-    *control, c_map = _join_hamiltonians(pulses, 'control', distinct, order)
-    *noise, n_map = _join_hamiltonians(pulses, 'noise', distinct, order)
+    c_opers, c_ids, c_blocks, c_maps, c_map, c_clash = _join_hamiltonians_core(distinct, order,
+                                                                               'control')
+    n_opers, n_ids, n_blocks, n_maps, n_map, n_clash = _join_hamiltonians_core(distinct, order,
+                                                                               'noise')
     dts = [pulse.dt for pulse in distinct]
-    dt = np.concatenate([dts[i] for i in order])
-    newpulse = PulseSequence.from_arrays(*control, *noise, dt, pulses[0].basis)
     taus = [pulse.tau for pulse in distinct]
-    newpulse.tau = sum(taus[i] for i in order)      # same left-to-right sum as over the pulses
-    return newpulse, c_map, n_map, distinct, order
+    c_coeffs = np.concatenate([c_blocks[i] for i in order], axis=1)
+    n_coeffs = np.concatenate([n_blocks[i] for i in order], axis=1)
+    dt = np.concatenate([dts[i] for i in order])
+    newpulse = PulseSequence.from_arrays(c_opers, c_ids, c_coeffs, n_opers, n_ids, n_coeffs, dt,
+                                         pulses[0].basis)
+    newpulse.tau = sum([taus[i] for i in order])      # same left-to-right sum as over the pulses
+
+    small = sum(b.nbytes for b in c_blocks) + sum(b.nbytes for b in n_blocks) <= _SEQUENCE_PLAN_MAX_BYTES
+    if (not c_clash and not n_clash and small
+            and all(np.asarray(x).dtype == np.float64 for x in dts)):
+        plan = _SequencePlan()
+        plan.refs = {id(p): weakref.ref(p) for p in distinct}
+        plan.control, plan.noise = (c_opers, c_ids), (n_opers, n_ids)
+        plan.n_control, plan.n_noise = len(c_ids), len(n_ids)
+        plan.blocks = {id(p): np.concatenate([cb, nb, np.asarray(t, dtype=float)[None]])
+                       for p, cb, nb, t in zip(distinct, c_blocks, n_blocks, dts)}
+        plan.maps = ({id(p): m for p, m in zip(distinct, c_maps)},
+                     {id(p): m for p, m in zip(distinct, n_maps)})
+        plan.taus = {id(p): tau for p, tau in zip(distinct, taus)}
+        column = {ident: i for i, ident in enumerate(n_ids.tolist())}
+        plan.present = {}
+        for p, m in zip(distinct, n_maps):
+            row = np.zeros(len(n_ids), dtype=bool)
+            row[[column[ident] for ident in m.values()]] = True
+            plan.present[id(p)] = row
+        plan.basis = pulses[0].basis
+        plan.library = None
+        plan.stamps = {id(p): p._stamp[0] for p in distinct}    # last: reading tau may have cached it
+        while len(_SEQUENCE_PLANS) >= _SEQUENCE_PLAN_LIMIT:
+            _SEQUENCE_PLANS.pop(next(iter(_SEQUENCE_PLANS)))
+        _SEQUENCE_PLANS[key] = plan
+    else:
+        plan = None
+    return newpulse, c_map, n_map, distinct, order, plan
 
 
 def concatenate_without_filter_function(pulses: Iterable[PulseSequence],
                                         return_identifier_mappings: bool = False) -> Any:
     """Concatenate the Hamiltonians only (reference ``:1599-1665``)."""
-    newpulse, c_map, n_map, _, _ = _join_pulses(pulses)
+    newpulse, c_map, n_map, _, _, _ = _join_pulses(pulses)
     if return_identifier_mappings:
         return newpulse, c_map, n_map
     return newpulse
 
 
-class _GateLibrary:
-    """Stacked arrays of a set of gate pulses (control matrices, total phases, Liouville and Hilbert
-    propagators) in the layout ``ffb_concatenate_many`` takes, mirrored on the device."""
-    __slots__ = ('refs', 'stacks', 'rank')
-
-
-_GATE_LIBRARIES = {}
-_GATE_LIBRARY_LIMIT = 8
-_GATE_LIBRARY_MAX_BYTES = 16 << 20
-
-
-def _gate_library(ctx, distinct, ctrl, phases, liouville, basis):
-    """Stacks for the fused concatenation call.  Sequences drawn from the same set of cached gate objects
-    (randomized benchmarking: 1000 sequences over 24 Cliffords) reuse ONE set of stacks that stays
-    mirrored in device memory: no per-call stacking, no per-call upload.  An entry is valid only while
-    every pulse still holds the very arrays it was built from (identity, not value)."""
-    import weakref
-    props = [pls.total_propagator for pls in distinct]
-    parts = list(zip(ctrl, phases, liouville, props))
-    ids = sorted(range(len(distinct)), key=lambda i: id(distinct[i]))
-    rank = [0]*len(distinct)
-    for r, i in enumerate(ids):
-        rank[i] = r
-    key = tuple(id(distinct[i]) for i in ids) + (id(basis),)
-    entry = _GATE_LIBRARIES.get(key)
-    if entry is not None:
-        for i in ids:
-            refs = entry.refs[rank[i]]
-            if refs[0]() is not distinct[i] or any(r() is not a for r, a in zip(refs[1:], parts[i])):
-                del _GATE_LIBRARIES[key]
-                entry = None
-                break
-        else:
-            if entry.refs[-1]() is not basis:
-                del _GATE_LIBRARIES[key]
-                entry = None
-    if entry is not None:
-        return (*entry.stacks, rank)
+def _gate_library(ctx, plan, distinct, omega, ctrl, phases, liouville, basis):
+    """Stacks for the fused concatenation call (control matrices, total phases, Liouville and Hilbert
+    propagators of the distinct gates, basis).  With a plan, sequences drawn from the same set of cached
+    gate objects (randomized benchmarking: 1000 sequences over 24 Cliffords) share ONE set of stacks
+    that stays mirrored in device memory: no per-call stacking, no per-call upload.  Returns
+    ``(lib_B, lib_ph, lib_L, lib_U, basis, rank)``; ``rank[i]`` is the row of ``distinct[i]``."""
+    if plan is not None and plan.library is not None and _same_grid(plan.library[0], omega):
+        stacks, rows = plan.library[1], plan.library[2]
+        return (*stacks, [rows[id(p)] for p in distinct])
     n = len(distinct)
+    props = [pls.total_propagator for pls in distinct]
     shapes = [((n,) + np.shape(ctrl[0]), np.complex128), ((n,) + np.shape(phases[0]), np.complex128),
               ((n,) + np.shape(liouville[0]), np.float64), ((n,) + np.shape(props[0]), np.complex128),
               (np.shape(basis), np.complex128)]
     total = sum(int(np.prod(sh))*np.dtype(dt).itemsize for sh, dt in shapes)
-    cacheable = total <= _GATE_LIBRARY_MAX_BYTES
-    if cacheable:
-        stacks = _lib.empty_many(shapes, ctx)
-    else:
-        stacks = [np.empty(sh, dtype=dt) for sh, dt in shapes]
-    for i in ids:
-        for stack, part in zip(stacks[:4], parts[i]):
-            stack[rank[i]] = part
+    keep = plan is not None and total <= (16 << 20)
+    stacks = _lib.empty_many(shapes, ctx) if keep else [np.empty(sh, dtype=dt) for sh, dt in shapes]
+    for i in range(n):
+        for stack, part in zip(stacks[:4], (ctrl[i], phases[i], liouville[i], props[i])):
+            stack[i] = part
     stacks[4][...] = np.asarray(basis)
-    if cacheable:
-        try:
-            refs = [tuple(weakref.ref(x) for x in (distinct[i],) + parts[i]) for i in ids]
-            refs.append(weakref.ref(basis))
-        except TypeError:       # something not weak-referenceable (a view created on the fly)
-            return (*stacks, rank)
+    if keep:
         for stack in stacks:
             _lib.mirror_input(ctx, stack)
-        entry = _GateLibrary()
-        entry.refs, entry.stacks, entry.rank = refs, tuple(stacks), None
-        while len(_GATE_LIBRARIES) >= _GATE_LIBRARY_LIMIT:
-            _GATE_LIBRARIES.pop(next(iter(_GATE_LIBRARIES)))
-        _GATE_LIBRARIES[key] = entry
-    return (*stacks, rank)
+        plan.library = (np.array(omega, copy=True), tuple(stacks), {id(p): i for i, p in enumerate(distinct)})
+        plan.stamps = {id(p): p._stamp[0] for p in distinct}   # gathering the parts may have cached some
+    return (*stacks, list(range(n)))
 
 
 _SAME_GRID = {}
@@ -861,7 +925,7 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
     if len(pulses) == 1:
         return copy.deepcopy(pulses[0])
 
-    newpulse, _, n_oper_mapping, distinct, inverse = _join_pulses(pulses)
+    newpulse, _, n_oper_mapping, distinct, inverse, plan = _join_pulses(pulses)
     have_propagators = all('total_propagator' in pls._data for pls in distinct)
 
     def host_total_propagator():
@@ -878,18 +942,22 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
     # which (renamed) noise operators does each pulse carry?  One row per distinct object and mapping
     # (positions share their object's mapping unless an identifier clash renamed something there)
     new_ids = newpulse.n_oper_identifiers.tolist()
-    column = {ident: i for i, ident in enumerate(new_ids)}
-    rows_by_mapping, present_rows = {}, []
-    for pos in range(len(pulses)):
-        mapping = n_oper_mapping[pos]
-        row = rows_by_mapping.get(id(mapping))
-        if row is None:
-            row = [False]*len(new_ids)
-            for ident in mapping.values():
-                row[column[ident]] = True
-            rows_by_mapping[id(mapping)] = row
-        present_rows.append(row)
-    n_opers_present = np.array(present_rows, dtype=bool)
+    if plan is not None:
+        present = np.array([plan.present[id(p)] for p in distinct])
+        n_opers_present = present[inverse]
+    else:
+        column = {ident: i for i, ident in enumerate(new_ids)}
+        rows_by_mapping, present_rows = {}, []
+        for pos in range(len(pulses)):
+            mapping = n_oper_mapping[pos]
+            row = rows_by_mapping.get(id(mapping))
+            if row is None:
+                row = [False]*len(new_ids)
+                for ident in mapping.values():
+                    row[column[ident]] = True
+                rows_by_mapping[id(mapping)] = row
+            present_rows.append(row)
+        n_opers_present = np.array(present_rows, dtype=bool)
 
     equal_n_opers = (n_opers_present.sum(axis=0) > 1).any()
     if omega is None:
@@ -898,7 +966,7 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         with_ctrl = [pls for pls in distinct if 'control_matrix' in pls._frequency_data]
         with_omega = with_ctrl or [pls for pls in distinct if 'omega' in pls._frequency_data]
         grids = _unique_by_identity(pls.omega for pls in with_omega)
-        equal_omega = bool(grids) and (len(grids) == 1 or util.all_array_equal(grids))
+        equal_omega = bool(grids) and all(_same_grid(grid, grids[0]) for grid in grids[1:])
         if not equal_omega:
             host_total_propagator()
             if calc_filter_function:
@@ -927,15 +995,20 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         return newpulse
 
     # per distinct pulse object: total phases, Liouville propagator, control matrix on this grid
+    # (not needed when the gates' stacks of an earlier sequence over the same gates are still valid)
+    lib_ready = (plan is not None and plan.library is not None and not calc_pulse_correlation_FF
+                 and which == 'fidelity' and _same_grid(plan.library[0], omega))
     lib_phases, lib_liouville, lib_ctrl = [], [], []
-    for pls in distinct:
-        ph, B = _frequency_entries(pls, ('total_phases', 'control_matrix'), omega)
-        lib_phases.append(pls.get_total_phases(omega) if ph is None else ph)
-        lib_ctrl.append(pls.get_control_matrix(omega, show_progressbar) if B is None else B)
-        lib_liouville.append(pls.total_propagator_liouville)
+    if not lib_ready:
+        for pls in distinct:
+            ph, B = _frequency_entries(pls, ('total_phases', 'control_matrix'), omega)
+            lib_phases.append(pls.get_total_phases(omega) if ph is None else ph)
+            lib_ctrl.append(pls.get_control_matrix(omega, show_progressbar) if B is None else B)
+            lib_liouville.append(pls.total_propagator_liouville)
 
     n_basis, n_omega = len(newpulse.basis), len(omega)
-    if (n_opers_present.all() and not calc_pulse_correlation_FF and which == 'fidelity'
+    if lib_ready or (
+            n_opers_present.all() and not calc_pulse_correlation_FF and which == 'fidelity'
             and n_basis <= 64 and n_omega and newpulse.basis.isherm
             and all(np.isrealobj(liou) for liou in lib_liouville)):
         # every gate carries every noise operator: the whole tail of this function (running
@@ -944,7 +1017,7 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         d = newpulse.c_opers.shape[-1]
         ctx = _lib.context()
         lib_B, lib_ph, lib_L, lib_U, basis, rank = _gate_library(
-            ctx, distinct, lib_ctrl, lib_phases, lib_liouville, newpulse.basis)
+            ctx, plan, distinct, omega, lib_ctrl, lib_phases, lib_liouville, newpulse.basis)
         index = np.array([rank[i] for i in inverse], dtype=np.int32)
         n_nops = lib_B.shape[1]
         U, liouville, total_phases, B, F = _lib.empty_many([   # one block, one download

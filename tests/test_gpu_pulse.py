@@ -536,7 +536,7 @@ def test_cexp_and_cexpm1(engine):
     rng = np.random.default_rng(3)
     x = rng.standard_normal((7, 50))*20
     x[0, :5] = [0.0, 1e-18, -1e-9, 1e-5, 3e-3]
-    np.testing.assert_allclose(ff.util.cexp(x), np.exp(1j*x), rtol=0, atol=4e-16)
+    np.testing.assert_allclose(ff.util.cexp(x), np.exp(1j*x), rtol=0, atol=1e-15)
     ref = oracle.cexpm1(x)
     got = ff.util.cexpm1(x)
     assert np.abs(got - ref).max() <= 1e-15
@@ -548,8 +548,8 @@ def test_cexp_and_cexpm1(engine):
         out = np.full(x.shape, 7 + 7j)
         res = fn(x, out=out, where=mask)
         assert res is out
-        np.testing.assert_allclose(out[mask], want[mask], rtol=0, atol=4e-16)
+        np.testing.assert_allclose(out[mask], want[mask], rtol=0, atol=1e-15)
         assert (out[~mask] == 7 + 7j).all()
         out2 = np.empty(x.shape, dtype=complex)
         assert fn(x, out=out2) is out2
-        np.testing.assert_allclose(out2, want, rtol=0, atol=4e-16)
+        np.testing.assert_allclose(out2, want, rtol=0, atol=1e-15)
