@@ -520,7 +520,12 @@ class PulseSequence:
             np.ascontiguousarray(liouville.real) if self.basis.isherm else liouville, self.basis)
         self._frequency_data.update(control_matrix=B, total_phases=phases, filter_function=F)
         self._mark_computed(B)
-        if infid is not None and self.d != d:
+        if infid is None:
+            return None
+        # a copy: the few numbers the caller keeps must not hold the whole result block (and its device
+        # mirror) alive after the pulse's caches are dropped
+        infid = np.array(infid)
+        if self.d != d:
             infid *= d/self.d
         return infid
 
