@@ -279,13 +279,18 @@ int ffb_allgather_columns(ffb_ctx* ctx, int rows, const int* counts, const doubl
   FFB_TRY(ffbi_allreduce_sum(ctx, token.as<double>(), 1));
   if (mine > 0) {
     const size_t bytes = (size_t)rows * mine * 16;
-    FFB_TRY(block.alloc(ctx, bytes));
-    FFB_TRY(ffb_h2d(ctx, block.p, local, bytes));
+    // a block that is still mirrored on the device (the filter function the pipeline just computed) is
+    // sent from there; otherwise it is uploaded first
+    const double2* src = static_cast<const double2*>(ffb_shadow_lookup(ctx, local, bytes));
+    if (!src) {
+      FFB_TRY(block.alloc(ctx, bytes));
+      FFB_TRY(ffb_h2d(ctx, block.p, local, bytes));
+      src = block.as<const double2>();
+    }
     Windows w;
     for (int r = 0; r < c.world; ++r) w.p[r] = reinterpret_cast<unsigned long long>(c.peer_data[r]);
     const int blocks = (int)std::min<size_t>((size_t)ctx->sm_count * 8, ceil_div_sz((size_t)rows * mine, 256));
-    peer_put_kernel<<<blocks, 256, 0, ctx->stream>>>(w, c.world, rows, mine, ld, col0,
-                                                      block.as<const double2>());
+    peer_put_kernel<<<blocks, 256, 0, ctx->stream>>>(w, c.world, rows, mine, ld, col0, src);
     FFB_LAUNCHED(ctx);
   }
   // (2) all blocks have landed everywhere

@@ -231,23 +231,28 @@ def allreduce_sum(arr: np.ndarray, group=None) -> np.ndarray:
     return host.numpy().reshape(arr.shape).copy()
 
 
-def allgather_frequency_axis(local: np.ndarray, n_omega: int, group=None) -> np.ndarray:
+def allgather_frequency_axis(local: np.ndarray, n_omega: int, group=None,
+                             halo: bool = True) -> np.ndarray:
     """Assemble an array whose last axis is the (sharded) frequency axis on every rank.  ``local`` is
-    this rank's block INCLUDING its halo point (the layout :func:`frequency_shard` describes); the
-    halo columns are dropped, every frequency is taken from the rank that owns it."""
+    this rank's block INCLUDING its halo point (the layout :func:`frequency_shard` describes; the
+    halo columns are dropped, every frequency is taken from the rank that owns it) -- or, with
+    ``halo=False``, exactly the frequencies :func:`owned_frequencies` assigns to this rank (then a
+    result array that is still mirrored on the device is gathered without touching the host copy)."""
     import torch
     import torch.distributed as dist
     rank, world = _world(group)
     if world == 1:
         return local
-    start, _ = frequency_shard(n_omega, rank, world)
     o0, o1 = owned_frequencies(n_omega, rank, world)
+    start = frequency_shard(n_omega, rank, world)[0] if halo else o0
     counts = [int(np.subtract(*owned_frequencies(n_omega, r, world)[::-1])) for r in range(world)]
     lead = local.shape[:-1]
     is_complex = np.iscomplexobj(local)
     peers = peer_group(group)
     if peers is not None:
-        mine = np.ascontiguousarray(local[..., o0 - start:o1 - start], dtype=np.complex128)
+        mine = local[..., o0 - start:o1 - start]
+        if mine.dtype != np.complex128 or not mine.flags.c_contiguous:
+            mine = np.ascontiguousarray(mine, dtype=np.complex128)
         rows = int(np.prod(lead)) if lead else 1
         out = peers.allgather_columns(mine.reshape(rows, o1 - o0), counts).reshape(lead + (n_omega,))
         return out if is_complex else np.ascontiguousarray(out.real)
@@ -367,8 +372,4 @@ def concatenate(pulses, omega, group=None, gather: bool = True):
         return new, None
     if world == 1:
         return new, F_local
-    # allgather_frequency_axis expects the rank's block including its halo point
-    pad = (stop - start) - (o1 - o0)
-    if pad > 0:
-        F_local = np.concatenate([F_local, np.zeros(F_local.shape[:-1] + (pad,), F_local.dtype)], -1)
-    return new, allgather_frequency_axis(F_local, len(omega), group)
+    return new, allgather_frequency_axis(F_local, len(omega), group, halo=False)

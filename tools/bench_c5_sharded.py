@@ -15,6 +15,11 @@ import os
 import sys
 import time
 
+# one JSON line on stdout: NCCL prints its version there at start-up, send everything else to stderr
+sys.stdout.flush()
+RESULT_OUT = os.fdopen(os.dup(1), 'w')
+os.dup2(2, 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -56,10 +61,7 @@ def main():
         F_local = new.get_filter_function(omega[o0:o1])
         barrier()
         t1 = time.perf_counter()
-        pad = (stop - start) - (o1 - o0)
-        if pad > 0:
-            F_local = np.concatenate([F_local, np.zeros(F_local.shape[:-1] + (pad,), F_local.dtype)], -1)
-        F = ffd.allgather_frequency_axis(F_local, len(omega)) if world > 1 else F_local
+        F = ffd.allgather_frequency_axis(F_local, len(omega), halo=False) if world > 1 else F_local
         barrier()
         t2 = time.perf_counter()
         return new, F, t1 - t0, t2 - t1
@@ -104,7 +106,7 @@ def main():
             'exchange': ('none' if world == 1 else 'peer windows over NVLink (ffb_allgather_columns)'
                          if peers is not None else 'NCCL all_gather_into_tensor'),
             'gathered_F_hermiticity': herm, 'gathered_vs_scratch_max_rel_diff': err,
-            'sharded_vs_single_gpu_max_rel_diff': single}), flush=True)
+            'sharded_vs_single_gpu_max_rel_diff': single}), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
