@@ -434,12 +434,13 @@ def measure(name, steps, warmup, env):
         'algorithmic_flops_per_unit': W, 'units_per_launch': G*n_local_max,
         'kernel_ms': kernel_ms, 'kernel_share_of_step': k_ms_max/dev_ms_max,
         'executed_tflops': executed, 'executed_frac': executed/peak,
-        'ncu_fp64_pipe_active_pct': ncu.get('fp64_pipe_active_pct'),
+        'ncu_pipe_active_pct': ncu.get('pipe_active_pct'),
+        'ncu_pipe_active_metric': ncu.get('pipe_active_metric'),
         'ncu_source': ncu.get('source'),
         'note': 'achieved counts the reference formulation (W = 8 n_nops n_basis d^2 + 12 d^2 per '
                 'seg*omega, SURVEY 8d); the kernel executes fewer flops by pairing (m,n)/(n,m) terms '
                 'of Hermitian operators, so frac can exceed executed_frac (and 1.0); '
-                'ncu_fp64_pipe_active_pct is sm__pipe_fp64_cycles_active of the ncu capture in '
+                'ncu_pipe_active_pct is the FP64 / DMMA pipe-active share of the ncu capture in '
                 'profiles/ (the utilisation figure); traffic is its DRAM bytes per launch '
                 '(algorithmic: operand stream + split-K partials + output, DESIGN 4.1)',
     }
