@@ -1558,6 +1558,14 @@ inline int warps_per_cta(int MT) { return MT >= 8 ? 4 : 8; }
 
 }  // namespace
 
+// fixed-point variant on the int8 tensor cores (ffb_ctrlmat_i8.cu; opt-in, d = 4)
+bool ffbi_ctrlmat_i8_eligible(int G, int d, int rows, int parts_j, int parts_k);
+int ffbi_ctrlmat_i8_prepare(ffb_ctx* ctx, int G, int rows, int n_krows, const double* Bbar,
+                            const double* Cbar, const double* eigvals, const double* dt,
+                            const double* t, DevBuf& stream, DevBuf& scales);
+int ffbi_ctrlmat_i8_run(ffb_ctx* ctx, int G, const double* omega, int n_omega, const DevBuf& stream,
+                        const DevBuf& scales, DevBuf& partial, int* S_out);
+
 int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int n_omega,
                         const double* eigvals, const double* eigvecs, const double* propagators,
                         const double* omega, const double* basis, const double* n_opers,
@@ -1596,13 +1604,15 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   static const bool fused_ok = !(getenv("FFB_DFMA_FUSED_PROLOGUE") && atoi(getenv("FFB_DFMA_FUSED_PROLOGUE")) == 0);
   const size_t pro_smem = (size_t)DFMA_PRO_SEGS * (n_jrows + n_krows) * dd * 16;
   const bool fused_prologue = use_dfma && fused_ok && pro_smem <= 160 * 1024;
-  DevBuf Bbar, Cbar, stream, partial;
+  const bool use_i8 = !use_dfma && ffbi_ctrlmat_i8_eligible(G, d, rows, parts_j, parts_k);
+  DevBuf Bbar, Cbar, stream, partial, i8_scales;
   if (!fused_prologue) {
     FFB_TRY(Bbar.alloc(ctx, (size_t)G * n_jrows * dd * 16));
     FFB_TRY(Cbar.alloc(ctx, (size_t)G * n_krows * dd * 16));
   }
-  FFB_TRY(stream.alloc(ctx, use_dfma ? (size_t)G * rec * sizeof(double)
-                                     : geo.rb_doubles * geo.n_rb * sizeof(double)));
+  if (!use_i8)
+    FFB_TRY(stream.alloc(ctx, use_dfma ? (size_t)G * rec * sizeof(double)
+                                       : geo.rb_doubles * geo.n_rb * sizeof(double)));
 
   if (fused_prologue) {
     auto launch = [&](auto kern) -> int {
@@ -1649,6 +1659,10 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
                                                           Bbar.as<double>(), Cbar.as<double>(),
                                                           eigvals, dt, t, stream.as<double>());
     FFB_LAUNCHED(ctx);
+  } else if (use_i8) {
+    // digit stream of the coefficients + per-segment constants (ffb_ctrlmat_i8.cu)
+    FFB_TRY(ffbi_ctrlmat_i8_prepare(ctx, G, rows, n_krows, Bbar.as<double>(), Cbar.as<double>(), eigvals,
+                                    dt, t, stream, i8_scales));
   } else {
     // operators of a pass's segments in shared memory when they fit
     const size_t stage_bytes = (size_t)(geo.transposed ? 1 : 4) * (n_jrows + n_krows) * 2 * dd * sizeof(double);
@@ -1669,6 +1683,16 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   // ---- omega-dependent part, per block of frequencies (one block unless the caller asked for more)
   const size_t ld_out = (size_t)n_omega_all;
   auto run_block = [&](const double* omega, int n_omega, double* out) -> int {
+  if (use_i8) {
+    int S_i8 = 1;
+    FFB_TRY(ffbi_ctrlmat_i8_run(ctx, G, omega, n_omega, stream, i8_scales, partial, &S_i8));
+    const size_t total = (size_t)n_nops * n_basis * n_omega;
+    const unsigned fblocks = (unsigned)std::min<size_t>(ceil_div_sz(total, 256), (size_t)ctx->sm_count * 16);
+    finalize_kernel<<<fblocks, 256, 0, ctx->stream>>>(S_i8, 96, n_nops, n_basis, 1, 1, n_omega, ld_out, 0,
+                                                      partial.as<double>(), out);
+    FFB_LAUNCHED(ctx);
+    return FFB_OK;
+  }
   if (use_dfma) {
     DfmaParams q;
     q.stream = stream.as<double>();
