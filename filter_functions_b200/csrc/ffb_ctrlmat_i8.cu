@@ -314,6 +314,7 @@ struct I8Params {
   int n_omega;
   int n_stages;                      // ceil(G / 4)
   int stages_per_chunk;
+  int debug;                         // FFB_I8_DEBUG: 1 = no MMAs issued, 2 = no operand generation (timing only)
 };
 
 // 4 x 4 byte transpose: words a..d (4 values, digits 0..3 in their bytes) -> one word per digit plane
@@ -415,6 +416,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) ctrlmat_i8_kernel(const I8Param
       const double* const cst = reinterpret_cast<const double*>(sP + STAGE_P + 2 * C_KSTEP) + c * I8_CONSTS;
       mbar_wait(&bar_empty[s], ph ^ 1u);   // the MMAs of the previous use of this stage are done
       mbar_wait(&bar_full_c[s], ph);       // constants (and coefficients) of this stage have landed
+      if (p.debug & 2) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full_p[s]);
+        continue;
+      }
       const double tg = cst[0], dtg = cst[1];
       if (__double_as_longlong(dtg) != __double_as_longlong(dt_prev)) {
         double sn, cs;
@@ -487,6 +493,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) ctrlmat_i8_kernel(const I8Param
         const unsigned sC = sP + STAGE_P;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
+          if (p.debug & 1) break;
           // P plane i (digit i) x coefficient planes j with i + j >= 4; level t = i + j at column 96 (t - 4);
           // two adjacent planes (adjacent levels) per instruction where possible
 #pragma unroll
@@ -605,6 +612,8 @@ int ffbi_ctrlmat_i8_run(ffb_ctx* ctx, int G, const double* omega, int n_omega, c
   p.n_omega = n_omega;
   p.n_stages = n_stages;
   p.stages_per_chunk = spc;
+  static const int debug = getenv("FFB_I8_DEBUG") ? atoi(getenv("FFB_I8_DEBUG")) : 0;
+  p.debug = debug;
   const size_t smem = (size_t)I8_STAGES * STAGE_BYTES + 1024;
   FFB_TRY(ffb_func_smem(ctx, ctrlmat_i8_kernel, smem));
   int slot = -1;

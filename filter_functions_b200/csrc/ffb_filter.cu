@@ -54,6 +54,185 @@ ff_fidelity_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld,
   }
 }
 
+// One-pass Gram variant for long basis sums (n_basis >= 32: d >= 6).  The kernel above reads row l once
+// per group of RT right rows, i.e. every element of B about L / RT * (1 + RT) / ... times through L2
+// (config 5, L = 18, n_basis = 256: 18 GB of L2 reads for 737 MB of data, 1.66 ms = 7 % of the HBM rate).
+// Here a CTA owns 32 frequencies and a PAIR OF ROW PANELS (PL = TL * NT rows each; one panel pair covers
+// all of config 5's 18 rows), streams the panels' rows once through a cp.async ring in shared memory
+// ([stage][panel][k][row][32 frequencies]: a warp reads 512 contiguous bytes, no bank conflicts) and every
+// warp accumulates one TL x TL register tile of the Gram matrix for its lane's frequency: 2 TL loads per
+// TL^2 complex multiply-adds.  Only tiles on or above the diagonal are computed, the mirror image is
+// written as the conjugate (F is exactly Hermitian, its diagonal exactly real, as in the reference where
+// conj(x) x has no imaginary part).  Algorithmic bytes: 16 (L n_basis + L^2) per frequency, read / written once.
+constexpr int GRAM_W = 32;       // frequencies per CTA
+constexpr int GRAM_KC = 4;       // basis elements per stage
+constexpr int GRAM_STAGES = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int TL, int NT, bool TRI>
+__global__ void __launch_bounds__((TRI ? NT * (NT + 1) / 2 : NT * NT) * 32)
+ff_gram_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, int n_panels,
+               const double2* __restrict__ B, double2* __restrict__ F) {
+  constexpr int PL = TL * NT;                 // rows per panel
+  // warps: one per register tile of the panel pair; TRI (a single panel): the tiles on or above the
+  // diagonal only
+  constexpr int NW = TRI ? NT * (NT + 1) / 2 : NT * NT;
+  extern __shared__ __align__(16) unsigned char gram_smem[];
+  const int L = P * n_nops;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // panel pair (pa <= pb) of this CTA
+  int pa = 0, pb = blockIdx.y;
+  while (pb >= n_panels - pa) {
+    pb -= n_panels - pa;
+    ++pa;
+  }
+  pb += pa;
+  const bool diag_pair = pa == pb;
+  const int n_pan = diag_pair ? 1 : 2;
+  const int w0 = blockIdx.x * GRAM_W;
+  const int w = min(w0 + lane, n_omega - 1);   // lanes beyond the grid repeat the last frequency
+  const size_t stage_elems = (size_t)n_pan * GRAM_KC * PL * GRAM_W;
+  double2* const ring = reinterpret_cast<double2*>(gram_smem);
+  const int n_chunks = (n_basis + GRAM_KC - 1) / GRAM_KC;
+
+  // rows of a stage: (panel, k, row) -> 32 lanes x 16 B; the warps take them round robin
+  auto load_stage = [&](int chunk) {
+    double2* const st = ring + (size_t)(chunk % GRAM_STAGES) * stage_elems;
+    const int k0 = chunk * GRAM_KC;
+    for (int row = warp; row < n_pan * GRAM_KC * PL; row += NW) {
+      const int pn = row / (GRAM_KC * PL), kk = (row / PL) % GRAM_KC, rr = row % PL;
+      const int l = min((pn ? pb : pa) * PL + rr, L - 1);      // padding rows repeat the last row
+      const int k = min(k0 + kk, n_basis - 1);
+      cp_async16(st + (size_t)row * GRAM_W + lane, B + ((size_t)l * n_basis + k) * ld + w);
+    }
+  };
+
+  int ta = warp / NT, tb = warp % NT;
+  if (TRI) {
+    ta = 0;
+    tb = warp;
+    while (tb >= NT - ta) {
+      tb -= NT - ta;
+      ++ta;
+    }
+    tb += ta;
+  }
+  const bool active = !diag_pair || ta <= tb;
+  const bool diag_tile = diag_pair && ta == tb;
+  double2 acc[TL][TL];
+#pragma unroll
+  for (int i = 0; i < TL; ++i)
+#pragma unroll
+    for (int j = 0; j < TL; ++j) acc[i][j] = make_double2(0.0, 0.0);
+
+  for (int c = 0; c < GRAM_STAGES - 1; ++c) {
+    if (c < n_chunks) load_stage(c);
+    cp_async_commit();
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    cp_async_wait<GRAM_STAGES - 2>();
+    __syncthreads();   // chunk c has landed for everybody; everybody is done with chunk c - 1
+    if (c + GRAM_STAGES - 1 < n_chunks) load_stage(c + GRAM_STAGES - 1);
+    cp_async_commit();
+    if (active) {
+      const double2* const st = ring + (size_t)(c % GRAM_STAGES) * stage_elems;
+      const double2* const sa = st + (size_t)(ta * TL) * GRAM_W + lane;
+      const double2* const sb = st + ((size_t)(diag_pair ? 0 : GRAM_KC * PL) + tb * TL) * GRAM_W + lane;
+      const int kc = min(GRAM_KC, n_basis - c * GRAM_KC);
+#pragma unroll
+      for (int kk = 0; kk < GRAM_KC; ++kk) {
+        if (kk < kc) {
+          double2 x[TL], y[TL];
+#pragma unroll
+          for (int i = 0; i < TL; ++i) x[i] = sa[(size_t)(kk * PL + i) * GRAM_W];
+#pragma unroll
+          for (int j = 0; j < TL; ++j) y[j] = sb[(size_t)(kk * PL + j) * GRAM_W];
+          if (diag_tile) {
+#pragma unroll
+            for (int i = 0; i < TL; ++i)
+#pragma unroll
+              for (int j = i; j < TL; ++j) {
+                acc[i][j].x = fma(x[i].x, y[j].x, acc[i][j].x);
+                acc[i][j].x = fma(x[i].y, y[j].y, acc[i][j].x);
+                acc[i][j].y = fma(x[i].x, y[j].y, acc[i][j].y);
+                acc[i][j].y = fma(-x[i].y, y[j].x, acc[i][j].y);
+              }
+          } else {
+#pragma unroll
+            for (int i = 0; i < TL; ++i)
+#pragma unroll
+              for (int j = 0; j < TL; ++j) {
+                acc[i][j].x = fma(x[i].x, y[j].x, acc[i][j].x);
+                acc[i][j].x = fma(x[i].y, y[j].y, acc[i][j].x);
+                acc[i][j].y = fma(x[i].x, y[j].y, acc[i][j].y);
+                acc[i][j].y = fma(-x[i].y, y[j].x, acc[i][j].y);
+              }
+          }
+        }
+      }
+    }
+  }
+  if (!active || w0 + lane >= n_omega) return;
+  auto f_index = [&](int l, int r) -> size_t {
+    const int g = l / n_nops, a = l % n_nops, h = r / n_nops, b = r % n_nops;
+    return ((((size_t)g * P + h) * n_nops + a) * n_nops + b) * ld + w;
+  };
+#pragma unroll
+  for (int i = 0; i < TL; ++i)
+#pragma unroll
+    for (int j = 0; j < TL; ++j) {
+      const int l = pa * PL + ta * TL + i, r = pb * PL + tb * TL + j;
+      if (l >= L || r >= L || (diag_tile && j < i)) continue;
+      if (l == r) {
+        F[f_index(l, l)] = make_double2(acc[i][j].x, 0.0);
+      } else {
+        F[f_index(l, r)] = acc[i][j];
+        F[f_index(r, l)] = make_double2(acc[i][j].x, -acc[i][j].y);
+      }
+    }
+}
+
+template <int TL, int NT, bool TRI>
+int launch_gram(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega, size_t ld, const double* B,
+                double* F) {
+  constexpr int PL = TL * NT;
+  const int L = P * n_nops;
+  const int n_panels = ceil_div(L, PL);
+  const size_t smem = (size_t)GRAM_STAGES * (n_panels > 1 ? 2 : 1) * GRAM_KC * PL * GRAM_W * 16;
+  FFB_TRY(ffb_func_smem(ctx, ff_gram_kernel<TL, NT, TRI>, smem));
+  dim3 grid(ceil_div(n_omega, GRAM_W), n_panels * (n_panels + 1) / 2);
+  ff_gram_kernel<TL, NT, TRI><<<grid, (TRI ? NT * (NT + 1) / 2 : NT * NT) * 32, smem, ctx->stream>>>(
+      P, n_nops, n_basis, n_omega, ld, n_panels, reinterpret_cast<const double2*>(B),
+      reinterpret_cast<double2*>(F));
+  FFB_LAUNCHED(ctx);
+  return FFB_OK;
+}
+
+// the Gram kernel pays when the basis sum is long and there are several rows to pair up
+bool gram_eligible(int L, int n_basis) {
+  static const bool off = getenv("FFB_FF_GRAM") && atoi(getenv("FFB_FF_GRAM")) == 0;
+  return !off && n_basis >= 32 && L >= 4 && L <= 4096;
+}
+
+int run_gram(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega, size_t ld, const double* B,
+             double* F) {
+  const int L = P * n_nops;
+  // one panel where the rows fit (upper-triangle tiles only: 3 / 6 / 10 / 6 warps), pairs of 16-row panels
+  // beyond (the 6 x 6 tile needs > 168 registers, which only a CTA of <= 8 warps gets)
+  if (L <= 8) return launch_gram<4, 2, true>(ctx, P, n_nops, n_basis, n_omega, ld, B, F);
+  if (L <= 12) return launch_gram<4, 3, true>(ctx, P, n_nops, n_basis, n_omega, ld, B, F);
+  if (L <= 16) return launch_gram<4, 4, true>(ctx, P, n_nops, n_basis, n_omega, ld, B, F);
+  if (L <= 18) return launch_gram<6, 3, true>(ctx, P, n_nops, n_basis, n_omega, ld, B, F);
+  return launch_gram<4, 4, false>(ctx, P, n_nops, n_basis, n_omega, ld, B, F);
+}
+
 // F[(l), (r), k, m, w] = conj(B[l,k,w]) B[r,m,w]   (write-bound outer product)
 __global__ void __launch_bounds__(256)
 ff_generalized_kernel(int P, int n_nops, int n_basis, int n_omega, const double2* __restrict__ B,
@@ -197,6 +376,8 @@ int ffbi_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_ome
   FFB_REQUIRE(ctx, L <= 65535 && (long long)L * n_basis <= 65535 * 1LL,
               "filter function: too many rows (%d x %d)", L, n_basis);
   const int wt = ceil_div(n_omega, 256);
+  if (!generalized && gram_eligible(L, n_basis))
+    return run_gram(ctx, P, n_nops, n_basis, n_omega, (size_t)n_omega, B, F);
   if (!generalized) {
     constexpr int RT = 4;
     dim3 grid(wt, L, ceil_div(L, RT));
@@ -220,6 +401,7 @@ int ffbi_filter_function_ld(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_
               n_basis, n_omega);
   const int L = P * n_nops;
   FFB_REQUIRE(ctx, L <= 65535, "filter function: too many rows (%d)", L);
+  if (gram_eligible(L, n_basis)) return run_gram(ctx, P, n_nops, n_basis, n_omega, ld, B, F);
   constexpr int RT = 4;
   dim3 grid(ceil_div(n_omega, 256), L, ceil_div(L, RT));
   ff_fidelity_kernel<RT><<<grid, 256, 0, ctx->stream>>>(

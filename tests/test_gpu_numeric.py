@@ -256,6 +256,29 @@ def test_filter_function(engine, n_nops, n_basis, n_omega, which):
     assert nerr(F, F_o) < 1e-13
 
 
+@pytest.mark.parametrize('P,n_nops,n_basis,n_omega', [
+    (1, 18, 256, 100),   # config 5's shape: one 18-row panel, 6 x 6 tiles
+    (1, 4, 32, 31), (1, 8, 36, 64), (1, 9, 64, 65), (1, 12, 37, 70), (1, 13, 35, 33), (1, 16, 64, 96),
+    (1, 17, 33, 45), (1, 19, 34, 40), (1, 32, 32, 33), (1, 40, 35, 10),   # two and three 16-row panels
+    (3, 7, 64, 50), (2, 9, 49, 1)])
+def test_filter_function_gram(engine, P, n_nops, n_basis, n_omega):
+    """The one-pass Gram kernel (n_basis >= 32, at least 4 rows): every tile shape, panel pairs, padding
+    rows, basis sums that are not a multiple of the stage depth, frequency tails; exact Hermiticity."""
+    rng = np.random.default_rng(P*1000 + n_nops*n_basis + n_omega)
+    shape = (P, n_nops, n_basis, n_omega)
+    B = rng.standard_normal(shape) + 1j*rng.standard_normal(shape)
+    if P == 1:
+        F = engine.numeric.calculate_filter_function(B[0], 'fidelity')
+        F_o = oracle.filter_function(B[0], 'fidelity')
+        assert np.array_equal(F, F.conj().swapaxes(0, 1))
+        assert np.all(F[np.arange(n_nops), np.arange(n_nops)].imag == 0)
+    else:
+        F = engine.numeric.calculate_pulse_correlation_filter_function(B, 'fidelity')
+        F_o = oracle.pulse_correlation_filter_function(B, 'fidelity')
+    assert F.shape == F_o.shape
+    assert nerr(F, F_o) < 1e-13
+
+
 @pytest.mark.parametrize('which', ['fidelity', 'generalized'])
 def test_pulse_correlation_filter_function(engine, which):
     rng = np.random.default_rng(23)
