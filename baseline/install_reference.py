@@ -48,5 +48,26 @@ def install(verbose: bool = True) -> str:
     return 'copy'
 
 
+def install_tests(verbose: bool = True) -> str:
+    """Stage the reference's own test-suite (``tests/`` + the ``examples/data`` fixtures it loads) under
+    ``baseline/_ref_tests`` (git-ignored, travels with ``gpurun``), byte-identical, so that
+    ``tools/run_reference_tests.py`` can run it against THIS package on the GPU box.  Returns 'copy',
+    'present' or 'unavailable'."""
+    target = os.path.join(HERE, '_ref_tests')
+    if not os.path.isdir(SOURCE):
+        return 'present' if os.path.isdir(os.path.join(target, 'tests')) else 'unavailable'
+    state = 'present'
+    for sub in ('tests', os.path.join('examples', 'data')):
+        src, dst = os.path.join(SOURCE, sub), os.path.join(target, sub)
+        if os.path.isdir(dst) and not filecmp.dircmp(src, dst, ignore=['__pycache__']).diff_files \
+                and not filecmp.dircmp(src, dst, ignore=['__pycache__']).left_only:
+            continue
+        shutil.rmtree(dst, ignore_errors=True)
+        shutil.copytree(src, dst, ignore=shutil.ignore_patterns('__pycache__'))
+        state = 'copy'
+    return state
+
+
 if __name__ == '__main__':
     print(install())
+    print('tests:', install_tests())

@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument('--cpu-seconds', type=float, default=12.0,
                     help='target duration of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-int8', action='store_true',
+                    help="skip the extra 'd4_int8' line (opt-in int8 tensor-core kernel)")
     return ap.parse_args()
 
 
@@ -260,12 +262,20 @@ def golden_parity(name, order, infid):
     return float(np.abs(got - want).max()/np.abs(want).max())
 
 
-def kernel_model(wl, n_omega_local, kernel_ms, peak):
+def kernel_model(wl, n_omega_local, kernel_ms, peak, int8=False):
     """Which control-matrix kernel instance ran and how many multiply-add flops it really issued
     (Hermitian-pair formulation, csrc/ffb_ctrlmat.cu header)."""
     G, d = wl.G, wl.d
     n_nops, n_basis = len(wl.n_opers), len(wl.basis)
     rows = n_nops*n_basis
+    if int8:
+        # csrc/ffb_ctrlmat_i8.cu: per seg*omega 15 digit-plane products of (re | im) x 96 rows x 16 K entries
+        ops = 2*2*15*96*16*G*n_omega_local/(kernel_ms*1e-3)*1e-12
+        return ('ctrlmat_i8_kernel',
+                'int8 tensor cores (tcgen05.mma.kind::i8, int32 accumulators in TMEM; 15 int8 digit-plane '
+                'products per FP64 product) fed by an FP64 operand generator (~260 FP64 instructions per '
+                'seg*omega); executed_tflops counts the int8 operations (TOP/s), executed_frac is against '
+                'the NOMINAL dense int8 peak of 4500 TOP/s', ops, ops/4500.0*peak)
     use_dfma = rows <= 16 and 2 <= d <= 3 and os.environ.get('FFB_CTRLMAT_DFMA', '1') != '0'
     n_pairs = d*(d - 1)//2
     if use_dfma:
@@ -293,12 +303,40 @@ def kernel_model(wl, n_omega_local, kernel_ms, peak):
         pair_rows = rows_pad
     # real multiply-adds per seg*omega: 2 per row for the diagonal unit, 4 per row and level pair
     executed = (2*rows_pad + 4*n_pairs*pair_rows)*2*G*n_omega_local/(kernel_ms*1e-3)*1e-12
-    return kernel, pipe, executed
+    return kernel, pipe, executed, executed
 
 
-def measure(name, steps, warmup, env):
+def measure(name, steps, warmup, env, int8=False):
     """One workload on this rank's GPU: device-resident value, e2e through the public API, roofline of
-    the control-matrix kernel.  Collective over the ranks (every rank calls it with the same name)."""
+    the control-matrix kernel.  Collective over the ranks (every rank calls it with the same name).
+    ``int8``: with the opt-in fixed-point control-matrix kernel on the int8 tensor cores
+    (FFB_CTRLMAT_INT8=1, d = 4 only)."""
+    if int8:
+        old = os.environ.get('FFB_CTRLMAT_INT8')
+        os.environ['FFB_CTRLMAT_INT8'] = '1'
+        try:
+            return _measure(name, steps, warmup, env, True)
+        finally:
+            if old is None:
+                os.environ.pop('FFB_CTRLMAT_INT8', None)
+            else:
+                os.environ['FFB_CTRLMAT_INT8'] = old
+    return _measure(name, steps, warmup, env, os.environ.get('FFB_CTRLMAT_INT8', '0') not in ('', '0'))
+
+
+def control_matrix_parity(name, B):
+    """Worst normalised deviation (per noise operator, scale = max |B| over the whole grid) of the control
+    matrix from the reference's own result on the frequencies the full-size fixture holds."""
+    path = os.path.join(ROOT, 'tests', 'golden', f'workload_full_{name}.npz')
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    pick = g['pick']
+    return float(max(np.abs(B[j][:, pick] - g['control_matrix'][j]).max()/g['scale'][j]
+                     for j in range(len(B))))
+
+
+def _measure(name, steps, warmup, env, int8):
     import ctypes
 
     import torch
@@ -411,6 +449,9 @@ def measure(name, steps, warmup, env):
     parity = {'device_vs_api': float(np.abs(dev_inf - api).max()/np.abs(api).max()),
               'vs_reference_fixture': golden_parity(name, order, api),
               'tolerance': 1e-10}
+    if world == 1:   # the control matrix the last timed call cached on the pulse
+        parity['control_matrix_vs_reference_fixture'] = control_matrix_parity(
+            name, pulse.get_control_matrix(wl.omega))
     if world > 1:
         # rank 0 evaluates the SAME global grid on its own GPU alone, outside the timed region
         if rank == 0:
@@ -425,15 +466,15 @@ def measure(name, steps, warmup, env):
     W = wl.flops_per_seg_omega
     n_local_max = -(-(n_total - 1)//world) + 1 if world > 1 else n_total
     achieved = W*G*n_local_max/(kernel_ms*1e-3)*1e-12
-    kernel, pipe, executed = kernel_model(wl, n_local_max, kernel_ms, peak)
-    ncu = env['ncu'].get(name, {}) if world == 1 else {}
+    kernel, pipe, executed, executed_vs_peak = kernel_model(wl, n_local_max, kernel_ms, peak, int8)
+    ncu = env['ncu'].get(name + ('_int8' if int8 else ''), {}) if world == 1 else {}
     roofline = {
-        'bound': 'tensor', 'pipe': pipe, 'kernel': kernel, 'achieved': achieved, 'peak': peak,
+        'bound': 'tensor', 'pipe': pipe, 'kernel': kernel, 'arithmetic': 'int8 fixed point' if int8 else 'f64', 'achieved': achieved, 'peak': peak,
         'unit': 'TFLOP/s', 'frac': achieved/peak, 'traffic': ncu.get('dram_bytes_per_launch'),
         'peak_source': env['peak_source'],
         'algorithmic_flops_per_unit': W, 'units_per_launch': G*n_local_max,
         'kernel_ms': kernel_ms, 'kernel_share_of_step': k_ms_max/dev_ms_max,
-        'executed_tflops': executed, 'executed_frac': executed/peak,
+        'executed_tflops': executed, 'executed_frac': executed_vs_peak/peak,
         'ncu_pipe_active_pct': ncu.get('pipe_active_pct'),
         'ncu_pipe_active_metric': ncu.get('pipe_active_metric'),
         'ncu_source': ncu.get('source'),
@@ -509,6 +550,13 @@ def run_b200(args):
     others = {}
     for name in extra:
         others[name] = measure(name, max(3, min(args.steps, 10)), min(args.warmup, 3), env)
+    if not args.no_int8 and 'd4' in [args.workload] + extra:
+        # the opt-in fixed-point kernel on the int8 tensor cores, same workload, its own parity figures
+        others['d4_int8'] = measure('d4', max(3, min(args.steps, 10)), min(args.warmup, 3), env, int8=True)
+        others['d4_int8']['note'] = (
+            'OPT-IN path (FFB_CTRLMAT_INT8=1), not the default and not the headline: Ozaki-style splitting '
+            'into five int8 digits per operand, tcgen05.mma.kind::i8 with exact int32 accumulation in TMEM; '
+            'deviation from the FP64 kernels ~1e-11 (inside the 1e-10 tolerance, see parity), DESIGN 4.9')
     sampler.stop_flag.set()
     sampler.join(timeout=1.0)
 

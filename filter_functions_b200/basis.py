@@ -1,10 +1,12 @@
 """Operator bases consumed by the engine as dense ``(n_basis, d, d)`` complex128 arrays.
 
-Host-side set-up, executed once per pulse; the reference's ``basis.py`` (815 lines, sparse trace
-tensors, basis completion) is out of scope.  What the hot path needs
-is restated here: the ``Basis`` ndarray subclass with the predicates the path branches on, the
-Pauli and generalised Gell-Mann constructors, and basis expansion.
+Host-side set-up, executed once per pulse (not a component to accelerate).
+What the hot path and its callers need is restated here: the ``Basis`` ndarray subclass with the
+predicates the path branches on, the Pauli and generalised Gell-Mann constructors, completion of a
+partial basis (``Basis.from_partial`` -- the CNOT example of the reference builds its basis that way)
+and basis expansion.  The trace tensor is dense (the reference keeps it in the ``sparse`` package).
 """
+import warnings
 from functools import cached_property
 from itertools import product
 from typing import Optional, Sequence
@@ -142,15 +144,30 @@ class Basis(np.ndarray):
     @cached_property
     def four_element_traces(self) -> np.ndarray:
         """T_ijkl = tr(C_i C_j C_k C_l) as a dense array (reference ``basis.py:330-348`` keeps it
-        sparse; dense is n_basis^4 * 16 B, fine for d <= 4)."""
+        sparse; dense is n_basis^4 * 16 B, fine for d <= 4).  The array answers ``todense()`` like the
+        reference's sparse tensor does, so code written against either works."""
         arr = self.view(np.ndarray)
         pair = np.einsum('iab,jbc->ijac', arr, arr)
-        return np.einsum('ijac,klca->ijkl', pair, pair)
+        return np.einsum('ijac,klca->ijkl', pair, pair).view(_DenseTensor)
+
+    @cached_property
+    def sparse(self) -> np.ndarray:
+        """The elements as an array that answers ``todense()`` (the reference returns a ``sparse.COO``
+        here, ``basis.py:325-328``; this package keeps bases dense)."""
+        return self.view(np.ndarray).view(_DenseTensor)
+
+    def tidyup(self, eps_scale: Optional[float] = None) -> None:
+        """Set entries below machine precision (times ``eps_scale``, default d^3) to zero, in place."""
+        arr = self.view(np.ndarray)
+        atol = self._eps*(self.d**3 if eps_scale is None else eps_scale)
+        arr.real[np.abs(arr.real) <= atol] = 0
+        arr.imag[np.abs(arr.imag) <= atol] = 0
+        self._invalidate_cached_properties()
 
     def _invalidate_cached_properties(self) -> None:
         """Forget the predicates computed for the previous contents (in-place changes)."""
         for name in ('isherm', 'isnorm', 'isorthogonal', 'isorthonorm', 'istraceless', 'iscomplete',
-                     'four_element_traces'):
+                     'four_element_traces', 'sparse'):
             self.__dict__.pop(name, None)
 
     def normalize(self, copy: bool = False):
@@ -164,6 +181,64 @@ class Basis(np.ndarray):
         if self.btype == 'GGM' and self.iscomplete:
             return ggm_expand(M, traceless, hermitian, tidyup)
         return expand(M, self, self.isnorm, hermitian, tidyup)
+
+    @classmethod
+    def from_partial(cls, partial_basis_array, traceless: Optional[bool] = None,
+                     btype: Optional[str] = None, labels: Optional[Sequence[str]] = None) -> 'Basis':
+        """A complete orthonormal basis that contains the given (orthogonal) elements, same contract as
+        the reference's ``Basis.from_partial`` (``basis.py:492-620``): the elements are normalised and
+        kept in order, the rest of the operator space is filled with an orthonormal set spanning the
+        orthogonal complement; ``traceless=True`` (default: if the given elements allow it) puts the
+        identity first and makes every other element traceless.  Raises ``ValueError`` for elements that
+        are not orthogonal, not traceless although a traceless basis was requested, or for a wrong
+        number of labels (len(elements) or d^2; new elements are labelled ``$C_{i}$``)."""
+        if labels is None:
+            own = getattr(partial_basis_array, 'labels', None)
+            if own is not None and len(own) == len(partial_basis_array):
+                labels = own
+        elems = cls(partial_basis_array)
+        elems.normalize(copy=False)
+        if not elems.isherm:
+            warnings.warn("(Some) elems not hermitian! The resulting basis also won't be.")
+        if not elems.isorthogonal:
+            raise ValueError('The basis elements are not orthogonal!')
+        if traceless is None:
+            traceless = elems.istraceless
+        elif traceless and not elems.istraceless:
+            raise ValueError('The basis elements are not traceless (up to an identity element) '
+                             'but a traceless basis was requested!')
+        d = elems.d
+        if labels is not None and len(labels) not in (len(elems), d*d):
+            raise ValueError(f'Got {len(labels)} labels but expected {len(elems)} or {d*d}')
+
+        # coordinates of the elements in the (orthonormal, Hermitian) GGM basis; a traceless basis keeps the
+        # identity apart: its coordinate is dropped, and with it an element that WAS the identity
+        frame = cls.ggm(d).view(np.ndarray)
+        coords = ggm_expand(elems.view(np.ndarray), traceless=traceless, hermitian=elems.isherm,
+                            tidyup=True)
+        if traceless:
+            identity, frame, coords = frame[:1], frame[1:], coords[..., 1:]
+        coords = coords[np.abs(coords).sum(axis=-1) != 0]
+        if coords.size:
+            # rows of V^H beyond the rank span the orthogonal complement of the given coordinates
+            _, sing, vh = np.linalg.svd(coords, full_matrices=True)
+            rank = int((sing > sing.max()*max(coords.shape)*np.finfo(float).eps).sum())
+            full = np.concatenate((coords, vh[rank:].conj()))
+            new = np.einsum('ij,jkl->ikl', full, frame)
+        else:
+            new = frame
+        if traceless:
+            new = np.concatenate((identity, new))
+        new = new.view(cls)
+        new.tidyup()
+        if labels is not None and len(labels) == len(elems):
+            labels = list(labels)
+            if traceless:   # the identity's label moves to the front with it
+                where = next((i for i, e in enumerate(elems.view(np.ndarray))
+                              if np.allclose(e, identity[0], rtol=elems._rtol, atol=elems._atol)), 0)
+                labels.insert(0, labels.pop(where))
+            labels += [f'$C_{{{i}}}$' for i in range(len(labels), len(new))]
+        return cls(new, btype=btype or 'From partial', labels=labels)
 
     @classmethod
     def pauli(cls, n: int) -> 'Basis':
@@ -194,6 +269,13 @@ class Basis(np.ndarray):
             diag[l] = -l
             out[2*n_sym + l] = np.diag(diag/np.sqrt(l*(l + 1)))
         return cls(out, btype='GGM', labels=[rf'$\Lambda_{{{i}}}$' for i in range(d*d)])
+
+
+class _DenseTensor(np.ndarray):
+    """Plain ndarray that also answers ``todense()`` (drop-in for the reference's sparse trace tensor)."""
+
+    def todense(self) -> np.ndarray:
+        return self.view(np.ndarray)
 
 
 def _norm(b) -> np.ndarray:

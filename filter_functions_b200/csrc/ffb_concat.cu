@@ -302,7 +302,7 @@ ff_batched_kernel(int n_nops, int n_basis, int n_omega, const double2* __restric
   for (int k = 0; k < n_basis; ++k) {
     const double2 x = Ba[(size_t)k * n_omega], y = Bb[(size_t)k * n_omega];
     re += x.x * y.x + x.y * y.y;
-    im += x.x * y.y - x.y * y.x;
+    im += __dsub_rn(__dmul_rn(x.x, y.y), __dmul_rn(x.y, y.x));   // exactly antisymmetric in (a, b), see ffb_filter.cu
   }
   F[(((size_t)s * n_nops + a) * n_nops + b) * n_omega + w] = make_double2(re, im);
 }

@@ -314,7 +314,9 @@ struct I8Params {
   int n_omega;
   int n_stages;                      // ceil(G / 4)
   int stages_per_chunk;
-  int debug;                         // FFB_I8_DEBUG: 1 = no MMAs issued, 2 = no operand generation (timing only)
+  int debug;                         // FFB_I8_DEBUG (timing experiments only): 1 = no MMAs issued, 2 = no operand
+                                     // generation, 4 = generation without the shared-memory stores, 8 = stores without
+                                     // the FP64 work
 };
 
 // 4 x 4 byte transpose: words a..d (4 values, digits 0..3 in their bytes) -> one word per digit plane
@@ -413,10 +415,25 @@ __global__ void __launch_bounds__(I8_THREADS, 1) ctrlmat_i8_kernel(const I8Param
       const int s = it % I8_STAGES;
       const unsigned ph = (unsigned)(it / I8_STAGES) & 1u;
       unsigned char* const sP = smem + (size_t)s * STAGE_BYTES;
-      const double* const cst = reinterpret_cast<const double*>(sP + STAGE_P + 2 * C_KSTEP) + c * I8_CONSTS;
+      const double* cst = reinterpret_cast<const double*>(sP + STAGE_P + 2 * C_KSTEP) + c * I8_CONSTS;
+      if (p.debug & 16)   // timing experiment: per-segment constants straight from global memory (L1 / L2)
+        cst = reinterpret_cast<const double*>(p.stream + (size_t)(st0 + it) * STAGE_C + 2 * C_KSTEP) + c * I8_CONSTS;
       mbar_wait(&bar_empty[s], ph ^ 1u);   // the MMAs of the previous use of this stage are done
       mbar_wait(&bar_full_c[s], ph);       // constants (and coefficients) of this stage have landed
       if (p.debug & 2) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full_p[s]);
+        continue;
+      }
+      if (p.debug & 8) {
+        const uint4 z = make_uint4(tid, it, 0u, 0u);
+        unsigned char* const tile = sP + (size_t)ks * P_KSTEP + (size_t)cc * 2048;
+#pragma unroll
+        for (int j = 0; j < I8_D; ++j) {
+          *reinterpret_cast<uint4*>(tile + (size_t)wl * 16 + j * P_PLANE) = z;
+          *reinterpret_cast<uint4*>(tile + (size_t)(I8_W + wl) * 16 + j * P_PLANE) = z;
+        }
+        fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_full_p[s]);
         continue;
@@ -461,8 +478,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) ctrlmat_i8_kernel(const I8Param
         vim[2 + 2 * q] = ph_re * d_im + ph_im * d_re;
       }
       unsigned char* const tile = sP + (size_t)ks * P_KSTEP + (size_t)cc * 2048;
-      store_digits(vre, p_scale, tile + (size_t)wl * 16);             // rows 0..63: real parts
-      store_digits(vim, p_scale, tile + (size_t)(I8_W + wl) * 16);    // rows 64..127: imaginary parts
+      bool do_store = true;
+      if (p.debug & 4) {  // timing experiment: all the arithmetic, none of the stores
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < 13; ++k) sum += vre[k] + vim[k];
+        do_store = sum == 1.2345e300;
+      }
+      if (do_store) {
+        store_digits(vre, p_scale, tile + (size_t)wl * 16);             // rows 0..63: real parts
+        store_digits(vim, p_scale, tile + (size_t)(I8_W + wl) * 16);    // rows 64..127: imaginary parts
+      }
       fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full_p[s]);

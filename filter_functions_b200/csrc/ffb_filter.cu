@@ -37,9 +37,12 @@ ff_fidelity_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld,
       const int r = r0 + i;
       if (r < L) {
         const double2 y = B[((size_t)r * n_basis + k) * ld + w];
-        // conj(x) * y
+        // conj(x) * y.  The imaginary part is formed from two ROUNDED products (no FMA contraction), as
+        // NumPy forms it: exchanging x and y then flips its sign exactly, so F[r, l] == conj(F[l, r]) bit
+        // for bit and the diagonal is exactly real -- properties the reference's results have and its
+        // users test for (tests/test_precision.py:549, tests/test_core.py:861 of the reference)
         acc[i].x += x.x * y.x + x.y * y.y;
-        acc[i].y += x.x * y.y - x.y * y.x;
+        acc[i].y += __dsub_rn(__dmul_rn(x.x, y.y), __dmul_rn(x.y, y.x));
       }
     }
   }
@@ -54,19 +57,22 @@ ff_fidelity_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld,
   }
 }
 
-// One-pass Gram variant for long basis sums (n_basis >= 32: d >= 6).  The kernel above reads row l once
-// per group of RT right rows, i.e. every element of B about L / RT * (1 + RT) / ... times through L2
-// (config 5, L = 18, n_basis = 256: 18 GB of L2 reads for 737 MB of data, 1.66 ms = 7 % of the HBM rate).
-// Here a CTA owns 32 frequencies and a PAIR OF ROW PANELS (PL = TL * NT rows each; one panel pair covers
-// all of config 5's 18 rows), streams the panels' rows once through a cp.async ring in shared memory
-// ([stage][panel][k][row][32 frequencies]: a warp reads 512 contiguous bytes, no bank conflicts) and every
-// warp accumulates one TL x TL register tile of the Gram matrix for its lane's frequency: 2 TL loads per
-// TL^2 complex multiply-adds.  Only tiles on or above the diagonal are computed, the mirror image is
-// written as the conjugate (F is exactly Hermitian, its diagonal exactly real, as in the reference where
-// conj(x) x has no imaginary part).  Algorithmic bytes: 16 (L n_basis + L^2) per frequency, read / written once.
-constexpr int GRAM_W = 32;       // frequencies per CTA
-constexpr int GRAM_KC = 4;       // basis elements per stage
-constexpr int GRAM_STAGES = 3;
+// One-pass Gram variant for long basis sums (n_basis >= 32: d >= 6).  The kernel above re-reads every row
+// of B once per group of RT right rows through L2 (config 5, L = 18, n_basis = 256: 18 GB of L2 reads for
+// 737 MB of data, 1.6 ms = 7 % of the HBM rate).  Here a CTA owns GRAM_W = 16 frequencies and a PAIR OF
+// ROW PANELS (PL = TL * NT rows each; one panel covers all of config 5's 18 rows), streams the panels' rows
+// ONCE through a cp.async ring in shared memory ([stage][k][row][16 frequencies]) and every warp accumulates
+// one TL x TL register tile of the Gram matrix: 2 TL shared-memory loads per TL^2 complex multiply-adds.
+// The two half-warps of a warp take the even and the odd basis elements of a stage for the same 16
+// frequencies and are added up by one shuffle at the end (16 instead of 32 frequencies per CTA: twice
+// the CTAs, so the last wave wastes half as much).  Only tiles on or above the diagonal are computed, the
+// mirror image is written as the conjugate (F is exactly Hermitian, its diagonal exactly real, as in the
+// reference where conj(x) x has no imaginary part).  Algorithmic bytes: 16 (L n_basis + L^2) per frequency,
+// read / written once; 4 L (L + 1) / 2 n_basis FP64 multiply-adds per frequency -- for L = 18 the FP64
+// pipe, not HBM, is the nearer roof (94 us against 120 us).
+constexpr int GRAM_W = 16;       // frequencies per CTA
+constexpr int GRAM_KC = 8;       // basis elements per stage (4 per half-warp)
+__host__ __device__ constexpr int gram_stages(bool tri) { return tri ? 4 : 3; }   // pairs of panels: 64 KB per stage
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
@@ -76,6 +82,33 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// acc[i][j] += conj(x_i) y_j for the basis elements kk = 2 m + half of one stage
+template <int TL, bool DIAG, bool WHOLE>
+__device__ __forceinline__ void gram_stage(const double2* __restrict__ sa, const double2* __restrict__ sb,
+                                           int rows_per_k, int n_k, double2 (&acc)[TL][TL]) {
+  // WHOLE: all GRAM_KC / 2 basis elements of the stage exist -- no guards, so that the loads of element
+  // m + 1 are scheduled under the multiply-adds of element m
+#pragma unroll
+  for (int m = 0; m < GRAM_KC / 2; ++m) {
+    if (WHOLE || m < n_k) {
+      double2 x[TL], y[TL];
+#pragma unroll
+      for (int i = 0; i < TL; ++i) x[i] = sa[(size_t)(2 * m * rows_per_k + i) * GRAM_W];
+#pragma unroll
+      for (int j = 0; j < TL; ++j) y[j] = sb[(size_t)(2 * m * rows_per_k + j) * GRAM_W];
+#pragma unroll
+      for (int i = 0; i < TL; ++i)
+#pragma unroll
+        for (int j = DIAG ? i : 0; j < TL; ++j) {
+          acc[i][j].x = fma(x[i].x, y[j].x, acc[i][j].x);
+          acc[i][j].x = fma(x[i].y, y[j].y, acc[i][j].x);
+          acc[i][j].y = fma(x[i].x, y[j].y, acc[i][j].y);
+          acc[i][j].y = fma(-x[i].y, y[j].x, acc[i][j].y);
+        }
+    }
+  }
+}
+
 template <int TL, int NT, bool TRI>
 __global__ void __launch_bounds__((TRI ? NT * (NT + 1) / 2 : NT * NT) * 32)
 ff_gram_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, int n_panels,
@@ -84,9 +117,12 @@ ff_gram_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, int n_pan
   // warps: one per register tile of the panel pair; TRI (a single panel): the tiles on or above the
   // diagonal only
   constexpr int NW = TRI ? NT * (NT + 1) / 2 : NT * NT;
+  constexpr int SLOTS = ((TRI ? 1 : 2) * PL + NW - 1) / NW;   // rows a warp copies per basis element
+  constexpr int GRAM_STAGES = gram_stages(TRI);
   extern __shared__ __align__(16) unsigned char gram_smem[];
   const int L = P * n_nops;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wl = lane & (GRAM_W - 1), half = lane >> 4;
   // panel pair (pa <= pb) of this CTA
   int pa = 0, pb = blockIdx.y;
   while (pb >= n_panels - pa) {
@@ -95,23 +131,41 @@ ff_gram_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, int n_pan
   }
   pb += pa;
   const bool diag_pair = pa == pb;
-  const int n_pan = diag_pair ? 1 : 2;
+  const int rows_per_k = (diag_pair ? 1 : 2) * PL;
   const int w0 = blockIdx.x * GRAM_W;
-  const int w = min(w0 + lane, n_omega - 1);   // lanes beyond the grid repeat the last frequency
-  const size_t stage_elems = (size_t)n_pan * GRAM_KC * PL * GRAM_W;
+  const int w = min(w0 + wl, n_omega - 1);   // lanes beyond the grid repeat the last frequency
+  const size_t stage_elems = (size_t)GRAM_KC * rows_per_k * GRAM_W;
   double2* const ring = reinterpret_cast<double2*>(gram_smem);
   const int n_chunks = (n_basis + GRAM_KC - 1) / GRAM_KC;
 
-  // rows of a stage: (panel, k, row) -> 32 lanes x 16 B; the warps take them round robin
+  // copies: the warp's rows rr = warp, warp + NW, ... of every basis element; the half-warps take the even
+  // and the odd elements.  src[s] walks along the basis axis, one stage (GRAM_KC elements) per call.
+  const double2* src[SLOTS];
+  int dst[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int rr = warp + s * NW;
+    const int l = min((rr < PL ? pa * PL + rr : pb * PL + rr - PL), L - 1);   // padding rows repeat the last row
+    src[s] = B + ((size_t)l * n_basis + half) * ld + w;
+    dst[s] = rr < rows_per_k ? (half * rows_per_k + rr) * GRAM_W + wl : -1;
+  }
+  int k_next = 0;   // first basis element of the next stage to be copied
   auto load_stage = [&](int chunk) {
     double2* const st = ring + (size_t)(chunk % GRAM_STAGES) * stage_elems;
-    const int k0 = chunk * GRAM_KC;
-    for (int row = warp; row < n_pan * GRAM_KC * PL; row += NW) {
-      const int pn = row / (GRAM_KC * PL), kk = (row / PL) % GRAM_KC, rr = row % PL;
-      const int l = min((pn ? pb : pa) * PL + rr, L - 1);      // padding rows repeat the last row
-      const int k = min(k0 + kk, n_basis - 1);
-      cp_async16(st + (size_t)row * GRAM_W + lane, B + ((size_t)l * n_basis + k) * ld + w);
+    const bool full = k_next + GRAM_KC <= n_basis;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      if (dst[s] >= 0) {
+#pragma unroll
+        for (int m = 0; m < GRAM_KC / 2; ++m) {
+          // the tail stage repeats the last basis element (never summed)
+          const ptrdiff_t koff = full ? 2 * m : min(k_next + 2 * m + half, n_basis - 1) - k_next - half;
+          cp_async16(st + dst[s] + (size_t)(2 * m * rows_per_k) * GRAM_W, src[s] + koff * (ptrdiff_t)ld);
+        }
+      }
+      src[s] += (size_t)GRAM_KC * ld;
     }
+    k_next += GRAM_KC;
   };
 
   int ta = warp / NT, tb = warp % NT;
@@ -142,48 +196,36 @@ ff_gram_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, int n_pan
     if (c + GRAM_STAGES - 1 < n_chunks) load_stage(c + GRAM_STAGES - 1);
     cp_async_commit();
     if (active) {
-      const double2* const st = ring + (size_t)(c % GRAM_STAGES) * stage_elems;
-      const double2* const sa = st + (size_t)(ta * TL) * GRAM_W + lane;
-      const double2* const sb = st + ((size_t)(diag_pair ? 0 : GRAM_KC * PL) + tb * TL) * GRAM_W + lane;
-      const int kc = min(GRAM_KC, n_basis - c * GRAM_KC);
-#pragma unroll
-      for (int kk = 0; kk < GRAM_KC; ++kk) {
-        if (kk < kc) {
-          double2 x[TL], y[TL];
-#pragma unroll
-          for (int i = 0; i < TL; ++i) x[i] = sa[(size_t)(kk * PL + i) * GRAM_W];
-#pragma unroll
-          for (int j = 0; j < TL; ++j) y[j] = sb[(size_t)(kk * PL + j) * GRAM_W];
-          if (diag_tile) {
-#pragma unroll
-            for (int i = 0; i < TL; ++i)
-#pragma unroll
-              for (int j = i; j < TL; ++j) {
-                acc[i][j].x = fma(x[i].x, y[j].x, acc[i][j].x);
-                acc[i][j].x = fma(x[i].y, y[j].y, acc[i][j].x);
-                acc[i][j].y = fma(x[i].x, y[j].y, acc[i][j].y);
-                acc[i][j].y = fma(-x[i].y, y[j].x, acc[i][j].y);
-              }
-          } else {
-#pragma unroll
-            for (int i = 0; i < TL; ++i)
-#pragma unroll
-              for (int j = 0; j < TL; ++j) {
-                acc[i][j].x = fma(x[i].x, y[j].x, acc[i][j].x);
-                acc[i][j].x = fma(x[i].y, y[j].y, acc[i][j].x);
-                acc[i][j].y = fma(x[i].x, y[j].y, acc[i][j].y);
-                acc[i][j].y = fma(-x[i].y, y[j].x, acc[i][j].y);
-              }
-          }
-        }
+      const double2* const st = ring + (size_t)(c % GRAM_STAGES) * stage_elems + (size_t)half * rows_per_k * GRAM_W + wl;
+      const double2* const sa = st + (size_t)(ta * TL) * GRAM_W;
+      const double2* const sb = st + (size_t)((diag_pair ? 0 : PL) + tb * TL) * GRAM_W;
+      // basis elements of this stage that exist for this half-warp
+      const int left = n_basis - c * GRAM_KC - half;
+      const int n_k = left >= GRAM_KC - 1 ? GRAM_KC / 2 : (left + 1) / 2;
+      if (n_k == GRAM_KC / 2) {
+        if (diag_tile) gram_stage<TL, true, true>(sa, sb, rows_per_k, n_k, acc);
+        else gram_stage<TL, false, true>(sa, sb, rows_per_k, n_k, acc);
+      } else {
+        if (diag_tile) gram_stage<TL, true, false>(sa, sb, rows_per_k, n_k, acc);
+        else gram_stage<TL, false, false>(sa, sb, rows_per_k, n_k, acc);
       }
     }
   }
-  if (!active || w0 + lane >= n_omega) return;
+  if (!active) return;
+  // even + odd basis elements
+#pragma unroll
+  for (int i = 0; i < TL; ++i)
+#pragma unroll
+    for (int j = 0; j < TL; ++j) {
+      acc[i][j].x += __shfl_xor_sync(0xffffffffu, acc[i][j].x, 16);
+      acc[i][j].y += __shfl_xor_sync(0xffffffffu, acc[i][j].y, 16);
+    }
+  if (w0 + wl >= n_omega) return;
   auto f_index = [&](int l, int r) -> size_t {
     const int g = l / n_nops, a = l % n_nops, h = r / n_nops, b = r % n_nops;
     return ((((size_t)g * P + h) * n_nops + a) * n_nops + b) * ld + w;
   };
+  // half-warp 0 writes the tile, half-warp 1 its mirror image
 #pragma unroll
   for (int i = 0; i < TL; ++i)
 #pragma unroll
@@ -191,9 +233,10 @@ ff_gram_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, int n_pan
       const int l = pa * PL + ta * TL + i, r = pb * PL + tb * TL + j;
       if (l >= L || r >= L || (diag_tile && j < i)) continue;
       if (l == r) {
-        F[f_index(l, l)] = make_double2(acc[i][j].x, 0.0);
-      } else {
+        if (half == 0) F[f_index(l, l)] = make_double2(acc[i][j].x, 0.0);
+      } else if (half == 0) {
         F[f_index(l, r)] = acc[i][j];
+      } else {
         F[f_index(r, l)] = make_double2(acc[i][j].x, -acc[i][j].y);
       }
     }
@@ -205,12 +248,194 @@ int launch_gram(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega, size_
   constexpr int PL = TL * NT;
   const int L = P * n_nops;
   const int n_panels = ceil_div(L, PL);
-  const size_t smem = (size_t)GRAM_STAGES * (n_panels > 1 ? 2 : 1) * GRAM_KC * PL * GRAM_W * 16;
+  const size_t smem = (size_t)gram_stages(TRI) * (TRI ? 1 : 2) * GRAM_KC * PL * GRAM_W * 16;
   FFB_TRY(ffb_func_smem(ctx, ff_gram_kernel<TL, NT, TRI>, smem));
   dim3 grid(ceil_div(n_omega, GRAM_W), n_panels * (n_panels + 1) / 2);
   ff_gram_kernel<TL, NT, TRI><<<grid, (TRI ? NT * (NT + 1) / 2 : NT * NT) * 32, smem, ctx->stream>>>(
       P, n_nops, n_basis, n_omega, ld, n_panels, reinterpret_cast<const double2*>(B),
       reinterpret_cast<double2*>(F));
+  FFB_LAUNCHED(ctx);
+  return FFB_OK;
+}
+
+// Single panel (L <= 18 rows: every first-order filter function with up to 18 noise operators).  The
+// 6 x 6 tile of the kernel above needs 244 registers, which leaves 6 warps per SM -- 1.5 per scheduler, and
+// an FP64 instruction keeps its scheduler's dispatch port for 2 cycles: the FP64 pipe sat at 32 %
+// (profiles/r02_ncu_ff_gram.txt).  Here a warp owns a 6 x 3 tile (x: 6 rows, y: 3 rows; ~130 registers),
+// so that all 12 tiles on or above the diagonal of an 18-row panel are resident as 12 warps, 3 per
+// scheduler; tiles the diagonal crosses skip the pairs below it at compile time (kinds LEFT / RIGHT),
+// and the warp -> tile table spreads the three kinds evenly over the schedulers (warp % 4).
+enum { GRAM_FULL = 0, GRAM_LEFT = 1, GRAM_RIGHT = 2 };
+
+template <int KIND, bool WHOLE, int KC>
+__device__ __forceinline__ void gram18_stage(const double2* __restrict__ sa, const double2* __restrict__ sb,
+                                             int rows_per_k, int n_k, double2 (&acc)[6][3]) {
+  // WHOLE: all KC / 2 basis elements of the stage exist -- no guards, so that the loads of element
+  // m + 1 are scheduled under the multiply-adds of element m
+#pragma unroll
+  for (int m = 0; m < KC / 2; ++m) {
+    if (WHOLE || m < n_k) {
+      double2 x[6], y[3];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) x[i] = sa[(size_t)(2 * m * rows_per_k + i) * GRAM_W];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) y[j] = sb[(size_t)(2 * m * rows_per_k + j) * GRAM_W];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (KIND == GRAM_LEFT && i > j) continue;
+          if (KIND == GRAM_RIGHT && i > j + 3) continue;
+          acc[i][j].x = fma(x[i].x, y[j].x, acc[i][j].x);
+          acc[i][j].x = fma(x[i].y, y[j].y, acc[i][j].x);
+          acc[i][j].y = fma(x[i].x, y[j].y, acc[i][j].y);
+          acc[i][j].y = fma(-x[i].y, y[j].x, acc[i][j].y);
+        }
+    }
+  }
+}
+
+// (ta, tb) of the warps of an 18-row panel: per scheduler F F L | F F L | F R L | F R R
+__constant__ unsigned char GRAM18_TILES[12][2] = {{0, 2}, {0, 4}, {1, 4}, {1, 5}, {0, 3}, {0, 5},
+                                                  {0, 1}, {1, 3}, {0, 0}, {1, 2}, {2, 4}, {2, 5}};
+
+template <int NTA, int KC, int STAGES>
+__global__ void __launch_bounds__(NTA * (NTA + 1) * 32, 1)
+ff_gram18_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, const double2* __restrict__ B,
+                 double2* __restrict__ F) {
+  constexpr int PL = 6 * NTA;
+  constexpr int NW = NTA * (NTA + 1);
+  constexpr int SLOTS = (PL + NW - 1) / NW;
+  extern __shared__ __align__(16) unsigned char gram_smem[];
+  const int L = P * n_nops;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wl = lane & (GRAM_W - 1), half = lane >> 4;
+  const int w0 = blockIdx.x * GRAM_W;
+  const int w = min(w0 + wl, n_omega - 1);
+  constexpr size_t stage_elems = (size_t)KC * PL * GRAM_W;
+  double2* const ring = reinterpret_cast<double2*>(gram_smem);
+  const int n_chunks = (n_basis + KC - 1) / KC;
+  const ptrdiff_t ld2 = 2 * (ptrdiff_t)ld;
+
+  const double2* src[SLOTS];
+  int dst[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int rr = warp + s * NW;
+    src[s] = B + ((size_t)min(rr, L - 1) * n_basis + half) * ld + w;   // padding rows repeat the last row
+    dst[s] = rr < PL ? (half * PL + rr) * GRAM_W + wl : -1;
+  }
+  int k_next = 0;
+  auto load_stage = [&](int chunk) {
+    double2* const st = ring + (size_t)(chunk % STAGES) * stage_elems;
+    if (k_next + KC <= n_basis) {
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s)
+        if (dst[s] >= 0) {
+          const double2* q = src[s];
+#pragma unroll
+          for (int m = 0; m < KC / 2; ++m, q += ld2)
+            cp_async16(st + dst[s] + (size_t)(2 * m * PL) * GRAM_W, q);
+        }
+    } else {   // tail stage: repeats the last basis element (never summed)
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s)
+        if (dst[s] >= 0) {
+#pragma unroll
+          for (int m = 0; m < KC / 2; ++m) {
+            const ptrdiff_t koff = min(k_next + 2 * m + half, n_basis - 1) - k_next - half;
+            cp_async16(st + dst[s] + (size_t)(2 * m * PL) * GRAM_W, src[s] + koff * (ptrdiff_t)ld);
+          }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) src[s] += (ptrdiff_t)KC * (ptrdiff_t)ld;
+    k_next += KC;
+  };
+
+  int ta, tb;
+  if (NTA == 3) {
+    ta = GRAM18_TILES[warp][0];
+    tb = GRAM18_TILES[warp][1];
+  } else {   // tiles (ta, tb >= 2 ta) in order
+    ta = 0;
+    tb = warp;
+    while (tb >= 2 * (NTA - ta)) {
+      tb -= 2 * (NTA - ta);
+      ++ta;
+    }
+    tb += 2 * ta;
+  }
+  const int kind = tb == 2 * ta ? GRAM_LEFT : tb == 2 * ta + 1 ? GRAM_RIGHT : GRAM_FULL;
+  double2 acc[6][3];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc[i][j] = make_double2(0.0, 0.0);
+
+  for (int c = 0; c < STAGES - 1; ++c) {
+    if (c < n_chunks) load_stage(c);
+    cp_async_commit();
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();   // chunk c has landed for everybody; everybody is done with chunk c - 1
+    if (c + STAGES - 1 < n_chunks) load_stage(c + STAGES - 1);
+    cp_async_commit();
+    const double2* const st = ring + (size_t)(c % STAGES) * stage_elems + (size_t)half * PL * GRAM_W + wl;
+    const double2* const sa = st + (size_t)(ta * 6) * GRAM_W;
+    const double2* const sb = st + (size_t)(tb * 3) * GRAM_W;
+    const int left = n_basis - c * KC - half;
+    const int n_k = left >= KC - 1 ? KC / 2 : (left + 1) / 2;
+    if (n_k == KC / 2) {
+      if (kind == GRAM_FULL) gram18_stage<GRAM_FULL, true, KC>(sa, sb, PL, n_k, acc);
+      else if (kind == GRAM_LEFT) gram18_stage<GRAM_LEFT, true, KC>(sa, sb, PL, n_k, acc);
+      else gram18_stage<GRAM_RIGHT, true, KC>(sa, sb, PL, n_k, acc);
+    } else {
+      if (kind == GRAM_FULL) gram18_stage<GRAM_FULL, false, KC>(sa, sb, PL, n_k, acc);
+      else if (kind == GRAM_LEFT) gram18_stage<GRAM_LEFT, false, KC>(sa, sb, PL, n_k, acc);
+      else gram18_stage<GRAM_RIGHT, false, KC>(sa, sb, PL, n_k, acc);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      acc[i][j].x += __shfl_xor_sync(0xffffffffu, acc[i][j].x, 16);
+      acc[i][j].y += __shfl_xor_sync(0xffffffffu, acc[i][j].y, 16);
+    }
+  if (w0 + wl >= n_omega) return;
+  auto f_index = [&](int l, int r) -> size_t {
+    const int g = l / n_nops, a = l % n_nops, h = r / n_nops, b = r % n_nops;
+    return ((((size_t)g * P + h) * n_nops + a) * n_nops + b) * ld + w;
+  };
+  // half-warp 0 writes the tile, half-warp 1 its mirror image
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int l = ta * 6 + i, r = tb * 3 + j;
+      if (l > r || r >= L) continue;
+      if (l == r) {
+        if (half == 0) F[f_index(l, l)] = make_double2(acc[i][j].x, 0.0);
+      } else if (half == 0) {
+        F[f_index(l, r)] = acc[i][j];
+      } else {
+        F[f_index(r, l)] = make_double2(acc[i][j].x, -acc[i][j].y);
+      }
+    }
+}
+
+template <int NTA>
+int launch_gram18(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega, size_t ld, const double* B,
+                  double* F) {
+  // 16 basis elements per stage, double buffered (72 KB per stage for 18 rows: enough bytes in flight per SM
+  // to cover the HBM latency; the per-stage bookkeeping and the block barrier are paid half as often)
+  constexpr int KC = 16, STAGES = 2;
+  const size_t smem = (size_t)STAGES * KC * 6 * NTA * GRAM_W * 16;
+  FFB_TRY((ffb_func_smem(ctx, ff_gram18_kernel<NTA, KC, STAGES>, smem)));
+  ff_gram18_kernel<NTA, KC, STAGES><<<ceil_div(n_omega, GRAM_W), NTA * (NTA + 1) * 32, smem, ctx->stream>>>(
+      P, n_nops, n_basis, n_omega, ld, reinterpret_cast<const double2*>(B), reinterpret_cast<double2*>(F));
   FFB_LAUNCHED(ctx);
   return FFB_OK;
 }
@@ -224,12 +449,12 @@ bool gram_eligible(int L, int n_basis) {
 int run_gram(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega, size_t ld, const double* B,
              double* F) {
   const int L = P * n_nops;
-  // one panel where the rows fit (upper-triangle tiles only: 3 / 6 / 10 / 6 warps), pairs of 16-row panels
-  // beyond (the 6 x 6 tile needs > 168 registers, which only a CTA of <= 8 warps gets)
+  // one panel: 4 x 4 tiles on or above the diagonal (3 / 6 / 10 warps) up to 16 rows -- HBM-bound there --,
+  // 6 x 3 tiles (12 warps) for 17 or 18 rows; pairs of 16-row panels beyond
   if (L <= 8) return launch_gram<4, 2, true>(ctx, P, n_nops, n_basis, n_omega, ld, B, F);
   if (L <= 12) return launch_gram<4, 3, true>(ctx, P, n_nops, n_basis, n_omega, ld, B, F);
   if (L <= 16) return launch_gram<4, 4, true>(ctx, P, n_nops, n_basis, n_omega, ld, B, F);
-  if (L <= 18) return launch_gram<6, 3, true>(ctx, P, n_nops, n_basis, n_omega, ld, B, F);
+  if (L <= 18) return launch_gram18<3>(ctx, P, n_nops, n_basis, n_omega, ld, B, F);
   return launch_gram<4, 4, false>(ctx, P, n_nops, n_basis, n_omega, ld, B, F);
 }
 
@@ -249,7 +474,8 @@ ff_generalized_kernel(int P, int n_nops, int n_basis, int n_omega, const double2
   const double2* Br = B + (size_t)r * n_basis * n_omega + w;
   for (int m = 0; m < n_basis; ++m) {
     const double2 y = Br[(size_t)m * n_omega];
-    dst[(size_t)m * n_omega] = make_double2(x.x * y.x + x.y * y.y, x.x * y.y - x.y * y.x);
+    dst[(size_t)m * n_omega] = make_double2(x.x * y.x + x.y * y.y,
+                                            __dsub_rn(__dmul_rn(x.x, y.y), __dmul_rn(x.y, y.x)));
   }
 }
 

@@ -156,10 +156,18 @@ def calculate_control_matrix_from_atomic(phases, control_matrix_atomic, propagat
     c_in, f_in = atomic_in.flags.c_contiguous, atomic_in.flags.f_contiguous
     atomic = _lib.as_c128(atomic_in)
     P, n_nops, n_basis, n_omega = atomic.shape
-    phases = _lib.as_c128(np.asarray(phases).reshape(P - 1, n_omega))
+    # the reference reads phases[g-1] and propagators_liouville[g-1] for g = 1 .. P-1 (numeric.py:691-701):
+    # arrays with more leading entries than P - 1 are legal, the rest is never looked at
+    phases = np.asarray(phases)
     Q = np.asarray(propagators_liouville)
+    if phases.ndim != 2 or phases.shape[0] < P - 1 or phases.shape[1] != n_omega:
+        raise ValueError(f'Expected phases of shape ({P - 1}, {n_omega}), not {phases.shape}')
+    if Q.ndim != 3 or Q.shape[0] < P - 1 or Q.shape[1:] != (n_basis, n_basis):
+        raise ValueError(f'Expected propagators_liouville of shape ({P - 1}, {n_basis}, {n_basis}), '
+                         f'not {Q.shape}')
+    phases = _lib.as_c128(phases[:P - 1])
     q_complex = np.iscomplexobj(Q)
-    Q = (_lib.as_c128(Q) if q_complex else _lib.as_f64(Q)).reshape(P - 1, n_basis, n_basis)
+    Q = _lib.as_c128(Q[:P - 1]) if q_complex else _lib.as_f64(Q[:P - 1])
     corr = which == 'correlations'
     out = _lib.empty((P, n_nops, n_basis, n_omega) if corr else (n_nops, n_basis, n_omega))
     ctx = _lib.context()

@@ -139,6 +139,11 @@ class PulseSequence:
     arrays.
     """
 
+    # A PulseSequence has __len__ / __getitem__ (slicing into segments), so np.array([pulse, ...]) would
+    # unpack it into single-segment pulses; the array interface declares it a 0-d object instead, as the
+    # reference does (``pulse_sequence.py:241-251``): np.array(list_of_pulses) is a 1-d object array.
+    __array_interface__ = {'shape': (), 'typestr': '|O', 'version': 3}
+
     def __new__(cls, *args, **kwargs):
         new = super().__new__(cls)
         stamp = new.__dict__['_stamp'] = [0]     # bumped by every attribute / cache change

@@ -16,7 +16,8 @@ from . import _lib
 __all__ = ['paulis', 'abs2', 'cexp', 'cexpm1', 'get_sample_frequencies', 'mdot', 'adot', 'integrate',
            'parse_optional_parameters', 'parse_spectrum', 'parse_operators',
            'get_indices_from_identifiers', 'is_sequence_like', 'hash_array_along_axis',
-           'all_array_equal', 'CalculationError', 'dot_HS', 'oper_equiv']
+           'all_array_equal', 'CalculationError', 'dot_HS', 'oper_equiv', 'tensor',
+           'remove_float_errors', 'progressbar', 'progressbar_range']
 
 #: Pauli matrices I, X, Y, Z (reference ``util.py:109-118``)
 paulis = np.array([[[1, 0], [0, 1]], [[0, 1], [1, 0]], [[0, -1j], [1j, 0]], [[1, 0], [0, -1]]],
@@ -115,7 +116,8 @@ def is_sequence_like(obj) -> bool:
 
 def parse_operators(opers, err_loc: str) -> ndarray:
     """Convert a sequence of operators to a (n, d, d) complex array (reference ``util.py:230-276``;
-    accepts ndarrays and anything exposing ``full()`` / ``to_array()`` / ``todense()``)."""
+    accepts ndarrays and anything exposing ``full()`` (QuTiP), ``to_array()``, ``todense()`` (sparse) or
+    ``data`` + ``dexp`` (qopt dense operators))."""
     parsed = []
     for oper in opers:
         if isinstance(oper, ndarray):
@@ -126,6 +128,8 @@ def parse_operators(opers, err_loc: str) -> ndarray:
             parsed.append(oper.to_array())
         elif hasattr(oper, 'todense'):
             parsed.append(oper.todense())
+        elif hasattr(oper, 'data') and hasattr(oper, 'dexp'):
+            parsed.append(oper.data)
         else:
             raise TypeError(f'Expected operators in {err_loc} to be NumPy arrays or QuTiP Qobjs!')
     parsed = np.asarray(parsed, dtype=complex)
@@ -223,3 +227,59 @@ def all_array_equal(it) -> bool:
 def progressbar_range(*args, show_progressbar: bool = False, **kwargs):
     """The engine computes all segments in one launch; the flag is accepted and ignored."""
     return range(*args)
+
+
+def progressbar(iterable, *args, **kwargs):
+    """The reference wraps loops in ``tqdm`` (``util.py:1112-1143``); here nothing loops on the host long
+    enough to need one, the iterable is returned unchanged."""
+    return iterable
+
+
+def tensor(*args, rank: int = 2, optimize=False) -> ndarray:
+    """Tensor (Kronecker) product over the last ``rank`` axes of the operands, broadcast over the leading
+    axes (same call signature and shape rules as the reference's ``util.tensor``, ``util.py:360-470``;
+    a 1-d operand of a rank-2 product is a row vector).  Host helper used to set up multi-qubit operators;
+    ``optimize`` is accepted for compatibility (the product is formed pairwise by broadcasting).
+    """
+    if not args:
+        raise TypeError('tensor() needs at least one operand')
+
+    def pair(a, b):
+        a_nd, b_nd = a.ndim, b.ndim
+        if a_nd < rank:
+            a = a.reshape((1,)*(rank - a_nd) + a.shape)
+        if b_nd < rank:
+            b = b.reshape((1,)*(rank - b_nd) + b.shape)
+        try:
+            lead = np.broadcast_shapes(a.shape[:-rank], b.shape[:-rank])
+        except ValueError:
+            raise ValueError(f'Incompatible shapes {a.shape} and {b.shape} for tensor product of rank '
+                             f'{rank}.') from None
+        ta, tb = a.shape[a.ndim - rank:], b.shape[b.ndim - rank:]
+        # a[..., i1, 1, i2, 1, ...] * b[..., 1, j1, 1, j2, ...] -> (..., i1 j1, i2 j2, ...)
+        a = np.broadcast_to(a, lead + ta).reshape(lead + tuple(x for n in ta for x in (n, 1)))
+        b = np.broadcast_to(b, lead + tb).reshape(lead + tuple(x for n in tb for x in (1, n)))
+        return (a*b).reshape(lead + tuple(m*n for m, n in zip(ta, tb)))
+
+    return functools.reduce(pair, (np.asanyarray(a) for a in args))
+
+
+def remove_float_errors(arr: ndarray, eps_scale=None) -> ndarray:
+    """Set entries (real and imaginary parts separately) that are below the dtype's machine precision
+    times ``eps_scale`` (default: the length of the last axis) to exactly zero, in place
+    (``util.py:909-938``).  Meant for arrays of norm ~ 1."""
+    arr = np.asanyarray(arr)
+    scale = eps_scale if eps_scale is not None else (arr.shape[-1] if arr.ndim else 1)
+    atol = np.finfo(arr.dtype).eps*scale
+    if np.iscomplexobj(arr):
+        if arr.ndim:
+            arr.real[np.abs(arr.real) <= atol] = 0
+            arr.imag[np.abs(arr.imag) <= atol] = 0
+        else:
+            arr = arr.dtype.type(complex(0 if abs(arr.real) <= atol else arr.real,
+                                         0 if abs(arr.imag) <= atol else arr.imag))
+    elif arr.ndim:
+        arr[np.abs(arr) <= atol] = 0
+    elif abs(arr) <= atol:
+        arr = arr.dtype.type(0)
+    return arr

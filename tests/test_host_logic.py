@@ -304,3 +304,100 @@ def test_concatenate_hamiltonians_randomized():
                 for row in set(range(len(ids))) - carried:
                     want = 0.0 if kind == 'c' else coeffs[row][0]
                     assert (coeffs[row, lo:hi] == want).all()
+
+
+def test_util_tensor_and_float_cleanup():
+    """util.tensor: Kronecker product over the last `rank` axes with broadcasting over the leading ones
+    (shape rules of the reference's docstring, util.py:367-378); util.remove_float_errors."""
+    rng = np.random.default_rng(5)
+    Z = np.diag([1, -1])
+    assert np.array_equal(util.tensor(Z, Z), np.kron(Z, Z))
+    A, B, C = (rng.standard_normal((2, 2)) + 1j*rng.standard_normal((2, 2)) for _ in range(3))
+    assert np.allclose(util.tensor(A, B, C), np.kron(np.kron(A, B), C))
+    assert np.array_equal(util.tensor(np.arange(2), np.arange(2, 5), rank=1), [0, 0, 0, 2, 3, 4])
+    shapes = [(((3, 4, 5, 2, 2), (3, 4, 5, 3, 3), 2), (3, 4, 5, 6, 6)),
+              (((7, 2, 3), (7, 4, 5), 2), (7, 8, 15)),
+              (((2, 3), (6, 4, 5), 2), (6, 8, 15)),
+              (((1, 3), (6, 1, 4), 2), (6, 1, 12)),
+              (((5, 2), (5, 3), 1), (5, 6)),
+              (((3, 1, 2), (2, 2, 2), 3), (6, 2, 4))]
+    for (sa, sb, rank), want in shapes:
+        a, b = rng.standard_normal(sa), rng.standard_normal(sb)
+        out = util.tensor(a, b, rank=rank)
+        assert out.shape == want
+    stack = rng.standard_normal((4, 10, 3, 2))
+    assert util.tensor(*stack, rank=1).shape == (10, 3, 16)
+    assert util.tensor(*stack, rank=2).shape == (10, 81, 16)
+    batch = util.tensor(stack[0], stack[1])
+    for i in range(10):
+        assert np.allclose(batch[i], np.kron(stack[0][i], stack[1][i]))
+    with pytest.raises(ValueError, match='Incompatible shapes'):
+        util.tensor(rng.standard_normal((3, 1, 2)), rng.standard_normal((2, 2, 2)))
+    with pytest.raises(TypeError):
+        util.tensor()
+    x = np.eye(3) + 1e-17*rng.standard_normal((3, 3))
+    assert np.array_equal(util.remove_float_errors(x), np.eye(3))
+    y = (1 + 1e-18j)*np.eye(2, dtype=complex)
+    assert np.array_equal(util.remove_float_errors(y), np.eye(2))
+    assert list(util.progressbar(range(3))) == [0, 1, 2]
+
+
+def test_basis_from_partial():
+    """Basis.from_partial (reference basis.py:492-620): given elements kept (normalised, in order), the
+    result complete, orthonormal and Hermitian, identity first for traceless bases, labels, errors."""
+    rng = np.random.default_rng(11)
+    for d in (2, 3, 4):
+        ggm = np.asarray(ff.Basis.ggm(d))
+        for n in (1, d, d*d - 1):
+            q, _ = np.linalg.qr(rng.standard_normal((d*d - 1, d*d - 1)))
+            part = 1.7*np.einsum('ij,jkl->ikl', q[:n], ggm[1:])          # traceless, orthogonal, norm 1.7
+            full = ff.Basis.from_partial(part)
+            assert full.shape == (d*d, d, d) and full.btype == 'From partial'
+            assert full.isherm and full.isorthonorm and full.iscomplete and full.istraceless
+            assert np.allclose(np.asarray(full)[0], np.eye(d)/np.sqrt(d))
+            assert np.allclose(np.asarray(full)[1:n + 1], part/1.7, atol=1e-13)
+        # not traceless: elements stay in front, no identity is inserted
+        part = np.zeros((2, d, d))
+        part[0, 0, 0] = part[1, 1, 1] = 1
+        full = ff.Basis.from_partial(part)
+        assert not full.istraceless and full.isorthonorm and full.iscomplete
+        assert np.allclose(np.asarray(full)[:2], part)
+        with pytest.raises(ValueError, match='traceless'):
+            ff.Basis.from_partial(part, traceless=True)
+    X, Y, Z = util.paulis[1:]
+    named = ff.Basis.from_partial([X, Y], labels=['X', 'Y'])
+    assert list(named.labels) == ['X', 'Y', '$C_{2}$', '$C_{3}$']     # as the reference labels them
+    with pytest.raises(ValueError, match='not orthogonal'):
+        ff.Basis.from_partial([X, X + Y])
+    with pytest.raises(ValueError, match='labels'):
+        ff.Basis.from_partial([X, Y], labels=['a'])
+    assert np.array_equal(ff.Basis.pauli(1).four_element_traces.todense(),
+                          np.asarray(ff.Basis.pauli(1).four_element_traces))
+
+
+def test_choi_and_complete_positivity():
+    """superoperator.liouville_to_choi / liouville_is_CP / liouville_is_cCP (reference
+    superoperator.py:87-256) on channels with known answers: a unitary channel is CP with Choi
+    eigenvalues (d, 0, ...), minus the identity map is not; a Lindblad-type generator is cCP but not CP."""
+    from filter_functions_b200 import superoperator as so
+    rng = np.random.default_rng(2)
+    for d in (2, 3):
+        basis = ff.Basis.ggm(d)
+        C = np.asarray(basis)
+        H = rng.standard_normal((d, d)) + 1j*rng.standard_normal((d, d))
+        w, v = np.linalg.eigh(H + H.conj().T)
+        U = (v*np.exp(-1j*w)) @ v.conj().T
+        L = np.einsum('iab,bc,jcd,da->ij', C, U, C, U.conj().T).real     # tr(C_i U C_j U^dagger)
+        choi = so.liouville_to_choi(L, basis)
+        direct = sum(L[i, j]*np.kron(C[j].T, C[i]) for i in range(d*d) for j in range(d*d))
+        assert np.allclose(choi, direct)
+        ok, (vals, _) = so.liouville_is_CP(L, basis, return_eig=True)
+        assert ok and np.allclose(sorted(vals)[-1], d) and np.allclose(sorted(vals)[:-1], 0, atol=1e-12)
+        assert not so.liouville_is_CP(-np.eye(d*d), basis)
+        # dephasing generator  K = sum_k (L_k (x) L_k^* - ...) in Liouville form:  D[rho] = Z rho Z - rho
+        Zd = np.diag(np.arange(d) - (d - 1)/2)
+        gen = np.einsum('iab,bc,jcd,da->ij', C, Zd, C, Zd).real - 0.5*np.einsum(
+            'iab,jbc,ca->ij', C, C, Zd @ Zd).real - 0.5*np.einsum('iab,bc,jca->ij', C, Zd @ Zd, C).real
+        assert so.liouville_is_cCP(gen, basis) and not so.liouville_is_CP(gen, basis)
+        stack = np.stack([L, -np.eye(d*d)])
+        assert list(so.liouville_is_CP(stack, basis)) == [True, False]
