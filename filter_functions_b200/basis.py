@@ -164,6 +164,11 @@ class Basis(np.ndarray):
         arr.imag[np.abs(arr.imag) <= atol] = 0
         self._invalidate_cached_properties()
 
+    def _print_checks(self) -> None:
+        """Debug aid of the reference's Basis (``basis.py:234-238``): the predicates, one per line."""
+        for name in ('isherm', 'istraceless', 'iscomplete', 'isorthonorm'):
+            print(f'{name} :\t {getattr(self, name)}')
+
     def _invalidate_cached_properties(self) -> None:
         """Forget the predicates computed for the previous contents (in-place changes)."""
         for name in ('isherm', 'isnorm', 'isorthogonal', 'isorthonorm', 'istraceless', 'iscomplete',

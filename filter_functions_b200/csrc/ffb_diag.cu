@@ -49,8 +49,11 @@ diag_kernel(int G, int d, int n_cops, const double* __restrict__ c_opers,
     if (c_coeffs != nullptr) {
       for (int i = 0; i < n_cops; ++i) {
         const double a = c_coeffs[(size_t)i * G + g];
-        h.re += a * c_opers[2 * ((size_t)i * dd + e)];
-        h.im += a * c_opers[2 * ((size_t)i * dd + e) + 1];
+        // rounded product, rounded sum, operators in order: the bits of np.einsum('ijk,il->ljk') in
+        // PulseSequence.diagonalize (pulse_sequence.py:582), so that H -- and everything derived from it --
+        // is the same whether the pulse or the caller formed the Hamiltonian
+        h.re = __dadd_rn(h.re, __dmul_rn(a, c_opers[2 * ((size_t)i * dd + e)]));
+        h.im = __dadd_rn(h.im, __dmul_rn(a, c_opers[2 * ((size_t)i * dd + e) + 1]));
       }
     } else {
       h.re = c_opers[2 * ((size_t)g * dd + e)];
@@ -214,8 +217,9 @@ __device__ __forceinline__ void diag_small_one(int G, int g, int n_cops,
       if (c_coeffs != nullptr) {
         for (int i = 0; i < n_cops; ++i) {
           const double a = c_coeffs[(size_t)i * G + g];
-          h.re += a * c_opers[2 * ((size_t)i * DD + r * D + c)];
-          h.im += a * c_opers[2 * ((size_t)i * DD + r * D + c) + 1];
+          // same bits as np.einsum('ijk,il->ljk') (see diag_kernel)
+          h.re = __dadd_rn(h.re, __dmul_rn(a, c_opers[2 * ((size_t)i * DD + r * D + c)]));
+          h.im = __dadd_rn(h.im, __dmul_rn(a, c_opers[2 * ((size_t)i * DD + r * D + c) + 1]));
         }
       } else {
         h.re = c_opers[2 * ((size_t)g * DD + r * D + c)];

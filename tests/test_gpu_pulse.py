@@ -553,3 +553,33 @@ def test_cexp_and_cexpm1(engine):
         out2 = np.empty(x.shape, dtype=complex)
         assert fn(x, out=out2) is out2
         np.testing.assert_allclose(out2, want, rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize('d,n_dt', [(2, 40), (3, 25), (4, 60), (5, 17), (9, 30)])
+def test_pulse_route_and_function_route_give_identical_bits(engine, d, n_dt):
+    """The reference's tests compare ``pulse.get_control_matrix(omega)`` with
+    ``numeric.calculate_control_matrix_from_scratch`` fed by ``numeric.diagonalize(np.einsum(...))`` at
+    rtol 1e-7 WITHOUT an absolute tolerance (tests/test_core.py:685-738 of the reference), which holds
+    there because both routes run the same NumPy code on the same Hamiltonian bits -- entries that are
+    structurally zero (identity basis element, traceless noise operators) are pure rounding noise and only
+    compare equal if the noise is the same.  Here the Hamiltonian the pulse forms on the device has the
+    bits of the reference's ``np.einsum('ijk,il->ljk', c_opers, c_coeffs)``, and everything downstream is
+    deterministic, so both routes must agree bit for bit."""
+    ff = engine
+    rng = np.random.default_rng(100*d + n_dt)
+    pulse = rand_pulse_sequence(ff, rng, d, n_dt, 4, 6)
+    H = np.einsum('il,ijk->ljk', pulse.c_coeffs, pulse.c_opers)
+    ev, V, Q = ff.numeric.diagonalize(H, pulse.dt)
+    omega = ff.util.get_sample_frequencies(pulse, n_samples=100)
+    B_pulse = pulse.get_control_matrix(omega)
+    assert np.array_equal(pulse.eigvals, ev)
+    assert np.array_equal(pulse.eigvecs, V)
+    assert np.array_equal(pulse.propagators, Q)
+    B_func = ff.numeric.calculate_control_matrix_from_scratch(
+        eigvals=ev, eigvecs=V, propagators=pulse.propagators, omega=omega, basis=pulse.basis,
+        n_opers=pulse.n_opers, n_coeffs=pulse.n_coeffs, dt=pulse.dt)
+    assert np.array_equal(B_pulse, B_func)
+    F = pulse.get_filter_function(omega)
+    assert np.array_equal(F, ff.numeric.calculate_filter_function(B_func))
+    assert np.array_equal(F, F.conj().swapaxes(0, 1))            # exactly Hermitian ...
+    assert np.all(F[np.arange(6), np.arange(6)].imag == 0)       # ... with an exactly real diagonal
