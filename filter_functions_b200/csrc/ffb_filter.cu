@@ -599,7 +599,7 @@ int ffbi_filter_function(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_ome
               "filter function: bad shape (P=%d, n_nops=%d, n_basis=%d, n_omega=%d)", P, n_nops,
               n_basis, n_omega);
   const int L = P * n_nops;
-  FFB_REQUIRE(ctx, L <= 65535 && (long long)L * n_basis <= 65535 * 1LL,
+  FFB_REQUIRE(ctx, L <= 65535 && (!generalized || (long long)L * n_basis <= 65535 * 1LL),
               "filter function: too many rows (%d x %d)", L, n_basis);
   const int wt = ceil_div(n_omega, 256);
   if (!generalized && gram_eligible(L, n_basis))

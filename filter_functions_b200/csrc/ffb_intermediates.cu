@@ -15,6 +15,8 @@
 // and the control matrix as the running sum of the steps, as the reference accumulates it.
 // These are store-bound streaming kernels (omega fastest everywhere except first_order_integral, whose
 // reference layout is (G, n_omega, d, d)).
+#include <algorithm>
+
 #include "ffb_common.cuh"
 
 namespace {
@@ -86,12 +88,12 @@ transform_raw_kernel(int G, int d, int n_nops, int n_basis, const double* __rest
 
 // phase_factors[g,w] and first_order_integral[g,w,m,n]; grid (omega tiles, G)
 __global__ void __launch_bounds__(128)
-integral_kernel(int d, int n_omega, const double* __restrict__ eigvals,
+integral_kernel(int g0, int d, int n_omega, const double* __restrict__ eigvals,
                 const double* __restrict__ omega, const double* __restrict__ dt,
                 const double* __restrict__ t, double2* __restrict__ phase_factors,
                 double2* __restrict__ integral) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  const int g = blockIdx.y;
+  const int g = g0 + blockIdx.y;   // the segment axis is walked in slices of <= 65535 (grid limit)
   if (w >= n_omega) return;
   const double om = omega[w], dtg = dt[g];
   double sn, cs;
@@ -122,12 +124,12 @@ integral_kernel(int d, int n_omega, const double* __restrict__ eigvals,
 
 // control_matrix_step[g,j,k,w]; grid (omega tiles, n_nops * n_basis, G)
 __global__ void __launch_bounds__(128)
-step_kernel(int G, int d, int n_nops, int n_basis, int n_omega,
+step_kernel(int g0, int G, int d, int n_nops, int n_basis, int n_omega,
             const double2* __restrict__ n_opers_transformed,
             const double2* __restrict__ basis_transformed, const double2* __restrict__ phase_factors,
             const double2* __restrict__ integral, double2* __restrict__ step) {
   extern __shared__ double2 coef[];  // M[m][n] = Bbar_j[m][n] * Cbar_k[n][m]
-  const int g = blockIdx.z;
+  const int g = g0 + blockIdx.z;
   const int j = blockIdx.y / n_basis, k = blockIdx.y % n_basis;
   const int dd = d * d;
   const double2* Bb = n_opers_transformed + ((size_t)j * G + g) * dd;
@@ -182,9 +184,8 @@ int ffbi_control_matrix_intermediates(ffb_ctx* ctx, int G, int d, int n_nops, in
   FFB_CHECK_DIM(ctx, d);
   FFB_REQUIRE(ctx, G >= 1 && d >= 1 && d <= 32 && n_nops >= 1 && n_basis >= 1 && n_omega >= 1,
               "control matrix intermediates: bad shape");
-  FFB_REQUIRE(ctx, G <= 65535 && (long long)n_nops * n_basis <= 65535,
-              "control matrix intermediates: G=%d or n_nops*n_basis=%d exceeds 65535", G,
-              n_nops * n_basis);
+  FFB_REQUIRE(ctx, (long long)n_nops * n_basis <= 65535,
+              "control matrix intermediates: n_nops*n_basis=%d exceeds 65535", n_nops * n_basis);
   const int dd = d * d;
   {
     const size_t smem = (size_t)6 * dd * sizeof(double);
@@ -195,17 +196,19 @@ int ffbi_control_matrix_intermediates(ffb_ctx* ctx, int G, int d, int n_nops, in
                                                         n_opers_transformed, basis_transformed);
     FFB_LAUNCHED(ctx);
   }
-  {
-    dim3 grid(ceil_div(n_omega, 128), G);
-    integral_kernel<<<grid, 128, 0, ctx->stream>>>(d, n_omega, eigvals, omega, dt, t,
+  for (int g0 = 0; g0 < G; g0 += 65535) {
+    const int gn = std::min(65535, G - g0);
+    dim3 grid(ceil_div(n_omega, 128), gn);
+    integral_kernel<<<grid, 128, 0, ctx->stream>>>(g0, d, n_omega, eigvals, omega, dt, t,
                                                    reinterpret_cast<double2*>(phase_factors),
                                                    reinterpret_cast<double2*>(first_order_integral));
     FFB_LAUNCHED(ctx);
   }
-  {
-    dim3 grid(ceil_div(n_omega, 128), n_nops * n_basis, G);
+  for (int g0 = 0; g0 < G; g0 += 65535) {
+    const int gn = std::min(65535, G - g0);
+    dim3 grid(ceil_div(n_omega, 128), n_nops * n_basis, gn);
     step_kernel<<<grid, 128, (size_t)dd * 16, ctx->stream>>>(
-        G, d, n_nops, n_basis, n_omega, reinterpret_cast<const double2*>(n_opers_transformed),
+        g0, G, d, n_nops, n_basis, n_omega, reinterpret_cast<const double2*>(n_opers_transformed),
         reinterpret_cast<const double2*>(basis_transformed),
         reinterpret_cast<const double2*>(phase_factors),
         reinterpret_cast<const double2*>(first_order_integral), reinterpret_cast<double2*>(step));

@@ -417,3 +417,27 @@ def test_control_matrix_intermediates(engine, d, G, n_nops, btype, n_omega):
     res, _ = engine.numeric.calculate_control_matrix_from_scratch(
         ev, V, Q, omega, basis, n_opers, n_coeffs, dt, cache_intermediates=True, out=out)
     assert res is out and nerr(out, B) == 0
+
+
+def test_control_matrix_intermediates_long_pulse(engine):
+    """More segments than one grid dimension holds (G > 65535): the materialising kernels walk the
+    segment axis in slices; checked against the fused kernel (whole result) and the oracle (tail slice
+    of the per-segment arrays, which only exists if the second slice was written)."""
+    d, G, n_nops, n_omega = 2, 66000, 1, 3
+    rng = np.random.default_rng(7)
+    c_opers, c_coeffs, n_opers, n_coeffs, dt, H = _setup(rng, d, G, n_nops)
+    ev, V, Q = engine.numeric.diagonalize(H, dt)
+    basis = oracle.pauli_basis(1)
+    omega = np.array([0.0, 0.37, 2.1])
+    B, inter = engine.numeric.calculate_control_matrix_from_scratch(
+        ev, V, Q, omega, basis, n_opers, n_coeffs, dt, cache_intermediates=True)
+    fused = engine.numeric.calculate_control_matrix_from_scratch(ev, V, Q, omega, basis, n_opers,
+                                                                 n_coeffs, dt)
+    assert nerr(B, fused) < TOL
+    assert inter['control_matrix_step'].shape == (G, n_nops, 4, n_omega)
+    tail = slice(G - 40, G)
+    t = np.concatenate(([0.0], dt.cumsum()))
+    _, ref = oracle.control_matrix_intermediates(ev[tail], V[tail], Q[G - 40:], omega, basis, n_opers,
+                                                 n_coeffs[:, tail], dt[tail], t=t[G - 40:])
+    for key in ('phase_factors', 'first_order_integral', 'control_matrix_step'):
+        assert nerr(inter[key][tail], ref[key]) < TOL, key
