@@ -267,19 +267,20 @@ int launch_gram(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega, size_
 // and the warp -> tile table spreads the three kinds evenly over the schedulers (warp % 4).
 enum { GRAM_FULL = 0, GRAM_LEFT = 1, GRAM_RIGHT = 2 };
 
-template <int KIND, bool WHOLE, int KC>
+template <int KIND, bool WHOLE, int KC, int GW>
 __device__ __forceinline__ void gram18_stage(const double2* __restrict__ sa, const double2* __restrict__ sb,
                                              int rows_per_k, int n_k, double2 (&acc)[6][3]) {
-  // WHOLE: all KC / 2 basis elements of the stage exist -- no guards, so that the loads of element
+  // WHOLE: all KC / NPH basis elements of the stage exist -- no guards, so that the loads of element
   // m + 1 are scheduled under the multiply-adds of element m
 #pragma unroll
-  for (int m = 0; m < KC / 2; ++m) {
+  constexpr int NPH = 32 / GW;
+  for (int m = 0; m < KC / NPH; ++m) {
     if (WHOLE || m < n_k) {
       double2 x[6], y[3];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) x[i] = sa[(size_t)(2 * m * rows_per_k + i) * GRAM_W];
+      for (int i = 0; i < 6; ++i) x[i] = sa[(size_t)(NPH * m * rows_per_k + i) * GW];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) y[j] = sb[(size_t)(2 * m * rows_per_k + j) * GRAM_W];
+      for (int j = 0; j < 3; ++j) y[j] = sb[(size_t)(NPH * m * rows_per_k + j) * GW];
 #pragma unroll
       for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -299,7 +300,7 @@ __device__ __forceinline__ void gram18_stage(const double2* __restrict__ sa, con
 __constant__ unsigned char GRAM18_TILES[12][2] = {{0, 2}, {0, 4}, {1, 4}, {1, 5}, {0, 3}, {0, 5},
                                                   {0, 1}, {1, 3}, {0, 0}, {1, 2}, {2, 4}, {2, 5}};
 
-template <int NTA, int KC, int STAGES>
+template <int NTA, int KC, int STAGES, int GW>
 __global__ void __launch_bounds__(NTA * (NTA + 1) * 32, 1)
 ff_gram18_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, const double2* __restrict__ B,
                  double2* __restrict__ F) {
@@ -309,13 +310,14 @@ ff_gram18_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, const d
   extern __shared__ __align__(16) unsigned char gram_smem[];
   const int L = P * n_nops;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wl = lane & (GRAM_W - 1), half = lane >> 4;
-  const int w0 = blockIdx.x * GRAM_W;
+  constexpr int NPH = 32 / GW;               // phases of the basis sum inside a warp (GW frequencies each)
+  const int wl = lane & (GW - 1), half = lane / GW;
+  const int w0 = blockIdx.x * GW;
   const int w = min(w0 + wl, n_omega - 1);
-  constexpr size_t stage_elems = (size_t)KC * PL * GRAM_W;
+  constexpr size_t stage_elems = (size_t)KC * PL * GW;
   double2* const ring = reinterpret_cast<double2*>(gram_smem);
   const int n_chunks = (n_basis + KC - 1) / KC;
-  const ptrdiff_t ld2 = 2 * (ptrdiff_t)ld;
+  const ptrdiff_t ld2 = NPH * (ptrdiff_t)ld;
 
   const double2* src[SLOTS];
   int dst[SLOTS];
@@ -323,7 +325,7 @@ ff_gram18_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, const d
   for (int s = 0; s < SLOTS; ++s) {
     const int rr = warp + s * NW;
     src[s] = B + ((size_t)min(rr, L - 1) * n_basis + half) * ld + w;   // padding rows repeat the last row
-    dst[s] = rr < PL ? (half * PL + rr) * GRAM_W + wl : -1;
+    dst[s] = rr < PL ? (half * PL + rr) * GW + wl : -1;
   }
   int k_next = 0;
   auto load_stage = [&](int chunk) {
@@ -334,17 +336,17 @@ ff_gram18_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, const d
         if (dst[s] >= 0) {
           const double2* q = src[s];
 #pragma unroll
-          for (int m = 0; m < KC / 2; ++m, q += ld2)
-            cp_async16(st + dst[s] + (size_t)(2 * m * PL) * GRAM_W, q);
+          for (int m = 0; m < KC / NPH; ++m, q += ld2)
+            cp_async16(st + dst[s] + (size_t)(NPH * m * PL) * GW, q);
         }
     } else {   // tail stage: repeats the last basis element (never summed)
 #pragma unroll
       for (int s = 0; s < SLOTS; ++s)
         if (dst[s] >= 0) {
 #pragma unroll
-          for (int m = 0; m < KC / 2; ++m) {
-            const ptrdiff_t koff = min(k_next + 2 * m + half, n_basis - 1) - k_next - half;
-            cp_async16(st + dst[s] + (size_t)(2 * m * PL) * GRAM_W, src[s] + koff * (ptrdiff_t)ld);
+          for (int m = 0; m < KC / NPH; ++m) {
+            const ptrdiff_t koff = min(k_next + NPH * m + half, n_basis - 1) - k_next - half;
+            cp_async16(st + dst[s] + (size_t)(NPH * m * PL) * GW, src[s] + koff * (ptrdiff_t)ld);
           }
         }
     }
@@ -382,34 +384,37 @@ ff_gram18_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, const d
     __syncthreads();   // chunk c has landed for everybody; everybody is done with chunk c - 1
     if (c + STAGES - 1 < n_chunks) load_stage(c + STAGES - 1);
     cp_async_commit();
-    const double2* const st = ring + (size_t)(c % STAGES) * stage_elems + (size_t)half * PL * GRAM_W + wl;
-    const double2* const sa = st + (size_t)(ta * 6) * GRAM_W;
-    const double2* const sb = st + (size_t)(tb * 3) * GRAM_W;
-    const int left = n_basis - c * KC - half;
-    const int n_k = left >= KC - 1 ? KC / 2 : (left + 1) / 2;
-    if (n_k == KC / 2) {
-      if (kind == GRAM_FULL) gram18_stage<GRAM_FULL, true, KC>(sa, sb, PL, n_k, acc);
-      else if (kind == GRAM_LEFT) gram18_stage<GRAM_LEFT, true, KC>(sa, sb, PL, n_k, acc);
-      else gram18_stage<GRAM_RIGHT, true, KC>(sa, sb, PL, n_k, acc);
+    const double2* const st = ring + (size_t)(c % STAGES) * stage_elems + (size_t)half * PL * GW + wl;
+    const double2* const sa = st + (size_t)(ta * 6) * GW;
+    const double2* const sb = st + (size_t)(tb * 3) * GW;
+    const int left = n_basis - c * KC - half;   // elements kk = NPH m + half of this chunk that exist
+    const int n_k = left >= KC - NPH + 1 ? KC / NPH : max(0, (left + NPH - 1) / NPH);
+    if (n_k == KC / NPH) {
+      if (kind == GRAM_FULL) gram18_stage<GRAM_FULL, true, KC, GW>(sa, sb, PL, n_k, acc);
+      else if (kind == GRAM_LEFT) gram18_stage<GRAM_LEFT, true, KC, GW>(sa, sb, PL, n_k, acc);
+      else gram18_stage<GRAM_RIGHT, true, KC, GW>(sa, sb, PL, n_k, acc);
     } else {
-      if (kind == GRAM_FULL) gram18_stage<GRAM_FULL, false, KC>(sa, sb, PL, n_k, acc);
-      else if (kind == GRAM_LEFT) gram18_stage<GRAM_LEFT, false, KC>(sa, sb, PL, n_k, acc);
-      else gram18_stage<GRAM_RIGHT, false, KC>(sa, sb, PL, n_k, acc);
+      if (kind == GRAM_FULL) gram18_stage<GRAM_FULL, false, KC, GW>(sa, sb, PL, n_k, acc);
+      else if (kind == GRAM_LEFT) gram18_stage<GRAM_LEFT, false, KC, GW>(sa, sb, PL, n_k, acc);
+      else gram18_stage<GRAM_RIGHT, false, KC, GW>(sa, sb, PL, n_k, acc);
     }
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      acc[i][j].x += __shfl_xor_sync(0xffffffffu, acc[i][j].x, 16);
-      acc[i][j].y += __shfl_xor_sync(0xffffffffu, acc[i][j].y, 16);
+#pragma unroll
+      for (int off = 16; off >= GW; off >>= 1) {   // the NPH partial sums, in a fixed order
+        acc[i][j].x += __shfl_xor_sync(0xffffffffu, acc[i][j].x, off);
+        acc[i][j].y += __shfl_xor_sync(0xffffffffu, acc[i][j].y, off);
+      }
     }
   if (w0 + wl >= n_omega) return;
   auto f_index = [&](int l, int r) -> size_t {
     const int g = l / n_nops, a = l % n_nops, h = r / n_nops, b = r % n_nops;
     return ((((size_t)g * P + h) * n_nops + a) * n_nops + b) * ld + w;
   };
-  // half-warp 0 writes the tile, half-warp 1 its mirror image
+  // phase 0 writes the tile, phase 1 its mirror image
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -420,7 +425,7 @@ ff_gram18_kernel(int P, int n_nops, int n_basis, int n_omega, size_t ld, const d
         if (half == 0) F[f_index(l, l)] = make_double2(acc[i][j].x, 0.0);
       } else if (half == 0) {
         F[f_index(l, r)] = acc[i][j];
-      } else {
+      } else if (half == 1) {
         F[f_index(r, l)] = make_double2(acc[i][j].x, -acc[i][j].y);
       }
     }
@@ -431,10 +436,12 @@ int launch_gram18(ffb_ctx* ctx, int P, int n_nops, int n_basis, int n_omega, siz
                   double* F) {
   // 16 basis elements per stage, double buffered (72 KB per stage for 18 rows: enough bytes in flight per SM
   // to cover the HBM latency; the per-stage bookkeeping and the block barrier are paid half as often)
-  constexpr int KC = 16, STAGES = 2;
-  const size_t smem = (size_t)STAGES * KC * 6 * NTA * GRAM_W * 16;
-  FFB_TRY((ffb_func_smem(ctx, ff_gram18_kernel<NTA, KC, STAGES>, smem)));
-  ff_gram18_kernel<NTA, KC, STAGES><<<ceil_div(n_omega, GRAM_W), NTA * (NTA + 1) * 32, smem, ctx->stream>>>(
+  // (8 frequencies per CTA -- four quarter-warps sharing the basis sum, 8.4 waves instead of 4.2 -- was
+  // measured slower: 0.283 vs 0.251 ms on config 5; the per-CTA prologue / epilogue is paid twice as often)
+  constexpr int GW = GRAM_W, KC = 16, STAGES = 2;
+  const size_t smem = (size_t)STAGES * KC * 6 * NTA * GW * 16;
+  FFB_TRY((ffb_func_smem(ctx, ff_gram18_kernel<NTA, KC, STAGES, GW>, smem)));
+  ff_gram18_kernel<NTA, KC, STAGES, GW><<<ceil_div(n_omega, GW), NTA * (NTA + 1) * 32, smem, ctx->stream>>>(
       P, n_nops, n_basis, n_omega, ld, reinterpret_cast<const double2*>(B), reinterpret_cast<double2*>(F));
   FFB_LAUNCHED(ctx);
   return FFB_OK;
