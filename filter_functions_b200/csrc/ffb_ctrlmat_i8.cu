@@ -24,9 +24,11 @@
 //               columns, per instruction where the target levels are adjacent: 9 instructions per K step),
 //     K       = 2 segments x 16 entries [diag, S_0, D_0, ..., S_5, D_5, 0, 0, 0],
 //     D       = level t = i + j at TMEM columns 96 (t - 4) .. (480 of the 512 columns).
-//   8 generator warps (thread = one frequency x one segment of the stage) -> P digit tiles in shared memory;
+//   12 generator warps (thread = one frequency x one segment of the stage; <= 128 registers, the digits of a
+//     value are extracted as soon as it exists) -> P digit tiles in shared memory;
 //   1 thread streams the coefficient digit tiles + per-segment constants with cp.async.bulk (mbarrier tx);
-//   1 thread issues the MMAs and commits them to the stage's "empty" barrier; 2-stage ring of 4 segments.
+//   1 thread issues the MMAs and commits them to the stage's "empty" barrier; 2-stage ring of 6 segments
+//     (3 K steps, 27 MMAs per stage; 106 KB per stage).
 //   Epilogue: TMEM -> registers (tcgen05.ld), Horner over the 5 levels in FP64, scale, split-K partial.
 #include <algorithm>
 #include <cstdlib>
@@ -38,9 +40,10 @@ namespace {
 constexpr int I8_ROWS = 96;      // coefficient rows per CTA (N of the MMA; fewer rows are zero padded)
 constexpr int I8_W = 64;         // frequencies per CTA: M = 128 = (re | im) x 64
 constexpr int I8_D = 5;          // digits per operand
-constexpr int I8_SEGS = 4;       // segments per stage = 2 K steps of 32
+constexpr int I8_SEGS = 6;       // segments per stage = 3 K steps of 32
+constexpr int I8_KS = I8_SEGS / 2;
 constexpr int I8_STAGES = 2;
-constexpr int I8_GEN_WARPS = 8;
+constexpr int I8_GEN_WARPS = 2 * I8_SEGS;   // thread = (frequency, segment of the stage): 64 x I8_SEGS items
 constexpr int I8_THREADS = I8_GEN_WARPS * 32 + 64;  // + producer warp + MMA warp
 constexpr int NP = 6;            // level pairs of d = 4
 constexpr int I8_CONSTS = 2 + 3 * NP;               // per segment: t, dt, Omega[6], cos[6], sin[6]
@@ -48,10 +51,10 @@ constexpr int P_PLANE = 128 * 32;                   // bytes of one digit plane 
 constexpr int P_KSTEP = I8_D * P_PLANE;
 constexpr int C_KSTEP = I8_D * I8_ROWS * 32;        // all five coefficient planes: one 480-row tile
 constexpr int C_LBO = I8_D * I8_ROWS * 16;          // 7680: between the two 16-byte K chunks
-constexpr int STAGE_P = 2 * P_KSTEP;                                 // 40960
-constexpr int STAGE_C = 2 * C_KSTEP + I8_SEGS * I8_CONSTS * 8;      // 30720 + 640
+constexpr int STAGE_P = I8_KS * P_KSTEP;                                 // 61440
+constexpr int STAGE_C = I8_KS * C_KSTEP + I8_SEGS * I8_CONSTS * 8;      // 46080 + 960
 constexpr int STAGE_BYTES = STAGE_P + STAGE_C;
-constexpr int I8_MAX_CHUNK_STAGES = 384;  // 1536 segments: 5 pairs x 24576 K entries x 2^14 < 2^31
+constexpr int I8_MAX_CHUNK_STAGES = 1536 / I8_SEGS;  // 1536 segments: 5 pairs x 24576 K entries x 2^14 < 2^31
 constexpr double I8_MAGIC = 6755399441055744.0 + 551911719040.0;  // 1.5 2^52 + sum_i 128 256^i
 
 // ---- math helpers (same formulas and constants as ffb_ctrlmat.cu) ------------------------------------
@@ -236,9 +239,9 @@ __device__ __forceinline__ void to_digits(double x, double scale, unsigned& lo, 
   hi = (unsigned)__double2hiint(y);
 }
 
-// Stream layout per stage of 4 segments:  [K step 0 | K step 1 | consts],  a K step being the 480-row tile
+// Stream layout per stage of I8_SEGS segments:  [K step 0 | K step 1 | K step 2 | consts],  a K step being the 480-row tile
 // [chunk cc = segment within the step][60 row groups][8 rows][16 bytes = kappa 0..15] with tall row
-// 96 j + r for digit plane j of row r;  consts = 4 x [t, dt, Omega[6], cos(Omega dt/2)[6], sin(..)[6]].
+// 96 j + r for digit plane j of row r;  consts = I8_SEGS x [t, dt, Omega[6], cos(Omega dt/2)[6], sin(..)[6]].
 __global__ void __launch_bounds__(I8_ROWS * I8_SEGS)
 i8_coeff_kernel(int G, int rows, int n_krows, const double2* __restrict__ Bbar,
                 const double2* __restrict__ Cbar, const double* __restrict__ eigvals,
@@ -299,7 +302,7 @@ i8_coeff_kernel(int G, int rows, int n_krows, const double2* __restrict__ Bbar,
         }
       }
     }
-    reinterpret_cast<double*>(stage + 2 * C_KSTEP)[threadIdx.x] = val;
+    reinterpret_cast<double*>(stage + I8_KS * C_KSTEP)[threadIdx.x] = val;
   }
 }
 
@@ -329,33 +332,44 @@ __device__ __forceinline__ void transpose4(unsigned a, unsigned b, unsigned c, u
   w[3] = __byte_perm(x1, y1, 0x7632);
 }
 
-// 13 values -> five digit planes of 16 bytes each, stored as row m of the P tile of (K step ks, chunk cc)
-__device__ __forceinline__ void store_digits(const double (&v)[13], double scale, unsigned char* tile) {
-  unsigned lo[13], hi[13];
+// Digits of the 13 values of one operand row, collected as the values are produced (so that the FP64 values
+// do not stay live): lo[k] = digits 0..3 of value k (one per byte), hi[k / 4] = digit 4 of four values.
+struct DigitRow {
+  unsigned lo[13];
+  unsigned hi[4];
+  __device__ __forceinline__ void clear() {
 #pragma unroll
-  for (int k = 0; k < 13; ++k) to_digits(v[k], scale, lo[k], hi[k]);
-  unsigned plane[I8_D][4];
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    unsigned w[4];
-    transpose4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3], w);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) plane[j][q] = w[j];
-    const unsigned t0 = __byte_perm(hi[4 * q], hi[4 * q + 1], 0x0040);
-    const unsigned t1 = __byte_perm(hi[4 * q + 2], hi[4 * q + 3], 0x0040);
-    plane[4][q] = __byte_perm(t0, t1, 0x5410);
+    for (int q = 0; q < 4; ++q) hi[q] = 0u;
   }
+  template <int K>
+  __device__ __forceinline__ void put(double v, double scale) {
+    unsigned l, h;
+    to_digits(v, scale, l, h);
+    lo[K] = l;
+    hi[K >> 2] |= (h & 0xFFu) << (8 * (K & 3));
+  }
+  // five digit planes of 16 bytes each, stored as one row of the P tile (plane stride P_PLANE)
+  __device__ __forceinline__ void store(unsigned char* tile) const {
+    unsigned plane[4][4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) plane[j][3] = __byte_perm(lo[12], 0u, 0x4440 + j);
-  plane[4][3] = hi[12] & 0xFFu;
+    for (int q = 0; q < 3; ++q) {
+      unsigned w[4];
+      transpose4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3], w);
 #pragma unroll
-  for (int j = 0; j < I8_D; ++j) {
+      for (int j = 0; j < 4; ++j) plane[j][q] = w[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) plane[j][3] = __byte_perm(lo[12], 0u, 0x4440 + j);
     // balanced digits: byte - 128 (the padding kappa 13..15 meet zero coefficients, their value is irrelevant)
-    *reinterpret_cast<uint4*>(tile + j * P_PLANE) =
-        make_uint4(plane[j][0] ^ 0x80808080u, plane[j][1] ^ 0x80808080u, plane[j][2] ^ 0x80808080u,
-                   plane[j][3] ^ 0x80808080u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(tile + j * P_PLANE) =
+          make_uint4(plane[j][0] ^ 0x80808080u, plane[j][1] ^ 0x80808080u, plane[j][2] ^ 0x80808080u,
+                     plane[j][3] ^ 0x80808080u);
+    *reinterpret_cast<uint4*>(tile + 4 * P_PLANE) =
+        make_uint4(hi[0] ^ 0x80808080u, hi[1] ^ 0x80808080u, hi[2] ^ 0x80808080u, hi[3] ^ 0x80808080u);
   }
-}
+};
 
 __global__ void __launch_bounds__(I8_THREADS, 1) ctrlmat_i8_kernel(const I8Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -415,9 +429,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) ctrlmat_i8_kernel(const I8Param
       const int s = it % I8_STAGES;
       const unsigned ph = (unsigned)(it / I8_STAGES) & 1u;
       unsigned char* const sP = smem + (size_t)s * STAGE_BYTES;
-      const double* cst = reinterpret_cast<const double*>(sP + STAGE_P + 2 * C_KSTEP) + c * I8_CONSTS;
+      const double* cst = reinterpret_cast<const double*>(sP + STAGE_P + I8_KS * C_KSTEP) + c * I8_CONSTS;
       if (p.debug & 16)   // timing experiment: per-segment constants straight from global memory (L1 / L2)
-        cst = reinterpret_cast<const double*>(p.stream + (size_t)(st0 + it) * STAGE_C + 2 * C_KSTEP) + c * I8_CONSTS;
+        cst = reinterpret_cast<const double*>(p.stream + (size_t)(st0 + it) * STAGE_C + I8_KS * C_KSTEP) + c * I8_CONSTS;
       mbar_wait(&bar_empty[s], ph ^ 1u);   // the MMAs of the previous use of this stage are done
       mbar_wait(&bar_full_c[s], ph);       // constants (and coefficients) of this stage have landed
       if (p.debug & 2) {
@@ -451,43 +465,50 @@ __global__ void __launch_bounds__(I8_THREADS, 1) ctrlmat_i8_kernel(const I8Param
       }
       double ph_re, ph_im;
       sincos_cw(w * tg, ph_im, ph_re);
-      double vre[13], vim[13];
-      vre[0] = ph_re * j0_re - ph_im * j0_im;
-      vim[0] = ph_re * j0_im + ph_im * j0_re;
+      // E = e^{i w t} sqrt2 e^{i w dt / 2}: the phase factor folded into the half-angle factor, so that the
+      // products below come out rotated already (8 FP64 operations per level pair less than rotating S, D)
+      const double e_re = ph_re * hc - ph_im * hs, e_im = ph_re * hs + ph_im * hc;
+      DigitRow dre, dim;
+      dre.clear();
+      dim.clear();
+      dre.put<0>(ph_re * j0_re - ph_im * j0_im, p_scale);
+      dim.put<0>(ph_re * j0_im + ph_im * j0_re, p_scale);
+      bool any_store = !(p.debug & 4);
 #pragma unroll
       for (int q = 0; q < NP; ++q) {
         const double Om = cst[2 + q], Ch = cst[2 + NP + q], Sh = cst[2 + 2 * NP + q];
-        const double t1 = hc * Ch, t3 = hs * Ch;
-        const double zp_re = fma(-hs, Sh, t1), zp_im = fma(hc, Sh, t3);
-        const double zm_re = fma(hs, Sh, t1), zm_im = fma(-hc, Sh, t3);
-        double jp_re, jp_im, jm_re, jm_im;
-        if (min(abs_hi(zp_im), abs_hi(zm_im)) < SMALL_SIN_HI) {  // removable singularity: direct evaluation
+        const double u1 = e_re * Ch, u3 = e_im * Ch, t3 = hs * Ch;
+        const double sp = fma(hc, Sh, t3), sm = fma(-hc, Sh, t3);     // sqrt2 sin((w +- Om) dt / 2)
+        double jp_re, jp_im, jm_re, jm_im;                              // e^{i w t} I(w +- Om)
+        if (min(abs_hi(sp), abs_hi(sm)) < SMALL_SIN_HI) {  // removable singularity: direct evaluation
           const cplx jp = integral_direct(w + Om, dtg), jm = integral_direct(w - Om, dtg);
-          jp_re = jp.re; jp_im = jp.im; jm_re = jm.re; jm_im = jm.im;
+          jp_re = ph_re * jp.re - ph_im * jp.im; jp_im = ph_re * jp.im + ph_im * jp.re;
+          jm_re = ph_re * jm.re - ph_im * jm.im; jm_im = ph_re * jm.im + ph_im * jm.re;
         } else {
-          const double fp = zp_im * rcp_nr(w + Om);
-          const double fm = zm_im * rcp_nr(w - Om);
-          jp_re = zp_re * fp; jp_im = zp_im * fp;
-          jm_re = zm_re * fm; jm_im = zm_im * fm;
+          const double fp = sp * rcp_nr(w + Om);
+          const double fm = sm * rcp_nr(w - Om);
+          jp_re = fma(-e_im, Sh, u1) * fp; jp_im = fma(e_re, Sh, u3) * fp;
+          jm_re = fma(e_im, Sh, u1) * fm;  jm_im = fma(-e_re, Sh, u3) * fm;
         }
-        const double s_re = jp_re + jm_re, s_im = jp_im + jm_im;
-        const double d_re = jm_im - jp_im, d_im = jp_re - jm_re;
-        vre[1 + 2 * q] = ph_re * s_re - ph_im * s_im;
-        vim[1 + 2 * q] = ph_re * s_im + ph_im * s_re;
-        vre[2 + 2 * q] = ph_re * d_re - ph_im * d_im;
-        vim[2 + 2 * q] = ph_re * d_im + ph_im * d_re;
+        // S = jp + jm, D = i (jp - jm)
+        if (q == 0) { dre.put<1>(jp_re + jm_re, p_scale); dim.put<1>(jp_im + jm_im, p_scale);
+                      dre.put<2>(jm_im - jp_im, p_scale); dim.put<2>(jp_re - jm_re, p_scale); }
+        if (q == 1) { dre.put<3>(jp_re + jm_re, p_scale); dim.put<3>(jp_im + jm_im, p_scale);
+                      dre.put<4>(jm_im - jp_im, p_scale); dim.put<4>(jp_re - jm_re, p_scale); }
+        if (q == 2) { dre.put<5>(jp_re + jm_re, p_scale); dim.put<5>(jp_im + jm_im, p_scale);
+                      dre.put<6>(jm_im - jp_im, p_scale); dim.put<6>(jp_re - jm_re, p_scale); }
+        if (q == 3) { dre.put<7>(jp_re + jm_re, p_scale); dim.put<7>(jp_im + jm_im, p_scale);
+                      dre.put<8>(jm_im - jp_im, p_scale); dim.put<8>(jp_re - jm_re, p_scale); }
+        if (q == 4) { dre.put<9>(jp_re + jm_re, p_scale); dim.put<9>(jp_im + jm_im, p_scale);
+                      dre.put<10>(jm_im - jp_im, p_scale); dim.put<10>(jp_re - jm_re, p_scale); }
+        if (q == 5) { dre.put<11>(jp_re + jm_re, p_scale); dim.put<11>(jp_im + jm_im, p_scale);
+                      dre.put<12>(jm_im - jp_im, p_scale); dim.put<12>(jp_re - jm_re, p_scale); }
       }
       unsigned char* const tile = sP + (size_t)ks * P_KSTEP + (size_t)cc * 2048;
-      bool do_store = true;
-      if (p.debug & 4) {  // timing experiment: all the arithmetic, none of the stores
-        double sum = 0.0;
-#pragma unroll
-        for (int k = 0; k < 13; ++k) sum += vre[k] + vim[k];
-        do_store = sum == 1.2345e300;
-      }
-      if (do_store) {
-        store_digits(vre, p_scale, tile + (size_t)wl * 16);             // rows 0..63: real parts
-        store_digits(vim, p_scale, tile + (size_t)(I8_W + wl) * 16);    // rows 64..127: imaginary parts
+      if (p.debug & 4) any_store = (dre.lo[12] ^ dim.lo[7] ^ dre.hi[1]) == 0x12345678u;  // timing experiment
+      if (any_store) {
+        dre.store(tile + (size_t)wl * 16);             // rows 0..63: real parts
+        dim.store(tile + (size_t)(I8_W + wl) * 16);    // rows 64..127: imaginary parts
       }
       fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
       __syncwarp();
@@ -518,7 +539,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) ctrlmat_i8_kernel(const I8Param
         const unsigned sP = smem_u32(smem + (size_t)s * STAGE_BYTES);
         const unsigned sC = sP + STAGE_P;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
+        for (int ks = 0; ks < I8_KS; ++ks) {
           if (p.debug & 1) break;
           // P plane i (digit i) x coefficient planes j with i + j >= 4; level t = i + j at column 96 (t - 4);
           // two adjacent planes (adjacent levels) per instruction where possible
