@@ -159,12 +159,28 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr, unsi
 __device__ __forceinline__ unsigned umma_idesc_s8(int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
+// COLL: use of the collector buffer of the A operand -- 0: none, 1: fill (keep A for the next MMA), 2: use
+// (reuse the kept A and keep it), 3: lastuse.  Consecutive MMAs of one P digit plane share A, which is then
+// read from shared memory once instead of once per instruction (the MMA phase is bound by operand reads).
+template <int COLL>
 __device__ __forceinline__ void umma_i8(unsigned tmem_d, unsigned long long da, unsigned long long db,
                                         unsigned idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
+  if (COLL == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
+  else if (COLL == 2)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8.collector::a::use [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
+  else if (COLL == 3)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(void* mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
@@ -546,12 +562,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1) ctrlmat_i8_kernel(const I8Param
 #pragma unroll
           for (int i = 0; i < I8_D; ++i) {
             const unsigned long long da = umma_desc(sP + ks * P_KSTEP + i * P_PLANE, 2048, 128);
-            int j = 4 - i;
+            const int n_mma = (i + 2) / 2;   // coefficient planes 4 - i .. 4 in groups of two
+            int j = 4 - i, m = 0;
             while (j <= 4) {
               const int nj = (j + 1 <= 4) ? 2 : 1;
               const unsigned long long db = umma_desc(sC + ks * C_KSTEP + j * (I8_ROWS * 16), C_LBO, 128);
-              umma_i8(tmem + (unsigned)((i + j - 4) * I8_ROWS), da, db, nj == 2 ? idesc192 : idesc96);
+              const unsigned d_at = tmem + (unsigned)((i + j - 4) * I8_ROWS);
+              const unsigned idesc = nj == 2 ? idesc192 : idesc96;
+              if (n_mma == 1) umma_i8<0>(d_at, da, db, idesc);
+              else if (m == 0) umma_i8<1>(d_at, da, db, idesc);
+              else if (m == n_mma - 1) umma_i8<3>(d_at, da, db, idesc);
+              else umma_i8<2>(d_at, da, db, idesc);
               j += nj;
+              ++m;
             }
           }
         }
