@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 final single-GPU pass: compute-sanitizer over the kernels new in this session, launch list of a
 # bench run, bench line + reference arm
-tag=${1:-r02h}
+tag=${1:-r02i}
 out=gpurun_out/$tag
 mkdir -p $out
 S=$out/sanitizer.txt
@@ -24,4 +24,10 @@ print('cpu_baseline', d['cpu_baseline'])
 r = json.load(open(sys.argv[2]))
 print('reference arm', r['value'], r['ms_per_step'], r['cpu_baseline']['kind'], r['cpu_baseline']['cores'])
 PY
+FFB_CTRLMAT_INT8=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ctrlmat_i8_kernel -s 3 -c 1 -f -o $out/prof_i8_d4 python bench.py --workload d4 --extra none --no-int8 --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_i8_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ff_gram -s 2 -c 1 -f -o $out/prof_ff_gram python tools/time_ff_kernel.py > $out/ncu_gram_full.log 2>&1
+timeout 300 python tools/time_ff_kernel.py > $out/ff_kernel.jsonl 2>/dev/null
+timeout 300 python tools/diag_propagator_error.py d4 c2 > $out/propagator_error.txt 2>&1
+timeout 300 python tools/bench_sequencing.py > $out/sequencing.jsonl 2> $out/sequencing.err || tail -3 $out/sequencing.err
+tail -3 $out/sequencing.jsonl | cut -c1-400
 ls -la $out
