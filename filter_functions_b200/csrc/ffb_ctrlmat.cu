@@ -1863,7 +1863,22 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   bool use_static = geo.n_pairs == 6 && !geo.transposed && p.pps == 1 && p.n_sp <= 2 &&
                     (MT == 12 || MT == 8 || MT == 6);
   if (const char* e = getenv("FFB_CTRLMAT_STATIC")) use_static = use_static && atoi(e) != 0;
-  if (use_static) {
+  // d = 8 (28 level pairs; 3 qubits): a pass of 29 units is streamed in 5 - 7 pieces; same kernel, the walk
+  // over the units of a pass fully unrolled
+  bool use_static8 = geo.n_pairs == 28 && !geo.transposed && p.pps == 1 &&
+                     ((MT == 12 && p.n_sp >= 5 && p.n_sp <= 7) || (MT == 8 && p.n_sp >= 4 && p.n_sp <= 6));
+  if (const char* e = getenv("FFB_CTRLMAT_STATIC")) use_static8 = use_static8 && atoi(e) != 0;
+  if (getenv("FFB_TRACE") && geo.n_pairs == 28)
+    fprintf(stderr, "[ffb trace] control matrix d = 8: MT %d n_sp %d pps %d transposed %d -> %s kernel\n", MT,
+            p.n_sp, p.pps, geo.transposed, use_static8 ? "static" : "generic");
+  if (use_static8) {
+    if (MT == 12 && p.n_sp == 5) FFB_TRY((launch_static<12, 4, 28, 5>(ctx, p, n_wtiles, geo.n_rb, S)));
+    else if (MT == 12 && p.n_sp == 6) FFB_TRY((launch_static<12, 4, 28, 6>(ctx, p, n_wtiles, geo.n_rb, S)));
+    else if (MT == 12) FFB_TRY((launch_static<12, 4, 28, 7>(ctx, p, n_wtiles, geo.n_rb, S)));
+    else if (p.n_sp == 4) FFB_TRY((launch_static<8, 4, 28, 4>(ctx, p, n_wtiles, geo.n_rb, S)));
+    else if (p.n_sp == 5) FFB_TRY((launch_static<8, 4, 28, 5>(ctx, p, n_wtiles, geo.n_rb, S)));
+    else FFB_TRY((launch_static<8, 4, 28, 6>(ctx, p, n_wtiles, geo.n_rb, S)));
+  } else if (use_static) {
     if (MT == 12 && p.n_sp == 2) FFB_TRY((launch_static<12, 4, 6, 2>(ctx, p, n_wtiles, geo.n_rb, S)));
     else if (MT == 12) FFB_TRY((launch_static<12, 4, 6, 1>(ctx, p, n_wtiles, geo.n_rb, S)));
     else if (MT == 8 && p.n_sp == 2) FFB_TRY((launch_static<8, 4, 6, 2>(ctx, p, n_wtiles, geo.n_rb, S)));
