@@ -1871,7 +1871,16 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
   if (getenv("FFB_TRACE") && geo.n_pairs == 28)
     fprintf(stderr, "[ffb trace] control matrix d = 8: MT %d n_sp %d pps %d transposed %d -> %s kernel\n", MT,
             p.n_sp, p.pps, geo.transposed, use_static8 ? "static" : "generic");
-  if (use_static8) {
+  // d = 16 in the transposed layout (short pulses: the gate pulses and the joined pulse of config 5): 30 units
+  // of four level pairs each + the diagonal unit per segment
+  bool use_static16 = geo.n_pairs == 30 && geo.transposed && p.pps == 1 && MT == 12 && p.n_sp == 7;
+  if (const char* e = getenv("FFB_CTRLMAT_STATIC")) use_static16 = use_static16 && atoi(e) != 0;
+  if (getenv("FFB_TRACE") && geo.n_pairs == 30)
+    fprintf(stderr, "[ffb trace] control matrix d = 16: MT %d n_sp %d pps %d transposed %d -> %s kernel\n", MT,
+            p.n_sp, p.pps, geo.transposed, use_static16 ? "static" : "generic");
+  if (use_static16) {
+    FFB_TRY((launch_static<12, 4, 30, 7>(ctx, p, n_wtiles, geo.n_rb, S)));
+  } else if (use_static8) {
     if (MT == 12 && p.n_sp == 5) FFB_TRY((launch_static<12, 4, 28, 5>(ctx, p, n_wtiles, geo.n_rb, S)));
     else if (MT == 12 && p.n_sp == 6) FFB_TRY((launch_static<12, 4, 28, 6>(ctx, p, n_wtiles, geo.n_rb, S)));
     else if (MT == 12) FFB_TRY((launch_static<12, 4, 28, 7>(ctx, p, n_wtiles, geo.n_rb, S)));
