@@ -441,3 +441,36 @@ def test_control_matrix_intermediates_long_pulse(engine):
                                                  n_coeffs[:, tail], dt[tail], t=t[G - 40:])
     for key in ('phase_factors', 'first_order_integral', 'control_matrix_step'):
         assert nerr(inter[key][tail], ref[key]) < TOL, key
+
+
+@pytest.mark.parametrize('d,G,n_nops,n_omega', [(8, 40, 3, 70), (8, 23, 1, 33), (8, 9, 6, 40), (16, 2, 18, 64),
+                                                (16, 1, 3, 40), (4, 50, 6, 70)])
+def test_static_and_generic_tensor_kernels_agree(engine, d, G, n_nops, n_omega):
+    """The statically scheduled DMMA kernel (d = 4; d = 8 with the pass in several pieces; the transposed
+    d = 16 layout of short pulses) against the generic kernel (FFB_CTRLMAT_STATIC=0, read per call) and
+    the oracle.  Uniform and non-uniform dt, omega = 0 and a negative frequency."""
+    import os
+    rng = np.random.default_rng(31*d + G + n_nops)
+    c_opers, c_coeffs, n_opers, n_coeffs, dt, H = _setup(rng, d, G, n_nops)
+    if G % 2:
+        dt = np.full(G, 0.37)
+    ev, V, Q = oracle.diagonalize(H, dt)
+    basis = oracle.ggm_basis(d)
+    omega = np.concatenate(([0.0, -0.21], np.geomspace(1e-3, 25, n_omega - 2)))
+    f = engine.numeric.calculate_control_matrix_from_scratch
+    old = os.environ.get('FFB_CTRLMAT_STATIC')
+    try:
+        os.environ['FFB_CTRLMAT_STATIC'] = '1'
+        B_static = f(ev, V, Q, omega, basis, n_opers, n_coeffs, dt)
+        os.environ['FFB_CTRLMAT_STATIC'] = '0'
+        B_generic = f(ev, V, Q, omega, basis, n_opers, n_coeffs, dt)
+    finally:
+        if old is None:
+            os.environ.pop('FFB_CTRLMAT_STATIC', None)
+        else:
+            os.environ['FFB_CTRLMAT_STATIC'] = old
+    B_o = oracle.control_matrix_from_scratch(ev, V, Q, omega, basis, n_opers, n_coeffs, dt)
+    for j in range(n_nops):
+        assert nerr(B_static[j], B_o[j]) < 1e-12
+        assert nerr(B_generic[j], B_o[j]) < 1e-12
+        assert nerr(B_static[j], B_generic[j]) < 1e-13
