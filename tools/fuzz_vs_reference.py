@@ -196,6 +196,50 @@ def main():
             check(tag, 'periodic filter function',
                   ffb.concatenate_periodic(p_new, reps).get_filter_function(omega),
                   ref.concatenate_periodic(p_ref, reps).get_filter_function(omega), tol=1e-9)
+    # concatenation of pulses that carry DIFFERENT (overlapping) sets of noise operators, omega supplied or cached
+    for case in range(args.cases//4):
+        d = int(rng.choice([2, 3, 4]))
+        pool = herm(rng, d, 4, True)
+        c_opers = herm(rng, d, 2, True)
+        sens = rng.uniform(0.5, 2, 4)
+        refs, news = [], []
+        for k in range(int(rng.integers(2, 5))):
+            G = int(rng.integers(1, 9))
+            pick = sorted(rng.choice(4, size=rng.integers(1, 5), replace=False))
+            const = bool(rng.integers(2))
+            n_coeffs = [np.full(G, sens[i]) if const else sens[i]*(1 + 0.1*rng.standard_normal(G)) for i in pick]
+            c_coeffs = rng.standard_normal((2, G))
+            dt = rng.uniform(0.2, 1.0, G)
+            for pkg, dst in ((ref, refs), (ffb, news)):
+                dst.append(pkg.PulseSequence(list(zip(c_opers, c_coeffs, ['X', 'Y'])),
+                                             [[pool[i], nc, f'N{i}'] for i, nc in zip(pick, n_coeffs)], dt,
+                                             pkg.Basis.ggm(d)))
+        omega = np.geomspace(1e-2, 20, int(rng.integers(2, 60)))
+        tag = f'mixed {case}: d={d} pulses={len(refs)}'
+        cached = bool(rng.integers(2))
+        try:
+            if cached:
+                for pr_, pn_ in zip(refs, news):
+                    pr_.cache_filter_function(omega)
+                    pn_.cache_filter_function(omega)
+                c_ref = ref.concatenate(refs, calc_filter_function=True)
+            else:
+                c_ref = ref.concatenate(refs, omega=omega, calc_filter_function=True)
+        except Exception as exc:   # noqa: BLE001
+            try:
+                ffb.concatenate(news, omega=None if cached else omega, calc_filter_function=True)
+                mismatches.append({'case': tag, 'what': 'reference raised, this package did not', 'err': repr(exc)})
+            except type(exc):
+                n_cmp += 1
+            continue
+        c_new = ffb.concatenate(news, omega=None if cached else omega, calc_filter_function=True)
+        check(tag, 'identifiers', np.array(list(c_new.n_oper_identifiers) == list(c_ref.n_oper_identifiers), float),
+              np.ones(()))
+        check(tag, 'n_coeffs', c_new.n_coeffs, c_ref.n_coeffs)
+        check(tag, 'filter function', c_new.get_filter_function(omega), c_ref.get_filter_function(omega))
+        check(tag, 'control matrix', c_new.get_control_matrix(omega), c_ref.get_control_matrix(omega))
+        check(tag, 'total propagator', c_new.total_propagator, c_ref.total_propagator)
+
     print(json.dumps({'cases': args.cases, 'seed': args.seed, 'comparisons': n_cmp, 'tolerance': TOL,
                       'worst_normalised_deviation': worst, 'mismatches': mismatches[:40],
                       'n_mismatches': len(mismatches)}))
