@@ -678,6 +678,10 @@ __device__ __forceinline__ void mma_diag(double (&acc_re)[MT][2], double (&acc_i
   }
 }
 
+// (Experiment, round 2: the six rows (j, 0) of an identity basis element carry no pair terms, so the 96 rows of the
+// d = 4 shapes need only 90 pair rows = 11.25 tiles.  Dropping the twelfth tile from the pair units outright buys 6.3 %
+// (16.55 -> 15.51 ms, wrong results); the two pair rows left over would have to go through a DFMA side path costing
+// about 2 % again, plus a row permutation in assemble / finalize -- not done.)
 template <int MT>
 __device__ __forceinline__ void mma_pair(double (&acc_re)[MT][2], double (&acc_im)[MT][2],
                                          const double* unit, int lane, const Vals& v) {
