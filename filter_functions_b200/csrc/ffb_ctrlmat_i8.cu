@@ -103,6 +103,15 @@ __device__ __forceinline__ double rcp_nr(double x) {
   return r;
 }
 
+// 1 / x to ~2^-46 (seed 2^-23, one Newton step): the operand is cut to 39 bits afterwards, so the second
+// Newton step of rcp_nr would be wasted (12 reciprocals per segment and frequency)
+__device__ __forceinline__ double rcp_nr1(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
 constexpr double SQRT2 = 1.41421356237309504880;
 constexpr int SMALL_SIN_HI = 0x3F56A09E;  // high word of 2^-10 sqrt(2)
 __device__ __forceinline__ int abs_hi(double x) { return __double2hiint(x) & 0x7fffffff; }
@@ -501,8 +510,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) ctrlmat_i8_kernel(const I8Param
           jp_re = ph_re * jp.re - ph_im * jp.im; jp_im = ph_re * jp.im + ph_im * jp.re;
           jm_re = ph_re * jm.re - ph_im * jm.im; jm_im = ph_re * jm.im + ph_im * jm.re;
         } else {
-          const double fp = sp * rcp_nr(w + Om);
-          const double fm = sm * rcp_nr(w - Om);
+          const double fp = sp * rcp_nr1(w + Om);
+          const double fm = sm * rcp_nr1(w - Om);
           jp_re = fma(-e_im, Sh, u1) * fp; jp_im = fma(e_re, Sh, u3) * fp;
           jm_re = fma(e_im, Sh, u1) * fm;  jm_im = fma(-e_re, Sh, u3) * fm;
         }
