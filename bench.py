@@ -301,6 +301,13 @@ def kernel_model(wl, n_omega_local, kernel_ms, peak, int8=False):
         rows_pad = n_rb*mt*8
         pipe = 'fp64 (DMMA.8x8x4; shares the 64 lane/clk/SM FP64 pipe with DFMA)'
         pair_rows = rows_pad
+        # two qubits, six noise operators, identity basis element: the six rows (j, 0) take no part in the
+        # pair units (88 rows through DMMA, 2 through the DFMA side path; csrc/ffb_ctrlmat.cu, SPLIT)
+        ident0 = bool((wl.basis[0] == wl.basis[0][0, 0].real*np.eye(d)).all())
+        if (static and d == 4 and n_nops == 6 and n_basis == 16 and ident0 and mt == 12 and n_rb == 1
+                and os.environ.get('FFB_CTRLMAT_SPLIT_IDENTITY', '1') != '0'):
+            kernel = 'ctrlmat_static_kernel (identity-row split)'
+            pair_rows = n_nops*(n_basis - 1)
     # real multiply-adds per seg*omega: 2 per row for the diagonal unit, 4 per row and level pair
     executed = (2*rows_pad + 4*n_pairs*pair_rows)*2*G*n_omega_local/(kernel_ms*1e-3)*1e-12
     return kernel, pipe, executed, executed
@@ -477,6 +484,9 @@ def _measure(name, steps, warmup, env, int8):
         'executed_tflops': executed, 'executed_frac': executed_vs_peak/peak,
         'ncu_pipe_active_pct': ncu.get('pipe_active_pct'),
         'ncu_pipe_active_metric': ncu.get('pipe_active_metric'),
+        'ncu_dmma_pipe_active_pct': ncu.get('dmma_pipe_active_pct'),
+        'ncu_fp64_pipe_active_pct': ncu.get('fp64_pipe_active_pct'),
+        'ncu_kernel': ncu.get('kernel'),
         'ncu_source': ncu.get('source'),
         'note': 'achieved counts the reference formulation (W = 8 n_nops n_basis d^2 + 12 d^2 per '
                 'seg*omega, SURVEY 8d); the kernel executes fewer flops by pairing (m,n)/(n,m) terms '
