@@ -294,8 +294,8 @@ def kernel_model(wl, n_omega_local, kernel_ms, peak, int8=False):
         rows_pad = -(-rows//8)*8
         tiles = rows_pad//8
         n_rb = -(-tiles//12)
-        mt = next(a for a in (1, 2, 3, 4, 6, 8, 12) if a >= -(-tiles//n_rb))
-        static = (d == 4 and mt in (6, 8, 12) and G >= 4
+        mt = next(a for a in (1, 2, 3, 4, 5, 6, 7, 8, 10, 12) if a >= -(-tiles//n_rb))
+        static = (d == 4 and mt in (6, 8, 10, 12) and G >= 4
                   and os.environ.get('FFB_CTRLMAT_STATIC', '1') != '0')
         kernel = 'ctrlmat_static_kernel' if static else 'ctrlmat_main_kernel'
         rows_pad = n_rb*mt*8

@@ -707,7 +707,7 @@ __device__ __forceinline__ void mma_pair(double (&acc_re)[MT][2], double (&acc_i
 }
 
 template <int MT, int NW>
-__global__ void __launch_bounds__(NW * 32, (MT <= 2 ? 3 : MT >= 12 ? 3 : 1))
+__global__ void __launch_bounds__(NW * 32, (MT <= 2 ? 3 : MT >= 10 ? 3 : 1))
 ctrlmat_main_kernel(const MainParams p) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
@@ -1019,7 +1019,7 @@ __device__ __forceinline__ void mma_pair_tiles(double (&acc_re)[MT][2], double (
 // lane owns (frequency, segment) = one B-fragment element, i.e. exactly the factor those rows need), added
 // into the tile's accumulators by shuffles at the end.  Measured on d4: 16.55 -> 15.9 ms.
 template <int MT, int NW, int NP, int NSP, bool SPLIT = false>
-__global__ void __launch_bounds__(NW * 32, (MT <= 2 ? 3 : MT >= 12 ? 3 : 1))
+__global__ void __launch_bounds__(NW * 32, (MT <= 2 ? 3 : MT >= 10 ? 3 : 1))
 ctrlmat_static_kernel(const MainParams p) {
   extern __shared__ __align__(16) double smem[];
   constexpr int NU = 1 + NP;
@@ -1604,7 +1604,9 @@ int occupancy(ffb_ctx* ctx, size_t smem, int* blocks) {
 }
 
 int pick_mt(int mt_total) {
-  static const int avail[] = {1, 2, 3, 4, 6, 8, 12};
+  // (5, 7, 10 row tiles: five noise operators in a two-qubit basis = 80 rows, four in a qutrit basis = 36
+  // rows, ...: a whole padding tile would cost 8 - 17 % of the DMMAs)
+  static const int avail[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12};
   const int n_rb = (mt_total + 11) / 12;
   const int need = (mt_total + n_rb - 1) / n_rb;
   for (int a : avail)
@@ -1622,11 +1624,14 @@ int pick_mt(int mt_total) {
     case 2: { constexpr int MT_ = 2, NW_ = 8; CALL; } break;        \
     case 3: { constexpr int MT_ = 3, NW_ = 8; CALL; } break;        \
     case 4: { constexpr int MT_ = 4, NW_ = 8; CALL; } break;        \
+    case 5: { constexpr int MT_ = 5, NW_ = 8; CALL; } break;        \
     case 6: { constexpr int MT_ = 6, NW_ = 8; CALL; } break;        \
+    case 7: { constexpr int MT_ = 7, NW_ = 4; CALL; } break;        \
     case 8: { constexpr int MT_ = 8, NW_ = 4; CALL; } break;        \
+    case 10: { constexpr int MT_ = 10, NW_ = 4; CALL; } break;      \
     default: { constexpr int MT_ = 12, NW_ = 4; CALL; } break;      \
   }
-inline int warps_per_cta(int MT) { return MT >= 8 ? 4 : 8; }
+inline int warps_per_cta(int MT) { return MT >= 7 ? 4 : 8; }
 
 }  // namespace
 
@@ -1940,7 +1945,7 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
 
   // d = 4 (6 level pairs), one pass per stage or a pass in two pieces: statically scheduled variant
   bool use_static = geo.n_pairs == 6 && !geo.transposed && p.pps == 1 && p.n_sp <= 2 &&
-                    (MT == 12 || MT == 8 || MT == 6);
+                    (MT == 12 || MT == 10 || MT == 8 || MT == 6);
   if (const char* e = getenv("FFB_CTRLMAT_STATIC")) use_static = use_static && atoi(e) != 0;
   // d = 8 (28 level pairs; 3 qubits): a pass of 29 units is streamed in 5 - 7 pieces; same kernel, the walk
   // over the units of a pass fully unrolled
@@ -1970,6 +1975,8 @@ int ffbi_control_matrix(ffb_ctx* ctx, int G, int d, int n_nops, int n_basis, int
     if (MT == 12 && p.n_sp == 2 && split_t) FFB_TRY((launch_static<12, 4, 6, 2, true>(ctx, p, n_wtiles, geo.n_rb, S)));
     else if (MT == 12 && p.n_sp == 2) FFB_TRY((launch_static<12, 4, 6, 2>(ctx, p, n_wtiles, geo.n_rb, S)));
     else if (MT == 12) FFB_TRY((launch_static<12, 4, 6, 1>(ctx, p, n_wtiles, geo.n_rb, S)));
+    else if (MT == 10 && p.n_sp == 2) FFB_TRY((launch_static<10, 4, 6, 2>(ctx, p, n_wtiles, geo.n_rb, S)));
+    else if (MT == 10) FFB_TRY((launch_static<10, 4, 6, 1>(ctx, p, n_wtiles, geo.n_rb, S)));
     else if (MT == 8 && p.n_sp == 2) FFB_TRY((launch_static<8, 4, 6, 2>(ctx, p, n_wtiles, geo.n_rb, S)));
     else if (MT == 8) FFB_TRY((launch_static<8, 4, 6, 1>(ctx, p, n_wtiles, geo.n_rb, S)));
     else if (p.n_sp == 2) FFB_TRY((launch_static<6, 8, 6, 2>(ctx, p, n_wtiles, geo.n_rb, S)));

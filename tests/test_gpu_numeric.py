@@ -444,7 +444,9 @@ def test_control_matrix_intermediates_long_pulse(engine):
 
 
 @pytest.mark.parametrize('d,G,n_nops,n_omega', [(8, 40, 3, 70), (8, 23, 1, 33), (8, 9, 6, 40), (16, 2, 18, 64),
-                                                (16, 1, 3, 40), (4, 50, 6, 70)])
+                                                (16, 1, 3, 40), (4, 50, 6, 70),
+                                                # 10, 5 and 7 row tiles (no whole padding tile), 4 x 10 tiles
+                                                (4, 44, 5, 70), (3, 30, 4, 50), (3, 21, 6, 40), (8, 6, 5, 33)])
 def test_static_and_generic_tensor_kernels_agree(engine, d, G, n_nops, n_omega):
     """The statically scheduled DMMA kernel (d = 4; d = 8 with the pass in several pieces; the transposed
     d = 16 layout of short pulses) against the generic kernel (FFB_CTRLMAT_STATIC=0, read per call) and

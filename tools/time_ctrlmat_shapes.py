@@ -16,7 +16,7 @@ import torch  # noqa: E402
 import ff_oracle as oracle  # noqa: E402
 from filter_functions_b200.device import DevicePulse  # noqa: E402
 
-SHAPES = [(8, 2000, 3, 5000), (8, 2000, 1, 5000), (8, 500, 6, 2000), (3, 4000, 3, 8000), (16, 100, 2, 2000)]
+SHAPES = [(4, 4000, 5, 8000), (8, 2000, 3, 5000), (8, 2000, 1, 5000), (8, 500, 6, 2000), (3, 4000, 3, 8000), (16, 100, 2, 2000)]
 
 
 def herm(rng, d, n):
