@@ -738,7 +738,7 @@ class _SequencePlan:
     sequence has been evaluated, the gates' stacked control matrices / phases / propagators mirrored in
     device memory (``library``).  Valid while the gates' stamps have not moved."""
     __slots__ = ('refs', 'stamps', 'control', 'noise', 'blocks', 'maps', 'n_control', 'n_noise',
-                 'taus', 'present', 'basis', 'library')
+                 'taus', 'present', 'present_c', 'basis', 'library')
 
 
 _SEQUENCE_PLANS = {}
@@ -755,7 +755,18 @@ def _plan_for(distinct):
             if plan.refs[i]() is not p or plan.stamps[i] != p._stamp[0]:
                 del _SEQUENCE_PLANS[key]
                 return key, None
-    return key, plan
+        return key, plan
+    # A sequence that happens to miss some gates of a library (29 % of 100-Clifford sequences miss at least
+    # one of the 24 Cliffords) can use the plan of a superset, provided its own gates together still carry
+    # every control and noise operator of that plan's join -- then its join has the same operators, (sorted)
+    # identifiers and mappings, and the gates' coefficient blocks are the same.
+    for other in _SEQUENCE_PLANS.values():
+        if len(other.refs) > len(key) and all(i in other.refs for i in key):
+            if (all(other.refs[id(p)]() is p and other.stamps[id(p)] == p._stamp[0] for p in distinct)
+                    and np.logical_or.reduce([other.present[i] for i in key]).all()
+                    and np.logical_or.reduce([other.present_c[i] for i in key]).all()):
+                return key, other
+    return key, None
 
 
 def _unique_by_identity(items):
@@ -767,7 +778,7 @@ def _unique_by_identity(items):
     return out
 
 
-def _join_pulses(pulses):
+def _join_pulses(pulses, want_maps: bool = True):
     """Host part of a concatenation: validation, joined Hamiltonians, new PulseSequence.  Returns
     ``(newpulse, control mapping, noise mapping, distinct pulse objects, position -> distinct index,
     plan or None)``.  Written for long sequences of recurring gates (randomized benchmarking): the outcome
@@ -792,6 +803,8 @@ def _join_pulses(pulses):
                                              joined[-1], pulses[0].basis)
         taus = [plan.taus[i] for i in ids]
         newpulse.tau = sum([taus[i] for i in order])
+        if not want_maps:      # concatenate() reads the plan's presence rows instead
+            return newpulse, None, None, distinct, order, plan
         c_maps, n_maps = [plan.maps[0][i] for i in ids], [plan.maps[1][i] for i in ids]
         c_map = {pos: c_maps[i] for pos, i in enumerate(order)}
         n_map = {pos: n_maps[i] for pos, i in enumerate(order)}
@@ -834,6 +847,12 @@ def _join_pulses(pulses):
             row = np.zeros(len(n_ids), dtype=bool)
             row[[column[ident] for ident in m.values()]] = True
             plan.present[id(p)] = row
+        column_c = {ident: i for i, ident in enumerate(c_ids.tolist())}
+        plan.present_c = {}
+        for p, m in zip(distinct, c_maps):
+            row = np.zeros(len(c_ids), dtype=bool)
+            row[[column_c[ident] for ident in m.values()]] = True
+            plan.present_c[id(p)] = row
         plan.basis = pulses[0].basis
         plan.library = None
         plan.stamps = {id(p): p._stamp[0] for p in distinct}    # last: reading tau may have cached it
@@ -869,7 +888,8 @@ def _gate_library(ctx, plan, distinct, omega, ctrl, phases, liouville, basis):
               ((n,) + np.shape(liouville[0]), np.float64), ((n,) + np.shape(props[0]), np.complex128),
               (np.shape(basis), np.complex128)]
     total = sum(int(np.prod(sh))*np.dtype(dt).itemsize for sh, dt in shapes)
-    keep = plan is not None and total <= (16 << 20)
+    # (a plan borrowed from a superset of these gates keeps only a library that covers all of ITS gates)
+    keep = plan is not None and total <= (16 << 20) and len(plan.refs) == n
     stacks = _lib.empty_many(shapes, ctx) if keep else [np.empty(sh, dtype=dt) for sh, dt in shapes]
     for i in range(n):
         for stack, part in zip(stacks[:4], (ctrl[i], phases[i], liouville[i], props[i])):
@@ -879,7 +899,8 @@ def _gate_library(ctx, plan, distinct, omega, ctrl, phases, liouville, basis):
         for stack in stacks:
             _lib.mirror_input(ctx, stack)
         plan.library = (np.array(omega, copy=True), tuple(stacks), {id(p): i for i, p in enumerate(distinct)})
-        plan.stamps = {id(p): p._stamp[0] for p in distinct}   # gathering the parts may have cached some
+        for p in distinct:                                     # gathering the parts may have cached some
+            plan.stamps[id(p)] = p._stamp[0]
     return (*stacks, list(range(n)))
 
 
@@ -935,7 +956,7 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
     if len(pulses) == 1:
         return copy.deepcopy(pulses[0])
 
-    newpulse, _, n_oper_mapping, distinct, inverse, plan = _join_pulses(pulses)
+    newpulse, _, n_oper_mapping, distinct, inverse, plan = _join_pulses(pulses, want_maps=False)
     have_propagators = all('total_propagator' in pls._data for pls in distinct)
 
     def host_total_propagator():
@@ -1039,7 +1060,7 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
         p = _lib.ptr
         _lib.keep_on_device(ctx)
         _lib.check(ctx, _lib.lib().ffb_concatenate_many(
-            ctx, 1, len(index), len(distinct), d, n_nops, n_basis, n_omega, p(index), p(lib_B),
+            ctx, 1, len(index), lib_B.shape[0], d, n_nops, n_basis, n_omega, p(index), p(lib_B),
             p(lib_ph), p(lib_L), p(lib_U), p(basis), None, 0, 0, p(omega_arr), p(U), p(liouville),
             p(B), p(F), None, p(tau), p(total_phases)))
         _lib.freeze_shadowed(ctx, total_phases, B, F)

@@ -401,3 +401,50 @@ def test_choi_and_complete_positivity():
         assert so.liouville_is_cCP(gen, basis) and not so.liouville_is_CP(gen, basis)
         stack = np.stack([L, -np.eye(d*d)])
         assert list(so.liouville_is_CP(stack, basis)) == [True, False]
+
+
+def test_join_plan_of_a_superset_is_only_borrowed_when_valid():
+    """A sequence over a SUBSET of a gate library uses the remembered plan of the whole library if (and only
+    if) its gates together still carry all operators of that plan's join; the result must be what a join from
+    scratch gives (same operators, identifiers, coefficient rows, mappings, tau)."""
+    from filter_functions_b200 import pulse_sequence as ps
+    rng = np.random.default_rng(17)
+    X, Y, Z = util.paulis[1:]
+    ops = {'X': X/2, 'Y': Y/2, 'Z': Z/2}
+
+    def gate(c_names, n_names, G):
+        return ff.PulseSequence([[ops[k], rng.standard_normal(G), k] for k in c_names],
+                                [[ops[k], np.ones(G), 'n' + k] for k in n_names], 1 - 0.5*rng.random(G))
+    library = [gate('XY', 'Z', 2), gate('X', 'Z', 1), gate('Y', 'ZX', 3), gate('XY', 'ZX', 2), gate('Y', 'Z', 1)]
+
+    def joined(seq):
+        new, cmap, nmap = concatenate_without_filter_function(seq, return_identifier_mappings=True)
+        return (new.c_opers, list(new.c_oper_identifiers), new.c_coeffs, new.n_opers,
+                list(new.n_oper_identifiers), new.n_coeffs, new.dt, new.tau, cmap, nmap)
+
+    ps._SEQUENCE_PLANS.clear()
+    joined(library)                                   # remembers the plan of the whole library
+    assert len(ps._SEQUENCE_PLANS) == 1
+    full = dict(ps._SEQUENCE_PLANS)
+    n_borrowed = 0
+    for trial in range(60):
+        picks = rng.integers(0, len(library), size=rng.integers(2, 9))
+        seq = [library[i] for i in picks]
+        ps._SEQUENCE_PLANS.clear()
+        ps._SEQUENCE_PLANS.update(full)               # only the whole library's plan is known
+        distinct, _ = ps._distinct_pulses(seq)
+        plan = ps._plan_for(distinct)[1]
+        carries_all = ({k for p in distinct for k in p.c_oper_identifiers} == {'X', 'Y'}
+                       and {k for p in distinct for k in p.n_oper_identifiers} == {'nX', 'nZ'})
+        assert (plan is not None) == carries_all
+        n_borrowed += plan is not None
+        got = joined(seq)
+        ps._SEQUENCE_PLANS.clear()
+        want = joined(seq)                            # from scratch
+        for a, b in zip(got, want):
+            if isinstance(a, np.ndarray):
+                assert a.shape == b.shape and np.array_equal(a, b)
+            else:
+                assert a == b
+    assert 5 < n_borrowed < 60
+    ps._SEQUENCE_PLANS.clear()
