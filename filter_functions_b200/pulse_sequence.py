@@ -789,9 +789,9 @@ def _join_pulses(pulses, want_maps: bool = True):
         pulses = tuple(pulses)
     except TypeError:
         raise TypeError(f'Expected pulses to be iterable, not {type(pulses)}')
-    if not all(isinstance(pulse, PulseSequence) for pulse in pulses):
-        raise TypeError('Can only concatenate PulseSequences!')
     distinct, order = _distinct_pulses(pulses)
+    if not all(isinstance(pulse, PulseSequence) for pulse in distinct):
+        raise TypeError('Can only concatenate PulseSequences!')
     key, plan = _plan_for(distinct)
     if plan is not None:
         ids = [id(p) for p in distinct]                     # per distinct object, then plain indexing
@@ -975,7 +975,10 @@ def concatenate(pulses: Iterable[PulseSequence], calc_pulse_correlation_FF: bool
     new_ids = newpulse.n_oper_identifiers.tolist()
     if plan is not None:
         present = np.array([plan.present[id(p)] for p in distinct])
-        n_opers_present = present[inverse]
+        # (every gate carries every operator -- the randomized-benchmarking case: the rows of all positions
+        # are then one broadcast row, not a gather over the sequence)
+        n_opers_present = (np.broadcast_to(present[0], (len(pulses), present.shape[1])) if present.all()
+                           else present[inverse])
     else:
         column = {ident: i for i, ident in enumerate(new_ids)}
         rows_by_mapping, present_rows = {}, []
